@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s of the MD-Bench short-range force path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU build (oracle/_ref)
+
+A "step" is one complete MD run of the workload: `ntimes` (200) velocity-Verlet timesteps of the
+Cu-FCC LJ system starting from the generated lattice, i.e. exactly what the reference's
+"Performance: ... million atom updates per second" line measures (verletlist/main.c:337-338),
+plus -- inside the timed region, which makes our number conservative -- the state reset, ghost
+setup, first neighbor build and first force that the reference excludes from TOTAL.
+Workload at N GPUs: Cu FCC 128^3 unit cells (8 388 608 atoms) PER GPU (weak scaling towards
+BASELINE config 5, 256^3 = 67M atoms at 8 GPUs), LJ sigma=eps=1, cutoff 2.5, skin 0.3, rebuild every
+20, verletlist full neighbor lists, DP.
+"""
+import argparse
+import importlib
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "atom-steps/sec (LJ Cu FCC, verletlist, full neighbor lists)"
+UNIT = "atom-steps/s"
+# algorithmic work of the LJ full-list force kernel per atom-step
+FLOP_PER_ATOM_STEP = 1429.0           # 8*L + 15*C, L = 76.035 listed, C = 54.74 inside the cutoff
+BYTES_PER_ATOM_STEP = {"dp": 365.0, "sp": 335.0}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.lines, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [q.strip() for q in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref, built from /root/reference by oracle/Makefile)
+def run_reference_binary(nx, ntimes, threads, variant="vl_dp_aos"):
+    """returns dict(atom_steps, total_s, perf) parsed from the reference's own report, or None"""
+    from refbind import ref_binary
+    exe = ref_binary(variant)
+    if exe is None:
+        return None
+    try:
+        with open("/proc/cpuinfo") as f:
+            if "avx512f" not in f.read():
+                return None
+    except OSError:
+        return None
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_SCHEDULE="static", OMP_PROC_BIND="close")
+    t0 = time.perf_counter()
+    try:
+        out = subprocess.run([exe, "-nx", str(nx), "-ny", str(nx), "-nz", str(nx), "-n", str(ntimes)],
+                             env=env, capture_output=True, text=True, timeout=900).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    wall = time.perf_counter() - t0
+    m = re.search(r"TOTAL ([0-9.]+)s FORCE ([0-9.]+)s NEIGH ([0-9.]+)s", out)
+    p = re.search(r"Performance: ([0-9.]+) million atom updates per second", out)
+    a = re.search(r"System: (\d+) atoms", out)
+    if not (m and p and a):
+        return None
+    return dict(atoms=int(a.group(1)), ntimes=ntimes, total_s=float(m.group(1)), force_s=float(m.group(2)),
+                neigh_s=float(m.group(3)), perf=float(p.group(1)) * 1e6, wall_s=wall)
+
+
+def run_port_oracle(nx, ntimes):
+    """fallback CPU baseline: the oracle restatement (single thread, scalar)"""
+    from portbind import OracleVL
+    o = OracleVL(True)
+    o.configure(nx=nx, ntimes=ntimes)
+    o.setup(create=True)
+    t0 = time.perf_counter()
+    o.run(ntimes)
+    dt = time.perf_counter() - t0
+    n = o.geti("Natoms")
+    return dict(atoms=n, ntimes=ntimes, total_s=dt, perf=n * ntimes / dt, wall_s=dt)
+
+
+def cpu_baseline(sample_nx=64, sample_steps=40):
+    thr = host_threads()
+    r = run_reference_binary(sample_nx, sample_steps, thr)
+    if r is not None:
+        return {"value": r["perf"], "unit": UNIT, "cores": thr, "kind": "reference",
+                "sample": "reference MDBench (GCC -Ofast AVX512 OpenMP static) Cu FCC %d^3 = %d atoms x %d steps; TOTAL %.2fs FORCE %.2fs NEIGH %.2fs"
+                          % (sample_nx, r["atoms"], sample_steps, r["total_s"], r["force_s"], r["neigh_s"])}
+    r = run_port_oracle(32, 20)
+    return {"value": r["perf"], "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle restatement (scalar C, 1 thread) Cu FCC 32^3 x 20 steps; reference binary not runnable on this host"}
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    thr = host_threads()
+    total_steps = args.steps + args.warmup
+    # bounded sample per step: ~8 s of CPU work -> the whole run stays within a few minutes
+    nx, nt = args.ref_nx, args.ref_ntimes
+    runs = []
+    kind = "reference"
+    for i in range(total_steps):
+        r = run_reference_binary(nx, nt, thr)
+        if r is None:
+            kind = "port"
+            r = run_port_oracle(32, 20)
+            thr = 1
+        if i >= args.warmup:
+            runs.append(r)
+    atom_steps = sum(r["atoms"] * r["ntimes"] for r in runs)
+    tsum = sum(r["total_s"] for r in runs)
+    val = atom_steps / tsum
+    sample = ("reference MDBench-vl_dp_aos Cu FCC %d^3 x %d steps per bench step" % (nx, nt)) if kind == "reference" \
+        else "oracle restatement Cu FCC 32^3 x 20 steps per bench step"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(r["wall_s"] for r in runs) / max(1, len(runs)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": "Cu FCC %dx%dx%d unit cells per GPU (%d atoms/GPU), LJ sigma=eps=1 rc=2.5 skin=0.3, reneigh 20, "
+                        "verletlist full neighbor lists, %s, %d timesteps per bench step (BASELINE config 1 physics at config 5 per-GPU size)"
+                        % (args.nx, args.nx, args.nx, 4 * args.nx ** 3, args.precision.upper(), args.ntimes),
+            "nx_per_gpu": args.nx, "ntimes": args.ntimes, "precision": args.precision,
+            "l2": "inputs larger than L2 (neighbor list %.1f GB + positions %.2f GB per GPU vs 126 MB L2)"
+                  % (4 * args.nx ** 3 * 100 * 4 / 1e9, 4 * args.nx ** 3 * 24 / 1e9),
+            "parallelism": "1 domain per GPU" if world == 1 else "replicas x%d (independent domains, no collective)" % world}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=128, help="unit cells per GPU per dimension")
+    ap.add_argument("--ntimes", type=int, default=200)
+    ap.add_argument("--precision", default="dp", choices=["dp", "sp"])
+    ap.add_argument("--half", type=int, default=0)
+    ap.add_argument("--ref-nx", type=int, default=64)
+    ap.add_argument("--ref-ntimes", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    m = importlib.import_module("md-bench_b200")
+    dp = args.precision == "dp"
+    P = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx,
+                         ntimes=args.ntimes, half_neigh=args.half)
+    sim = m.Simulation(P, device=local)
+    sim.setStream(torch.cuda.current_stream().cuda_stream)
+    natoms = sim.createAtom()
+    sim.setup(adjust=True)
+    sim.saveState()
+    listed0, inside0 = sim.countPairs()
+
+    def one_step():
+        sim.restoreState()
+        sim.setup(adjust=False)
+        return sim.run(args.ntimes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    sim.resetKernelStats()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        rec, _ = one_step()
+    ev1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = sim.kernelStats()["launches"]
+    listed1, inside1 = sim.countPairs()
+    value = natoms * world * args.ntimes * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (LJ force): CUDA-event time per launch, measured live ----
+    sim.setTiming(True)
+    sim.resetKernelStats()
+    _, tm = one_step()
+    ks = sim.kernelStats()
+    sim.setTiming(False)
+    f_ms = ks["force_ms"] / max(1, ks["force_launches"])
+    peak_tf = m.measure_fma_peak(m.DP if dp else m.SP, local)
+    ach_tf = FLOP_PER_ATOM_STEP * natoms / (f_ms * 1e-3) * 1e-12
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    ach_gbs = BYTES_PER_ATOM_STEP[args.precision] * natoms / (f_ms * 1e-3) * 1e-9
+    roofline = {"kernel": "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
+                "bound": "fp64" if dp else "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                "peak_source": "measured in this run: FMA issue micro-benchmark (md-bench_b200/csrc/peaks.cu)",
+                "ms_per_launch": f_ms, "flop_per_atom_step": FLOP_PER_ATOM_STEP,
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                        "bytes_per_atom_step": BYTES_PER_ATOM_STEP[args.precision], "peak_source": hbm_src},
+                "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
+                "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"]),
+                "pairs_per_atom": {"listed_t0": listed0 / natoms, "in_cutoff_t0": inside0 / natoms,
+                                   "listed_end": listed1 / natoms, "in_cutoff_end": inside1 / natoms}}
+
+    # ---- e2e: same metric through the C ABI with HOST buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        sim.restoreState()
+        real = np.float64 if dp else np.float32
+        tdt = torch.float64 if dp else torch.float32
+        hx = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+        hv = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+        ox = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+        ov = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+        sim.get("x", out=hx.numpy())
+        sim.get("v", out=hv.numpy())
+        ksteps = max(1, min(args.steps, 3))
+        for it in range(1 + ksteps):
+            if it == 1:
+                barrier()
+                t0 = time.perf_counter()
+            sim.setAtoms(hx.numpy(), hv.numpy())      # H2D from pinned host memory
+            sim.setup(adjust=False)
+            rec_e, _ = sim.run(args.ntimes)            # thermo records come back D2H
+            sim.get("x", out=ox.numpy())               # D2H of the final state
+            sim.get("v", out=ov.numpy())
+        barrier()
+        te = time.perf_counter() - t0
+        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+        nb = natoms * 3 * np.dtype(real).itemsize
+        e2e = {"value": natoms * world * args.ntimes * ksteps / te, "unit": UNIT, "h2d_bytes_per_step": 2 * nb,
+               "d2h_bytes_per_step": 2 * nb + 8 * 3 * len(rec_e), "steps": ksteps,
+               "final_T": float(rec_e[-1][1])}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64" if dp else "f32", "data": "synthetic", "config": workload_config(args, world),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,180 @@
+/*
+ * mdb200.h -- C ABI of libmdb200: a B200 (sm_100a) implementation of MD-Bench's short-range force
+ * hot path (binning -> neighbor build -> LJ/EAM force -> velocity-Verlet -> PBC ghosts).
+ *
+ * This is the drop-in boundary.  MD-Bench's "plugin API" is a set of global C function pointers
+ * (reference src/verletlist/force.h:16-17, neighbor.h:55-56, integrate.h:12-14, pbc.h:15-17) plus
+ * a few plain functions called from main.c (setupPbc pbc.h:22, setupNeighbor neighbor.h:59,
+ * initDevice device.h:20, computeThermo/adjustThermo thermo.h).  Every entry point below names
+ * the reference interface it replaces.  The reference passes its Atom/Neighbor/Parameter structs,
+ * whose layout depends on compile-time -DPRECISION / -DAOS; here the same choices are RUN-TIME
+ * fields of mdb_params and all state lives behind an opaque handle, so one library serves the
+ * SP/DP and AOS/SOA builds of the driver.  INTEGRATION.md shows the shim that binds these entry
+ * points to the reference's function pointers.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++ or torch types.
+ *   - host buffers are `precision`-typed (float for MDB_SP, double for MDB_DP) and laid out as the
+ *     reference's atom_x()/atom_y()/atom_z() macros expect (verletlist/atom.h:51-73):
+ *       MDB_AOS: x points to 3*n reals {x0,y0,z0,x1,...}; y,z are ignored (may be NULL);
+ *       MDB_SOA: x,y,z point to n reals each.
+ *   - functions returning int return 0 on success, non-zero on failure; mdb_last_error() gives the
+ *     message.  (The reference prints and exit()s, common/device.c:15-21; the driver in
+ *     md-bench_b200/driver does the same on a non-zero return.)
+ *   - there is NO CPU fallback: without a CUDA device mdb_create() fails.
+ *   - one mdb_ctx = one spatial domain on one GPU; not re-entrant per ctx (like the reference's
+ *     file-static state), distinct ctx are independent.
+ */
+#ifndef MDB200_H
+#define MDB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB200_ABI_VERSION 1
+
+enum { MDB_SP = 1, MDB_DP = 2 };     /* = reference -DPRECISION (config.mk:103-107) */
+enum { MDB_AOS = 0, MDB_SOA = 1 };   /* = reference DATA_LAYOUT / -DAOS (config.mk:100-102) */
+enum { MDB_FF_LJ = 0, MDB_FF_EAM = 1 }; /* = enum forcetype, verletlist/force.h:19 */
+
+/* Mirror of the reference's Parameter (common/parameter.h:27-61); same field names and meaning.
+ * Reals are passed as double and narrowed to `precision` exactly where the reference narrows. */
+typedef struct mdb_params {
+    int precision;     /* MDB_SP | MDB_DP */
+    int layout;        /* MDB_AOS | MDB_SOA: layout of HOST buffers passed to/from this library */
+    int force_field;   /* MDB_FF_LJ | MDB_FF_EAM */
+    double epsilon, sigma, temp, rho, mass;
+    int ntypes, ntimes, nstat, reneigh_every, half_neigh;
+    double dt, skin, cutforce;
+    int nx, ny, nz;
+    int pbc_x, pbc_y, pbc_z;
+    /* box from an input file (readers set xlo..zhi, atom.c:199-562); from_input = 0 -> generated
+     * FCC lattice box nx*lattice (main.c:42-45) */
+    int from_input;
+    double xlo, xhi, ylo, yhi, zlo, zhi;
+    /* EAM overrides (initEam, common/eam_utils.c:27-35) are applied by mdb_setEam() */
+} mdb_params;
+
+typedef struct mdb_ctx mdb_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int         mdb_abi_version(void);
+const char* mdb_last_error(void);
+/* defaults of initParameter, common/parameter.c:16-51 (precision DP, layout AOS) */
+void        mdb_default_params(mdb_params* p);
+/* replaces initAtom/initPbc/initStats/initNeighbor + initDevice (main.c:47-51,68; device_spec.c:11).
+ * device = CUDA ordinal.  Derives lattice, box, cutneigh = cutforce + skin (main.c:233), sigma6,
+ * dtforce (parameter.c:115-120).  Returns NULL on failure. */
+mdb_ctx*    mdb_create(const mdb_params* p, int device);
+void        mdb_destroy(mdb_ctx* c);
+/* run all work of this ctx on the given cudaStream_t (passed as void*); NULL = ctx-owned stream */
+int         mdb_setStream(mdb_ctx* c, void* cuda_stream);
+int         mdb_sync(mdb_ctx* c);
+
+/* ---- atoms ---------------------------------------------------------------------------------- */
+/* createAtom (verletlist/atom.c:67-187): FCC lattice + Park-Miller velocities, generated on the
+ * device with the reference's emission order (so atom indices match). Returns Natoms or <0. */
+long long   mdb_createAtom(mdb_ctx* c);
+/* what the file readers (atom.c:199-562) hand over: n atoms from HOST buffers */
+int         mdb_setAtoms(mdb_ctx* c, long long n, const void* x, const void* y, const void* z,
+                         const void* vx, const void* vy, const void* vz, const int* type);
+/* same, buffers already resident in device memory (same precision/layout rules) */
+int         mdb_setAtomsDevice(mdb_ctx* c, long long n, const void* x, const void* y, const void* z,
+                               const void* vx, const void* vy, const void* vz, const int* type);
+/* copy local atoms back to HOST buffers; which = 'x' | 'v' | 'f'; with_ghosts!=0 appends the
+ * ghost atoms (x only), i.e. Nlocal+Nghost entries as in the reference's arrays */
+int         mdb_getAtoms(mdb_ctx* c, int which, int with_ghosts, void* x, void* y, void* z);
+/* Natoms, Nlocal, Nghost, Nmax, maxneighs (Atom / Neighbor scalar fields) */
+int         mdb_getCounts(mdb_ctx* c, long long* Natoms, long long* Nlocal, long long* Nghost,
+                          long long* Nmax, int* maxneighs);
+/* keep / restore a device-side copy of the current x,v (bench: restart a run without H2D) */
+int         mdb_saveState(mdb_ctx* c);
+int         mdb_restoreState(mdb_ctx* c);
+
+/* ---- thermo (common/thermo.c) ----------------------------------------------------------------- */
+int         mdb_setupThermo(mdb_ctx* c);                         /* setupThermo, thermo.c:30-53 */
+int         mdb_adjustThermo(mdb_ctx* c);                        /* adjustThermo, thermo.c:82-122 */
+/* computeThermo, thermo.c:55-80: kinetic temperature and pressure of the local atoms */
+int         mdb_computeThermo(mdb_ctx* c, double* T, double* P);
+
+/* ---- operators: one entry point per reference function pointer ------------------------------ */
+int         mdb_setupNeighbor(mdb_ctx* c);                       /* neighbor.c:64-184 */
+int         mdb_setupPbc(mdb_ctx* c);                            /* pbc.c:98-227 (on the device) */
+int         mdb_updatePbc(mdb_ctx* c, int reneigh);              /* UpdatePbcFunction updatePbc, pbc.c:42-55 */
+int         mdb_updateAtomsPbc(mdb_ctx* c, int reneigh);         /* updateAtomsPbc, pbc.c:59-84 */
+int         mdb_buildNeighbor(mdb_ctx* c);                       /* BuildNeighborFunction, neighbor.c:186-264 (+binatoms 329-358) */
+/* ComputeForceFunction (force.h:16): return the seconds spent, like the reference; <0 on error */
+double      mdb_computeForce(mdb_ctx* c);                        /* dispatch of initForce, force.c:13-34 */
+double      mdb_computeForceLJFullNeigh(mdb_ctx* c);             /* force_lj.c:14-105 */
+double      mdb_computeForceLJHalfNeigh(mdb_ctx* c);             /* force_lj.c:107-198 */
+double      mdb_computeForceEam(mdb_ctx* c);                     /* force_eam.c:19-231 */
+int         mdb_initialIntegrate(mdb_ctx* c, int reneigh);       /* IntegrationFunction, integrate.c:21-31 */
+int         mdb_finalIntegrate(mdb_ctx* c, int reneigh);         /* integrate.c:33-40 */
+
+/* ---- driver-level flow ------------------------------------------------------------------------ */
+/* main.c:58-72 after the atoms exist: setupNeighbor, setupThermo, [adjustThermo if adjust!=0],
+ * setupPbc, updatePbc, buildNeighbor */
+int         mdb_setup(mdb_ctx* c, int adjust);
+int         mdb_reneighbour(mdb_ctx* c);                         /* main.c:76-95 */
+/* main.c:244-288: thermo(0), first force, nsteps iterations, thermo(-1).  The whole loop is
+ * enqueued on the ctx stream without host round-trips except one flag read per rebuild.
+ * thermo_out (may be NULL) receives up to max_records (step, T, P) triples; *nrecords their count.
+ * timers (may be NULL) = {TOTAL, FORCE, NEIGH} seconds as the reference reports them
+ * (TOTAL excludes the first force call, main.c:250-252); FORCE/NEIGH are only split out when
+ * mdb_setTiming(c, 1) was called (adds event records + syncs per phase). */
+int         mdb_run(mdb_ctx* c, int nsteps, double* thermo_out, int max_records, int* nrecords,
+                    double* timers);
+int         mdb_setTiming(mdb_ctx* c, int on);
+/* accumulated CUDA-event time (ms) and launch count of the force kernel since the last reset
+ * (only collected while timing is on); used by bench.py for the roofline */
+int         mdb_getKernelStats(mdb_ctx* c, double* force_ms, long long* force_launches,
+                               double* neigh_ms, long long* neigh_launches,
+                               long long* total_launches);
+int         mdb_resetKernelStats(mdb_ctx* c);
+
+/* ---- EAM (common/eam_utils.c, verletlist/force_eam.c) ---------------------------------------- */
+/* hand over funcfl tables as read from the potential file (0-based frho[nrho], zr[nr], rhor[nr],
+ * doubles): applies initEam's overrides (mass, cutforce = cut, cutneigh = cut + 1, temp = 600,
+ * dt = 0.001, rho = 0.07041125; eam_utils.c:27-35) and builds the spline tables (file2array,
+ * array2spline, interpolate; eam_utils.c:95-284).  Call before mdb_createAtom/mdb_setup. */
+int         mdb_setEam(mdb_ctx* c, int nrho, double drho, int nr, double dr, double cut, double mass,
+                       const double* frho, const double* zr, const double* rhor);
+/* or hand over finished spline tables (precision-typed) */
+int         mdb_setEamSplines(mdb_ctx* c, int nr, int nrho, int nr_tot, int nrho_tot, double rdr,
+                              double rdrho, const void* rhor_spline, const void* frho_spline,
+                              const void* z2r_spline);
+int         mdb_getEamSplines(mdb_ctx* c, int* nr, int* nrho, int* nr_tot, int* nrho_tot,
+                              double* rdr, double* rdrho, void* rhor_spline, void* frho_spline,
+                              void* z2r_spline);
+
+/* ---- parity accessors (what the reference keeps in host-visible arrays) ------------------------ */
+/* Neighbor.numneigh[Nlocal] and Neighbor.neighbors as row-major rows of `row_stride` ints
+ * (neighbor.h:18-28); indices are the reference's (ghost g has index Nlocal+g). */
+int         mdb_getNeighbors(mdb_ctx* c, int* numneigh, int* neighbors, int row_stride);
+/* Atom.border_map and the file-static PBCx/y/z of pbc.c:17-18, Nghost entries each */
+int         mdb_getGhostMap(mdb_ctx* c, int* border_map, int* PBCx, int* PBCy, int* PBCz);
+/* bin geometry of setupNeighbor (neighbor.c:24-38): ints {nbinx,nbiny,nbinz,mbinx,mbiny,mbinz,
+ * mbinxlo,mbinylo,mbinzlo,mbins,nstencil,max bin count}, reals {bininvx,y,z,binsizex,y,z,
+ * cutneighsq,cutneigh,xprd,yprd,zprd,lattice,dtforce,cutforce} */
+int         mdb_getNeighborParams(mdb_ctx* c, int ints[12], double reals[14]);
+int         mdb_getStencil(mdb_ctx* c, int* stencil);            /* nstencil ints */
+int         mdb_getBinCounts(mdb_ctx* c, int* bincount);          /* mbins ints, after buildNeighbor */
+int         mdb_getEamFp(mdb_ctx* c, void* fp, int with_ghosts);   /* Eam.fp after computeForceEam */
+
+/* ---- workload counters for the roofline (verletlist/stats.h:13-18 equivalents) ----------------- */
+/* listed pairs (sum of numneigh) of the current list, and pairs inside the force cutoff for the
+ * current positions; computed on demand by a counting kernel */
+int         mdb_countPairs(mdb_ctx* c, long long* listed, long long* in_cutoff);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+/* FMA issue-rate micro-benchmark on `device`: dense FP32 (MDB_SP) or FP64 (MDB_DP) vector peak in
+ * TFLOP/s (FMA = 2 flop).  The roofline denominator for the force kernels. */
+int         mdb_measureFmaPeak(int precision, int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDB200_H */

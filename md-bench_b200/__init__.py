@@ -1,0 +1,337 @@
+"""md-bench_b200 -- host-side mirror of MD-Bench's operator interface over libmdb200 (C ABI,
+include/mdb200.h), for tests and bench.py.
+
+The method names follow the reference's function pointers / driver functions
+(computeForce, buildNeighbor, initialIntegrate, finalIntegrate, updatePbc, updateAtomsPbc, setupPbc,
+setupNeighbor, reneighbour, computeThermo, adjustThermo; reference src/verletlist/{force,neighbor,
+integrate,pbc}.h and main.c) so parity tests read like the reference's own driver.
+
+This package never imports anything from oracle/ and has no CPU path: constructing a Simulation
+without a CUDA device raises MdbError.  (The directory name contains a hyphen; import it with
+importlib.import_module("md-bench_b200") -- see tests/conftest.py.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SP, DP = 1, 2
+AOS, SOA = 0, 1
+FF_LJ, FF_EAM = 0, 1
+
+
+class MdbError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """struct mdb_params (include/mdb200.h) <- reference Parameter, common/parameter.h:27-61"""
+    _fields_ = [
+        ("precision", C.c_int), ("layout", C.c_int), ("force_field", C.c_int),
+        ("epsilon", C.c_double), ("sigma", C.c_double), ("temp", C.c_double), ("rho", C.c_double),
+        ("mass", C.c_double),
+        ("ntypes", C.c_int), ("ntimes", C.c_int), ("nstat", C.c_int), ("reneigh_every", C.c_int),
+        ("half_neigh", C.c_int),
+        ("dt", C.c_double), ("skin", C.c_double), ("cutforce", C.c_double),
+        ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+        ("pbc_x", C.c_int), ("pbc_y", C.c_int), ("pbc_z", C.c_int),
+        ("from_input", C.c_int),
+        ("xlo", C.c_double), ("xhi", C.c_double), ("ylo", C.c_double), ("yhi", C.c_double),
+        ("zlo", C.c_double), ("zhi", C.c_double),
+    ]
+
+
+EXPORTS = [
+    "mdb_abi_version", "mdb_last_error", "mdb_default_params", "mdb_create", "mdb_destroy",
+    "mdb_setStream", "mdb_sync", "mdb_createAtom", "mdb_setAtoms", "mdb_setAtomsDevice",
+    "mdb_getAtoms", "mdb_getCounts", "mdb_saveState", "mdb_restoreState", "mdb_setupThermo",
+    "mdb_adjustThermo", "mdb_computeThermo", "mdb_setupNeighbor", "mdb_setupPbc", "mdb_updatePbc",
+    "mdb_updateAtomsPbc", "mdb_buildNeighbor", "mdb_computeForce", "mdb_computeForceLJFullNeigh",
+    "mdb_computeForceLJHalfNeigh", "mdb_computeForceEam", "mdb_initialIntegrate",
+    "mdb_finalIntegrate", "mdb_setup", "mdb_reneighbour", "mdb_run", "mdb_setTiming",
+    "mdb_getKernelStats", "mdb_resetKernelStats", "mdb_setEam", "mdb_setEamSplines",
+    "mdb_getEamSplines", "mdb_getNeighbors", "mdb_getGhostMap", "mdb_getNeighborParams",
+    "mdb_getStencil", "mdb_getBinCounts", "mdb_getEamFp", "mdb_countPairs", "mdb_measureFmaPeak",
+]
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(HERE, "libmdb200.so")
+
+
+def load_library(build=True):
+    """dlopen libmdb200.so (building it first if sources are newer). Fails loudly if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build and _build.needs_build():
+        _build.build()
+    if not os.path.exists(lib_path()):
+        raise MdbError("libmdb200.so is missing: run `python md-bench_b200/build.py` (no CPU fallback exists)")
+    L = C.CDLL(lib_path())
+    L.mdb_last_error.restype = C.c_char_p
+    L.mdb_create.restype = C.c_void_p
+    L.mdb_create.argtypes = [C.POINTER(Params), C.c_int]
+    L.mdb_createAtom.restype = C.c_longlong
+    for f in ("mdb_computeForce", "mdb_computeForceLJFullNeigh", "mdb_computeForceLJHalfNeigh",
+              "mdb_computeForceEam"):
+        getattr(L, f).restype = C.c_double
+        getattr(L, f).argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def default_params(**kw):
+    L = load_library()
+    p = Params()
+    L.mdb_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def measure_fma_peak(precision=DP, device=0):
+    """FP32/FP64 vector FMA peak of `device` in TFLOP/s (micro-benchmark in csrc/peaks.cu)"""
+    L = load_library()
+    t = C.c_double()
+    if L.mdb_measureFmaPeak(precision, device, C.byref(t)) != 0:
+        raise MdbError("mdb_measureFmaPeak failed")
+    return t.value
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Simulation:
+    """One simulation domain on one GPU (opaque mdb_ctx)."""
+
+    def __init__(self, params=None, device=0, **kw):
+        self.L = load_library()
+        self.params = params if params is not None else default_params(**kw)
+        self.dp = self.params.precision == DP
+        self.aos = self.params.layout == AOS
+        self.np_real = np.float64 if self.dp else np.float32
+        h = self.L.mdb_create(C.byref(self.params), device)
+        if not h:
+            raise MdbError(self.L.mdb_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mdb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+
+    # ---- atoms ----
+    def createAtom(self):
+        n = self.L.mdb_createAtom(self.h)
+        if n < 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+        return n
+
+    def _pack(self, a):
+        """(n,3) array -> host buffers in this ctx's layout"""
+        a = np.ascontiguousarray(a, dtype=self.np_real)
+        if self.aos:
+            return [a, None, None]
+        return [np.ascontiguousarray(a[:, k]) for k in range(3)]
+
+    def setAtoms(self, x, v=None, type=None):
+        n = x.shape[0]
+        bx = self._pack(x)
+        bv = self._pack(v) if v is not None else [None] * 3
+        t = None if type is None else np.ascontiguousarray(type, dtype=np.int32)
+        self._ck(self.L.mdb_setAtoms(self.h, C.c_longlong(n), *[_vp(b) for b in bx],
+                                     *[_vp(b) for b in bv], _vp(t)))
+
+    def setAtomsDevice(self, n, ptrs_x, ptrs_v=(None, None, None), type_ptr=None):
+        cv = lambda p: None if p is None else C.c_void_p(p)
+        self._ck(self.L.mdb_setAtomsDevice(self.h, C.c_longlong(n), *[cv(p) for p in ptrs_x],
+                                           *[cv(p) for p in ptrs_v], cv(type_ptr)))
+
+    def counts(self):
+        v = [C.c_longlong() for _ in range(4)]
+        mn = C.c_int()
+        self._ck(self.L.mdb_getCounts(self.h, *[C.byref(q) for q in v], C.byref(mn)))
+        return dict(Natoms=v[0].value, Nlocal=v[1].value, Nghost=v[2].value, Nmax=v[3].value,
+                    maxneighs=mn.value)
+
+    def get(self, what, ghosts=False, out=None):
+        """x / v / f as an (n,3) array in the reference's index order.  `out` (AOS layout only):
+        a preallocated C-contiguous (n,3) array, e.g. a view of pinned host memory."""
+        c = self.counts()
+        n = c["Nlocal"] + (c["Nghost"] if (ghosts and what == "x") else 0)
+        if self.aos:
+            a = out if out is not None else np.empty((n, 3), dtype=self.np_real)
+            assert a.shape == (n, 3) and a.dtype == self.np_real and a.flags["C_CONTIGUOUS"]
+            self._ck(self.L.mdb_getAtoms(self.h, ord(what), int(ghosts), _vp(a), None, None))
+            return a
+        cols = [np.empty(n, dtype=self.np_real) for _ in range(3)]
+        self._ck(self.L.mdb_getAtoms(self.h, ord(what), int(ghosts), *[_vp(q) for q in cols]))
+        return np.stack(cols, axis=1)
+
+    def saveState(self): self._ck(self.L.mdb_saveState(self.h))
+    def restoreState(self): self._ck(self.L.mdb_restoreState(self.h))
+    def setStream(self, stream_ptr): self._ck(self.L.mdb_setStream(self.h, C.c_void_p(stream_ptr)))
+    def sync(self): self._ck(self.L.mdb_sync(self.h))
+
+    # ---- operators (names of the reference's function pointers) ----
+    def setupNeighbor(self): self._ck(self.L.mdb_setupNeighbor(self.h))
+    def setupThermo(self): self._ck(self.L.mdb_setupThermo(self.h))
+    def adjustThermo(self): self._ck(self.L.mdb_adjustThermo(self.h))
+    def setupPbc(self): self._ck(self.L.mdb_setupPbc(self.h))
+    def updatePbc(self, reneigh=False): self._ck(self.L.mdb_updatePbc(self.h, int(reneigh)))
+    def updateAtomsPbc(self, reneigh=True): self._ck(self.L.mdb_updateAtomsPbc(self.h, int(reneigh)))
+    def buildNeighbor(self): self._ck(self.L.mdb_buildNeighbor(self.h))
+    def initialIntegrate(self, reneigh=False): self._ck(self.L.mdb_initialIntegrate(self.h, int(reneigh)))
+    def finalIntegrate(self, reneigh=False): self._ck(self.L.mdb_finalIntegrate(self.h, int(reneigh)))
+    def reneighbour(self): self._ck(self.L.mdb_reneighbour(self.h))
+    def setup(self, adjust=True): self._ck(self.L.mdb_setup(self.h, int(adjust)))
+
+    def _force(self, fn):
+        t = fn(self.h)
+        if t < 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+        return t
+
+    def computeForce(self): return self._force(self.L.mdb_computeForce)
+    def computeForceLJFullNeigh(self): return self._force(self.L.mdb_computeForceLJFullNeigh)
+    def computeForceLJHalfNeigh(self): return self._force(self.L.mdb_computeForceLJHalfNeigh)
+    def computeForceEam(self): return self._force(self.L.mdb_computeForceEam)
+
+    def computeThermo(self):
+        T, P = C.c_double(), C.c_double()
+        self._ck(self.L.mdb_computeThermo(self.h, C.byref(T), C.byref(P)))
+        return T.value, P.value
+
+    thermo = computeThermo
+
+    def step(self, n):
+        """one iteration of the reference time loop (verletlist/main.c:258-273), operator by operator"""
+        reneigh = (n + 1) % self.params.reneigh_every == 0
+        self.initialIntegrate(reneigh)
+        if reneigh:
+            self.reneighbour()
+        else:
+            self.updatePbc(False)
+        self.computeForce()
+        self.finalIntegrate(reneigh)
+        return reneigh
+
+    def run(self, nsteps):
+        """mdb_run: whole time loop on the device. Returns (thermo records (k,3), timers dict)."""
+        nstat = max(1, self.params.nstat)
+        out = np.zeros(3 * (nsteps // nstat + 4))
+        nrec = C.c_int()
+        tm = (C.c_double * 3)()
+        self._ck(self.L.mdb_run(self.h, nsteps, _vp(out), len(out) // 3, C.byref(nrec), tm))
+        return out[:3 * nrec.value].reshape(-1, 3), dict(TOTAL=tm[0], FORCE=tm[1], NEIGH=tm[2])
+
+    def setTiming(self, on): self._ck(self.L.mdb_setTiming(self.h, int(on)))
+
+    def kernelStats(self):
+        fm, nm = C.c_double(), C.c_double()
+        fl, nl, tl = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        self._ck(self.L.mdb_getKernelStats(self.h, C.byref(fm), C.byref(fl), C.byref(nm), C.byref(nl),
+                                           C.byref(tl)))
+        return dict(force_ms=fm.value, force_launches=fl.value, neigh_ms=nm.value,
+                    neigh_launches=nl.value, launches=tl.value)
+
+    def resetKernelStats(self): self._ck(self.L.mdb_resetKernelStats(self.h))
+
+    # ---- EAM ----
+    def setEam(self, nrho, drho, nr, dr, cut, mass, frho, zr, rhor):
+        a = [np.ascontiguousarray(t, dtype=np.float64) for t in (frho, zr, rhor)]
+        d = C.c_double
+        self._ck(self.L.mdb_setEam(self.h, nrho, d(drho), nr, d(dr), d(cut), d(mass), *[_vp(t) for t in a]))
+
+    def setEamSplines(self, nr, nrho, nr_tot, nrho_tot, rdr, rdrho, rhor, frho, z2r):
+        a = [np.ascontiguousarray(t, dtype=self.np_real) for t in (rhor, frho, z2r)]
+        self._ck(self.L.mdb_setEamSplines(self.h, nr, nrho, nr_tot, nrho_tot, C.c_double(rdr),
+                                          C.c_double(rdrho), *[_vp(t) for t in a]))
+
+    def getEamSplines(self):
+        iv = [C.c_int() for _ in range(4)]
+        dv = [C.c_double() for _ in range(2)]
+        args = [C.byref(q) for q in iv] + [C.byref(q) for q in dv]
+        self._ck(self.L.mdb_getEamSplines(self.h, *args, None, None, None))
+        nr, nrho, nr_tot, nrho_tot = [q.value for q in iv]
+        rh, z2 = np.empty(nr_tot, self.np_real), np.empty(nr_tot, self.np_real)
+        fr = np.empty(nrho_tot, self.np_real)
+        self._ck(self.L.mdb_getEamSplines(self.h, *args, _vp(rh), _vp(fr), _vp(z2)))
+        return dict(nr=nr, nrho=nrho, nr_tot=nr_tot, nrho_tot=nrho_tot, rdr=dv[0].value,
+                    rdrho=dv[1].value, rhor_spline=rh, frho_spline=fr, z2r_spline=z2)
+
+    def getEamFp(self, ghosts=False):
+        c = self.counts()
+        n = c["Nlocal"] + (c["Nghost"] if ghosts else 0)
+        a = np.empty(n, self.np_real)
+        self._ck(self.L.mdb_getEamFp(self.h, _vp(a), int(ghosts)))
+        return a
+
+    # ---- parity accessors ----
+    def neighbors(self):
+        c = self.counts()
+        nn = np.empty(c["Nlocal"], np.int32)
+        nb = np.empty((c["Nlocal"], c["maxneighs"]), np.int32)
+        self._ck(self.L.mdb_getNeighbors(self.h, _vp(nn), _vp(nb), c["maxneighs"]))
+        return nn, nb
+
+    def numneigh(self):
+        c = self.counts()
+        nn = np.empty(c["Nlocal"], np.int32)
+        self._ck(self.L.mdb_getNeighbors(self.h, _vp(nn), None, 0))
+        return nn
+
+    def sorted_neighbor_sets(self):
+        nn, nb = self.neighbors()
+        return nn, [np.sort(nb[i, :nn[i]]) for i in range(len(nn))]
+
+    def ghostMap(self):
+        ng = self.counts()["Nghost"]
+        a = [np.empty(ng, np.int32) for _ in range(4)]
+        self._ck(self.L.mdb_getGhostMap(self.h, *[_vp(q) for q in a]))
+        return dict(border_map=a[0], PBCx=a[1], PBCy=a[2], PBCz=a[3])
+
+    def neighborParams(self):
+        iv = (C.c_int * 12)()
+        rv = (C.c_double * 14)()
+        self._ck(self.L.mdb_getNeighborParams(self.h, iv, rv))
+        ik = ["nbinx", "nbiny", "nbinz", "mbinx", "mbiny", "mbinz", "mbinxlo", "mbinylo", "mbinzlo",
+              "mbins", "nstencil", "max_bin_count"]
+        rk = ["bininvx", "bininvy", "bininvz", "binsizex", "binsizey", "binsizez", "cutneighsq",
+              "cutneigh", "xprd", "yprd", "zprd", "lattice", "dtforce", "cutforce"]
+        d = dict(zip(ik, list(iv)))
+        d.update(zip(rk, list(rv)))
+        st = np.empty(d["nstencil"], np.int32)
+        self._ck(self.L.mdb_getStencil(self.h, _vp(st)))
+        d["stencil"] = st
+        return d
+
+    def binCounts(self):
+        m = self.neighborParams()["mbins"]
+        a = np.empty(m, np.int32)
+        self._ck(self.L.mdb_getBinCounts(self.h, _vp(a)))
+        return a
+
+    def countPairs(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        self._ck(self.L.mdb_countPairs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value

@@ -1,0 +1,183 @@
+// eam_kernels.cuh -- EAM: host-side table builder (runs once) and the three device passes.
+// Reference: common/eam_utils.c:95-284 (file2array, array2spline, interpolate) and
+// verletlist/force_eam.c:19-231 (density + embedding derivative, ghost fp copy, pair force).
+#pragma once
+#include <vector>
+
+#include "mdb_util.cuh"
+
+namespace mdb {
+
+template <class real> struct EamTables {
+    int nr = 0, nrho = 0, nr_tot = 0, nrho_tot = 0;
+    real rdr = 0, rdrho = 0;
+    bool ready = false;
+};
+
+// 4-point Lagrange regrid, common/eam_utils.c:125-140 (used for frho, rhor and zr)
+template <class real> static double eam_lagrange(const std::vector<real>& tab, int ntab, double dtab, double r)
+{
+    const double sixth = 1.0 / 6.0;
+    double p = r / dtab + 1.0;
+    int k    = (int)(p);
+    k        = k < ntab - 2 ? k : ntab - 2;
+    k        = k > 2 ? k : 2;
+    p -= k;
+    p = p < 2.0 ? p : 2.0;
+    const double cof1 = -sixth * p * (p - 1.0) * (p - 2.0);
+    const double cof2 = 0.5 * (p * p - 1.0) * (p - 2.0);
+    const double cof3 = -0.5 * p * (p + 1.0) * (p - 2.0);
+    const double cof4 = sixth * p * (p * p - 1.0);
+    return cof1 * tab[k - 1] + cof2 * tab[k] + cof3 * tab[k + 1] + cof4 * tab[k + 2];
+}
+
+// cubic spline coefficients, 7 per knot: common/eam_utils.c:253-284
+template <class real> static void eam_interpolate(int n, real delta, const std::vector<real>& f, std::vector<real>& s)
+{
+    for (int m = 1; m <= n; m++) s[m * 7 + 6] = f[m];
+    s[1 * 7 + 5]       = s[2 * 7 + 6] - s[1 * 7 + 6];
+    s[2 * 7 + 5]       = 0.5 * (s[3 * 7 + 6] - s[1 * 7 + 6]);
+    s[(n - 1) * 7 + 5] = 0.5 * (s[n * 7 + 6] - s[(n - 2) * 7 + 6]);
+    s[n * 7 + 5]       = s[n * 7 + 6] - s[(n - 1) * 7 + 6];
+    for (int m = 3; m <= n - 2; m++)
+        s[m * 7 + 5] = ((s[(m - 2) * 7 + 6] - s[(m + 2) * 7 + 6]) + 8.0 * (s[(m + 1) * 7 + 6] - s[(m - 1) * 7 + 6])) / 12.0;
+    for (int m = 1; m <= n - 1; m++) {
+        s[m * 7 + 4] = 3.0 * (s[(m + 1) * 7 + 6] - s[m * 7 + 6]) - 2.0 * s[m * 7 + 5] - s[(m + 1) * 7 + 5];
+        s[m * 7 + 3] = s[m * 7 + 5] + s[(m + 1) * 7 + 5] - 2.0 * (s[(m + 1) * 7 + 6] - s[m * 7 + 6]);
+    }
+    s[n * 7 + 4] = 0.0;
+    s[n * 7 + 3] = 0.0;
+    for (int m = 1; m <= n; m++) {
+        s[m * 7 + 2] = s[m * 7 + 5] / delta;
+        s[m * 7 + 1] = 2.0 * s[m * 7 + 4] / delta;
+        s[m * 7 + 0] = 3.0 * s[m * 7 + 3] / delta;
+    }
+}
+
+// funcfl tables (0-based, as read from the file) -> spline tables.  One element type only
+// (ntypes == 1), as in the reference's funcfl path.
+template <class real>
+static void build_eam_tables(int nrho, real fdrho, int nr, real fdr, const double* frho0, const double* zr0,
+    const double* rhor0, EamTables<real>& t, std::vector<real>& rhor_spline, std::vector<real>& frho_spline,
+    std::vector<real>& z2r_spline)
+{
+    // readEamFile shifts the tables to 1-based, eam_utils.c:85-90
+    std::vector<real> frho(nrho + 1, 0), rhor(nr + 1, 0), zr(nr + 1, 0);
+    for (int i = nrho; i > 0; i--) frho[i] = (real)frho0[i - 1];
+    for (int i = nr; i > 0; i--) { rhor[i] = (real)rhor0[i - 1]; zr[i] = (real)zr0[i - 1]; }
+    const real edr = fdr, edrho = fdrho; // MAX(0, file value), eam_utils.c:107-108
+    const double rmax = (nr - 1) * fdr, rhomax = (nrho - 1) * fdrho;
+    const int enr = (int)(rmax / edr + 0.5), enrho = (int)(rhomax / edrho + 0.5);
+    std::vector<real> afrho(enrho + 1, 0), arhor(enr + 1, 0), az2r(enr + 1, 0);
+    for (int m = 1; m <= enrho; m++) afrho[m] = (real)eam_lagrange(frho, nrho, fdrho, (m - 1) * edrho);
+    for (int m = 1; m <= enr; m++) arhor[m] = (real)eam_lagrange(rhor, nr, fdr, (m - 1) * edr);
+    for (int m = 1; m <= enr; m++) {
+        const double r = (m - 1) * edr;
+        const double zri = eam_lagrange(zr, nr, fdr, r), zrj = eam_lagrange(zr, nr, fdr, r);
+        az2r[m] = (real)(27.2 * 0.529 * zri * zrj); // eam_utils.c:218
+    }
+    t.rdr = (real)(1.0 / edr);
+    t.rdrho = (real)(1.0 / edrho);
+    t.nr = enr;
+    t.nrho = enrho;
+    t.nrho_tot = (enrho + 1) * 7 + 64;
+    t.nr_tot = (enr + 1) * 7 + 64;
+    t.nrho_tot -= t.nrho_tot % 64; // eam_utils.c:226-229
+    t.nr_tot -= t.nr_tot % 64;
+    frho_spline.assign(t.nrho_tot, 0);
+    rhor_spline.assign(t.nr_tot, 0);
+    z2r_spline.assign(t.nr_tot, 0);
+    eam_interpolate(enrho, edrho, afrho, frho_spline);
+    eam_interpolate(enr, edr, arhor, rhor_spline);
+    eam_interpolate(enr, edr, az2r, z2r_spline);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: rho_i and the embedding derivative fp[i]; force_eam.c:49-112
+template <class real>
+__global__ void __launch_bounds__(128) k_eam_density(int nlocal, real cutforcesq, EamTables<real> t,
+    const real* __restrict__ rhor_spline, const real* __restrict__ frho_spline,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride, real* __restrict__ fp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    real rhoi     = 0;
+    for (int k = 0; k < nn; k++) {
+        const int j   = __ldg(nbT + (size_t)k * nstride + i);
+        const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < cutforcesq) {
+            real p = sqrt(rsq) * t.rdr + (real)1.0;
+            int m  = (int)(p);
+            m      = m < t.nr - 1 ? m : t.nr - 1;
+            p -= m;
+            p = p < (real)1.0 ? p : (real)1.0;
+            const real* s = rhor_spline + m * 7;
+            rhoi += ((__ldg(s + 3) * p + __ldg(s + 4)) * p + __ldg(s + 5)) * p + __ldg(s + 6);
+        }
+    }
+    real p = (real)1.0 * rhoi * t.rdrho + (real)1.0;
+    int m  = (int)(p);
+    m      = max(1, min(m, t.nrho - 1));
+    p -= m;
+    p = min(p, (real)1.0);
+    const real* s = frho_spline + m * 7;
+    fp[i]         = (__ldg(s + 0) * p + __ldg(s + 1)) * p + __ldg(s + 2);
+}
+
+// fp of ghosts = fp of their source atom; force_eam.c:118-120 (the second halo exchange when decomposed)
+template <class real>
+__global__ void k_eam_ghost_fp(int nlocal, int nghost, const int* __restrict__ border_map, real* __restrict__ fp)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nghost) fp[nlocal + g] = fp[border_map[g]];
+}
+
+// pass 2: pair force; force_eam.c:127-224
+template <class real>
+__global__ void __launch_bounds__(128) k_eam_force(int nlocal, real cutforcesq, EamTables<real> t,
+    const real* __restrict__ rhor_spline, const real* __restrict__ z2r_spline, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const real* __restrict__ fp,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride, real* __restrict__ fx,
+    real* __restrict__ fy, real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i], fpi = fp[i];
+    const int nn = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    for (int k = 0; k < nn; k++) {
+        const int j   = __ldg(nbT + (size_t)k * nstride + i);
+        const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < cutforcesq) {
+            const real r = sqrt(rsq);
+            real p       = r * t.rdr + (real)1.0;
+            int m        = (int)(p);
+            m            = m < t.nr - 1 ? m : t.nr - 1;
+            p -= m;
+            p = p < (real)1.0 ? p : (real)1.0;
+            const real* rs = rhor_spline + m * 7;
+            const real* zs = z2r_spline + m * 7;
+            const real rhoip = (__ldg(rs + 0) * p + __ldg(rs + 1)) * p + __ldg(rs + 2);
+            const real z2p   = (__ldg(zs + 0) * p + __ldg(zs + 1)) * p + __ldg(zs + 2);
+            const real z2    = ((__ldg(zs + 3) * p + __ldg(zs + 4)) * p + __ldg(zs + 5)) * p + __ldg(zs + 6);
+            const real recip = (real)1.0 / r;
+            const real phi   = z2 * recip;
+            const real phip  = z2p * recip - phi * recip;
+            const real psip  = fpi * rhoip + fp[j] * rhoip + phip;
+            const real fpair = -psip * recip;
+            fix += dx * fpair;
+            fiy += dy * fpair;
+            fiz += dz * fpair;
+        }
+    }
+    fx[i] = fix;
+    fy[i] = fiy;
+    fz[i] = fiz;
+}
+
+} // namespace mdb

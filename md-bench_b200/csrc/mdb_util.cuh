@@ -1,0 +1,85 @@
+// mdb_util.cuh -- error handling, device buffers, launch accounting, exact-rounding helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+namespace mdb {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline std::string fmt(const char* f, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+#define MDB_CUDA(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            throw ::mdb::Error(::mdb::fmt("[CUDA Error]: %s: %s (%s:%d)", #expr,                 \
+                cudaGetErrorString(e__), __FILE__, __LINE__));                                   \
+    } while (0)
+
+// Every kernel launch of the library goes through this macro: it counts launches (bench.py's
+// gpu_launches) and checks the launch status.
+#define MDB_LAUNCH(counter, kernel, grid, block, smem, stream, ...)                              \
+    do {                                                                                         \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                              \
+        ++(counter);                                                                             \
+        MDB_CUDA(cudaPeekAtLastError());                                                         \
+    } while (0)
+
+inline size_t round_up(size_t n, size_t m) { return (n + m - 1) / m * m; }
+inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// Growable device buffer. Growth is geometric (x1.25) so that 67M-atom systems do not reallocate
+// in the reference's 20000-element steps (verletlist/atom.c:17).
+template <class T> struct DBuf {
+    T* p       = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n, bool keep, cudaStream_t s)
+    {
+        if (n <= cap) return;
+        size_t ncap = round_up(n > cap + cap / 4 ? n : cap + cap / 4, 1024);
+        T* q        = nullptr;
+        MDB_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+        if (p && keep && cap) MDB_CUDA(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        if (p) {
+            MDB_CUDA(cudaStreamSynchronize(s));
+            MDB_CUDA(cudaFree(p));
+        }
+        p   = q;
+        cap = ncap;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+    }
+};
+
+// Round-to-nearest single operations that the compiler may not contract or re-associate.  Used
+// wherever bits decide list membership: bin index, ghost coordinates, list distance.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+} // namespace mdb

@@ -1,0 +1,61 @@
+// sim.cuh -- host-side state and orchestration of one simulation domain on one GPU.
+// SimBase is the precision-erased interface the C ABI (mdb200.cu) talks to; Sim<real> implements it.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/mdb200.h"
+#include "mdb_util.cuh"
+
+namespace mdb {
+
+struct SimBase {
+    virtual ~SimBase() {}
+    virtual void setStream(cudaStream_t s)                                                   = 0;
+    virtual void sync()                                                                      = 0;
+    virtual long long createAtom()                                                           = 0;
+    virtual void setAtoms(long long n, const void* x, const void* y, const void* z, const void* vx,
+        const void* vy, const void* vz, const int* type, bool on_device)                     = 0;
+    virtual void getAtoms(int which, bool ghosts, void* x, void* y, void* z)                 = 0;
+    virtual void getCounts(long long* c, int* maxneighs)                                     = 0;
+    virtual void saveState()                                                                 = 0;
+    virtual void restoreState()                                                              = 0;
+    virtual void setupThermo()                                                               = 0;
+    virtual void adjustThermo()                                                              = 0;
+    virtual void computeThermo(double* T, double* P)                                         = 0;
+    virtual void setupNeighbor()                                                             = 0;
+    virtual void setupPbc()                                                                  = 0;
+    virtual void updatePbc()                                                                 = 0;
+    virtual void updateAtomsPbc()                                                            = 0;
+    virtual void buildNeighbor()                                                             = 0;
+    virtual double computeForce(int which)                                                   = 0;
+    virtual void initialIntegrate()                                                          = 0;
+    virtual void finalIntegrate()                                                            = 0;
+    virtual void setup(bool adjust)                                                          = 0;
+    virtual void reneighbour()                                                               = 0;
+    virtual void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) = 0;
+    virtual void getNeighbors(int* numneigh, int* neighbors, int row_stride)                 = 0;
+    virtual void getGhostMap(int* bm, int* px, int* py, int* pz)                             = 0;
+    virtual void getNeighborParams(int* ints, double* reals)                                 = 0;
+    virtual void getStencil(int* st)                                                         = 0;
+    virtual void getBinCounts(int* bc)                                                       = 0;
+    virtual void countPairs(long long* listed, long long* inside)                            = 0;
+    virtual void setEam(int nrho, double drho, int nr, double dr, double cut, double mass,
+        const double* frho, const double* zr, const double* rhor)                            = 0;
+    virtual void setEamSplines(int nr, int nrho, int nr_tot, int nrho_tot, double rdr, double rdrho,
+        const void* rhor, const void* frho, const void* z2r)                                 = 0;
+    virtual void getEamSplines(int* nr, int* nrho, int* nr_tot, int* nrho_tot, double* rdr,
+        double* rdrho, void* rhor, void* frho, void* z2r)                                    = 0;
+    virtual void getEamFp(void* fp, bool ghosts)                                             = 0;
+
+    bool timing             = false;
+    double force_ms         = 0, neigh_ms = 0;
+    long long force_launches = 0, neigh_launches = 0, launches = 0;
+};
+
+enum { FORCE_DISPATCH = 0, FORCE_LJ_FULL = 1, FORCE_LJ_HALF = 2, FORCE_EAM = 3 };
+
+SimBase* make_sim(const mdb_params& p, int device);
+
+} // namespace mdb

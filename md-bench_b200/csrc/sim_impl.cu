@@ -1,0 +1,762 @@
+// sim_impl.cu -- Sim<real>: one verletlist simulation domain resident on one B200.
+// Host code here only orchestrates: every per-atom operation is a kernel in vl_kernels.cuh /
+// eam_kernels.cuh; the only device->host traffic inside the time loop is one small flag read per
+// neighbor rebuild (ghost total, bin / list overflow).
+#include <initializer_list>
+
+#include "sim.cuh"
+#include "scan.cuh"
+#include "vl_kernels.cuh"
+#include "eam_kernels.cuh"
+
+namespace mdb {
+
+template <class real> struct Sim final : SimBase {
+    mdb_params P;
+    int device;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    // ---- Parameter fields in working precision (reference common/parameter.h:27-61) ----
+    real epsilon, sigma, sigma6, temp, rho, mass, dt, dtforce, skin, cutforce, cutneigh, lattice;
+    real xprd, yprd, zprd, xlo, xhi, ylo, yhi, zlo, zhi;
+    // ---- thermo scales (common/thermo.c:14-26) ----
+    real mvv2e = 1, dof_boltz = 1, t_scale = 1, p_scale = 1;
+    bool thermo_ready = false;
+    // ---- atoms ----
+    long long Natoms = 0;
+    int Nlocal = 0, Nghost = 0;
+    DBuf<real> x, y, z, vx, vy, vz, fx, fy, fz, sx, sy, sz, svx, svy, svz, stage;
+    DBuf<int> type, border_map, ghost_code, ghost_cnt, ghost_off;
+    DBuf<unsigned> ghost_msk;
+    int saved_n = 0;
+    // ---- neighbor (verletlist/neighbor.c:24-38) ----
+    BinGeom<real> bg {};
+    real binsizex, binsizey, binsizez, cutneighsq;
+    int nstencil = 0, maxneighs = 100, max_bin_count = 0;
+    size_t nstride = 0;
+    bool neigh_ready = false;
+    std::vector<int> h_stencil;
+    DBuf<int> stencil, atom_bin, bincount, binstart, cursor, binatoms, numneigh, neighbors, rows;
+    Scanner scanner;
+    // ---- eam ----
+    EamTables<real> eam;
+    DBuf<real> fp, rhor_spline, frho_spline, z2r_spline;
+    // ---- scratch ----
+    int* h_flags      = nullptr; // pinned: [0] ghost total, [1] max neighbors, [2] max bin count
+    DBuf<int> d_flags;
+    double* h_red = nullptr; // pinned
+    DBuf<double> d_partial, d_red, d_thermo;
+    DBuf<unsigned long long> d_cnt;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+
+    Sim(const mdb_params& p, int dev) : P(p), device(dev)
+    {
+        MDB_CUDA(cudaSetDevice(device));
+        MDB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        stream = own_stream;
+        MDB_CUDA(cudaMallocHost(&h_flags, 16 * sizeof(int)));
+        MDB_CUDA(cudaMallocHost(&h_red, 16 * sizeof(double)));
+        MDB_CUDA(cudaEventCreate(&ev0));
+        MDB_CUDA(cudaEventCreate(&ev1));
+        MDB_CUDA(cudaEventCreate(&evA));
+        MDB_CUDA(cudaEventCreate(&evB));
+        scanner.launches = &launches;
+        d_flags.ensure(16, false, stream);
+        d_red.ensure(16, false, stream);
+        d_partial.ensure(RED_BLOCKS * 4, false, stream);
+        d_cnt.ensure(4, false, stream);
+        derive();
+    }
+    ~Sim() override
+    {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &fx, &fy, &fz, &sx, &sy, &sz, &svx, &svy,
+                 &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline })
+            b->release();
+        for (DBuf<int>* b : { &type, &border_map, &ghost_code, &ghost_cnt, &ghost_off, &stencil,
+                 &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
+            b->release();
+        ghost_msk.release();
+        d_partial.release();
+        d_red.release();
+        d_thermo.release();
+        d_cnt.release();
+        scanner.release();
+        cudaFreeHost(h_flags);
+        cudaFreeHost(h_red);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        cudaEventDestroy(evA);
+        cudaEventDestroy(evB);
+        cudaStreamDestroy(own_stream);
+    }
+
+    // initParameter + command line (common/parameter.c:16-51, verletlist/main.c:233, 42-45).
+    // Each value is narrowed to `real` where the reference assigns to an MD_FLOAT field.
+    void derive()
+    {
+        epsilon  = (real)P.epsilon;
+        sigma    = (real)P.sigma;
+        real s2  = sigma * sigma; // parameter.c:118-119
+        sigma6   = s2 * s2 * s2;
+        temp     = (real)P.temp;
+        rho      = (real)P.rho;
+        mass     = (real)P.mass;
+        dt       = (real)P.dt;
+        dtforce  = (real)(0.5 * (double)dt); // parameter.c:115
+        skin     = (real)P.skin;
+        cutforce = (real)P.cutforce;
+        cutneigh = cutforce + skin; // main.c:233
+        if (P.force_field == MDB_FF_EAM) cutneigh = (real)((double)cutforce + 1.0); // eam_utils.c:30
+        lattice  = (real)pow((4.0 / (double)rho), (1.0 / 3.0));
+        if (P.from_input) {
+            xlo = (real)P.xlo; xhi = (real)P.xhi; ylo = (real)P.ylo; yhi = (real)P.yhi;
+            zlo = (real)P.zlo; zhi = (real)P.zhi;
+            xprd = xhi - xlo; yprd = yhi - ylo; zprd = zhi - zlo;
+        } else {
+            xprd = P.nx * lattice; yprd = P.ny * lattice; zprd = P.nz * lattice;
+            xlo = ylo = zlo = 0; xhi = xprd; yhi = yprd; zhi = zprd;
+        }
+    }
+
+    void setStream(cudaStream_t s) override
+    {
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        stream = s ? s : own_stream;
+    }
+    void sync() override { MDB_CUDA(cudaStreamSynchronize(stream)); }
+
+    void zero3(real* a, real* b, real* c, size_t n)
+    {
+        MDB_CUDA(cudaMemsetAsync(a, 0, n * sizeof(real), stream));
+        MDB_CUDA(cudaMemsetAsync(b, 0, n * sizeof(real), stream));
+        MDB_CUDA(cudaMemsetAsync(c, 0, n * sizeof(real), stream));
+    }
+    void ensure_atoms(size_t n, bool keep)
+    {
+        for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &fx, &fy, &fz }) b->ensure(n, keep, stream);
+        type.ensure(n, keep, stream);
+    }
+
+    // ------------------------------------------------------------------ atoms
+    long long createAtom() override
+    {
+        derive();
+        Natoms = 4LL * P.nx * P.ny * P.nz;
+        if (Natoms > 2000000000LL) throw Error("createAtom: more than 2e9 atoms per domain");
+        Nlocal = (int)Natoms;
+        Nghost = 0;
+        ensure_atoms((size_t)Nlocal + Nlocal / 4 + 1024, false);
+        MDB_LAUNCH(launches, k_create_atoms<real>, grid_for(Natoms, 256), 256, 0, stream, P.nx, P.ny,
+            P.nz, lattice, x.p, y.p, z.p, vx.p, vy.p, vz.p, type.p);
+        zero3(fx.p, fy.p, fz.p, Nlocal);
+        neigh_ready = false;
+        return Natoms;
+    }
+
+    void load3(long long n, const void* a, const void* b, const void* c, real* dx, real* dy, real* dz,
+        bool on_device)
+    {
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (P.layout == MDB_AOS) {
+            if (on_device) {
+                MDB_LAUNCH(launches, k_aos_to_soa<real>, grid_for(n, 256), 256, 0, stream, (size_t)n,
+                    (const real*)a, dx, dy, dz);
+            } else {
+                stage.ensure(3 * n, false, stream);
+                MDB_CUDA(cudaMemcpyAsync(stage.p, a, 3 * n * sizeof(real), kind, stream));
+                MDB_LAUNCH(launches, k_aos_to_soa<real>, grid_for(n, 256), 256, 0, stream, (size_t)n,
+                    (const real*)stage.p, dx, dy, dz);
+            }
+        } else {
+            MDB_CUDA(cudaMemcpyAsync(dx, a, n * sizeof(real), kind, stream));
+            MDB_CUDA(cudaMemcpyAsync(dy, b, n * sizeof(real), kind, stream));
+            MDB_CUDA(cudaMemcpyAsync(dz, c, n * sizeof(real), kind, stream));
+        }
+    }
+
+    void setAtoms(long long n, const void* ax, const void* ay, const void* az, const void* avx,
+        const void* avy, const void* avz, const int* atype, bool on_device) override
+    {
+        if (n <= 0 || n > 2000000000LL) throw Error("setAtoms: bad atom count");
+        derive();
+        Natoms = n;
+        Nlocal = (int)n;
+        Nghost = 0;
+        ensure_atoms((size_t)n + n / 4 + 1024, false);
+        load3(n, ax, ay, az, x.p, y.p, z.p, on_device);
+        if (avx) load3(n, avx, avy, avz, vx.p, vy.p, vz.p, on_device);
+        else zero3(vx.p, vy.p, vz.p, n);
+        if (atype)
+            MDB_CUDA(cudaMemcpyAsync(type.p, atype, n * sizeof(int),
+                on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+        else MDB_CUDA(cudaMemsetAsync(type.p, 0, n * sizeof(int), stream));
+        zero3(fx.p, fy.p, fz.p, n);
+        MDB_CUDA(cudaStreamSynchronize(stream)); // host buffers may be reused by the caller
+        neigh_ready = false;
+    }
+
+    void getAtoms(int which, bool ghosts, void* ax, void* ay, void* az) override
+    {
+        const real *a, *b, *c;
+        if (which == 'x') { a = x.p; b = y.p; c = z.p; }
+        else if (which == 'v') { a = vx.p; b = vy.p; c = vz.p; }
+        else if (which == 'f') { a = fx.p; b = fy.p; c = fz.p; }
+        else throw Error("getAtoms: which must be 'x', 'v' or 'f'");
+        const size_t n = (size_t)Nlocal + ((ghosts && which == 'x') ? Nghost : 0);
+        if (P.layout == MDB_AOS) {
+            stage.ensure(3 * n, false, stream);
+            MDB_LAUNCH(launches, k_soa_to_aos<real>, grid_for(n, 256), 256, 0, stream, n, a, b, c, stage.p);
+            MDB_CUDA(cudaMemcpyAsync(ax, stage.p, 3 * n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+        } else {
+            MDB_CUDA(cudaMemcpyAsync(ax, a, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(ay, b, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(az, c, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+        }
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void getCounts(long long* c, int* mn) override
+    {
+        c[0] = Natoms; c[1] = Nlocal; c[2] = Nghost; c[3] = (long long)x.cap;
+        *mn  = maxneighs;
+    }
+
+    void saveState() override
+    {
+        const size_t n = Nlocal;
+        DBuf<real>* dst[] = { &sx, &sy, &sz, &svx, &svy, &svz };
+        DBuf<real>* src[] = { &x, &y, &z, &vx, &vy, &vz };
+        for (int k = 0; k < 6; k++) {
+            dst[k]->ensure(n, false, stream);
+            MDB_CUDA(cudaMemcpyAsync(dst[k]->p, src[k]->p, n * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+        }
+        saved_n = Nlocal;
+    }
+    void restoreState() override
+    {
+        if (!saved_n) throw Error("restoreState: nothing saved");
+        const size_t n = saved_n;
+        DBuf<real>* src[] = { &sx, &sy, &sz, &svx, &svy, &svz };
+        DBuf<real>* dst[] = { &x, &y, &z, &vx, &vy, &vz };
+        for (int k = 0; k < 6; k++)
+            MDB_CUDA(cudaMemcpyAsync(dst[k]->p, src[k]->p, n * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+        zero3(fx.p, fy.p, fz.p, n);
+        Nlocal = saved_n;
+        Nghost = 0;
+    }
+
+    // ------------------------------------------------------------------ thermo
+    void setupThermo() override // common/thermo.c:30-53
+    {
+        const long long natoms = Natoms;
+        if (P.force_field == MDB_FF_LJ) {
+            mvv2e     = (real)1.0;
+            dof_boltz = (real)(natoms * 3 - 3);
+            t_scale   = mvv2e / dof_boltz;
+            p_scale   = (real)(1.0 / 3 / (double)xprd / (double)yprd / (double)zprd);
+        } else {
+            mvv2e     = (real)1.036427e-04;
+            dof_boltz = (real)((double)(natoms * 3 - 3) * 8.617343e-05);
+            t_scale   = mvv2e / dof_boltz;
+            p_scale   = (real)(1.602176e+06 / 3 / (double)xprd / (double)yprd / (double)zprd);
+            if (!thermo_ready) dtforce = dtforce / mvv2e; // thermo.c:51 (once per setup)
+        }
+        thermo_ready = true;
+    }
+
+    // sums {vx, vy, vz, m v^2} over local atoms -> out (device, 4 doubles)
+    void vel_sums(double* out)
+    {
+        const int nb = (int)std::min<size_t>(RED_BLOCKS, grid_for(Nlocal, RED_THREADS));
+        MDB_LAUNCH(launches, k_vel_partial<real>, nb, RED_THREADS, 0, stream, Nlocal, vx.p, vy.p, vz.p,
+            mass, d_partial.p);
+        MDB_LAUNCH(launches, k_vel_final, 1, RED_THREADS, 0, stream, nb, d_partial.p, out);
+    }
+    void read_red()
+    {
+        MDB_CUDA(cudaMemcpyAsync(h_red, d_red.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    void thermo_from_sum(double msum, double* T, double* Pr) // thermo.c:64-65
+    {
+        real t = (real)msum;
+        t      = t * t_scale;
+        real p = (t * dof_boltz) * p_scale;
+        *T     = t;
+        *Pr    = p;
+    }
+    void computeThermo(double* T, double* Pr) override // common/thermo.c:55-80
+    {
+        if (!thermo_ready) setupThermo();
+        vel_sums(d_red.p);
+        read_red();
+        thermo_from_sum(h_red[3], T, Pr);
+    }
+    void adjustThermo() override // common/thermo.c:82-122
+    {
+        if (!thermo_ready) setupThermo();
+        vel_sums(d_red.p);
+        read_red();
+        const real vxtot = (real)h_red[0] / (real)Natoms, vytot = (real)h_red[1] / (real)Natoms,
+                   vztot = (real)h_red[2] / (real)Natoms;
+        MDB_LAUNCH(launches, k_vel_shift<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, vx.p, vy.p,
+            vz.p, vxtot, vytot, vztot);
+        vel_sums(d_red.p);
+        read_red();
+        real t = (real)h_red[3];
+        t *= t_scale;
+        const real factor = (real)sqrt((double)(temp / t));
+        MDB_LAUNCH(launches, k_vel_scale<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, vx.p, vy.p,
+            vz.p, factor);
+    }
+
+    // ------------------------------------------------------------------ neighbor geometry
+    real bindist(int i, int j, int k) const // verletlist/neighbor.c:267-296
+    {
+        real delx = i > 0 ? (i - 1) * binsizex : (i == 0 ? (real)0.0 : (i + 1) * binsizex);
+        real dely = j > 0 ? (j - 1) * binsizey : (j == 0 ? (real)0.0 : (j + 1) * binsizey);
+        real delz = k > 0 ? (k - 1) * binsizez : (k == 0 ? (real)0.0 : (k + 1) * binsizez);
+        return (delx * delx + dely * dely + delz * delz);
+    }
+    void setupNeighbor() override // verletlist/neighbor.c:43-62 + 64-184
+    {
+        const real SMALL = (real)1.0e-6, FACTOR = (real)0.999;
+        const real neighscale = (real)(5.0 / 6.0);
+        real bx = P.nx * lattice, by = P.ny * lattice, bz = P.nz * lattice;
+        bg.nbinx = (int)(neighscale * P.nx);
+        bg.nbiny = (int)(neighscale * P.ny);
+        bg.nbinz = (int)(neighscale * P.nz);
+        if (P.from_input) { bx = xprd; by = yprd; bz = zprd; }
+        const real lox = 0, hix = bx, loy = 0, hiy = by, loz = 0, hiz = bz;
+        cutneighsq = cutneigh * cutneigh;
+        if (P.from_input) {
+            binsizex = binsizey = binsizez = (real)((double)cutneigh * 0.5);
+            bg.nbinx = (int)((xhi - xlo) / binsizex);
+            bg.nbiny = (int)((yhi - ylo) / binsizey);
+            bg.nbinz = (int)((zhi - zlo) / binsizez);
+            if (bg.nbinx == 0) bg.nbinx = 1;
+            if (bg.nbiny == 0) bg.nbiny = 1;
+            if (bg.nbinz == 0) bg.nbinz = 1;
+            bg.bininvx = bg.nbinx / (xhi - xlo);
+            bg.bininvy = bg.nbiny / (yhi - ylo);
+            bg.bininvz = bg.nbinz / (zhi - zlo);
+        } else {
+            binsizex   = bx / bg.nbinx;
+            binsizey   = by / bg.nbiny;
+            binsizez   = bz / bg.nbinz;
+            bg.bininvx = (real)(1.0 / (double)binsizex);
+            bg.bininvy = (real)(1.0 / (double)binsizey);
+            bg.bininvz = (real)(1.0 / (double)binsizez);
+        }
+        int mhix, mhiy, mhiz;
+        real coord;
+        coord      = lox - cutneigh - SMALL * bx;
+        bg.mbinxlo = (int)(coord * bg.bininvx);
+        if (coord < (real)0.0) bg.mbinxlo -= 1;
+        coord = hix + cutneigh + SMALL * bx;
+        mhix  = (int)(coord * bg.bininvx);
+        coord      = loy - cutneigh - SMALL * by;
+        bg.mbinylo = (int)(coord * bg.bininvy);
+        if (coord < (real)0.0) bg.mbinylo -= 1;
+        coord = hiy + cutneigh + SMALL * by;
+        mhiy  = (int)(coord * bg.bininvy);
+        coord      = loz - cutneigh - SMALL * bz;
+        bg.mbinzlo = (int)(coord * bg.bininvz);
+        if (coord < (real)0.0) bg.mbinzlo -= 1;
+        coord = hiz + cutneigh + SMALL * bz;
+        mhiz  = (int)(coord * bg.bininvz);
+        bg.mbinxlo -= 1; mhix += 1; bg.mbinx = mhix - bg.mbinxlo + 1;
+        bg.mbinylo -= 1; mhiy += 1; bg.mbiny = mhiy - bg.mbinylo + 1;
+        bg.mbinzlo -= 1; mhiz += 1; bg.mbinz = mhiz - bg.mbinzlo + 1;
+        int nextx = (int)(cutneigh * bg.bininvx);
+        if (nextx * binsizex < FACTOR * cutneigh) nextx++;
+        int nexty = (int)(cutneigh * bg.bininvy);
+        if (nexty * binsizey < FACTOR * cutneigh) nexty++;
+        int nextz = (int)(cutneigh * bg.bininvz);
+        if (nextz * binsizez < FACTOR * cutneigh) nextz++;
+        h_stencil.clear();
+        for (int k = -nextz; k <= nextz; k++)
+            for (int j = -nexty; j <= nexty; j++)
+                for (int i = -nextx; i <= nextx; i++)
+                    if (bindist(i, j, k) < cutneighsq)
+                        h_stencil.push_back(k * bg.mbiny * bg.mbinx + j * bg.mbinx + i);
+        nstencil       = (int)h_stencil.size();
+        const long long mb = (long long)bg.mbinx * bg.mbiny * bg.mbinz;
+        if (mb > 2000000000LL) throw Error("setupNeighbor: too many bins");
+        bg.mbins = (int)mb;
+        bg.xprd = bx; bg.yprd = by; bg.zprd = bz;
+        if (!P.from_input) { xprd = bx; yprd = by; zprd = bz; }
+        stencil.ensure(nstencil, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(stencil.p, h_stencil.data(), nstencil * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        bincount.ensure(bg.mbins + 2, false, stream);
+        binstart.ensure(bg.mbins + 3, false, stream);
+        cursor.ensure(bg.mbins + 2, false, stream);
+        neigh_ready = true;
+    }
+
+    // ------------------------------------------------------------------ PBC
+    PbcGeom<real> pbc_geom() const
+    {
+        PbcGeom<real> g;
+        g.xprd = xprd; g.yprd = yprd; g.zprd = zprd; g.cutneigh = cutneigh;
+        g.xhi_cut = xprd - cutneigh; g.yhi_cut = yprd - cutneigh; g.zhi_cut = zprd - cutneigh;
+        g.pbc_x = P.pbc_x; g.pbc_y = P.pbc_y; g.pbc_z = P.pbc_z;
+        return g;
+    }
+    void setupPbc() override // verletlist/pbc.c:98-227
+    {
+        ghost_msk.ensure(Nlocal, false, stream);
+        ghost_cnt.ensure(Nlocal, false, stream);
+        ghost_off.ensure(Nlocal, false, stream);
+        MDB_LAUNCH(launches, k_ghost_count<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, pbc_geom(),
+            x.p, y.p, z.p, ghost_msk.p, ghost_cnt.p);
+        scanner.exclusive(ghost_cnt.p, ghost_off.p, Nlocal, d_flags.p + 0, stream);
+        MDB_CUDA(cudaMemcpyAsync(h_flags, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        Nghost = h_flags[0];
+        ensure_atoms((size_t)Nlocal + Nghost, true); // growAtom, atom.c:590-618
+        border_map.ensure(Nghost, false, stream);    // growPbc, pbc.c:230-242
+        ghost_code.ensure(Nghost, false, stream);
+        MDB_LAUNCH(launches, k_ghost_fill, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, ghost_msk.p,
+            ghost_off.p, border_map.p, ghost_code.p, type.p);
+    }
+    void updatePbc() override // verletlist/pbc.c:42-55
+    {
+        if (Nghost == 0) return;
+        MDB_LAUNCH(launches, k_update_pbc<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost, xprd,
+            yprd, zprd, border_map.p, ghost_code.p, x.p, y.p, z.p);
+    }
+    void updateAtomsPbc() override // verletlist/pbc.c:59-84
+    {
+        MDB_LAUNCH(launches, k_update_atoms_pbc<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, xprd,
+            yprd, zprd, x.p, y.p, z.p);
+    }
+
+    // ------------------------------------------------------------------ neighbor build
+    void bin_atoms() // binatoms, verletlist/neighbor.c:329-358
+    {
+        const int nall = Nlocal + Nghost;
+        const int nb   = bg.mbins + 1; // coord2bin's "+ 1" can reach index mbins
+        atom_bin.ensure(nall, false, stream);
+        binatoms.ensure(nall, false, stream);
+        MDB_CUDA(cudaMemsetAsync(bincount.p, 0, (nb + 1) * sizeof(int), stream));
+        MDB_CUDA(cudaMemsetAsync(cursor.p, 0, (nb + 1) * sizeof(int), stream));
+        MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, 2 * sizeof(int), stream));
+        MDB_LAUNCH(launches, k_bin_count<real>, grid_for(nall, 256), 256, 0, stream, nall, bg, x.p, y.p, z.p,
+            atom_bin.p, bincount.p);
+        scanner.exclusive(bincount.p, binstart.p, nb, binstart.p + nb, stream);
+        MDB_LAUNCH(launches, k_bin_fill, grid_for(nall, 256), 256, 0, stream, nall, atom_bin.p, binstart.p,
+            cursor.p, binatoms.p);
+        MDB_LAUNCH(launches, k_bin_sort, grid_for(nb, 128), 128, 0, stream, nb, binstart.p, binatoms.p,
+            d_flags.p + 2);
+    }
+
+    void buildNeighbor() override // verletlist/neighbor.c:186-264
+    {
+        if (!neigh_ready) setupNeighbor();
+        float ms = 0;
+        if (timing) MDB_CUDA(cudaEventRecord(evA, stream));
+        bin_atoms();
+        nstride = round_up((size_t)Nlocal, 32);
+        numneigh.ensure(nstride, false, stream);
+        for (;;) {
+            neighbors.ensure((size_t)maxneighs * nstride, false, stream);
+            MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
+            MDB_LAUNCH(launches, k_build_neighbor<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                P.half_neigh, bg, cutneighsq, x.p, y.p, z.p, binstart.p, binatoms.p, stencil.p, nstencil,
+                maxneighs, nstride, numneigh.p, neighbors.p, d_flags.p + 1);
+            neigh_launches++;
+            MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaStreamSynchronize(stream));
+            max_bin_count = h_flags[2];
+            if (h_flags[1] >= maxneighs) { // neighbor.c:247-262
+                maxneighs = (int)(h_flags[1] * 1.2);
+                continue;
+            }
+            break;
+        }
+        if (timing) {
+            MDB_CUDA(cudaEventRecord(evB, stream));
+            MDB_CUDA(cudaEventSynchronize(evB));
+            MDB_CUDA(cudaEventElapsedTime(&ms, evA, evB));
+            neigh_ms += ms;
+        }
+    }
+
+    // ------------------------------------------------------------------ force
+    void launch_force(int which)
+    {
+        if (which == FORCE_DISPATCH)
+            which = P.force_field == MDB_FF_EAM ? FORCE_EAM : (P.half_neigh ? FORCE_LJ_HALF : FORCE_LJ_FULL);
+        if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
+        if (which == FORCE_EAM) {
+            launch_eam();
+        } else {
+            LJConst<real> c { cutforce * cutforce, sigma6, epsilon };
+            if (which == FORCE_LJ_FULL) {
+                MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
+                    x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, fx.p, fy.p, fz.p);
+            } else {
+                zero3(fx.p, fy.p, fz.p, Nlocal);
+                MDB_LAUNCH(launches, k_force_lj_half<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
+                    x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, fx.p, fy.p, fz.p);
+            }
+        }
+        force_launches++;
+        if (timing) {
+            float ms = 0;
+            MDB_CUDA(cudaEventRecord(ev1, stream));
+            MDB_CUDA(cudaEventSynchronize(ev1));
+            MDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            force_ms += ms;
+        }
+    }
+    void launch_eam()
+    {
+        if (!eam.ready) throw Error("computeForceEam: no EAM tables (call mdb_setEam first)");
+        fp.ensure((size_t)Nlocal + Nghost, false, stream);
+        const real cfsq = cutforce * cutforce;
+        MDB_LAUNCH(launches, k_eam_density<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cfsq, eam,
+            rhor_spline.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, fp.p);
+        if (Nghost)
+            MDB_LAUNCH(launches, k_eam_ghost_fp<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost,
+                border_map.p, fp.p);
+        MDB_LAUNCH(launches, k_eam_force<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cfsq, eam,
+            rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, nstride, fx.p, fy.p,
+            fz.p);
+    }
+    // ComputeForceFunction: returns elapsed seconds like the reference (force.h:16)
+    double computeForce(int which) override
+    {
+        if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_buildNeighbor first)");
+        const bool t = timing;
+        timing       = true;
+        const double before = force_ms;
+        launch_force(which);
+        timing = t;
+        const double el = (force_ms - before) * 1e-3;
+        if (!t) force_ms = before;
+        return el;
+    }
+
+    // ------------------------------------------------------------------ integrate
+    void initialIntegrate() override // verletlist/integrate.c:21-31
+    {
+        MDB_LAUNCH(launches, k_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
+            dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
+    }
+    void finalIntegrate() override // verletlist/integrate.c:33-40
+    {
+        MDB_LAUNCH(launches, k_final_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, dtforce,
+            vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
+    }
+
+    // ------------------------------------------------------------------ driver flow
+    void setup(bool adjust) override // verletlist/main.c:58-72
+    {
+        setupNeighbor();
+        thermo_ready = false;
+        derive_dtforce();
+        setupThermo();
+        if (adjust) adjustThermo();
+        setupPbc();
+        updatePbc();
+        buildNeighbor();
+    }
+    void derive_dtforce()
+    {
+        dtforce = (real)(0.5 * (double)dt);
+        if (P.force_field == MDB_FF_EAM) dtforce = (real)(0.5 * (double)dt / (double)mass); // eam_utils.c:35
+    }
+    void reneighbour() override // verletlist/main.c:76-95
+    {
+        updateAtomsPbc();
+        setupPbc();
+        updatePbc();
+        buildNeighbor();
+    }
+    void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) override
+    {
+        if (!thermo_ready) setupThermo();
+        const int nstat = P.nstat > 0 ? P.nstat : nsteps + 1;
+        const int every = P.reneigh_every > 0 ? P.reneigh_every : nsteps + 1;
+        const int maxrec = nsteps / nstat + 3;
+        d_thermo.ensure((size_t)4 * maxrec, false, stream);
+        std::vector<int> rec_step;
+        auto record = [&](int step) {
+            vel_sums(d_thermo.p + 4 * rec_step.size());
+            rec_step.push_back(step);
+        };
+        const double f0 = force_ms, n0 = neigh_ms;
+        record(0);            // main.c:244
+        launch_force(FORCE_DISPATCH); // main.c:250
+        MDB_CUDA(cudaEventRecord(run_ev(0), stream)); // timer[TOTAL] starts after the first force, main.c:252
+        for (int n = 0; n < nsteps; n++) {
+            const bool reneigh = (n + 1) % every == 0; // main.c:259
+            initialIntegrate();
+            if (reneigh) reneighbour();
+            else updatePbc();
+            launch_force(FORCE_DISPATCH);
+            finalIntegrate();
+            if (!((n + 1) % nstat) && (n + 1) < nsteps) record(n + 1); // main.c:275-280
+        }
+        MDB_CUDA(cudaEventRecord(run_ev(1), stream));
+        record(nsteps); // computeThermo(-1), main.c:288
+        std::vector<double> h(4 * rec_step.size());
+        MDB_CUDA(cudaMemcpyAsync(h.data(), d_thermo.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0;
+        MDB_CUDA(cudaEventElapsedTime(&ms, run_ev(0), run_ev(1)));
+        int nr = 0;
+        for (size_t r = 0; r < rec_step.size(); r++) {
+            if (thermo_out && nr < max_records) {
+                thermo_out[3 * nr] = rec_step[r];
+                thermo_from_sum(h[4 * r + 3], &thermo_out[3 * nr + 1], &thermo_out[3 * nr + 2]);
+                nr++;
+            }
+        }
+        if (nrecords) *nrecords = nr;
+        if (timers) {
+            timers[0] = ms * 1e-3;
+            timers[1] = (force_ms - f0) * 1e-3;
+            timers[2] = (neigh_ms - n0) * 1e-3;
+        }
+    }
+    cudaEvent_t run_events[2] = { nullptr, nullptr };
+    cudaEvent_t run_ev(int k)
+    {
+        if (!run_events[k]) MDB_CUDA(cudaEventCreate(&run_events[k]));
+        return run_events[k];
+    }
+
+    // ------------------------------------------------------------------ parity accessors
+    void getNeighbors(int* nn, int* nb, int row_stride) override
+    {
+        if (nstride == 0) throw Error("getNeighbors: no neighbor list");
+        MDB_CUDA(cudaMemcpyAsync(nn, numneigh.p, Nlocal * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (nb) {
+            rows.ensure((size_t)Nlocal * row_stride, false, stream);
+            MDB_LAUNCH(launches, k_untranspose, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, row_stride,
+                nstride, numneigh.p, neighbors.p, rows.p);
+            MDB_CUDA(cudaMemcpyAsync(nb, rows.p, (size_t)Nlocal * row_stride * sizeof(int),
+                cudaMemcpyDeviceToHost, stream));
+        }
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    void getGhostMap(int* bm, int* px, int* py, int* pz) override
+    {
+        std::vector<int> code(Nghost);
+        MDB_CUDA(cudaMemcpyAsync(bm, border_map.p, Nghost * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaMemcpyAsync(code.data(), ghost_code.p, Nghost * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        for (int g = 0; g < Nghost; g++) {
+            px[g] = (code[g] & 3) - 1;
+            py[g] = ((code[g] >> 2) & 3) - 1;
+            pz[g] = ((code[g] >> 4) & 3) - 1;
+        }
+    }
+    void getNeighborParams(int* I, double* R) override
+    {
+        if (!neigh_ready) setupNeighbor();
+        const int iv[12] = { bg.nbinx, bg.nbiny, bg.nbinz, bg.mbinx, bg.mbiny, bg.mbinz, bg.mbinxlo,
+            bg.mbinylo, bg.mbinzlo, bg.mbins, nstencil, max_bin_count };
+        const double rv[14] = { (double)bg.bininvx, (double)bg.bininvy, (double)bg.bininvz, (double)binsizex,
+            (double)binsizey, (double)binsizez, (double)cutneighsq, (double)cutneigh, (double)xprd,
+            (double)yprd, (double)zprd, (double)lattice, (double)dtforce, (double)cutforce };
+        memcpy(I, iv, sizeof iv);
+        memcpy(R, rv, sizeof rv);
+    }
+    void getStencil(int* st) override
+    {
+        if (!neigh_ready) setupNeighbor();
+        memcpy(st, h_stencil.data(), nstencil * sizeof(int));
+    }
+    void getBinCounts(int* bc) override
+    {
+        // reference bincount[] is indexed by coord2bin's value directly
+        MDB_CUDA(cudaMemcpyAsync(bc, bincount.p, bg.mbins * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    void countPairs(long long* listed, long long* inside) override
+    {
+        MDB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), stream));
+        MDB_LAUNCH(launches, k_count_pairs<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+            cutforce * cutforce, x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, d_cnt.p);
+        unsigned long long h[2];
+        MDB_CUDA(cudaMemcpyAsync(h, d_cnt.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        *listed = (long long)h[0];
+        *inside = (long long)h[1];
+    }
+
+    // ------------------------------------------------------------------ EAM tables (host, once)
+    void upload_splines(const std::vector<real>& rh, const std::vector<real>& fr, const std::vector<real>& z2)
+    {
+        rhor_spline.ensure(rh.size(), false, stream);
+        frho_spline.ensure(fr.size(), false, stream);
+        z2r_spline.ensure(z2.size(), false, stream);
+        MDB_CUDA(cudaMemcpyAsync(rhor_spline.p, rh.data(), rh.size() * sizeof(real), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(frho_spline.p, fr.data(), fr.size() * sizeof(real), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(z2r_spline.p, z2.data(), z2.size() * sizeof(real), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        h_rhor = rh; h_frho = fr; h_z2r = z2;
+        eam.ready = true;
+    }
+    std::vector<real> h_rhor, h_frho, h_z2r;
+
+    void setEam(int nrho, double drho_, int nr, double dr_, double cut_, double mass_, const double* frho0,
+        const double* zr0, const double* rhor0) override
+    {
+        // initEam overrides, common/eam_utils.c:27-35 (Funcfl fields are MD_FLOAT)
+        const real fdrho = (real)drho_, fdr = (real)dr_, fcut = (real)cut_, fmass = (real)mass_;
+        P.force_field = MDB_FF_EAM;
+        P.mass = (double)fmass; P.cutforce = (double)fcut; P.temp = 600.0; P.dt = 0.001; P.rho = 0.07041125;
+        derive();
+        cutneigh = (real)((double)cutforce + 1.0);
+        derive_dtforce();
+        std::vector<real> rh, fr, z2;
+        build_eam_tables<real>(nrho, fdrho, nr, fdr, frho0, zr0, rhor0, eam, rh, fr, z2);
+        upload_splines(rh, fr, z2);
+    }
+    void setEamSplines(int nr, int nrho, int nr_tot, int nrho_tot, double rdr, double rdrho, const void* rhor,
+        const void* frho, const void* z2r) override
+    {
+        eam.nr = nr; eam.nrho = nrho; eam.nr_tot = nr_tot; eam.nrho_tot = nrho_tot;
+        eam.rdr = (real)rdr; eam.rdrho = (real)rdrho;
+        std::vector<real> rh((const real*)rhor, (const real*)rhor + nr_tot),
+            fr((const real*)frho, (const real*)frho + nrho_tot), z2((const real*)z2r, (const real*)z2r + nr_tot);
+        upload_splines(rh, fr, z2);
+    }
+    void getEamSplines(int* nr, int* nrho, int* nr_tot, int* nrho_tot, double* rdr, double* rdrho, void* rhor,
+        void* frho, void* z2r) override
+    {
+        if (!eam.ready) throw Error("getEamSplines: no EAM tables");
+        *nr = eam.nr; *nrho = eam.nrho; *nr_tot = eam.nr_tot; *nrho_tot = eam.nrho_tot;
+        *rdr = (double)eam.rdr; *rdrho = (double)eam.rdrho;
+        if (rhor) memcpy(rhor, h_rhor.data(), h_rhor.size() * sizeof(real));
+        if (frho) memcpy(frho, h_frho.data(), h_frho.size() * sizeof(real));
+        if (z2r) memcpy(z2r, h_z2r.data(), h_z2r.size() * sizeof(real));
+    }
+    void getEamFp(void* out, bool ghosts) override
+    {
+        const size_t n = (size_t)Nlocal + (ghosts ? Nghost : 0);
+        MDB_CUDA(cudaMemcpyAsync(out, fp.p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+};
+
+SimBase* make_sim(const mdb_params& p, int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error("mdb_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) throw Error(fmt("mdb_create: device %d out of range (%d devices)", device, ndev));
+    if (p.precision == MDB_DP) return new Sim<double>(p, device);
+    if (p.precision == MDB_SP) return new Sim<float>(p, device);
+    throw Error("mdb_create: precision must be MDB_SP or MDB_DP");
+}
+
+} // namespace mdb

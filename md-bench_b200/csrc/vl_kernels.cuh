@@ -1,0 +1,529 @@
+// vl_kernels.cuh -- sm_100a kernels of the verletlist hot path.
+// Data layout in HBM: SoA (x[],y[],z[], vx.., fx..), locals first then ghosts; the neighbor list
+// is stored TRANSPOSED, neighbors[k * nstride + i], so a warp's k-th index load is one coalesced
+// 128-byte request (the reference's row-major rows are rebuilt only for parity read-back).
+#pragma once
+#include "mdb_util.cuh"
+
+namespace mdb {
+
+// ---------------------------------------------------------------------------------------------
+// geometry of setupNeighbor (reference verletlist/neighbor.c:24-38)
+template <class real> struct BinGeom {
+    real xprd, yprd, zprd;
+    real bininvx, bininvy, bininvz;
+    int nbinx, nbiny, nbinz;
+    int mbinxlo, mbinylo, mbinzlo;
+    int mbinx, mbiny, mbinz, mbins;
+};
+
+// coord2bin, verletlist/neighbor.c:298-327, including the stray "+ 1".  Each product is a single
+// rounded multiply (no contraction), the cast truncates toward zero like C's (int).
+template <class real> __device__ __forceinline__ int axis2bin(real v, real prd, real bininv, int nbin, int mlo)
+{
+    if (v >= prd) return (int)mul_rn(sub_rn(v, prd), bininv) + nbin - mlo;
+    if (v >= (real)0.0) return (int)mul_rn(v, bininv) - mlo;
+    return (int)mul_rn(v, bininv) - mlo - 1;
+}
+template <class real> __device__ __forceinline__ int coord2bin(const BinGeom<real>& g, real x, real y, real z)
+{
+    const int ix = axis2bin(x, g.xprd, g.bininvx, g.nbinx, g.mbinxlo);
+    const int iy = axis2bin(y, g.yprd, g.bininvy, g.nbiny, g.mbinylo);
+    const int iz = axis2bin(z, g.zprd, g.bininvz, g.nbinz, g.mbinzlo);
+    int b        = iz * g.mbiny * g.mbinx + iy * g.mbinx + ix + 1;
+    // a blown-up simulation must not turn into an out-of-bounds write
+    return b < 0 ? 0 : (b > g.mbins ? g.mbins : b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// createAtom, verletlist/atom.c:67-187.  One thread per FCC site (i+j+k even).  The reference
+// emits atoms while walking 8x8x8 sub-boxes of the half-lattice; because 2*n{x,y,z} and 8 are even
+// every (sub-)box holds exactly half of its sites, which gives the emission index in closed form.
+__device__ __forceinline__ double park_miller(int& seed) // common/util.c:24-33
+{
+    const int IA = 16807, IM = 2147483647, IQ = 127773, IR = 2836;
+    const int k  = seed / IQ;
+    seed         = IA * (seed - k * IQ) - IR * k;
+    if (seed < 0) seed += IM;
+    return (1.0 / IM) * seed;
+}
+
+template <class real>
+__global__ void k_create_atoms(int nx, int ny, int nz, real alat, real* __restrict__ x,
+    real* __restrict__ y, real* __restrict__ z, real* __restrict__ vx, real* __restrict__ vy,
+    real* __restrict__ vz, int* __restrict__ type)
+{
+    const long long t     = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = 4LL * nx * ny * nz;
+    if (t >= total) return;
+    const int ih = (int)(t % nx);
+    const int j  = (int)((t / nx) % (2 * ny));
+    const int k  = (int)(t / ((long long)nx * 2 * ny));
+    const int i  = 2 * ih + ((j + k) & 1);
+    const int ox = i >> 3, sx = i & 7, oy = j >> 3, sy = j & 7, oz = k >> 3, sz = k & 7;
+    const int bx = min(8, 2 * nx - 8 * ox), by = min(8, 2 * ny - 8 * oy), bz = min(8, 2 * nz - 8 * oz);
+    long long sites = 8LL * oz * (2LL * nx) * (2LL * ny) // complete layers of boxes
+                      + (2LL * nx) * (8LL * oy) * bz      // complete rows of boxes in this layer
+                      + (8LL * ox) * by * bz;             // boxes before this one in the row
+    long long a = sites / 2 + (long long)sz * (bx * by / 2) + (long long)sy * (bx / 2) +
+                  (((sy + sz) & 1) ? sx / 2 : (sx + 1) / 2);
+    int n = k * (2 * ny) * (2 * nx) + j * (2 * nx) + i + 1;
+    double v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        for (int m = 0; m < 5; m++) park_miller(n);
+        v[c] = park_miller(n);
+    }
+    // 0.5 * alat * i is evaluated in double and narrowed on assignment (atom.c:126-128)
+    x[a]    = (real)(0.5 * (double)alat * i);
+    y[a]    = (real)(0.5 * (double)alat * j);
+    z[a]    = (real)(0.5 * (double)alat * k);
+    vx[a]   = (real)v[0];
+    vy[a]   = (real)v[1];
+    vz[a]   = (real)v[2];
+    type[a] = 0; // rand() % ntypes with ntypes == 1 (atom.c:158)
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic two-stage sum reductions (thermo, adjustThermo).  Accumulation in double.
+constexpr int RED_THREADS = 256;
+constexpr int RED_BLOCKS  = 1184; // 148 SMs x 8 resident blocks
+
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double sh[RED_THREADS / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < RED_THREADS / 32 ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int d = 4; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    }
+    __syncthreads();
+    return v; // valid in thread 0
+}
+
+// partial[b*4 + {0,1,2,3}] = sum vx, sum vy, sum vz, sum (vx^2+vy^2+vz^2)*mass over the block's atoms
+template <class real>
+__global__ void __launch_bounds__(RED_THREADS) k_vel_partial(int n, const real* __restrict__ vx,
+    const real* __restrict__ vy, const real* __restrict__ vz, real mass, double* __restrict__ partial)
+{
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const real a = vx[i], b = vy[i], c = vz[i];
+        s0 += a;
+        s1 += b;
+        s2 += c;
+        s3 += (double)((a * a + b * b + c * c) * mass);
+    }
+    s0 = block_sum(s0);
+    s1 = block_sum(s1);
+    s2 = block_sum(s2);
+    s3 = block_sum(s3);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x * 4 + 0] = s0;
+        partial[blockIdx.x * 4 + 1] = s1;
+        partial[blockIdx.x * 4 + 2] = s2;
+        partial[blockIdx.x * 4 + 3] = s3;
+    }
+}
+// out[0..3] = sums over blocks
+__global__ void __launch_bounds__(RED_THREADS) k_vel_final(int nblocks, const double* __restrict__ partial, double* __restrict__ out)
+{
+    for (int c = 0; c < 4; c++) {
+        double s = 0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partial[b * 4 + c];
+        s = block_sum(s);
+        if (threadIdx.x == 0) out[c] = s;
+    }
+}
+
+// adjustThermo steps, common/thermo.c:98-102 and 117-121
+template <class real>
+__global__ void k_vel_shift(int n, real* vx, real* vy, real* vz, real sx, real sy, real sz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { vx[i] -= sx; vy[i] -= sy; vz[i] -= sz; }
+}
+template <class real> __global__ void k_vel_scale(int n, real* vx, real* vy, real* vz, real f)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { vx[i] *= f; vy[i] *= f; vz[i] *= f; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// velocity-Verlet halves, verletlist/integrate.c:21-31 / 33-40
+template <class real>
+__global__ void k_initial_integrate(int n, real dtforce, real dt, real* __restrict__ x,
+    real* __restrict__ y, real* __restrict__ z, real* __restrict__ vx, real* __restrict__ vy,
+    real* __restrict__ vz, const real* __restrict__ fx, const real* __restrict__ fy,
+    const real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const real a = vx[i] + dtforce * fx[i], b = vy[i] + dtforce * fy[i], c = vz[i] + dtforce * fz[i];
+    vx[i] = a; vy[i] = b; vz[i] = c;
+    x[i]  = x[i] + dt * a;
+    y[i]  = y[i] + dt * b;
+    z[i]  = z[i] + dt * c;
+}
+template <class real>
+__global__ void k_final_integrate(int n, real dtforce, real* __restrict__ vx, real* __restrict__ vy,
+    real* __restrict__ vz, const real* __restrict__ fx, const real* __restrict__ fy,
+    const real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vx[i] += dtforce * fx[i];
+    vy[i] += dtforce * fy[i];
+    vz[i] += dtforce * fz[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// PBC.  Ghost image codes in the order of the reference's ADDGHOST ladder (verletlist/pbc.c:
+// 107-224): 6 faces, 8 corners, 12 edges (x-z, y-z, x-y).  need[axis] = +1: requires coordinate
+// < cutneigh (image shifted by +prd); -1: requires coordinate >= prd - cutneigh.
+__constant__ signed char c_img[26][3] = {
+    { +1, 0, 0 }, { -1, 0, 0 }, { 0, +1, 0 }, { 0, -1, 0 }, { 0, 0, +1 }, { 0, 0, -1 },
+    { +1, +1, +1 }, { +1, -1, +1 }, { +1, +1, -1 }, { +1, -1, -1 },
+    { -1, +1, +1 }, { -1, -1, +1 }, { -1, +1, -1 }, { -1, -1, -1 },
+    { +1, 0, +1 }, { +1, 0, -1 }, { -1, 0, +1 }, { -1, 0, -1 },
+    { 0, +1, +1 }, { 0, +1, -1 }, { 0, -1, +1 }, { 0, -1, -1 },
+    { +1, +1, 0 }, { -1, +1, 0 }, { +1, -1, 0 }, { -1, -1, 0 } };
+
+template <class real> struct PbcGeom {
+    real xprd, yprd, zprd, cutneigh;
+    real xhi_cut, yhi_cut, zhi_cut; // prd - cutneigh, rounded once like the reference's (xprd - cutneigh)
+    int pbc_x, pbc_y, pbc_z;
+};
+
+template <class real> __device__ __forceinline__ unsigned ghost_mask(const PbcGeom<real>& g, real x, real y, real z)
+{
+    const bool lo[3] = { x < g.cutneigh, y < g.cutneigh, z < g.cutneigh };
+    const bool hi[3] = { x >= g.xhi_cut, y >= g.yhi_cut, z >= g.zhi_cut };
+    const bool en[3] = { g.pbc_x != 0, g.pbc_y != 0, g.pbc_z != 0 };
+    unsigned m       = 0;
+#pragma unroll
+    for (int b = 0; b < 26; b++) {
+        bool ok = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int d = c_img[b][a];
+            if (d > 0) ok = ok && en[a] && lo[a];
+            if (d < 0) ok = ok && en[a] && hi[a];
+        }
+        if (ok) m |= 1u << b;
+    }
+    return m;
+}
+
+// setupPbc pass 1 (pbc.c:98-227): per local atom, which of the 26 images exist
+template <class real>
+__global__ void k_ghost_count(int nlocal, PbcGeom<real> g, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, unsigned* __restrict__ mask,
+    int* __restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const unsigned m = ghost_mask(g, x[i], y[i], z[i]);
+    mask[i]          = m;
+    count[i]         = __popc(m);
+}
+// setupPbc pass 2: ghost index = exclusive scan of the counts in atom order + rank of the image in
+// the ladder, i.e. exactly the reference's Nghost++ order.  code = (dx+1) | (dy+1)<<2 | (dz+1)<<4.
+__global__ void k_ghost_fill(int nlocal, const unsigned* __restrict__ mask,
+    const int* __restrict__ offset, int* __restrict__ border_map, int* __restrict__ code,
+    int* __restrict__ type)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    unsigned m = mask[i];
+    int g      = offset[i];
+    const int t = type[i];
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        border_map[g]    = i;
+        code[g]          = (c_img[b][0] + 1) | ((c_img[b][1] + 1) << 2) | ((c_img[b][2] + 1) << 4);
+        type[nlocal + g] = t;
+        g++;
+    }
+}
+// updatePbc, pbc.c:42-55: x[nlocal+g] = x[border_map[g]] + PBCx[g]*xprd as ONE fma (the
+// reference's -Ofast build contracts it; ghost coordinates feed the list build).
+template <class real>
+__global__ void k_update_pbc(int nlocal, int nghost, real xprd, real yprd, real zprd,
+    const int* __restrict__ border_map, const int* __restrict__ code, real* __restrict__ x,
+    real* __restrict__ y, real* __restrict__ z)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nghost) return;
+    const int s = border_map[g], c = code[g];
+    x[nlocal + g] = fma_rn((real)((c & 3) - 1), xprd, x[s]);
+    y[nlocal + g] = fma_rn((real)(((c >> 2) & 3) - 1), yprd, y[s]);
+    z[nlocal + g] = fma_rn((real)(((c >> 4) & 3) - 1), zprd, z[s]);
+}
+// updateAtomsPbc, pbc.c:59-84
+template <class real> __device__ __forceinline__ real wrap1(real v, real prd)
+{
+    if (v < (real)0.0) return add_rn(v, prd);
+    if (v >= prd) return sub_rn(v, prd);
+    return v;
+}
+template <class real>
+__global__ void k_update_atoms_pbc(int nlocal, real xprd, real yprd, real zprd, real* __restrict__ x,
+    real* __restrict__ y, real* __restrict__ z)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    x[i] = wrap1(x[i], xprd);
+    y[i] = wrap1(y[i], yprd);
+    z[i] = wrap1(z[i], zprd);
+}
+
+// ---------------------------------------------------------------------------------------------
+// binatoms, verletlist/neighbor.c:329-358, as a counting sort: histogram -> scan -> fill -> sort
+// each bin ascending (= the reference's insertion order, so rows come out in the same order).
+template <class real>
+__global__ void k_bin_count(int nall, BinGeom<real> g, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, int* __restrict__ atom_bin,
+    int* __restrict__ bincount)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nall) return;
+    const int b = coord2bin(g, x[i], y[i], z[i]);
+    atom_bin[i] = b;
+    atomicAdd(&bincount[b], 1);
+}
+__global__ void k_bin_fill(int nall, const int* __restrict__ atom_bin, const int* __restrict__ binstart,
+    int* __restrict__ cursor, int* __restrict__ binatoms)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nall) return;
+    const int b                          = atom_bin[i];
+    binatoms[binstart[b] + atomicAdd(&cursor[b], 1)] = i;
+}
+__global__ void k_bin_sort(int nbins, const int* __restrict__ binstart, int* __restrict__ binatoms,
+    int* __restrict__ maxcount)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt     = 0;
+    if (b < nbins) {
+        const int s = binstart[b];
+        cnt         = binstart[b + 1] - s;
+        int* a      = binatoms + s;
+        for (int i = 1; i < cnt; i++) { // insertion sort; bins hold ~8 atoms
+            const int v = a[i];
+            int j       = i - 1;
+            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+            a[j + 1] = v;
+        }
+    }
+    cnt = __reduce_max_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt > 0) atomicMax(maxcount, cnt);
+}
+
+// buildNeighbor, verletlist/neighbor.c:186-264.  One thread per local atom scans the stencil bins.
+// rsq = fma(dx,dx,fma(dy,dy,dz*dz)) is the exact expression of the reference build,
+// the inclusion test is "<=" (neighbor.c:240).  Rows are written transposed; entries beyond
+// maxneighs are counted but not stored and the host re-runs with a larger maxneighs.
+template <class real>
+__global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, BinGeom<real> g,
+    real cutneighsq, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, const int* __restrict__ binstart, const int* __restrict__ binatoms,
+    const int* __restrict__ stencil, int nstencil, int maxneighs, size_t nstride,
+    int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n       = 0;
+    if (i < nlocal) {
+        const real xt = x[i], yt = y[i], zt = z[i];
+        const int ibin = coord2bin(g, xt, yt, zt);
+        for (int k = 0; k < nstencil; k++) {
+            const int jbin = ibin + __ldg(&stencil[k]);
+            if (jbin < 0 || jbin > g.mbins) continue;
+            const int s = __ldg(&binstart[jbin]), e = __ldg(&binstart[jbin + 1]);
+            for (int m = s; m < e; m++) {
+                const int j = __ldg(&binatoms[m]);
+                if (j == i || (half && j < i)) continue;
+                const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
+                const real rsq = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz)));
+                if (rsq <= cutneighsq) {
+                    if (n < maxneighs) neighbors[(size_t)n * nstride + i] = j;
+                    n++;
+                }
+            }
+        }
+        numneigh[i] = n;
+    }
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
+// parity read-back: transposed list -> the reference's row-major rows
+__global__ void k_untranspose(int nlocal, int row_stride, size_t nstride, const int* __restrict__ numneigh,
+    const int* __restrict__ nbT, int* __restrict__ rows)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const int n = min(numneigh[i], row_stride);
+    for (int k = 0; k < n; k++) rows[(size_t)i * row_stride + k] = nbT[(size_t)k * nstride + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// LJ 12-6 force, full neighbor lists: verletlist/force_lj.c:14-105.  One thread per local atom,
+// transposed list, 4 neighbors in flight per thread.
+template <class real> struct LJConst {
+    real cutforcesq, sigma6, epsilon;
+};
+
+template <class real> __device__ __forceinline__ real lj_pair(real rsq, const LJConst<real>& c)
+{
+    const real sr2 = (real)1.0 / rsq;
+    const real sr6 = sr2 * sr2 * sr2 * c.sigma6;
+    return (real)48.0 * sr6 * (sr6 - (real)0.5) * sr2 * c.epsilon;
+}
+
+template <class real>
+__global__ void __launch_bounds__(128) k_force_lj_full(int nlocal, LJConst<real> c,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride,
+    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    const int* nb = nbT + i;
+    int k         = 0;
+    for (; k + 4 <= nn; k += 4) {
+        int j[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) j[u] = __ldg(nb + (size_t)(k + u) * nstride);
+        real dx[4], dy[4], dz[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            dx[u] = xt - x[j[u]];
+            dy[u] = yt - y[j[u]];
+            dz[u] = zt - z[j[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+            if (rsq < c.cutforcesq) {
+                const real f = lj_pair(rsq, c);
+                fix += dx[u] * f;
+                fiy += dy[u] * f;
+                fiz += dz[u] * f;
+            }
+        }
+    }
+    for (; k < nn; k++) {
+        const int j   = __ldg(nb + (size_t)k * nstride);
+        const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < c.cutforcesq) {
+            const real f = lj_pair(rsq, c);
+            fix += dx * f;
+            fiy += dy * f;
+            fiz += dz * f;
+        }
+    }
+    fx[i] = fix;
+    fy[i] = fiy;
+    fz[i] = fiz;
+}
+
+// LJ force, half neighbor lists: verletlist/force_lj.c:107-198.  The reaction force on local j
+// (force_lj.c:176-180) is scattered with native FP atomics (RED.ADD.F64/F32); forces are zeroed by
+// the caller first, as the reference does (force_lj.c:123-127).
+template <class real>
+__global__ void __launch_bounds__(128) k_force_lj_half(int nlocal, LJConst<real> c,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride, real* fx, real* fy,
+    real* fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    const int* nb = nbT + i;
+    for (int k = 0; k < nn; k++) {
+        const int j   = __ldg(nb + (size_t)k * nstride);
+        const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < c.cutforcesq) {
+            const real f = lj_pair(rsq, c);
+            fix += dx * f;
+            fiy += dy * f;
+            fiz += dz * f;
+            if (j < nlocal) {
+                atomicAdd(&fx[j], -dx * f);
+                atomicAdd(&fy[j], -dy * f);
+                atomicAdd(&fz[j], -dz * f);
+            }
+        }
+    }
+    atomicAdd(&fx[i], fix);
+    atomicAdd(&fy[i], fiy);
+    atomicAdd(&fz[i], fiz);
+}
+
+// workload counters (the reference's Stats, verletlist/stats.h:13-18): listed pairs and pairs
+// inside the force cutoff for the current positions
+template <class real>
+__global__ void k_count_pairs(int nlocal, real cutforcesq, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh,
+    const int* __restrict__ nbT, size_t nstride, unsigned long long* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long listed = 0, inside = 0;
+    if (i < nlocal) {
+        const real xt = x[i], yt = y[i], zt = z[i];
+        const int nn  = numneigh[i];
+        listed        = nn;
+        for (int k = 0; k < nn; k++) {
+            const int j   = nbT[(size_t)k * nstride + i];
+            const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
+            if (dx * dx + dy * dy + dz * dz < cutforcesq) inside++;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        listed += __shfl_down_sync(0xffffffffu, listed, d);
+        inside += __shfl_down_sync(0xffffffffu, inside, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], listed);
+        atomicAdd(&out[1], inside);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-layout conversion: AoS {x,y,z}* <-> SoA
+template <class real>
+__global__ void k_aos_to_soa(size_t n, const real* __restrict__ a, real* __restrict__ x,
+    real* __restrict__ y, real* __restrict__ z)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = a[3 * i + 0];
+    y[i] = a[3 * i + 1];
+    z[i] = a[3 * i + 2];
+}
+template <class real>
+__global__ void k_soa_to_aos(size_t n, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, real* __restrict__ a)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[3 * i + 0] = x[i];
+    a[3 * i + 1] = y[i];
+    a[3 * i + 2] = z[i];
+}
+
+} // namespace mdb

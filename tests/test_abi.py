@@ -1,0 +1,76 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/mdb200.h declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, load_pkg
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "mdb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdb_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    m = load_pkg()
+    L = m.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    # and the python mirror binds exactly the declared surface
+    assert sorted(m.EXPORTS) == syms
+
+
+def test_abi_version_and_default_params():
+    m = load_pkg()
+    L = m.load_library()
+    assert L.mdb_abi_version() == 1
+    p = m.default_params()
+    # initParameter defaults, reference common/parameter.c:16-51
+    assert (p.nx, p.ny, p.nz) == (32, 32, 32)
+    assert p.ntimes == 200 and p.nstat == 100 and p.reneigh_every == 20 and p.half_neigh == 0
+    assert p.dt == 0.005 and p.cutforce == 2.5 and p.skin == 0.3 and p.temp == 1.44
+    assert p.rho == 0.8442 and p.epsilon == 1.0 and p.sigma == 1.0 and p.mass == 1.0
+    assert (p.pbc_x, p.pbc_y, p.pbc_z) == (1, 1, 1) and p.ntypes == 1
+    assert p.precision == m.DP and p.layout == m.AOS and p.force_field == m.FF_LJ
+
+
+def test_params_struct_size_matches_header():
+    # the ctypes mirror must have the C struct's size: compile a one-liner against the header
+    import subprocess
+    import tempfile
+    m = load_pkg()
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write('#include <stdio.h>\n#include "mdb200.h"\nint main(void){printf("%zu\\n", sizeof(mdb_params));return 0;}\n')
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        n = int(subprocess.check_output([exe]).decode())
+    assert n == C.sizeof(m.Params)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not fall back to anything."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = load_pkg()
+    with pytest.raises(m.MdbError) as e:
+        m.Simulation()
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, smoke() and bench.py's cpu_baseline leg may touch oracle/."""
+    pk = os.path.join(ROOT, "md-bench_b200")
+    for dp, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("no oracle", "") or f == "__init__.py" and \
+                    "never imports anything from oracle" in txt, os.path.join(dp, f)
