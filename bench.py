@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--ref-ntimes", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sort", action="store_true", help="A/B: keep the reference atom order internally")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,6 +221,8 @@ def main():
                          ntimes=args.ntimes, half_neigh=args.half)
     sim = m.Simulation(P, device=local)
     sim.setStream(torch.cuda.current_stream().cuda_stream)
+    if args.no_sort:
+        sim.setOption("sort_atoms", 0)
     natoms = sim.createAtom()
     sim.setup(adjust=True)
     sim.saveState()

@@ -70,6 +70,10 @@ void        mdb_default_params(mdb_params* p);
  * dtforce (parameter.c:115-120).  Returns NULL on failure. */
 mdb_ctx*    mdb_create(const mdb_params* p, int device);
 void        mdb_destroy(mdb_ctx* c);
+/* tuning switches (A/B measurements, debugging).  "sort_atoms" (default 1): keep the local atoms
+ * sorted by neighbor bin internally (the reference's SORT_ATOMS, neighbor.c:360-426, with the
+ * permutation tracked so that every accessor below still speaks the reference's atom numbering). */
+int         mdb_setOption(mdb_ctx* c, const char* name, double value);
 /* run all work of this ctx on the given cudaStream_t (passed as void*); NULL = ctx-owned stream */
 int         mdb_setStream(mdb_ctx* c, void* cuda_stream);
 int         mdb_sync(mdb_ctx* c);

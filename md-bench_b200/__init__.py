@@ -46,7 +46,7 @@ class Params(C.Structure):
 
 EXPORTS = [
     "mdb_abi_version", "mdb_last_error", "mdb_default_params", "mdb_create", "mdb_destroy",
-    "mdb_setStream", "mdb_sync", "mdb_createAtom", "mdb_setAtoms", "mdb_setAtomsDevice",
+    "mdb_setOption", "mdb_setStream", "mdb_sync", "mdb_createAtom", "mdb_setAtoms", "mdb_setAtomsDevice",
     "mdb_getAtoms", "mdb_getCounts", "mdb_saveState", "mdb_restoreState", "mdb_setupThermo",
     "mdb_adjustThermo", "mdb_computeThermo", "mdb_setupNeighbor", "mdb_setupPbc", "mdb_updatePbc",
     "mdb_updateAtomsPbc", "mdb_buildNeighbor", "mdb_computeForce", "mdb_computeForceLJFullNeigh",
@@ -186,6 +186,15 @@ class Simulation:
         cols = [np.empty(n, dtype=self.np_real) for _ in range(3)]
         self._ck(self.L.mdb_getAtoms(self.h, ord(what), int(ghosts), *[_vp(q) for q in cols]))
         return np.stack(cols, axis=1)
+
+    # rows of the neighbor list come back in the reference's ORDER (stencil order x ascending index)
+    # only when the internal spatial sort is off; as sorted index SETS they always agree
+    row_order_exact = False
+
+    def setOption(self, name, value):
+        self._ck(self.L.mdb_setOption(self.h, name.encode(), C.c_double(value)))
+        if name == "sort_atoms":
+            self.row_order_exact = not value
 
     def saveState(self): self._ck(self.L.mdb_saveState(self.h))
     def restoreState(self): self._ck(self.L.mdb_restoreState(self.h))

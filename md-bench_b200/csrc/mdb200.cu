@@ -189,6 +189,7 @@ int mdb_getNeighborParams(mdb_ctx* c, int ints[12], double reals[14]) { MDB_TRY(
 int mdb_getStencil(mdb_ctx* c, int* st) { MDB_TRY(c->sim->getStencil(st)) }
 int mdb_getBinCounts(mdb_ctx* c, int* bc) { MDB_TRY(c->sim->getBinCounts(bc)) }
 int mdb_getEamFp(mdb_ctx* c, void* fp, int with_ghosts) { MDB_TRY(c->sim->getEamFp(fp, with_ghosts != 0)) }
+int mdb_setOption(mdb_ctx* c, const char* name, double value) { MDB_TRY(c->sim->setOption(name, value)) }
 int mdb_countPairs(mdb_ctx* c, long long* listed, long long* in_cutoff) { MDB_TRY(c->sim->countPairs(listed, in_cutoff)) }
 
 } // extern "C"

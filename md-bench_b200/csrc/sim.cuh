@@ -48,6 +48,7 @@ struct SimBase {
     virtual void getEamSplines(int* nr, int* nrho, int* nr_tot, int* nrho_tot, double* rdr,
         double* rdrho, void* rhor, void* frho, void* z2r)                                    = 0;
     virtual void getEamFp(void* fp, bool ghosts)                                             = 0;
+    virtual void setOption(const char* name, double value)                                   = 0;
 
     bool timing             = false;
     double force_ms         = 0, neigh_ms = 0;

@@ -2,6 +2,7 @@
 // Host code here only orchestrates: every per-atom operation is a kernel in vl_kernels.cuh /
 // eam_kernels.cuh; the only device->host traffic inside the time loop is one small flag read per
 // neighbor rebuild (ghost total, bin / list overflow).
+#include <algorithm>
 #include <initializer_list>
 
 #include "sim.cuh"
@@ -24,8 +25,15 @@ template <class real> struct Sim final : SimBase {
     // ---- atoms ----
     long long Natoms = 0;
     int Nlocal = 0, Nghost = 0;
+    // Internal order: local atoms are kept sorted by neighbor bin (sort_atoms(), re-done at every
+    // rebuild) so that the gathers of the force and list kernels hit few cache lines per warp;
+    // orig[p] is the reference's index of the atom in slot p, and every accessor of the C ABI
+    // translates back, so callers only ever see the reference's numbering.
     DBuf<real> x, y, z, vx, vy, vz, fx, fy, fz, sx, sy, sz, svx, svy, svz, stage;
-    DBuf<int> type, border_map, ghost_code, ghost_cnt, ghost_off;
+    DBuf<real> x2, y2, z2, vx2, vy2, vz2, fx2, fy2, fz2, tx, ty, tz;
+    DBuf<int> type, border_map, ghost_code, ghost_cnt, ghost_off, orig, orig2, type2, extmap, nn_ext;
+    bool sort_enabled = true, extmap_valid = false;
+    std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
     DBuf<unsigned> ghost_msk;
     int saved_n = 0;
     // ---- neighbor (verletlist/neighbor.c:24-38) ----
@@ -71,8 +79,10 @@ template <class real> struct Sim final : SimBase {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &fx, &fy, &fz, &sx, &sy, &sz, &svx, &svy,
-                 &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline })
+                 &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline, &x2, &y2, &z2, &vx2, &vy2,
+                 &vz2, &fx2, &fy2, &fz2, &tx, &ty, &tz })
             b->release();
+        for (DBuf<int>* b : { &orig, &orig2, &type2, &extmap, &nn_ext }) b->release();
         for (DBuf<int>* b : { &type, &border_map, &ghost_code, &ghost_cnt, &ghost_off, &stencil,
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
             b->release();
@@ -136,6 +146,12 @@ template <class real> struct Sim final : SimBase {
     {
         for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &fx, &fy, &fz }) b->ensure(n, keep, stream);
         type.ensure(n, keep, stream);
+        orig.ensure(n, keep, stream);
+    }
+    void reset_order() // internal order := the caller's (reference) order
+    {
+        MDB_LAUNCH(launches, k_iota, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, orig.p);
+        extmap_valid = false;
     }
 
     // ------------------------------------------------------------------ atoms
@@ -150,6 +166,7 @@ template <class real> struct Sim final : SimBase {
         MDB_LAUNCH(launches, k_create_atoms<real>, grid_for(Natoms, 256), 256, 0, stream, P.nx, P.ny,
             P.nz, lattice, x.p, y.p, z.p, vx.p, vy.p, vz.p, type.p);
         zero3(fx.p, fy.p, fz.p, Nlocal);
+        reset_order();
         neigh_ready = false;
         return Natoms;
     }
@@ -192,6 +209,7 @@ template <class real> struct Sim final : SimBase {
                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
         else MDB_CUDA(cudaMemsetAsync(type.p, 0, n * sizeof(int), stream));
         zero3(fx.p, fy.p, fz.p, n);
+        reset_order();
         MDB_CUDA(cudaStreamSynchronize(stream)); // host buffers may be reused by the caller
         neigh_ready = false;
     }
@@ -203,15 +221,22 @@ template <class real> struct Sim final : SimBase {
         else if (which == 'v') { a = vx.p; b = vy.p; c = vz.p; }
         else if (which == 'f') { a = fx.p; b = fy.p; c = fz.p; }
         else throw Error("getAtoms: which must be 'x', 'v' or 'f'");
-        const size_t n = (size_t)Nlocal + ((ghosts && which == 'x') ? Nghost : 0);
+        const bool wg  = ghosts && which == 'x' && Nghost > 0;
+        const size_t n = (size_t)Nlocal + (wg ? Nghost : 0);
+        // back to the reference's numbering: slot p -> orig[p] (ghosts: reference ghost order)
+        const int* map = orig.p;
+        if (wg) { build_extmap(); map = extmap.p; }
+        tx.ensure(n, false, stream); ty.ensure(n, false, stream); tz.ensure(n, false, stream);
+        MDB_LAUNCH(launches, k_scatter_orig<real>, grid_for(n, 256), 256, 0, stream, (int)n, map, a, b, c,
+            tx.p, ty.p, tz.p);
         if (P.layout == MDB_AOS) {
             stage.ensure(3 * n, false, stream);
-            MDB_LAUNCH(launches, k_soa_to_aos<real>, grid_for(n, 256), 256, 0, stream, n, a, b, c, stage.p);
+            MDB_LAUNCH(launches, k_soa_to_aos<real>, grid_for(n, 256), 256, 0, stream, n, tx.p, ty.p, tz.p, stage.p);
             MDB_CUDA(cudaMemcpyAsync(ax, stage.p, 3 * n * sizeof(real), cudaMemcpyDeviceToHost, stream));
         } else {
-            MDB_CUDA(cudaMemcpyAsync(ax, a, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
-            MDB_CUDA(cudaMemcpyAsync(ay, b, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
-            MDB_CUDA(cudaMemcpyAsync(az, c, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(ax, tx.p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(ay, ty.p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(az, tz.p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
         }
         MDB_CUDA(cudaStreamSynchronize(stream));
     }
@@ -222,15 +247,14 @@ template <class real> struct Sim final : SimBase {
         *mn  = maxneighs;
     }
 
-    void saveState() override
+    void saveState() override // stored in the reference's atom order
     {
         const size_t n = Nlocal;
-        DBuf<real>* dst[] = { &sx, &sy, &sz, &svx, &svy, &svz };
-        DBuf<real>* src[] = { &x, &y, &z, &vx, &vy, &vz };
-        for (int k = 0; k < 6; k++) {
-            dst[k]->ensure(n, false, stream);
-            MDB_CUDA(cudaMemcpyAsync(dst[k]->p, src[k]->p, n * sizeof(real), cudaMemcpyDeviceToDevice, stream));
-        }
+        for (DBuf<real>* b : { &sx, &sy, &sz, &svx, &svy, &svz }) b->ensure(n, false, stream);
+        MDB_LAUNCH(launches, k_scatter_orig<real>, grid_for(n, 256), 256, 0, stream, (int)n, orig.p, x.p, y.p,
+            z.p, sx.p, sy.p, sz.p);
+        MDB_LAUNCH(launches, k_scatter_orig<real>, grid_for(n, 256), 256, 0, stream, (int)n, orig.p, vx.p, vy.p,
+            vz.p, svx.p, svy.p, svz.p);
         saved_n = Nlocal;
     }
     void restoreState() override
@@ -244,6 +268,7 @@ template <class real> struct Sim final : SimBase {
         zero3(fx.p, fy.p, fz.p, n);
         Nlocal = saved_n;
         Nghost = 0;
+        reset_order();
     }
 
     // ------------------------------------------------------------------ thermo
@@ -396,6 +421,79 @@ template <class real> struct Sim final : SimBase {
         neigh_ready = true;
     }
 
+    // ------------------------------------------------------------------ spatial sort
+    // sortAtom (verletlist/neighbor.c:360-426; main.c:63-66,82-88) -- always on here, because on
+    // the GPU it is what makes the neighbor gathers coalesce: counting sort of the local atoms by
+    // bin, ties broken by reference index (so the order is a pure function of positions and ids).
+    void sort_atoms()
+    {
+        if (!sort_enabled || Nlocal == 0) return;
+        if (!neigh_ready) setupNeighbor();
+        const int nb = bg.mbins + 1;
+        atom_bin.ensure(Nlocal, false, stream);
+        binatoms.ensure(Nlocal, false, stream);
+        MDB_CUDA(cudaMemsetAsync(bincount.p, 0, (nb + 1) * sizeof(int), stream));
+        MDB_CUDA(cudaMemsetAsync(cursor.p, 0, (nb + 1) * sizeof(int), stream));
+        MDB_LAUNCH(launches, k_bin_count<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, bg, x.p, y.p, z.p,
+            atom_bin.p, bincount.p);
+        scanner.exclusive(bincount.p, binstart.p, nb, binstart.p + nb, stream);
+        MDB_LAUNCH(launches, k_bin_fill, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, atom_bin.p, binstart.p,
+            cursor.p, binatoms.p);
+        MDB_LAUNCH(launches, k_bin_sort, grid_for(nb, 128), 128, 0, stream, nb, binstart.p, binatoms.p, orig.p,
+            d_flags.p + 3);
+        const size_t cap = x.cap;
+        for (DBuf<real>* b : { &x2, &y2, &z2, &vx2, &vy2, &vz2, &fx2, &fy2, &fz2 }) b->ensure(cap, false, stream);
+        type2.ensure(cap, false, stream);
+        orig2.ensure(cap, false, stream);
+        MDB_LAUNCH(launches, k_permute_atoms<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, binatoms.p, x.p,
+            y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p, type.p, orig.p, x2.p, y2.p, z2.p, vx2.p, vy2.p, vz2.p,
+            fx2.p, fy2.p, fz2.p, type2.p, orig2.p);
+        std::swap(x, x2); std::swap(y, y2); std::swap(z, z2);
+        std::swap(vx, vx2); std::swap(vy, vy2); std::swap(vz, vz2);
+        std::swap(fx, fx2); std::swap(fy, fy2); std::swap(fz, fz2);
+        std::swap(type, type2); std::swap(orig, orig2);
+        extmap_valid = false;
+    }
+
+    // internal index -> reference index for locals AND ghosts.  The reference numbers ghosts in the
+    // order of its serial setupPbc loop: by source atom (reference index), then by position in the
+    // ADDGHOST ladder (pbc.c:107-224).  Only needed for parity read-back, so done lazily on the host.
+    void build_extmap()
+    {
+        if (extmap_valid) return;
+        static const signed char img[26][3] = { { +1, 0, 0 }, { -1, 0, 0 }, { 0, +1, 0 }, { 0, -1, 0 },
+            { 0, 0, +1 }, { 0, 0, -1 }, { +1, +1, +1 }, { +1, -1, +1 }, { +1, +1, -1 }, { +1, -1, -1 },
+            { -1, +1, +1 }, { -1, -1, +1 }, { -1, +1, -1 }, { -1, -1, -1 }, { +1, 0, +1 }, { +1, 0, -1 },
+            { -1, 0, +1 }, { -1, 0, -1 }, { 0, +1, +1 }, { 0, +1, -1 }, { 0, -1, +1 }, { 0, -1, -1 },
+            { +1, +1, 0 }, { -1, +1, 0 }, { +1, -1, 0 }, { -1, -1, 0 } };
+        int rank_of_code[64];
+        for (int b = 0; b < 26; b++)
+            rank_of_code[(img[b][0] + 1) | ((img[b][1] + 1) << 2) | ((img[b][2] + 1) << 4)] = b;
+        h_orig.resize(Nlocal);
+        h_bm.resize(Nghost);
+        h_code.resize(Nghost);
+        MDB_CUDA(cudaMemcpyAsync(h_orig.data(), orig.p, Nlocal * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (Nghost) {
+            MDB_CUDA(cudaMemcpyAsync(h_bm.data(), border_map.p, Nghost * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(h_code.data(), ghost_code.p, Nghost * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        }
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        std::vector<long long> key(Nghost);
+        h_ghost_order.resize(Nghost);
+        for (int g = 0; g < Nghost; g++) {
+            key[g]           = (long long)h_orig[h_bm[g]] * 32 + rank_of_code[h_code[g] & 63];
+            h_ghost_order[g] = g;
+        }
+        std::sort(h_ghost_order.begin(), h_ghost_order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        std::vector<int> h_ext((size_t)Nlocal + Nghost);
+        for (int p = 0; p < Nlocal; p++) h_ext[p] = h_orig[p];
+        for (int r = 0; r < Nghost; r++) h_ext[(size_t)Nlocal + h_ghost_order[r]] = Nlocal + r;
+        extmap.ensure(h_ext.size(), false, stream);
+        MDB_CUDA(cudaMemcpyAsync(extmap.p, h_ext.data(), h_ext.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        extmap_valid = true;
+    }
+
     // ------------------------------------------------------------------ PBC
     PbcGeom<real> pbc_geom() const
     {
@@ -421,6 +519,7 @@ template <class real> struct Sim final : SimBase {
         ghost_code.ensure(Nghost, false, stream);
         MDB_LAUNCH(launches, k_ghost_fill, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, ghost_msk.p,
             ghost_off.p, border_map.p, ghost_code.p, type.p);
+        extmap_valid = false;
     }
     void updatePbc() override // verletlist/pbc.c:42-55
     {
@@ -450,7 +549,7 @@ template <class real> struct Sim final : SimBase {
         MDB_LAUNCH(launches, k_bin_fill, grid_for(nall, 256), 256, 0, stream, nall, atom_bin.p, binstart.p,
             cursor.p, binatoms.p);
         MDB_LAUNCH(launches, k_bin_sort, grid_for(nb, 128), 128, 0, stream, nb, binstart.p, binatoms.p,
-            d_flags.p + 2);
+            (const int*)nullptr, d_flags.p + 2);
     }
 
     void buildNeighbor() override // verletlist/neighbor.c:186-264
@@ -466,7 +565,7 @@ template <class real> struct Sim final : SimBase {
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
             MDB_LAUNCH(launches, k_build_neighbor<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
                 P.half_neigh, bg, cutneighsq, x.p, y.p, z.p, binstart.p, binatoms.p, stencil.p, nstencil,
-                maxneighs, nstride, numneigh.p, neighbors.p, d_flags.p + 1);
+                maxneighs, nstride, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));
@@ -561,6 +660,7 @@ template <class real> struct Sim final : SimBase {
         derive_dtforce();
         setupThermo();
         if (adjust) adjustThermo();
+        sort_atoms(); // main.c:63-66 (SORT_ATOMS)
         setupPbc();
         updatePbc();
         buildNeighbor();
@@ -573,6 +673,7 @@ template <class real> struct Sim final : SimBase {
     void reneighbour() override // verletlist/main.c:76-95
     {
         updateAtomsPbc();
+        sort_atoms(); // main.c:82-88 (SORT_ATOMS; here at every rebuild)
         setupPbc();
         updatePbc();
         buildNeighbor();
@@ -635,26 +736,26 @@ template <class real> struct Sim final : SimBase {
     void getNeighbors(int* nn, int* nb, int row_stride) override
     {
         if (nstride == 0) throw Error("getNeighbors: no neighbor list");
-        MDB_CUDA(cudaMemcpyAsync(nn, numneigh.p, Nlocal * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        if (nb) {
-            rows.ensure((size_t)Nlocal * row_stride, false, stream);
-            MDB_LAUNCH(launches, k_untranspose, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, row_stride,
-                nstride, numneigh.p, neighbors.p, rows.p);
+        build_extmap();
+        nn_ext.ensure(Nlocal, false, stream);
+        if (nb) rows.ensure((size_t)Nlocal * row_stride, false, stream);
+        MDB_LAUNCH(launches, k_untranspose, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, row_stride, nstride,
+            numneigh.p, neighbors.p, extmap.p, nb ? rows.p : (int*)nullptr, nn_ext.p);
+        MDB_CUDA(cudaMemcpyAsync(nn, nn_ext.p, Nlocal * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (nb)
             MDB_CUDA(cudaMemcpyAsync(nb, rows.p, (size_t)Nlocal * row_stride * sizeof(int),
                 cudaMemcpyDeviceToHost, stream));
-        }
         MDB_CUDA(cudaStreamSynchronize(stream));
     }
     void getGhostMap(int* bm, int* px, int* py, int* pz) override
     {
-        std::vector<int> code(Nghost);
-        MDB_CUDA(cudaMemcpyAsync(bm, border_map.p, Nghost * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        MDB_CUDA(cudaMemcpyAsync(code.data(), ghost_code.p, Nghost * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        MDB_CUDA(cudaStreamSynchronize(stream));
-        for (int g = 0; g < Nghost; g++) {
-            px[g] = (code[g] & 3) - 1;
-            py[g] = ((code[g] >> 2) & 3) - 1;
-            pz[g] = ((code[g] >> 4) & 3) - 1;
+        build_extmap();
+        for (int r = 0; r < Nghost; r++) { // reference ghost order
+            const int g = h_ghost_order[r], code = h_code[g];
+            bm[r] = h_orig[h_bm[g]];
+            px[r] = (code & 3) - 1;
+            py[r] = ((code >> 2) & 3) - 1;
+            pz[r] = ((code >> 4) & 3) - 1;
         }
     }
     void getNeighborParams(int* I, double* R) override
@@ -741,9 +842,20 @@ template <class real> struct Sim final : SimBase {
     }
     void getEamFp(void* out, bool ghosts) override
     {
-        const size_t n = (size_t)Nlocal + (ghosts ? Nghost : 0);
-        MDB_CUDA(cudaMemcpyAsync(out, fp.p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+        const bool wg  = ghosts && Nghost > 0;
+        const size_t n = (size_t)Nlocal + (wg ? Nghost : 0);
+        const int* map = orig.p;
+        if (wg) { build_extmap(); map = extmap.p; }
+        tx.ensure(n, false, stream); ty.ensure(n, false, stream); tz.ensure(n, false, stream);
+        MDB_LAUNCH(launches, k_scatter_orig<real>, grid_for(n, 256), 256, 0, stream, (int)n, map, fp.p, fp.p, fp.p,
+            tx.p, ty.p, tz.p);
+        MDB_CUDA(cudaMemcpyAsync(out, tx.p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    void setOption(const char* name, double v) override
+    {
+        if (!strcmp(name, "sort_atoms")) sort_enabled = v != 0;
+        else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };
 

@@ -306,8 +306,9 @@ __global__ void k_bin_fill(int nall, const int* __restrict__ atom_bin, const int
     binatoms[binstart[b] + atomicAdd(&cursor[b], 1)] = i;
 }
 __global__ void k_bin_sort(int nbins, const int* __restrict__ binstart, int* __restrict__ binatoms,
-    int* __restrict__ maxcount)
+    const int* __restrict__ key, int* __restrict__ maxcount)
 {
+    // key == nullptr: ascending atom index; else ascending key[atom] (the atom's reference index)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt     = 0;
     if (b < nbins) {
@@ -315,14 +316,54 @@ __global__ void k_bin_sort(int nbins, const int* __restrict__ binstart, int* __r
         cnt         = binstart[b + 1] - s;
         int* a      = binatoms + s;
         for (int i = 1; i < cnt; i++) { // insertion sort; bins hold ~8 atoms
-            const int v = a[i];
-            int j       = i - 1;
-            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+            const int v  = a[i];
+            const int kv = key ? key[v] : v;
+            int j        = i - 1;
+            while (j >= 0 && (key ? key[a[j]] : a[j]) > kv) { a[j + 1] = a[j]; j--; }
             a[j + 1] = v;
         }
     }
     cnt = __reduce_max_sync(0xffffffffu, cnt);
     if ((threadIdx.x & 31) == 0 && cnt > 0) atomicMax(maxcount, cnt);
+}
+
+// sortAtom (verletlist/neighbor.c:360-426, the reference's optional SORT_ATOMS step): permute the
+// local atoms into bin order.  perm[q] = old index of the atom that moves to slot q.  Unlike the
+// reference the permutation is tracked (orig[] = reference index of each slot), so everything the
+// caller sees keeps the reference's atom numbering.
+template <class real>
+__global__ void k_permute_atoms(int n, const int* __restrict__ perm, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const real* __restrict__ vx,
+    const real* __restrict__ vy, const real* __restrict__ vz, const real* __restrict__ fx,
+    const real* __restrict__ fy, const real* __restrict__ fz, const int* __restrict__ type,
+    const int* __restrict__ orig, real* __restrict__ nx, real* __restrict__ ny, real* __restrict__ nz,
+    real* __restrict__ nvx, real* __restrict__ nvy, real* __restrict__ nvz, real* __restrict__ nfx,
+    real* __restrict__ nfy, real* __restrict__ nfz, int* __restrict__ ntype, int* __restrict__ norig)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int o = perm[q];
+    nx[q] = x[o]; ny[q] = y[o]; nz[q] = z[o];
+    nvx[q] = vx[o]; nvy[q] = vy[o]; nvz[q] = vz[o];
+    nfx[q] = fx[o]; nfy[q] = fy[o]; nfz[q] = fz[o];
+    ntype[q] = type[o];
+    norig[q] = orig[o];
+}
+__global__ void k_iota(int n, int* __restrict__ a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+// out[orig[p]] = in[p] for locals: back to the reference's atom order
+template <class real>
+__global__ void k_scatter_orig(int n, const int* __restrict__ orig, const real* __restrict__ a,
+    const real* __restrict__ b, const real* __restrict__ c, real* __restrict__ oa, real* __restrict__ ob,
+    real* __restrict__ oc)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int o = orig[p];
+    oa[o] = a[p]; ob[o] = b[p]; oc[o] = c[p];
 }
 
 // buildNeighbor, verletlist/neighbor.c:186-264.  One thread per local atom scans the stencil bins.
@@ -334,12 +375,14 @@ __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, Bi
     real cutneighsq, const real* __restrict__ x, const real* __restrict__ y,
     const real* __restrict__ z, const int* __restrict__ binstart, const int* __restrict__ binatoms,
     const int* __restrict__ stencil, int nstencil, int maxneighs, size_t nstride,
-    int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n)
+    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors,
+    int* __restrict__ max_n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n       = 0;
     if (i < nlocal) {
         const real xt = x[i], yt = y[i], zt = z[i];
+        const int oi  = orig[i]; // the atom's index in the reference's numbering
         const int ibin = coord2bin(g, xt, yt, zt);
         for (int k = 0; k < nstencil; k++) {
             const int jbin = ibin + __ldg(&stencil[k]);
@@ -347,7 +390,9 @@ __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, Bi
             const int s = __ldg(&binstart[jbin]), e = __ldg(&binstart[jbin + 1]);
             for (int m = s; m < e; m++) {
                 const int j = __ldg(&binatoms[m]);
-                if (j == i || (half && j < i)) continue;
+                // neighbor.c:224 "j < i" is a statement about reference indices; ghosts (reference
+                // index >= Nlocal) are never dropped
+                if (j == i || (half && j < nlocal && orig[j] < oi)) continue;
                 const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
                 const real rsq = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz)));
                 if (rsq <= cutneighsq) {
@@ -362,14 +407,19 @@ __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, Bi
     if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
 }
 
-// parity read-back: transposed list -> the reference's row-major rows
+// parity read-back: transposed list in internal numbering -> the reference's row-major rows in the
+// reference's numbering (extmap: internal index -> reference index, locals and ghosts)
 __global__ void k_untranspose(int nlocal, int row_stride, size_t nstride, const int* __restrict__ numneigh,
-    const int* __restrict__ nbT, int* __restrict__ rows)
+    const int* __restrict__ nbT, const int* __restrict__ extmap, int* __restrict__ rows,
+    int* __restrict__ numneigh_ext)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlocal) return;
+    const int e     = extmap[i];
+    numneigh_ext[e] = numneigh[i];
+    if (!rows) return;
     const int n = min(numneigh[i], row_stride);
-    for (int k = 0; k < n; k++) rows[(size_t)i * row_stride + k] = nbT[(size_t)k * nstride + i];
+    for (int k = 0; k < n; k++) rows[(size_t)e * row_stride + k] = extmap[nbT[(size_t)k * nstride + i]];
 }
 
 // ---------------------------------------------------------------------------------------------
