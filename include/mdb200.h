@@ -70,9 +70,13 @@ void        mdb_default_params(mdb_params* p);
  * dtforce (parameter.c:115-120).  Returns NULL on failure. */
 mdb_ctx*    mdb_create(const mdb_params* p, int device);
 void        mdb_destroy(mdb_ctx* c);
-/* tuning switches (A/B measurements, debugging).  "sort_atoms" (default 1): keep the local atoms
- * sorted by neighbor bin internally (the reference's SORT_ATOMS, neighbor.c:360-426, with the
- * permutation tracked so that every accessor below still speaks the reference's atom numbering). */
+/* tuning switches (A/B measurements, debugging):
+ *  "sort_atoms" (default 0, like the reference's SORT_ATOMS build option): re-sort the local atoms by
+ *      neighbor bin at every rebuild (neighbor.c:360-426); the permutation is tracked, every accessor
+ *      below still speaks the reference's atom numbering.
+ *  "sort_order" 0 = the reference's x-fastest bin order, 1 = Morton order of the bins.
+ *  "list_layout" 0 = transposed, 1 = row-major rows, 2 (default) = k-major tiles of 32 atoms.
+ *  "force_variant", "neigh_variant": kernel generations kept for A/B. */
 int         mdb_setOption(mdb_ctx* c, const char* name, double value);
 /* run all work of this ctx on the given cudaStream_t (passed as void*); NULL = ctx-owned stream */
 int         mdb_setStream(mdb_ctx* c, void* cuda_stream);

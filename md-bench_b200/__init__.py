@@ -189,7 +189,7 @@ class Simulation:
 
     # rows of the neighbor list come back in the reference's ORDER (stencil order x ascending index)
     # only when the internal spatial sort is off; as sorted index SETS they always agree
-    row_order_exact = False
+    row_order_exact = True
 
     def setOption(self, name, value):
         self._ck(self.L.mdb_setOption(self.h, name.encode(), C.c_double(value)))

@@ -98,7 +98,7 @@ template <class real>
 __global__ void __launch_bounds__(128) k_eam_density(int nlocal, real cutforcesq, EamTables<real> t,
     const real* __restrict__ rhor_spline, const real* __restrict__ frho_spline,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride, real* __restrict__ fp)
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* __restrict__ fp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlocal) return;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) k_eam_density(int nlocal, real cutforcesq
     const int nn  = numneigh[i];
     real rhoi     = 0;
     for (int k = 0; k < nn; k++) {
-        const int j   = __ldg(nbT + (size_t)k * nstride + i);
+        const int j   = __ldg(nbT + L.base(i) + (size_t)k * L.sk);
         const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
         const real rsq = dx * dx + dy * dy + dz * dz;
         if (rsq < cutforcesq) {
@@ -141,7 +141,7 @@ template <class real>
 __global__ void __launch_bounds__(128) k_eam_force(int nlocal, real cutforcesq, EamTables<real> t,
     const real* __restrict__ rhor_spline, const real* __restrict__ z2r_spline, const real* __restrict__ x,
     const real* __restrict__ y, const real* __restrict__ z, const real* __restrict__ fp,
-    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride, real* __restrict__ fx,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* __restrict__ fx,
     real* __restrict__ fy, real* __restrict__ fz)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, real cutforcesq, 
     const int nn = numneigh[i];
     real fix = 0, fiy = 0, fiz = 0;
     for (int k = 0; k < nn; k++) {
-        const int j   = __ldg(nbT + (size_t)k * nstride + i);
+        const int j   = __ldg(nbT + L.base(i) + (size_t)k * L.sk);
         const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
         const real rsq = dx * dx + dy * dy + dz * dz;
         if (rsq < cutforcesq) {

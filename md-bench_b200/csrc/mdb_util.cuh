@@ -71,6 +71,21 @@ template <class T> struct DBuf {
     }
 };
 
+// Addressing of the neighbor list: element (i,k) lives at base(i) + k*sk.  Atoms are grouped in tiles
+// of G = 2^gshift consecutive atoms; inside a tile the entries are stored k-major ([k][atom]), tiles
+// follow each other.  G = 1: the reference's row-major rows; G = 32: one warp's k-th entries are one
+// coalesced 128-byte line and a warp streams through one contiguous tile; G >= Nlocal (gshift 31):
+// fully transposed.
+struct NbLayout {
+    size_t tile_stride; // ints per tile = G * rowlen
+    size_t sk;          // = G
+    int gshift;
+    __host__ __device__ __forceinline__ size_t base(int i) const
+    {
+        return (size_t)((unsigned)i >> gshift) * tile_stride + ((unsigned)i & ((1u << gshift) - 1u));
+    }
+};
+
 // Round-to-nearest single operations that the compiler may not contract or re-associate.  Used
 // wherever bits decide list membership: bin index, ghost coordinates, list distance.
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }

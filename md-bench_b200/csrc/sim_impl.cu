@@ -32,7 +32,21 @@ template <class real> struct Sim final : SimBase {
     DBuf<real> x, y, z, vx, vy, vz, fx, fy, fz, sx, sy, sz, svx, svy, svz, stage;
     DBuf<real> x2, y2, z2, vx2, vy2, vz2, fx2, fy2, fz2, tx, ty, tz;
     DBuf<int> type, border_map, ghost_code, ghost_cnt, ghost_off, orig, orig2, type2, extmap, nn_ext;
-    bool sort_enabled = true, extmap_valid = false;
+    // Spatial sort of the local atoms (the reference's SORT_ATOMS build option, off by default there
+    // too, config.mk:23).  Off by default: for the benchmark lattices the generator's order is already
+    // spatially compact and its lattice regularity makes the gathers of neighbouring lanes fall on
+    // consecutive atoms (A/B in profiles/r1_ab.txt: force 1.49 ms unsorted vs 1.67 ms sorted at 8.4M
+    // atoms).  Turn it on (mdb_setOption "sort_atoms") for long runs of diffusing systems.
+    bool sort_enabled = false, extmap_valid = false;
+    int force_variant = 1, neigh_variant = 3, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
+    int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
+    bool bin_rank_ready = false;
+    DBuf<int> bin_rank;
+    NbLayout LL { 0, 0, 0 };                                    // element (i,k) at neighbors[LL.base(i) + k*LL.sk]
+    DBuf<float> xf, yf, zf;
+    DBuf<float4> pk;
+    DBuf<int> run_off, run_len;
+    int nruns = 0;
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
     DBuf<unsigned> ghost_msk;
     int saved_n = 0;
@@ -82,11 +96,12 @@ template <class real> struct Sim final : SimBase {
                  &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline, &x2, &y2, &z2, &vx2, &vy2,
                  &vz2, &fx2, &fy2, &fz2, &tx, &ty, &tz })
             b->release();
-        for (DBuf<int>* b : { &orig, &orig2, &type2, &extmap, &nn_ext }) b->release();
+        for (DBuf<int>* b : { &orig, &orig2, &type2, &extmap, &nn_ext, &bin_rank }) b->release();
         for (DBuf<int>* b : { &type, &border_map, &ghost_code, &ghost_cnt, &ghost_off, &stencil,
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
             b->release();
         ghost_msk.release();
+        xf.release(); yf.release(); zf.release(); pk.release(); run_off.release(); run_len.release();
         d_partial.release();
         d_red.release();
         d_thermo.release();
@@ -414,11 +429,23 @@ template <class real> struct Sim final : SimBase {
         if (!P.from_input) { xprd = bx; yprd = by; zprd = bz; }
         stencil.ensure(nstencil, false, stream);
         MDB_CUDA(cudaMemcpyAsync(stencil.p, h_stencil.data(), nstencil * sizeof(int), cudaMemcpyHostToDevice, stream));
+        // runs of consecutive offsets (x-adjacent bins, adjacent in the CSR) for k_build_neighbor_v3
+        std::vector<int> ro, rl;
+        for (int k = 0; k < nstencil; k++) {
+            if (!ro.empty() && h_stencil[k] == ro.back() + rl.back()) rl.back()++;
+            else { ro.push_back(h_stencil[k]); rl.push_back(1); }
+        }
+        nruns = (int)ro.size();
+        run_off.ensure(nruns, false, stream);
+        run_len.ensure(nruns, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(run_off.p, ro.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(run_len.p, rl.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
         bincount.ensure(bg.mbins + 2, false, stream);
         binstart.ensure(bg.mbins + 3, false, stream);
         cursor.ensure(bg.mbins + 2, false, stream);
         neigh_ready = true;
+        bin_rank_ready = false;
     }
 
     // ------------------------------------------------------------------ spatial sort
@@ -434,8 +461,9 @@ template <class real> struct Sim final : SimBase {
         binatoms.ensure(Nlocal, false, stream);
         MDB_CUDA(cudaMemsetAsync(bincount.p, 0, (nb + 1) * sizeof(int), stream));
         MDB_CUDA(cudaMemsetAsync(cursor.p, 0, (nb + 1) * sizeof(int), stream));
+        if (sort_order == 1 && !bin_rank_ready) build_bin_rank();
         MDB_LAUNCH(launches, k_bin_count<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, bg, x.p, y.p, z.p,
-            atom_bin.p, bincount.p);
+            sort_order == 1 ? bin_rank.p : (const int*)nullptr, atom_bin.p, bincount.p);
         scanner.exclusive(bincount.p, binstart.p, nb, binstart.p + nb, stream);
         MDB_LAUNCH(launches, k_bin_fill, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, atom_bin.p, binstart.p,
             cursor.p, binatoms.p);
@@ -453,6 +481,36 @@ template <class real> struct Sim final : SimBase {
         std::swap(fx, fx2); std::swap(fy, fy2); std::swap(fz, fz2);
         std::swap(type, type2); std::swap(orig, orig2);
         extmap_valid = false;
+    }
+
+    // Sort order of the bins for sort_atoms: along a Morton (Z-order) curve, so that the ~27 bins an
+    // atom's neighbors live in map to a few contiguous memory chunks in all three dimensions (with the
+    // reference's x-fastest bin order every (y,z) stencil row is a separate memory region).
+    void build_bin_rank()
+    {
+        const int nb = bg.mbins + 1;
+        std::vector<unsigned long long> key(nb);
+        auto spread = [](unsigned long long v) { // 21 bits -> every third bit
+            v &= 0x1fffff;
+            v = (v | v << 32) & 0x1f00000000ffffULL;
+            v = (v | v << 16) & 0x1f0000ff0000ffULL;
+            v = (v | v << 8) & 0x100f00f00f00f00fULL;
+            v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+            v = (v | v << 2) & 0x1249249249249249ULL;
+            return v;
+        };
+        for (int b = 0; b < nb; b++) {
+            const int l  = b > 0 ? b - 1 : 0; // undo coord2bin's "+ 1"
+            const int ix = l % bg.mbinx, iy = (l / bg.mbinx) % bg.mbiny, iz = l / (bg.mbinx * bg.mbiny);
+            key[b] = ((spread(ix) | spread(iy) << 1 | spread(iz) << 2) << 32) | (unsigned)b;
+        }
+        std::sort(key.begin(), key.end());
+        std::vector<int> rank(nb);
+        for (int r = 0; r < nb; r++) rank[(int)(key[r] & 0xffffffffu)] = r;
+        bin_rank.ensure(nb, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(bin_rank.p, rank.data(), nb * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        bin_rank_ready = true;
     }
 
     // internal index -> reference index for locals AND ghosts.  The reference numbers ghosts in the
@@ -544,7 +602,7 @@ template <class real> struct Sim final : SimBase {
         MDB_CUDA(cudaMemsetAsync(cursor.p, 0, (nb + 1) * sizeof(int), stream));
         MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, 2 * sizeof(int), stream));
         MDB_LAUNCH(launches, k_bin_count<real>, grid_for(nall, 256), 256, 0, stream, nall, bg, x.p, y.p, z.p,
-            atom_bin.p, bincount.p);
+            (const int*)nullptr, atom_bin.p, bincount.p);
         scanner.exclusive(bincount.p, binstart.p, nb, binstart.p + nb, stream);
         MDB_LAUNCH(launches, k_bin_fill, grid_for(nall, 256), 256, 0, stream, nall, atom_bin.p, binstart.p,
             cursor.p, binatoms.p);
@@ -552,20 +610,69 @@ template <class real> struct Sim final : SimBase {
             (const int*)nullptr, d_flags.p + 2);
     }
 
+    // Bounds of the single-precision pre-test of k_build_neighbor_v2: a candidate whose float rsq is
+    // below lo is certainly inside cutneighsq, above hi certainly outside.  Error model: each float
+    // coordinate is off by <= M*2^-24 (M = largest |coordinate|), so each difference by
+    // E = 2*M*2^-24 + d*2^-23; |rsq_f - rsq| <= 2*sqrt(3)*d*E + 3*E^2 + O(2^-22)*rsq with d <= cutneigh.
+    // The margin takes 8x that bound.  For SP the band collapses to the exact test itself.
+    void list_margin(float& lo, float& hi) const
+    {
+        const double M = std::max({ (double)xprd, (double)yprd, (double)zprd }) + 2.0 * (double)cutneigh;
+        const double d = (double)cutneigh * 1.01;
+        const double E = 2.0 * M * ldexp(1.0, -24) + d * ldexp(1.0, -23);
+        const double m = 8.0 * (2.0 * 1.7320508 * d * E + 3.0 * E * E) + (double)cutneighsq * 2e-6;
+        lo = (float)((double)cutneighsq - m);
+        hi = (float)((double)cutneighsq + m);
+        if (sizeof(real) == 4) { lo = -1.0f; } // SP: always run the exact (float) expression
+    }
     void buildNeighbor() override // verletlist/neighbor.c:186-264
     {
         if (!neigh_ready) setupNeighbor();
         float ms = 0;
         if (timing) MDB_CUDA(cudaEventRecord(evA, stream));
         bin_atoms();
+        if (neigh_variant >= 2) { // candidates packed in CSR order
+            const int nall = Nlocal + Nghost;
+            pk.ensure(nall, false, stream);
+            MDB_LAUNCH(launches, k_pack_binned<real>, grid_for(nall, 256), 256, 0, stream, nall, binatoms.p, x.p, y.p,
+                z.p, pk.p);
+        } else if (neigh_variant != 0) { // float copies of the positions for the pre-test
+            const int nall = Nlocal + Nghost;
+            xf.ensure(nall, false, stream); yf.ensure(nall, false, stream); zf.ensure(nall, false, stream);
+            MDB_LAUNCH(launches, k_to_float<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, z.p, xf.p,
+                yf.p, zf.p);
+        }
         nstride = round_up((size_t)Nlocal, 32);
         numneigh.ensure(nstride, false, stream);
         for (;;) {
-            neighbors.ensure((size_t)maxneighs * nstride, false, stream);
+            const size_t rowlen = round_up((size_t)maxneighs, 8);
+            if (list_layout == 1) LL = NbLayout { rowlen, 1, 0 };
+            else if (list_layout == 2) LL = NbLayout { 32 * rowlen, 32, 5 };
+            else LL = NbLayout { 0, nstride, 31 };
+            neighbors.ensure(rowlen * nstride, false, stream);
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
-            MDB_LAUNCH(launches, k_build_neighbor<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                P.half_neigh, bg, cutneighsq, x.p, y.p, z.p, binstart.p, binatoms.p, stencil.p, nstencil,
-                maxneighs, nstride, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            if (neigh_variant == 0) {
+                MDB_LAUNCH(launches, k_build_neighbor<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                    P.half_neigh, bg, cutneighsq, x.p, y.p, z.p, binstart.p, binatoms.p, stencil.p, nstencil,
+                    maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            } else if (neigh_variant >= 2) {
+                float lo, hi;
+                list_margin(lo, hi);
+                if (neigh_variant == 2)
+                    MDB_LAUNCH(launches, k_build_neighbor_v3<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                        P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p,
+                        nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+                else
+                    MDB_LAUNCH(launches, k_build_neighbor_v4<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                        P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p,
+                        nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            } else {
+                float lo, hi;
+                list_margin(lo, hi);
+                MDB_LAUNCH(launches, k_build_neighbor_v2<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                    P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, xf.p, yf.p, zf.p, binstart.p, binatoms.p,
+                    stencil.p, nstencil, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            }
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));
@@ -595,12 +702,32 @@ template <class real> struct Sim final : SimBase {
         } else {
             LJConst<real> c { cutforce * cutforce, sigma6, epsilon };
             if (which == FORCE_LJ_FULL) {
-                MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
-                    x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, fx.p, fy.p, fz.p);
+                LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6,
+                    (real)24.0 * epsilon * sigma6 };
+                if (force_variant >= 3 && LL.sk == 1) { // lanes-per-atom kernels need row-major rows
+                    const size_t nthr = (size_t)Nlocal * (force_variant == 4 ? 16 : (force_variant == 5 ? 4 : 8));
+                    if (force_variant == 4)
+                        MDB_LAUNCH(launches, (k_force_lj_full_v3<real, 16, 2>), grid_for(nthr, 128), 128, 0, stream,
+                            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL.tile_stride, fx.p, fy.p, fz.p);
+                    else if (force_variant == 5)
+                        MDB_LAUNCH(launches, (k_force_lj_full_v3<real, 4, 4>), grid_for(nthr, 128), 128, 0, stream,
+                            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL.tile_stride, fx.p, fy.p, fz.p);
+                    else
+                        MDB_LAUNCH(launches, (k_force_lj_full_v3<real, 8, 2>), grid_for(nthr, 128), 128, 0, stream,
+                            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL.tile_stride, fx.p, fy.p, fz.p);
+                } else if (force_variant == 0)
+                    MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
+                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                else if (force_variant == 2)
+                    MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 8>), grid_for(Nlocal, 128), 128, 0, stream,
+                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                else
+                    MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 4>), grid_for(Nlocal, 128), 128, 0, stream,
+                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
             } else {
                 zero3(fx.p, fy.p, fz.p, Nlocal);
                 MDB_LAUNCH(launches, k_force_lj_half<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
-                    x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, fx.p, fy.p, fz.p);
+                    x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
             }
         }
         force_launches++;
@@ -618,12 +745,12 @@ template <class real> struct Sim final : SimBase {
         fp.ensure((size_t)Nlocal + Nghost, false, stream);
         const real cfsq = cutforce * cutforce;
         MDB_LAUNCH(launches, k_eam_density<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cfsq, eam,
-            rhor_spline.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, fp.p);
+            rhor_spline.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fp.p);
         if (Nghost)
             MDB_LAUNCH(launches, k_eam_ghost_fp<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost,
                 border_map.p, fp.p);
         MDB_LAUNCH(launches, k_eam_force<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cfsq, eam,
-            rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, nstride, fx.p, fy.p,
+            rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p,
             fz.p);
     }
     // ComputeForceFunction: returns elapsed seconds like the reference (force.h:16)
@@ -739,7 +866,7 @@ template <class real> struct Sim final : SimBase {
         build_extmap();
         nn_ext.ensure(Nlocal, false, stream);
         if (nb) rows.ensure((size_t)Nlocal * row_stride, false, stream);
-        MDB_LAUNCH(launches, k_untranspose, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, row_stride, nstride,
+        MDB_LAUNCH(launches, k_untranspose, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, row_stride, LL,
             numneigh.p, neighbors.p, extmap.p, nb ? rows.p : (int*)nullptr, nn_ext.p);
         MDB_CUDA(cudaMemcpyAsync(nn, nn_ext.p, Nlocal * sizeof(int), cudaMemcpyDeviceToHost, stream));
         if (nb)
@@ -784,7 +911,7 @@ template <class real> struct Sim final : SimBase {
     {
         MDB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), stream));
         MDB_LAUNCH(launches, k_count_pairs<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-            cutforce * cutforce, x.p, y.p, z.p, numneigh.p, neighbors.p, nstride, d_cnt.p);
+            cutforce * cutforce, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, d_cnt.p);
         unsigned long long h[2];
         MDB_CUDA(cudaMemcpyAsync(h, d_cnt.p, sizeof h, cudaMemcpyDeviceToHost, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
@@ -855,6 +982,10 @@ template <class real> struct Sim final : SimBase {
     void setOption(const char* name, double v) override
     {
         if (!strcmp(name, "sort_atoms")) sort_enabled = v != 0;
+        else if (!strcmp(name, "force_variant")) force_variant = (int)v;
+        else if (!strcmp(name, "neigh_variant")) neigh_variant = (int)v;
+        else if (!strcmp(name, "list_layout")) list_layout = (int)v;
+        else if (!strcmp(name, "sort_order")) sort_order = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

@@ -1,7 +1,8 @@
 // vl_kernels.cuh -- sm_100a kernels of the verletlist hot path.
 // Data layout in HBM: SoA (x[],y[],z[], vx.., fx..), locals first then ghosts; the neighbor list
-// is stored TRANSPOSED, neighbors[k * nstride + i], so a warp's k-th index load is one coalesced
-// 128-byte request (the reference's row-major rows are rebuilt only for parity read-back).
+// is addressed as neighbors[i*si + k*sk]: row-major rows (si = row length, sk = 1; what the
+// lanes-per-atom force kernel wants) or transposed (si = 1, sk = row stride; coalesced for one
+// thread per atom).  The reference's own numbering/rows are rebuilt only for parity read-back.
 #pragma once
 #include "mdb_util.cuh"
 
@@ -288,12 +289,15 @@ __global__ void k_update_atoms_pbc(int nlocal, real xprd, real yprd, real zprd, 
 // each bin ascending (= the reference's insertion order, so rows come out in the same order).
 template <class real>
 __global__ void k_bin_count(int nall, BinGeom<real> g, const real* __restrict__ x,
-    const real* __restrict__ y, const real* __restrict__ z, int* __restrict__ atom_bin,
-    int* __restrict__ bincount)
+    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ rank,
+    int* __restrict__ atom_bin, int* __restrict__ bincount)
 {
+    // rank == nullptr: key = the reference's bin index; else key = rank[bin] (sort order of the bins,
+    // e.g. along a Morton curve, used only by sort_atoms)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nall) return;
-    const int b = coord2bin(g, x[i], y[i], z[i]);
+    int b = coord2bin(g, x[i], y[i], z[i]);
+    if (rank) b = rank[b];
     atom_bin[i] = b;
     atomicAdd(&bincount[b], 1);
 }
@@ -374,7 +378,7 @@ template <class real>
 __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, BinGeom<real> g,
     real cutneighsq, const real* __restrict__ x, const real* __restrict__ y,
     const real* __restrict__ z, const int* __restrict__ binstart, const int* __restrict__ binatoms,
-    const int* __restrict__ stencil, int nstencil, int maxneighs, size_t nstride,
+    const int* __restrict__ stencil, int nstencil, int maxneighs, NbLayout L,
     const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors,
     int* __restrict__ max_n)
 {
@@ -396,7 +400,212 @@ __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, Bi
                 const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
                 const real rsq = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz)));
                 if (rsq <= cutneighsq) {
-                    if (n < maxneighs) neighbors[(size_t)n * nstride + i] = j;
+                    if (n < maxneighs) neighbors[L.base(i) + (size_t)n * L.sk] = j;
+                    n++;
+                }
+            }
+        }
+        numneigh[i] = n;
+    }
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
+// ---- v2 list build --------------------------------------------------------------------------------
+// The membership test must be the reference's exact expression, but 87% of the ~604 candidates per
+// atom are far outside the cutoff.  For DP a single-precision pre-test on float copies of the
+// positions classifies every candidate as certainly-inside / certainly-outside / uncertain, with a
+// margin that bounds the float rounding error (host: list_margin()); only the uncertain band
+// (~1e-4 of the candidates) runs the exact FP64 expression.  The resulting SET is identical to the
+// exact test's (tests compare it bit for bit with the oracle); FP64 work drops ~600x and the
+// gathered bytes halve.  For SP the float expression IS the exact test.
+template <class real>
+__global__ void k_to_float(int n, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, float* __restrict__ xf, float* __restrict__ yf, float* __restrict__ zf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xf[i] = (float)x[i];
+    yf[i] = (float)y[i];
+    zf[i] = (float)z[i];
+}
+
+template <class real>
+__global__ void __launch_bounds__(128) k_build_neighbor_v2(int nlocal, int half, BinGeom<real> g,
+    real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, const float* __restrict__ xf, const float* __restrict__ yf,
+    const float* __restrict__ zf, const int* __restrict__ binstart, const int* __restrict__ binatoms,
+    const int* __restrict__ stencil, int nstencil, int maxneighs, NbLayout L,
+    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors,
+    int* __restrict__ max_n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n       = 0;
+    if (i < nlocal) {
+        const real xt = x[i], yt = y[i], zt = z[i];
+        const float xs = xf[i], ys = yf[i], zs = zf[i];
+        const int oi   = half ? orig[i] : 0;
+        const int ibin = coord2bin(g, xt, yt, zt);
+        int* out       = neighbors + L.base(i);
+        for (int k = 0; k < nstencil; k++) {
+            const int jbin = ibin + __ldg(&stencil[k]);
+            if (jbin < 0 || jbin > g.mbins) continue;
+            const int s = __ldg(&binstart[jbin]), e = __ldg(&binstart[jbin + 1]);
+            for (int m = s; m < e; m++) {
+                const int j = __ldg(&binatoms[m]);
+                const float dxs = xs - __ldg(xf + j), dys = ys - __ldg(yf + j), dzs = zs - __ldg(zf + j);
+                const float rs  = dxs * dxs + dys * dys + dzs * dzs;
+                if (rs > hi || j == i) continue;
+                if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
+                bool in = rs < lo;
+                if (!in) { // uncertain band: the reference's exact expression
+                    const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
+                    in = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq;
+                }
+                if (in) {
+                    if (n < maxneighs) out[(size_t)n * L.sk] = j;
+                    n++;
+                }
+            }
+        }
+        numneigh[i] = n;
+    }
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
+// ---- v3 list build --------------------------------------------------------------------------------
+// ncu r1_v2: the v2 kernel is instruction-bound (issue 74%, ~49 warp instructions per candidate):
+// a dependent index load + three position loads with 64-bit address arithmetic per candidate, and
+// an 81-iteration outer loop whose per-bin trip counts diverge across the lanes of a warp.  v3:
+//  * candidates are pre-packed in bin (CSR) order as float4 {x, y, z, index-as-bits}: ONE 16-byte
+//    load per candidate, coalesced / broadcast, no dependent load;
+//  * the 81-bin stencil is walked as 21 RUNS of x-adjacent bins (adjacent bins are adjacent in the
+//    CSR), so the inner loop runs over ~22-37 candidates at a time;
+//  * same exactness rule as v2 (float pre-test with an error-bounded margin, exact FP64 expression
+//    only in the uncertain band; for SP the float expression is the reference's own).
+template <class real>
+__global__ void k_pack_binned(int nall, const int* __restrict__ binatoms, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, float4* __restrict__ pk)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nall) return;
+    const int j = binatoms[m];
+    pk[m]       = make_float4((float)x[j], (float)y[j], (float)z[j], __int_as_float(j));
+}
+
+template <class real>
+__global__ void __launch_bounds__(128) k_build_neighbor_v3(int nlocal, int half, BinGeom<real> g,
+    real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, const float4* __restrict__ pk, const int* __restrict__ binstart,
+    const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs,
+    NbLayout L, const int* __restrict__ orig, int* __restrict__ numneigh,
+    int* __restrict__ neighbors, int* __restrict__ max_n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n       = 0;
+    if (i < nlocal) {
+        const real xt = x[i], yt = y[i], zt = z[i];
+        const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
+        const int oi   = half ? orig[i] : 0;
+        const int ibin = coord2bin(g, xt, yt, zt);
+        int* out       = neighbors + L.base(i);
+        for (int r = 0; r < nruns; r++) {
+            int b0 = ibin + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
+            b0 = max(b0, 0);
+            b1 = min(b1, g.mbins + 1);
+            if (b1 <= b0) continue;
+            const int s = __ldg(&binstart[b0]), e = __ldg(&binstart[b1]);
+            for (int m = s; m < e; m++) {
+                const float4 c = __ldg(&pk[m]);
+                bool in;
+                if (sizeof(real) == 4) { // SP: this IS the reference's expression
+                    const float dx = __fsub_rn(xs, c.x), dy = __fsub_rn(ys, c.y), dz = __fsub_rn(zs, c.z);
+                    in = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))) <= (float)cutneighsq;
+                    if (!in) continue;
+                } else {
+                    const float dx = xs - c.x, dy = ys - c.y, dz = zs - c.z;
+                    const float rs = dx * dx + dy * dy + dz * dz;
+                    if (rs > hi) continue;
+                    in = rs < lo;
+                }
+                const int j = __float_as_int(c.w);
+                if (j == i) continue;
+                if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
+                if (!in) { // uncertain band: the reference's exact FP64 expression
+                    const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
+                    if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
+                }
+                if (n < maxneighs) out[(size_t)n * L.sk] = j;
+                n++;
+            }
+        }
+        numneigh[i] = n;
+    }
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
+// ---- v4 list build: v3 + two-phase chunks ---------------------------------------------------------
+// ncu r1_v3n (source page): in v3 the append path (29 instructions: 64-bit row addressing, bound and
+// half-list checks) runs at ~8/32 lanes for almost every candidate, because with a 13% hit rate some
+// lane of the warp always passes.  v4 walks each run in chunks of 32 candidates: phase 1 only records
+// pass / uncertain BITS (branch-free, ~11 instructions per candidate), phase 2 pops the set bits and
+// appends -- its trip count is the number of hits, not the number of candidates.
+template <class real>
+__global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half, BinGeom<real> g,
+    real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, const float4* __restrict__ pk, const int* __restrict__ binstart,
+    const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs,
+    NbLayout L, const int* __restrict__ orig, int* __restrict__ numneigh,
+    int* __restrict__ neighbors, int* __restrict__ max_n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n       = 0;
+    if (i < nlocal) {
+        const real xt = x[i], yt = y[i], zt = z[i];
+        const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
+        const float cut = (float)cutneighsq;
+        const int oi   = half ? orig[i] : 0;
+        const int ibin = coord2bin(g, xt, yt, zt);
+        int* out       = neighbors + L.base(i);
+        for (int r = 0; r < nruns; r++) {
+            int b0 = ibin + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
+            b0 = max(b0, 0);
+            b1 = min(b1, g.mbins + 1);
+            if (b1 <= b0) continue;
+            const int s = __ldg(&binstart[b0]), e = __ldg(&binstart[b1]);
+            for (int c0 = s; c0 < e; c0 += 32) {
+                const float4* p = pk + c0;
+                const int cnt   = min(32, e - c0);
+                unsigned pass = 0, unc = 0;
+#pragma unroll 8
+                for (int t = 0; t < cnt; t++) {
+                    const float4 c = __ldg(p + t);
+                    if (sizeof(real) == 4) { // SP: the reference's own expression
+                        const float dx = __fsub_rn(xs, c.x), dy = __fsub_rn(ys, c.y), dz = __fsub_rn(zs, c.z);
+                        const float rs = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
+                        pass |= (rs <= cut ? 1u : 0u) << t;
+                    } else {
+                        const float dx = xs - c.x, dy = ys - c.y, dz = zs - c.z;
+                        const float rs = dx * dx + dy * dy + dz * dz;
+                        pass |= (rs < lo ? 1u : 0u) << t;
+                        unc |= ((rs >= lo && rs <= hi) ? 1u : 0u) << t;
+                    }
+                }
+                unsigned todo = pass | unc;
+                while (todo) {
+                    const int t = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int j = __float_as_int(__ldg(&p[t].w));
+                    if (j == i) continue;
+                    if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
+                    if ((unc >> t) & 1u) { // uncertain band: the reference's exact FP64 expression
+                        const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
+                        if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
+                    }
+                    if (n < maxneighs) *out = j;
+                    out += L.sk;
                     n++;
                 }
             }
@@ -409,7 +618,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, Bi
 
 // parity read-back: transposed list in internal numbering -> the reference's row-major rows in the
 // reference's numbering (extmap: internal index -> reference index, locals and ghosts)
-__global__ void k_untranspose(int nlocal, int row_stride, size_t nstride, const int* __restrict__ numneigh,
+__global__ void k_untranspose(int nlocal, int row_stride, NbLayout L, const int* __restrict__ numneigh,
     const int* __restrict__ nbT, const int* __restrict__ extmap, int* __restrict__ rows,
     int* __restrict__ numneigh_ext)
 {
@@ -419,7 +628,7 @@ __global__ void k_untranspose(int nlocal, int row_stride, size_t nstride, const 
     numneigh_ext[e] = numneigh[i];
     if (!rows) return;
     const int n = min(numneigh[i], row_stride);
-    for (int k = 0; k < n; k++) rows[(size_t)e * row_stride + k] = extmap[nbT[(size_t)k * nstride + i]];
+    for (int k = 0; k < n; k++) rows[(size_t)e * row_stride + k] = extmap[nbT[L.base(i) + (size_t)k * L.sk]];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,7 +648,7 @@ template <class real> __device__ __forceinline__ real lj_pair(real rsq, const LJ
 template <class real>
 __global__ void __launch_bounds__(128) k_force_lj_full(int nlocal, LJConst<real> c,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
     real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,12 +656,12 @@ __global__ void __launch_bounds__(128) k_force_lj_full(int nlocal, LJConst<real>
     const real xt = x[i], yt = y[i], zt = z[i];
     const int nn  = numneigh[i];
     real fix = 0, fiy = 0, fiz = 0;
-    const int* nb = nbT + i;
+    const int* nb = nbT + L.base(i);
     int k         = 0;
     for (; k + 4 <= nn; k += 4) {
         int j[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) j[u] = __ldg(nb + (size_t)(k + u) * nstride);
+        for (int u = 0; u < 4; u++) j[u] = __ldg(nb + (size_t)(k + u) * L.sk);
         real dx[4], dy[4], dz[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -472,7 +681,7 @@ __global__ void __launch_bounds__(128) k_force_lj_full(int nlocal, LJConst<real>
         }
     }
     for (; k < nn; k++) {
-        const int j   = __ldg(nb + (size_t)k * nstride);
+        const int j   = __ldg(nb + (size_t)k * L.sk);
         const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
         const real rsq = dx * dx + dy * dy + dz * dz;
         if (rsq < c.cutforcesq) {
@@ -487,13 +696,161 @@ __global__ void __launch_bounds__(128) k_force_lj_full(int nlocal, LJConst<real>
     fz[i] = fiz;
 }
 
+// ---- v2: same contract, tuned for the FP64 pipe --------------------------------------------------
+// * reciprocal by rcp.approx.ftz.f64 (MUFU, ~20 bits) + two Newton steps (4 DFMA) instead of the
+//   IEEE division sequence (~9 FP64-pipe instructions + slow-path call); result within ~1 ulp.
+// * force = s*s^3*(A*s^3 - B) with A = 48 eps sigma6^2, B = 24 eps sigma6 (5 instead of 7 multiplies)
+// * neighbor indices of the NEXT group of 4 are requested before the current group is evaluated.
+__device__ __forceinline__ double rcp_nr(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y        = fma(y, e, y);
+    e        = fma(-a, y, 1.0);
+    y        = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ float rcp_nr(float a) { return __frcp_rn(a); }
+
+template <class real> struct LJConst2 {
+    real cutforcesq, A, B;
+};
+template <class real> __device__ __forceinline__ real lj_pair2(real rsq, const LJConst2<real>& c)
+{
+    const real s  = rcp_nr(rsq);
+    const real s3 = s * s * s;
+    return (s * s3) * (c.A * s3 - c.B);
+}
+
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<real> c,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
+    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    const int* nb   = nbT + L.base(i);
+    const int nfull = nn - nn % U;
+    int j[U], jn[U];
+    if (nfull > 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = __ldg(nb + (size_t)u * L.sk);
+    }
+    for (int k = 0; k < nfull; k += U) {
+        real dx[U], dy[U], dz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            dx[u] = xt - __ldg(x + j[u]);
+            dy[u] = yt - __ldg(y + j[u]);
+            dz[u] = zt - __ldg(z + j[u]);
+        }
+        nb += (size_t)U * L.sk;
+        if (k + U < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = __ldg(nb + (size_t)u * L.sk);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+            if (rsq < c.cutforcesq) {
+                const real f = lj_pair2(rsq, c);
+                fix += dx[u] * f;
+                fiy += dy[u] * f;
+                fiz += dz[u] * f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = jn[u];
+    }
+    for (int k = nfull; k < nn; k++) {
+        const int jj  = __ldg(nb);
+        nb += L.sk;
+        const real dx = xt - __ldg(x + jj), dy = yt - __ldg(y + jj), dz = zt - __ldg(z + jj);
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < c.cutforcesq) {
+            const real f = lj_pair2(rsq, c);
+            fix += dx * f;
+            fiy += dy * f;
+            fiz += dz * f;
+        }
+    }
+    fx[i] = fix;
+    fy[i] = fiy;
+    fz[i] = fiz;
+}
+
+// ---- v3: LPA lanes per atom, row-major list ---------------------------------------------------------
+// With one thread per atom every lane gathers a DIFFERENT neighbor, ~22 distinct 32-byte sectors per
+// 64-bit request, and the L1 data pipe (bank conflicts) becomes the limiter (ncu r1_v2: l1tex 89%,
+// FP64 pipe 42%).  Here LPA consecutive lanes share one atom and read CONSECUTIVE entries of its row;
+// rows are sorted by memory position (bin order), so the lanes of a group hit short contiguous runs
+// of positions.  Partial sums are combined with warp shuffles.
+template <class real, int LPA, int U>
+__global__ void __launch_bounds__(128) k_force_lj_full_v3(int nlocal, LJConst2<real> c,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const int* __restrict__ numneigh, const int* __restrict__ nbr, size_t rowlen,
+    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i         = (int)(tid / LPA);
+    const int sub       = (int)(tid % LPA);
+    const bool valid    = i < nlocal;
+    const int ii        = valid ? i : nlocal - 1;
+    const real xt = x[ii], yt = y[ii], zt = z[ii];
+    const int nn   = valid ? numneigh[ii] : 0;
+    const int* row = nbr + (size_t)ii * rowlen;
+    real fix = 0, fiy = 0, fiz = 0;
+    for (int k = sub; k < nn; k += U * LPA) {
+        int j[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            ok[u] = k + u * LPA < nn;
+            j[u]  = ok[u] ? __ldg(row + k + u * LPA) : ii;
+        }
+        real dx[U], dy[U], dz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            dx[u] = xt - __ldg(x + j[u]);
+            dy[u] = yt - __ldg(y + j[u]);
+            dz[u] = zt - __ldg(z + j[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+            if (ok[u] && rsq < c.cutforcesq) {
+                const real f = lj_pair2(rsq, c);
+                fix += dx[u] * f;
+                fiy += dy[u] * f;
+                fiz += dz[u] * f;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = LPA / 2; d > 0; d >>= 1) {
+        fix += __shfl_xor_sync(0xffffffffu, fix, d);
+        fiy += __shfl_xor_sync(0xffffffffu, fiy, d);
+        fiz += __shfl_xor_sync(0xffffffffu, fiz, d);
+    }
+    if (sub == 0 && valid) {
+        fx[i] = fix;
+        fy[i] = fiy;
+        fz[i] = fiz;
+    }
+}
+
 // LJ force, half neighbor lists: verletlist/force_lj.c:107-198.  The reaction force on local j
 // (force_lj.c:176-180) is scattered with native FP atomics (RED.ADD.F64/F32); forces are zeroed by
 // the caller first, as the reference does (force_lj.c:123-127).
 template <class real>
 __global__ void __launch_bounds__(128) k_force_lj_half(int nlocal, LJConst<real> c,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const int* __restrict__ numneigh, const int* __restrict__ nbT, size_t nstride, real* fx, real* fy,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* fx, real* fy,
     real* fz)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -501,9 +858,9 @@ __global__ void __launch_bounds__(128) k_force_lj_half(int nlocal, LJConst<real>
     const real xt = x[i], yt = y[i], zt = z[i];
     const int nn  = numneigh[i];
     real fix = 0, fiy = 0, fiz = 0;
-    const int* nb = nbT + i;
+    const int* nb = nbT + L.base(i);
     for (int k = 0; k < nn; k++) {
-        const int j   = __ldg(nb + (size_t)k * nstride);
+        const int j   = __ldg(nb + (size_t)k * L.sk);
         const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
         const real rsq = dx * dx + dy * dy + dz * dz;
         if (rsq < c.cutforcesq) {
@@ -528,7 +885,7 @@ __global__ void __launch_bounds__(128) k_force_lj_half(int nlocal, LJConst<real>
 template <class real>
 __global__ void k_count_pairs(int nlocal, real cutforcesq, const real* __restrict__ x,
     const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh,
-    const int* __restrict__ nbT, size_t nstride, unsigned long long* __restrict__ out)
+    const int* __restrict__ nbT, NbLayout L, unsigned long long* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long listed = 0, inside = 0;
@@ -537,7 +894,7 @@ __global__ void k_count_pairs(int nlocal, real cutforcesq, const real* __restric
         const int nn  = numneigh[i];
         listed        = nn;
         for (int k = 0; k < nn; k++) {
-            const int j   = nbT[(size_t)k * nstride + i];
+            const int j   = nbT[L.base(i) + (size_t)k * L.sk];
             const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
             if (dx * dx + dy * dy + dz * dz < cutforcesq) inside++;
         }

