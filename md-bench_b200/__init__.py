@@ -6,7 +6,7 @@ The method names follow the reference's function pointers / driver functions
 setupNeighbor, reneighbour, computeThermo, adjustThermo; reference src/verletlist/{force,neighbor,
 integrate,pbc}.h and main.c) so parity tests read like the reference's own driver.
 
-This package never imports anything from oracle/ and has no CPU path: constructing a Simulation
+This package never touches the parity checker under the repo's oracle directory and has no CPU path: constructing a Simulation
 without a CUDA device raises MdbError.  (The directory name contains a hyphen; import it with
 importlib.import_module("md-bench_b200") -- see tests/conftest.py.)
 """
