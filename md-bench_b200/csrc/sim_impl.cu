@@ -39,6 +39,7 @@ template <class real> struct Sim final : SimBase {
     // atoms).  Turn it on (mdb_setOption "sort_atoms") for long runs of diffusing systems.
     bool sort_enabled = false, extmap_valid = false;
     int force_variant = 1, neigh_variant = 3, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
+    bool fuse_integrate = true;
     int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
     bool bin_rank_ready = false;
     DBuf<int> bin_rank;
@@ -128,7 +129,8 @@ template <class real> struct Sim final : SimBase {
         rho      = (real)P.rho;
         mass     = (real)P.mass;
         dt       = (real)P.dt;
-        dtforce  = (real)(0.5 * (double)dt); // parameter.c:115
+        derive_dtforce();                    // parameter.c:115 / eam_utils.c:35
+        thermo_ready = false;                // setupThermo re-applies its EAM scaling (thermo.c:51)
         skin     = (real)P.skin;
         cutforce = (real)P.cutforce;
         cutneigh = cutforce + skin; // main.c:233
@@ -821,14 +823,23 @@ template <class real> struct Sim final : SimBase {
         record(0);            // main.c:244
         launch_force(FORCE_DISPATCH); // main.c:250
         MDB_CUDA(cudaEventRecord(run_ev(0), stream)); // timer[TOTAL] starts after the first force, main.c:252
+        bool initial_done = false; // step n's initialIntegrate already applied by the fused kernel
         for (int n = 0; n < nsteps; n++) {
             const bool reneigh = (n + 1) % every == 0; // main.c:259
-            initialIntegrate();
+            if (!initial_done) initialIntegrate();
             if (reneigh) reneighbour();
             else updatePbc();
             launch_force(FORCE_DISPATCH);
-            finalIntegrate();
-            if (!((n + 1) % nstat) && (n + 1) < nsteps) record(n + 1); // main.c:275-280
+            const bool rec = !((n + 1) % nstat) && (n + 1) < nsteps; // main.c:275-280
+            if (rec || n + 1 == nsteps || !fuse_integrate) {
+                finalIntegrate();
+                initial_done = false;
+                if (rec) record(n + 1);
+            } else { // finalIntegrate(n) + initialIntegrate(n+1) in one pass
+                MDB_LAUNCH(launches, k_final_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
+                    dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
+                initial_done = true;
+            }
         }
         MDB_CUDA(cudaEventRecord(run_ev(1), stream));
         record(nsteps); // computeThermo(-1), main.c:288
@@ -986,6 +997,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "neigh_variant")) neigh_variant = (int)v;
         else if (!strcmp(name, "list_layout")) list_layout = (int)v;
         else if (!strcmp(name, "sort_order")) sort_order = (int)v;
+        else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

@@ -182,6 +182,26 @@ __global__ void k_final_integrate(int n, real dtforce, real* __restrict__ vx, re
     vz[i] += dtforce * fz[i];
 }
 
+// finalIntegrate of step n fused with initialIntegrate of step n+1 (used by the device-resident loop
+// when no thermo record falls between them): one pass over x, v, f instead of two.  The arithmetic
+// is the same sequence of operations as the two kernels above, so the result is bit-identical.
+template <class real>
+__global__ void k_final_initial_integrate(int n, real dtforce, real dt, real* __restrict__ x,
+    real* __restrict__ y, real* __restrict__ z, real* __restrict__ vx, real* __restrict__ vy,
+    real* __restrict__ vz, const real* __restrict__ fx, const real* __restrict__ fy,
+    const real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const real f0 = fx[i], f1 = fy[i], f2 = fz[i];
+    real a = vx[i] + dtforce * f0, b = vy[i] + dtforce * f1, c = vz[i] + dtforce * f2; // final(n)
+    a = a + dtforce * f0; b = b + dtforce * f1; c = c + dtforce * f2;                    // initial(n+1)
+    vx[i] = a; vy[i] = b; vz[i] = c;
+    x[i]  = x[i] + dt * a;
+    y[i]  = y[i] + dt * b;
+    z[i]  = z[i] + dt * c;
+}
+
 // ---------------------------------------------------------------------------------------------
 // PBC.  Ghost image codes in the order of the reference's ADDGHOST ladder (verletlist/pbc.c:
 // 107-224): 6 faces, 8 corners, 12 edges (x-z, y-z, x-y).  need[axis] = +1: requires coordinate

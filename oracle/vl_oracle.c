@@ -255,7 +255,8 @@ EXPORT void ovl_setup_thermo(OVL* o)
         o->dof_boltz = (natoms * 3 - 3) * 8.617343e-05;
         o->t_scale   = o->mvv2e / o->dof_boltz;
         o->p_scale   = 1.602176e+06 / 3 / o->xprd / o->yprd / o->zprd;
-        o->dtforce /= o->mvv2e; /* thermo.c:51 */
+        o->dtforce = 0.5 * o->dt / o->mass; /* initEam, eam_utils.c:35 (kept idempotent: setup may run twice) */
+        o->dtforce /= o->mvv2e;             /* thermo.c:51 */
     }
 }
 

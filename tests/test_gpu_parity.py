@@ -240,3 +240,164 @@ def test_reference_library_direct_if_runnable():
     f, fr = s.get("f"), r.get("f")
     assert np.abs(f - fr).max() <= 1e-10 * np.abs(fr).max()
     s.close()
+
+
+# ---- BASELINE config 3: argon, half neighbor lists -------------------------------------------------
+@pytest.mark.parametrize("sort", [False, True])
+def test_cuda_argon_half_lists(golden_dir, sort):
+    from cases import argon_cuda, argon_oracle, row_checksums
+    g = np.load(os.path.join(golden_dir, "argon_half.npz"))
+    s = argon_cuda(g, sort)
+    c = s.counts()
+    assert c["Nghost"] == int(g["nghost0"]) and c["maxneighs"] == int(g["maxneighs0"])
+    nn, nb = s.neighbors()
+    assert np.array_equal(nn, g["numneigh0"])
+    s1, s2 = row_checksums(nn, nb)
+    assert np.array_equal(s1, g["rowsum0"]) and np.array_equal(s2, g["rowsq0"])
+    o = argon_oracle(g)
+    off, flat = csr_sets(nn, nb)
+    off2, flat2 = csr_sets(o.get("numneigh"), o.get("neighbors"))
+    assert np.array_equal(flat, flat2)                       # full sets against the oracle
+    assert np.array_equal(s.get("x", ghosts=True), o.get("x", ghosts=True))
+    s.computeForce()
+    assert np.abs(s.get("f") - g["f0"]).max() <= 1e-10 * np.abs(g["f0"]).max()
+    T, P = s.thermo()
+    assert abs(T - g["thermo0"][0]) <= 1e-12 * T
+    rec, _ = s.run(200)
+    assert rel_err(s.get("x"), g["xN"]) < 1e-10 and rel_err(s.get("v"), g["vN"]) < 1e-10
+    assert np.abs(s.get("f") - g["fN"]).max() <= 1e-10 * np.abs(g["fN"]).max()
+    nn, nb = s.neighbors()
+    s1, s2 = row_checksums(nn, nb)
+    assert np.array_equal(nn, g["numneighN"]) and np.array_equal(s1, g["rowsumN"]) and np.array_equal(s2, g["rowsqN"])
+    assert s.counts()["Nghost"] == int(g["nghostN"])
+    assert abs(rec[-1][1] - g["thermoN"][0]) <= 1e-10 * g["thermoN"][0]
+    s.close()
+
+
+# ---- EAM (verletlist): tables, three passes, BASELINE config 4 ---------------------------------------
+@pytest.mark.parametrize("sort", [False, True])
+def test_cuda_eam_lattice(golden_dir, sort):
+    from cases import eam_cuda, eam_oracle, row_checksums
+    g = np.load(os.path.join(golden_dir, "eam_cu_nx5.npz"))
+    s = eam_cuda(g, sort=sort)
+    t = s.getEamSplines()
+    for k in ("nr", "nrho", "nr_tot", "nrho_tot"):
+        assert t[k] == int(g["eam_" + k]), k
+    assert t["rdr"] == float(g["eam_rdr"]) and t["rdrho"] == float(g["eam_rdrho"])
+    for k in ("rhor_spline", "frho_spline", "z2r_spline"):
+        ref = g["eam_" + k]
+        assert np.abs(t[k][7:] - ref[7:]).max() <= 1e-13 * np.abs(ref).max(), k
+    npar = s.neighborParams()
+    assert abs(npar["cutforce"] - g["params"][0]) < 1e-15 and abs(npar["cutneigh"] - g["params"][1]) < 1e-15
+    assert abs(npar["dtforce"] - g["params"][3]) <= 1e-15 * g["params"][3]
+    assert s.counts()["Nghost"] == int(g["nghost0"])
+    s.setAtoms(g["x0"], g["v0"]); s.setup(adjust=False)            # identical velocity bits
+    nn, nb = s.neighbors()
+    s1, s2 = row_checksums(nn, nb)
+    assert np.array_equal(nn, g["numneigh0"]) and np.array_equal(s1, g["rowsum0"]) and np.array_equal(s2, g["rowsq0"])
+    s.computeForceEam()
+    assert np.abs(s.getEamFp(ghosts=True) - g["fp0"]).max() <= 1e-11 * np.abs(g["fp0"]).max()
+    assert np.abs(s.get("f") - g["f0"]).max() <= 1e-9
+    rec, _ = s.run(int(g["nsteps"]))
+    assert abs(rec[-1][1] - g["thermoN"][0]) <= 1e-9 * g["thermoN"][0]
+    assert rel_err(s.get("v"), g["vN"]) < 1e-9 and rel_err(s.get("x"), g["xN"]) < 1e-9
+    assert np.abs(s.get("f") - g["fN"]).max() <= 1e-9 * np.abs(g["fN"]).max()
+    assert s.counts()["Nghost"] == int(g["nghostN"])
+    s.close()
+
+
+def test_cuda_eam_copper_melting_200_steps(golden_dir):
+    """BASELINE config 4: copper_melting (32 000 atoms from the LAMMPS dump), Cu_u3 funcfl, 200 steps:
+    the reference's `step temp pressure` lines and the oracle on the first 25 steps."""
+    from cases import eam_cuda, eam_oracle
+    g = np.load(os.path.join(golden_dir, "eam_cu_melting.npz"))
+    s = eam_cuda(g, from_dump=True)
+    assert s.counts()["Nghost"] == int(g["nghost0"])
+    assert np.array_equal(s.numneigh(), g["numneigh0"])
+    s.computeForceEam()
+    assert np.abs(s.getEamFp(ghosts=True) - g["fp0"]).max() <= 1e-11 * np.abs(g["fp0"]).max()
+    # the dump starts on the perfect lattice: net forces are cancellation noise (SURVEY 8c)
+    assert np.abs(s.get("f") - g["f0"]).max() <= max(1e-10 * np.abs(g["f0"]).max(), 1e-9)
+    rec, _ = s.run(200)
+    assert len(rec) == len(g["records"])
+    for (st, T, P), (gs, gT, gP) in zip(rec, g["records"]):
+        assert int(st) == int(gs) and abs(T - gT) <= 6e-7 * gT and abs(P - gP) <= 6e-7 * gP, (st, T, gT)
+    assert abs(rec[-1][1] - g["thermoN"][0]) <= 1e-9 * g["thermoN"][0]
+    assert s.counts()["Nghost"] == int(g["nghostN"])
+    s.close()
+
+
+# ---- the C driver: reference command line, report format, file readers ------------------------------
+def _driver():
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "md-bench_b200", "driver", "MDBench-VL-B200")
+    if not os.path.exists(exe):
+        import subprocess
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    return exe
+
+
+def _thermo_lines(out):
+    import re
+    return [(int(a), b, c) for a, b, c in re.findall(r"^(-?\d+)\t(\S+)\t(\S+)$", out, flags=re.M)]
+
+
+@pytest.mark.parametrize("extra", [[], ["--operators"], ["--layout", "soa"], ["--sort"]])
+def test_driver_default_run_prints_reference_report(golden_dir, extra):
+    import subprocess
+    th = json.load(open(os.path.join(golden_dir, "thermo_lj.json")))
+    t = [q for q in th if q["variant"] == "vl_dp_aos" and q["nx"] == 32 and q["half"] == 0][0]
+    out = subprocess.run([_driver()] + extra, capture_output=True, text=True, timeout=300).stdout
+    lines = _thermo_lines(out)
+    assert [l[0] for l in lines] == [0, 100, 200]
+    for (st, T, P), (gs, gT, gP) in zip(lines, t["records"]):
+        assert "%e" % gT == T and "%e" % gP == P, (st, T, P, gT, gP)      # the printed 7 digits
+    assert "System: 131072 atoms %d ghost atoms, Steps: 200" % t["nghost"] in out
+    assert "million atom updates per second" in out and "TOTAL" in out and "Kernel: CUDA-sm_100a" in out
+
+
+def test_driver_reads_gro_and_param_file(golden_dir, tmp_path):
+    """-p params -i input.gro -half 1 (BASELINE config 3): inputs rebuilt from the fixture"""
+    import subprocess
+    g = np.load(os.path.join(golden_dir, "argon_half.npz"))
+    gro = tmp_path / "input.gro"
+    with open(gro, "w") as f:
+        f.write("Liquid Argon t=   0.00000 step= 0\n %d\n" % len(g["x0"]))
+        for i, (x, v) in enumerate(zip(g["x0"], g["v0"])):
+            f.write("%5dAr      Ar%5d%8.3f%8.3f%8.3f%8.4f%8.4f%8.4f\n" % (i + 1, i + 1, x[0], x[1], x[2], v[0], v[1], v[2]))
+        f.write("   %.5f   %.5f   %.5f\n" % (g["box"][1], g["box"][3], g["box"][5]))
+    conf = tmp_path / "params.conf"
+    eps, sig, cutf, skin, dt, temp, rho, mass = [float(v) for v in g["params"]]
+    conf.write_text("mass %.17g\nsigma %.17g\nepsilon %.17g\nntimes 250000\ndt %.17g\ntemp %.17g\nx_out_freq 500\n"
+                    "v_out_freq 5\ncutforce %.17g\nskin %.17g\nreneigh_every %d\nnstat %d   # comment\n"
+                    % (mass, sig, eps, dt, temp, cutf, skin, int(g["ints"][0]), int(g["ints"][1])))
+    out = subprocess.run([_driver(), "-p", str(conf), "-i", str(gro), "-half", "1", "-n", "200"],
+                         capture_output=True, text=True, timeout=300).stdout
+    lines = _thermo_lines(out)
+    assert lines[0][0] == 0 and lines[-1][0] == 200
+    assert lines[0][1] == "%e" % g["thermo0"][0] and lines[0][2] == "%e" % g["thermo0"][1]
+    assert lines[-1][1] == "%e" % g["thermoN"][0] and lines[-1][2] == "%e" % g["thermoN"][1]
+    assert "System: 1000 atoms %d ghost atoms" % int(g["nghostN"]) in out
+    assert "Read 1000 atoms from" in out
+
+
+def test_driver_eam_funcfl_file(golden_dir, tmp_path):
+    """-f eam -e <funcfl> -nx 5 -n 45: the potential file is rebuilt from the fixture's tables"""
+    import subprocess
+    g = np.load(os.path.join(golden_dir, "eam_cu_nx5.npz"))
+    pot = tmp_path / "Cu_test.eam"
+    with open(pot, "w") as f:
+        f.write("funcfl table rebuilt from tests/golden/eam_cu_nx5.npz\n")
+        f.write("   29 %.17g 3.6150 FCC\n" % float(g["funcfl_mass"]))
+        f.write("%d %.17g %d %.17g %.17g\n" % (int(g["funcfl_nrho"]), float(g["funcfl_drho"]), int(g["funcfl_nr"]),
+                                               float(g["funcfl_dr"]), float(g["funcfl_cut"])))
+        for arr in (g["funcfl_frho"], g["funcfl_zr"], g["funcfl_rhor"]):
+            for k in range(0, len(arr), 5):
+                f.write(" ".join("%.17g" % v for v in arr[k:k + 5]) + "\n")
+    out = subprocess.run([_driver(), "-f", "eam", "-e", str(pot), "-nx", "5", "-ny", "5", "-nz", "5", "-n", "45"],
+                         capture_output=True, text=True, timeout=300).stdout
+    lines = _thermo_lines(out)
+    assert [l[0] for l in lines] == [0, 45]
+    for (st, T, P), (gs, gT, gP) in zip(lines, g["records"]):
+        assert abs(float(T) - gT) <= 2e-6 * gT and abs(float(P) - gP) <= 2e-6 * gP, (st, T, gT)
+    assert "Force field: eam" in out
