@@ -177,6 +177,60 @@ int         mdb_getEamFp(mdb_ctx* c, void* fp, int with_ghosts);   /* Eam.fp aft
  * current positions; computed on demand by a counting kernel */
 int         mdb_countPairs(mdb_ctx* c, long long* listed, long long* in_cutoff);
 
+/* ---- multi-GPU: spatial decomposition ----------------------------------------------- */
+/* The reference runs one domain ("replicas only").  Here a box may be cut into gx*gy*gz bricks, each
+ * with a ghost shell of width cutneigh; what is generalised is the setupPbc / updatePbc /
+ * updateAtomsPbc trio (verletlist/pbc.c:98-227, 42-55, 59-84): a periodic image now comes from the
+ * neighbor brick in that direction (which is the brick itself along an axis with one brick, i.e. the
+ * reference's scheme).  Bricks are dealt to processes in consecutive blocks (one process per GPU;
+ * #bricks must be a multiple of #processes).  Bricks of one process exchange by device copies,
+ * bricks of different processes by NCCL send/recv over NVLink (NCCL is dlopen()ed on first use).
+ * Atoms carry GLOBAL tags = the index createAtom (atom.c:67-187) gives them in the undecomposed box,
+ * so results are comparable with a single-domain run atom by atom. */
+typedef struct mdb_dd mdb_dd;
+int         mdb_dd_uniqueIdBytes(void);                 /* sizeof(ncclUniqueId) */
+int         mdb_dd_getUniqueId(void* id);               /* process 0 calls this, the launcher broadcasts it */
+/* host-only: the send (send!=0) or receive slots of `brick`: directions of the ADDGHOST ladder
+ * (pbc.c:107-224) ordered by (peer brick, direction), their peer bricks and owning processes;
+ * returns the number of slots or <0.  No CUDA call: used to check that all ranks derive one plan. */
+int         mdb_dd_plan(int gx, int gy, int gz, int perx, int pery, int perz, int nprocs, int brick,
+                        int send, int dir[26], int peer[26], int owner[26]);
+/* host-only: the transfer schedule of one exchange as process `proc` executes it, given
+ * cnt[brick*26 + direction] = entries each brick sends per direction.  ops receives 7 ints per
+ * transfer {kind 0 copy/1 send/2 recv, src brick, dst brick, first entry in src's send list, first
+ * entry in dst's receive area, entries, peer process}; returns the number of transfers. */
+int         mdb_dd_schedule(int gx, int gy, int gz, int perx, int pery, int perz, int nprocs, int proc,
+                            const int* cnt, int max_ops, int* ops);
+/* p = parameters of the WHOLE box (nx,ny,nz multiples of gx,gy,gz).  nccl_id may be NULL iff nprocs == 1 */
+mdb_dd*     mdb_dd_create(const mdb_params* p, int gx, int gy, int gz, int nprocs, int proc,
+                          const void* nccl_id, int device);
+void        mdb_dd_destroy(mdb_dd* d);
+int         mdb_dd_setStream(mdb_dd* d, void* cuda_stream);
+int         mdb_dd_sync(mdb_dd* d);
+long long   mdb_dd_createAtom(mdb_dd* d);               /* createAtom per brick; returns global Natoms */
+int         mdb_dd_setEam(mdb_dd* d, int nrho, double drho, int nr, double dr, double cut, double mass,
+                          const double* frho, const double* zr, const double* rhor);
+int         mdb_dd_setup(mdb_dd* d, int adjust);        /* main.c:58-72 over all bricks */
+int         mdb_dd_reneighbour(mdb_dd* d);              /* main.c:76-95: migrate, ghosts, lists */
+int         mdb_dd_run(mdb_dd* d, int nsteps, double* thermo_out, int max_records, int* nrecords,
+                       double* timers);                 /* main.c:244-288, thermo summed over all bricks */
+int         mdb_dd_computeThermo(mdb_dd* d, double* T, double* P);
+/* v = {global Natoms, local atoms of this process, ghosts of this process, largest maxneighs, bricks here} */
+int         mdb_dd_getCounts(mdb_dd* d, long long v[5]);
+/* local atoms of this process (SoA host buffers of `precision` reals; positions in the global frame)
+ * and their global tags (may be NULL) */
+int         mdb_dd_getAtoms(mdb_dd* d, int which, int* tags, void* x, void* y, void* z);
+/* neighbor lists of the local atoms with every entry translated to its global tag (images map to the
+ * tag of their source atom): tags[n], numneigh[n], rows[n*stride] */
+int         mdb_dd_getNeighborTags(mdb_dd* d, int* tags, int* numneigh, int* rows, int stride);
+int         mdb_dd_saveState(mdb_dd* d);
+int         mdb_dd_restoreState(mdb_dd* d);
+int         mdb_dd_setOption(mdb_dd* d, const char* name, double value);
+int         mdb_dd_setTiming(mdb_dd* d, int on);
+int         mdb_dd_getKernelStats(mdb_dd* d, double* force_ms, long long* force_launches, double* neigh_ms,
+                                  long long* neigh_launches, long long* total_launches, double* comm_ms);
+int         mdb_dd_resetKernelStats(mdb_dd* d);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* FMA issue-rate micro-benchmark on `device`: dense FP32 (MDB_SP) or FP64 (MDB_DP) vector peak in
  * TFLOP/s (FMA = 2 flop).  The roofline denominator for the force kernels. */

@@ -55,6 +55,11 @@ EXPORTS = [
     "mdb_getKernelStats", "mdb_resetKernelStats", "mdb_setEam", "mdb_setEamSplines",
     "mdb_getEamSplines", "mdb_getNeighbors", "mdb_getGhostMap", "mdb_getNeighborParams",
     "mdb_getStencil", "mdb_getBinCounts", "mdb_getEamFp", "mdb_countPairs", "mdb_measureFmaPeak",
+    "mdb_dd_uniqueIdBytes", "mdb_dd_getUniqueId", "mdb_dd_plan", "mdb_dd_schedule", "mdb_dd_create", "mdb_dd_destroy",
+    "mdb_dd_setStream", "mdb_dd_sync", "mdb_dd_createAtom", "mdb_dd_setEam", "mdb_dd_setup",
+    "mdb_dd_reneighbour", "mdb_dd_run", "mdb_dd_computeThermo", "mdb_dd_getCounts", "mdb_dd_getAtoms",
+    "mdb_dd_getNeighborTags", "mdb_dd_saveState", "mdb_dd_restoreState", "mdb_dd_setOption",
+    "mdb_dd_setTiming", "mdb_dd_getKernelStats", "mdb_dd_resetKernelStats",
 ]
 
 _lib = None
@@ -82,6 +87,10 @@ def load_library(build=True):
               "mdb_computeForceEam"):
         getattr(L, f).restype = C.c_double
         getattr(L, f).argtypes = [C.c_void_p]
+    L.mdb_dd_create.restype = C.c_void_p
+    L.mdb_dd_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.mdb_dd_createAtom.restype = C.c_longlong
+    L.mdb_dd_createAtom.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -344,3 +353,145 @@ class Simulation:
         a, b = C.c_longlong(), C.c_longlong()
         self._ck(self.L.mdb_countPairs(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+# ---- multi-GPU: spatial decomposition -----------------------------------------------------------
+def dd_plan(grid, brick, send=True, nprocs=1, periodic=(1, 1, 1)):
+    """host-only: slots of `brick` as (direction, peer brick, owning process) triples (mdb_dd_plan)"""
+    L = load_library()
+    d, p, o = (C.c_int * 26)(), (C.c_int * 26)(), (C.c_int * 26)()
+    n = L.mdb_dd_plan(grid[0], grid[1], grid[2], periodic[0], periodic[1], periodic[2], nprocs, brick, int(send), d, p, o)
+    if n < 0:
+        raise MdbError(L.mdb_last_error().decode())
+    return [(d[k], p[k], o[k]) for k in range(n)]
+
+
+def dd_schedule(grid, nprocs, proc, cnt, periodic=(1, 1, 1)):
+    """host-only: transfers of one exchange as `proc` executes them (mdb_dd_schedule); cnt[nbricks, 26]"""
+    L = load_library()
+    cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+    nb = grid[0] * grid[1] * grid[2]
+    assert cnt.shape == (nb, 26)
+    ops = np.zeros((nb * 27, 7), np.int32)
+    n = L.mdb_dd_schedule(grid[0], grid[1], grid[2], periodic[0], periodic[1], periodic[2], nprocs, proc,
+                          _vp(cnt), len(ops), _vp(ops))
+    if n < 0:
+        raise MdbError(L.mdb_last_error().decode())
+    keys = ("kind", "src", "dst", "src_start", "dst_start", "len", "peer_proc")
+    return [dict(zip(keys, map(int, ops[k]))) for k in range(n)]
+
+
+def dd_grid(nprocs):
+    """brick grid used by bench.py for N GPUs: 1 -> 1x1x1, 2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2"""
+    g = [1, 1, 1]
+    a = 0
+    while g[0] * g[1] * g[2] < nprocs:
+        g[a % 3] *= 2
+        a += 1
+    if g[0] * g[1] * g[2] != nprocs:
+        raise ValueError("number of processes must be a power of two")
+    return tuple(g)
+
+
+def dd_unique_id():
+    L = load_library()
+    buf = (C.c_char * L.mdb_dd_uniqueIdBytes())()
+    if L.mdb_dd_getUniqueId(buf) != 0:
+        raise MdbError(L.mdb_last_error().decode())
+    return bytes(buf)
+
+
+class Decomposition:
+    """The bricks of a spatially decomposed box owned by this process (opaque mdb_dd).  `params`
+    describe the WHOLE box; same driver-level method names as Simulation."""
+
+    def __init__(self, params, grid, nprocs=1, proc=0, nccl_id=None, device=0):
+        self.L = load_library()
+        self.params = params
+        self.dp = params.precision == DP
+        self.np_real = np.float64 if self.dp else np.float32
+        self.grid = tuple(grid)
+        idbuf = None if nccl_id is None else C.create_string_buffer(nccl_id, len(nccl_id))
+        h = self.L.mdb_dd_create(C.byref(params), grid[0], grid[1], grid[2], nprocs, proc,
+                                 None if idbuf is None else C.cast(idbuf, C.c_void_p), device)
+        if not h:
+            raise MdbError(self.L.mdb_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mdb_dd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+
+    def createAtom(self):
+        n = self.L.mdb_dd_createAtom(self.h)
+        if n < 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+        return n
+
+    def setEam(self, nrho, drho, nr, dr, cut, mass, frho, zr, rhor):
+        a = [np.ascontiguousarray(t, dtype=np.float64) for t in (frho, zr, rhor)]
+        d = C.c_double
+        self._ck(self.L.mdb_dd_setEam(self.h, nrho, d(drho), nr, d(dr), d(cut), d(mass), *[_vp(t) for t in a]))
+
+    def setStream(self, stream_ptr): self._ck(self.L.mdb_dd_setStream(self.h, C.c_void_p(stream_ptr)))
+    def sync(self): self._ck(self.L.mdb_dd_sync(self.h))
+    def setup(self, adjust=True): self._ck(self.L.mdb_dd_setup(self.h, int(adjust)))
+    def reneighbour(self): self._ck(self.L.mdb_dd_reneighbour(self.h))
+    def saveState(self): self._ck(self.L.mdb_dd_saveState(self.h))
+    def restoreState(self): self._ck(self.L.mdb_dd_restoreState(self.h))
+    def setOption(self, name, value): self._ck(self.L.mdb_dd_setOption(self.h, name.encode(), C.c_double(value)))
+    def setTiming(self, on): self._ck(self.L.mdb_dd_setTiming(self.h, int(on)))
+    def resetKernelStats(self): self._ck(self.L.mdb_dd_resetKernelStats(self.h))
+
+    def computeThermo(self):
+        T, P = C.c_double(), C.c_double()
+        self._ck(self.L.mdb_dd_computeThermo(self.h, C.byref(T), C.byref(P)))
+        return T.value, P.value
+
+    def run(self, nsteps):
+        nstat = max(1, self.params.nstat)
+        out = np.zeros(3 * (nsteps // nstat + 4))
+        nrec = C.c_int()
+        tm = (C.c_double * 3)()
+        self._ck(self.L.mdb_dd_run(self.h, nsteps, _vp(out), len(out) // 3, C.byref(nrec), tm))
+        return out[:3 * nrec.value].reshape(-1, 3), dict(TOTAL=tm[0], FORCE=tm[1], NEIGH=tm[2])
+
+    def counts(self):
+        v = (C.c_longlong * 5)()
+        self._ck(self.L.mdb_dd_getCounts(self.h, v))
+        return dict(Natoms=v[0], Nlocal=v[1], Nghost=v[2], maxneighs=int(v[3]), bricks=int(v[4]))
+
+    def get(self, what):
+        """(tags, (n,3) array) of this process's local atoms; positions in the global frame"""
+        n = self.counts()["Nlocal"]
+        tags = np.empty(n, np.int32)
+        cols = [np.empty(n, self.np_real) for _ in range(3)]
+        self._ck(self.L.mdb_dd_getAtoms(self.h, ord(what), _vp(tags), *[_vp(q) for q in cols]))
+        return tags, np.stack(cols, axis=1)
+
+    def neighborTags(self):
+        c = self.counts()
+        n, st = c["Nlocal"], c["maxneighs"]
+        tags, nn = np.empty(n, np.int32), np.empty(n, np.int32)
+        rows = np.empty((n, st), np.int32)
+        self._ck(self.L.mdb_dd_getNeighborTags(self.h, _vp(tags), _vp(nn), _vp(rows), st))
+        return tags, nn, rows
+
+    def kernelStats(self):
+        fm, nm, cm = C.c_double(), C.c_double(), C.c_double()
+        fl, nl, tl = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        self._ck(self.L.mdb_dd_getKernelStats(self.h, C.byref(fm), C.byref(fl), C.byref(nm), C.byref(nl),
+                                              C.byref(tl), C.byref(cm)))
+        return dict(force_ms=fm.value, force_launches=fl.value, neigh_ms=nm.value, neigh_launches=nl.value,
+                    launches=tl.value, comm_ms=cm.value)

@@ -1,0 +1,505 @@
+// dd_group.cuh -- DomainGroup<real>: the bricks of a spatially decomposed box that live in THIS process,
+// driven in lockstep on one stream, plus the transport between bricks:
+//   * bricks of the same process: device-to-device copies (also how a single GPU runs a decomposed box
+//     for the parity tests);
+//   * bricks of other processes (one process per GPU): NCCL send/recv over NVLink, grouped per phase.
+// Every process derives the same transfer schedule from the allgathered slot counts, so both ends of
+// a transfer enumerate it at the same position (NCCL matches sends and receives of a pair in order).
+// The reference has no decomposition; the per-brick operators are the single-domain ones (sim_impl.cu)
+// and only the setupPbc/updatePbc/updateAtomsPbc trio (pbc.c) is generalised (dd_kernels.cuh).
+// (textually included at the end of sim_impl.cu, inside namespace mdb)
+
+template <class real> struct DomainGroup final : DDBase {
+    typedef Sim<real> Brick;
+    Topo topo;
+    int proc = 0, first = 0, nlocal_bricks = 0, device = 0;
+    mdb_params G; // global parameters
+    std::vector<Brick*> bricks;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    NcclApi::comm_t comm = nullptr;
+    long long gNatoms = 0, launches = 0;
+    bool timing = false;
+    double comm_ms = 0;
+
+    DBuf<int> d_off_all;
+    DBuf<double> d_sum;
+    int* h_off_all = nullptr; // pinned, nbricks*32
+    double* h_sum  = nullptr; // pinned
+    std::vector<int> cnt;     // [nbricks*26] entries per (sending brick, direction) of the last exchange
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+
+    enum OpKind { COPY, SEND, RECV };
+    struct Op {
+        OpKind kind;
+        const void* src;
+        void* dst;
+        size_t bytes;
+        int peer;
+    };
+    std::vector<Op> pos_ops, fp_ops;
+
+    DomainGroup(const mdb_params& g, const int grid[3], int nprocs, int proc_, const void* nccl_id, int dev)
+        : proc(proc_), device(dev), G(g)
+    {
+        for (int a = 0; a < 3; a++) topo.g[a] = grid[a];
+        topo.periodic[0] = g.pbc_x; topo.periodic[1] = g.pbc_y; topo.periodic[2] = g.pbc_z;
+        topo.nbricks = grid[0] * grid[1] * grid[2];
+        topo.nprocs  = nprocs;
+        if (topo.nbricks < 1 || nprocs < 1 || topo.nbricks % nprocs) throw Error("decomposition: #bricks must be a multiple of #processes");
+        if (proc < 0 || proc >= nprocs) throw Error("decomposition: bad process index");
+        if (g.from_input) throw Error("decomposition: only generated lattices (nx, ny, nz) are supported");
+        if (g.nx % grid[0] || g.ny % grid[1] || g.nz % grid[2]) throw Error("decomposition: nx/ny/nz must be multiples of the brick grid");
+        nlocal_bricks = topo.nbricks / nprocs;
+        first         = proc * nlocal_bricks;
+        MDB_CUDA(cudaSetDevice(device));
+        MDB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        stream = own_stream;
+        for (auto& e : ev) MDB_CUDA(cudaEventCreate(&e));
+        MDB_CUDA(cudaMallocHost(&h_off_all, (size_t)topo.nbricks * 32 * sizeof(int)));
+        MDB_CUDA(cudaMallocHost(&h_sum, 4096 * sizeof(double)));
+        d_off_all.ensure((size_t)topo.nbricks * 32, false, stream);
+        d_sum.ensure(4096, false, stream);
+        cnt.assign((size_t)topo.nbricks * 26, 0);
+        gNatoms = 4LL * g.nx * g.ny * g.nz;
+        mdb_params L = g;
+        L.nx = g.nx / grid[0]; L.ny = g.ny / grid[1]; L.nz = g.nz / grid[2];
+        const int gn[3] = { g.nx, g.ny, g.nz };
+        for (int k = 0; k < nlocal_bricks; k++) {
+            Brick* b = new Brick(L, device);
+            b->brick_init(&topo, first + k, gn, gNatoms);
+            b->d_off = d_off_all.p + (size_t)(first + k) * 32;
+            b->setStream(stream);
+            bricks.push_back(b);
+        }
+        if (nprocs > 1) {
+            if (!nccl_id) throw Error("decomposition over several processes needs the NCCL unique id of process 0");
+            NcclApi& N = nccl_api();
+            N.load();
+            NcclApi::unique_id id;
+            memcpy(&id, nccl_id, sizeof id);
+            MDB_NCCL(N.CommInitRank(&comm, nprocs, id, proc));
+        }
+    }
+    ~DomainGroup() override
+    {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        if (comm) nccl_api().CommDestroy(comm);
+        for (Brick* b : bricks) { b->brick_release(); delete b; }
+        d_off_all.release();
+        d_sum.release();
+        cudaFreeHost(h_off_all);
+        cudaFreeHost(h_sum);
+        for (auto& e : ev) cudaEventDestroy(e);
+        cudaStreamDestroy(own_stream);
+    }
+    void setStream(cudaStream_t s) override
+    {
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        stream = s ? s : own_stream;
+        for (Brick* b : bricks) b->setStream(stream);
+    }
+    void sync() override { MDB_CUDA(cudaStreamSynchronize(stream)); }
+    bool mine(int b) const { return topo.owner(b) == proc; }
+    Brick* local(int b) const { return bricks[b - first]; }
+
+    // ------------------------------------------------------------------ transport
+    // after phase B of every local brick: all slot offsets to every process and to the host
+    void gather_offsets()
+    {
+        if (topo.nprocs > 1) {
+            const size_t n = (size_t)nlocal_bricks * 32;
+            MDB_NCCL(nccl_api().AllGather(d_off_all.p + (size_t)first * 32, d_off_all.p, n, NcclApi::Int32, comm, stream));
+        }
+        MDB_CUDA(cudaMemcpyAsync(h_off_all, d_off_all.p, (size_t)topo.nbricks * 32 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        for (int b = 0; b < topo.nbricks; b++) {
+            int dir[26], peer[26];
+            const int ns = topo.slots(b, true, dir, peer);
+            for (int d = 0; d < 26; d++) cnt[(size_t)b * 26 + d] = 0;
+            for (int k = 0; k < ns; k++) cnt[(size_t)b * 26 + dir[k]] = h_off_all[b * 32 + k + 1] - h_off_all[b * 32 + k];
+        }
+    }
+    // what brick r receives: segments (sender, first entry, length) in (sender, direction) order
+    struct Seg {
+        int sender, start, len;
+    };
+    int incoming(int r, std::vector<Seg>& segs) const
+    {
+        int dir[26], peer[26];
+        const int ns = topo.slots(r, false, dir, peer);
+        segs.clear();
+        int total = 0;
+        for (int k = 0; k < ns; k++) {
+            const int n = cnt[(size_t)peer[k] * 26 + dir[k]];
+            if (segs.empty() || segs.back().sender != peer[k]) segs.push_back(Seg { peer[k], total, 0 });
+            segs.back().len += n;
+            total += n;
+        }
+        return total;
+    }
+    // schedule of one exchange (dd_schedule) with pointers: W arrays of `elem` bytes per entry.
+    // src(S) = send buffer of local brick S (per-peer SoA segments), dst(R, k) = k-th destination array of
+    // local brick R at the first entry to be written.
+    template <class SrcFn, class DstFn> void build_ops(std::vector<Op>& ops, int W, size_t elem, bool migrate, SrcFn src, DstFn dst)
+    {
+        ops.clear();
+        std::vector<Xfer> plan;
+        dd_schedule(topo, proc, cnt.data(), plan);
+        for (const Xfer& t : plan) {
+            if (t.kind != 2) { // the sender's own table must agree with the plan derived from the counts
+                int ps = 0, pl = 0;
+                local(t.src)->brick_segment(migrate, t.dst, &ps, &pl);
+                if (pl != t.len || ps != t.src_start) throw Error("decomposition: send/receive segment mismatch");
+            }
+            for (int k = 0; k < W; k++) {
+                const char* s = t.kind != 2 ? (const char*)src(local(t.src)) + ((size_t)W * t.src_start + (size_t)k * t.len) * elem : nullptr;
+                char* d       = t.kind != 1 ? (char*)dst(local(t.dst), k) + (size_t)t.dst_start * elem : nullptr;
+                const size_t bytes = (size_t)t.len * elem;
+                ops.push_back(Op { t.kind == 0 ? COPY : (t.kind == 1 ? SEND : RECV), s, d, bytes, t.peer_proc });
+            }
+        }
+    }
+    void run_ops(const std::vector<Op>& ops)
+    {
+        NcclApi& N = nccl_api();
+        bool grouped = false;
+        for (const Op& o : ops) {
+            if (o.kind == COPY) {
+                MDB_CUDA(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToDevice, stream));
+            } else {
+                if (!grouped) { MDB_NCCL(N.GroupStart()); grouped = true; }
+                if (o.kind == SEND) MDB_NCCL(N.Send(o.src, o.bytes, NcclApi::Int8, o.peer, comm, stream));
+                else MDB_NCCL(N.Recv(o.dst, o.bytes, NcclApi::Int8, o.peer, comm, stream));
+            }
+        }
+        if (grouped) MDB_NCCL(N.GroupEnd());
+    }
+    void sum_over_procs(double* h, int n) // h[0..n) += the other processes' (h is pinned)
+    {
+        if (topo.nprocs == 1) return;
+        MDB_CUDA(cudaMemcpyAsync(d_sum.p, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        MDB_NCCL(nccl_api().AllReduce(d_sum.p, d_sum.p, n, NcclApi::Float64, NcclApi::Sum, comm, stream));
+        MDB_CUDA(cudaMemcpyAsync(h, d_sum.p, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // ------------------------------------------------------------------ atoms
+    long long createAtom() override
+    {
+        for (Brick* b : bricks) b->brick_createAtom();
+        return gNatoms;
+    }
+    void setEam(int nrho, double drho, int nr, double dr, double cut, double mass, const double* frho, const double* zr,
+        const double* rhor) override
+    {
+        G.force_field = MDB_FF_EAM;
+        for (Brick* b : bricks) b->setEam(nrho, drho, nr, dr, cut, mass, frho, zr, rhor);
+    }
+
+    // ------------------------------------------------------------------ thermo (common/thermo.c)
+    void global_vel_sums(double out[4])
+    {
+        for (size_t k = 0; k < bricks.size(); k++) bricks[k]->vel_sums(d_sum.p + 4 * k);
+        MDB_CUDA(cudaMemcpyAsync(h_sum + 8, d_sum.p, 4 * bricks.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        for (int c = 0; c < 4; c++) {
+            h_sum[c] = 0;
+            for (size_t k = 0; k < bricks.size(); k++) h_sum[c] += h_sum[8 + 4 * k + c];
+        }
+        sum_over_procs(h_sum, 4);
+        for (int c = 0; c < 4; c++) out[c] = h_sum[c];
+    }
+    void computeThermo(double* T, double* P) override
+    {
+        for (Brick* b : bricks)
+            if (!b->thermo_ready) b->setupThermo();
+        double s[4];
+        global_vel_sums(s);
+        bricks[0]->thermo_from_sum(s[3], T, P);
+    }
+    void adjustThermo() // thermo.c:82-122 over all bricks
+    {
+        double s[4];
+        global_vel_sums(s);
+        const real vxtot = (real)s[0] / (real)gNatoms, vytot = (real)s[1] / (real)gNatoms, vztot = (real)s[2] / (real)gNatoms;
+        for (Brick* b : bricks)
+            MDB_LAUNCH(launches, k_vel_shift<real>, grid_for(b->Nlocal, 256), 256, 0, stream, b->Nlocal, b->vx.p, b->vy.p,
+                b->vz.p, vxtot, vytot, vztot);
+        global_vel_sums(s);
+        real t = (real)s[3];
+        t *= bricks[0]->t_scale;
+        const real factor = (real)sqrt((double)(bricks[0]->temp / t));
+        for (Brick* b : bricks)
+            MDB_LAUNCH(launches, k_vel_scale<real>, grid_for(b->Nlocal, 256), 256, 0, stream, b->Nlocal, b->vx.p, b->vy.p,
+                b->vz.p, factor);
+    }
+
+    // ------------------------------------------------------------------ ghosts: setupPbc + updatePbc across bricks
+    void setupGhosts()
+    {
+        for (Brick* b : bricks) b->brick_border_A();
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        for (Brick* b : bricks) b->brick_sendlist_B(false);
+        gather_offsets();
+        std::vector<Seg> segs;
+        for (Brick* b : bricks) {
+            b->brick_finish_table(false, h_off_all + b->brick_id * 32);
+            b->brick_ghost_alloc(incoming(b->brick_id, segs));
+        }
+        // ghost type + tag (once per rebuild), then the per-step schedules
+        std::vector<Op> int_ops;
+        build_ops(int_ops, 2, sizeof(int), false, [](Brick* s) { return (const void*)s->dd_isend.p; },
+            [](Brick* r, int k) { return (void*)((k == 0 ? r->type.p : r->orig.p) + r->Nlocal); });
+        for (Brick* b : bricks) b->brick_pack_ints();
+        run_ops(int_ops);
+        build_ops(pos_ops, 3, sizeof(real), false, [](Brick* s) { return (const void*)s->dd_sendbuf.p; },
+            [](Brick* r, int k) { return (void*)((k == 0 ? r->x.p : (k == 1 ? r->y.p : r->z.p)) + r->Nlocal); });
+        if (G.force_field == MDB_FF_EAM)
+            build_ops(fp_ops, 1, sizeof(real), false, [](Brick* s) { return (const void*)s->dd_sendbuf.p; },
+                [](Brick* r, int) { return (void*)(r->fp.p + r->Nlocal); });
+    }
+    void forward() // updatePbc (pbc.c:42-55): fresh positions of the border atoms to their images
+    {
+        if (timing) MDB_CUDA(cudaEventRecord(ev[2], stream));
+        for (Brick* b : bricks) b->brick_pack_pos();
+        run_ops(pos_ops);
+        if (timing) {
+            float ms = 0;
+            MDB_CUDA(cudaEventRecord(ev[3], stream));
+            MDB_CUDA(cudaEventSynchronize(ev[3]));
+            MDB_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[3]));
+            comm_ms += ms;
+        }
+    }
+    // ------------------------------------------------------------------ migration: updateAtomsPbc across bricks
+    void migrate()
+    {
+        for (Brick* b : bricks) b->brick_migrate_A();
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        for (Brick* b : bricks) b->brick_sendlist_B(true);
+        gather_offsets();
+        std::vector<Seg> segs;
+        std::vector<int> nin(bricks.size());
+        for (size_t k = 0; k < bricks.size(); k++) {
+            Brick* b = bricks[k];
+            b->brick_finish_table(true, h_off_all + b->brick_id * 32);
+            nin[k] = incoming(b->brick_id, segs);
+            b->brick_migrate_pack(nin[k]);
+        }
+        std::vector<Op> ops;
+        build_ops(ops, 6, sizeof(real), true, [](Brick* s) { return (const void*)s->dd_sendbuf.p; },
+            [](Brick* r, int k) {
+                real* a[6] = { r->x.p, r->y.p, r->z.p, r->vx.p, r->vy.p, r->vz.p };
+                return (void*)(a[k] + r->nstay);
+            });
+        run_ops(ops);
+        build_ops(ops, 2, sizeof(int), true, [](Brick* s) { return (const void*)s->dd_isend.p; },
+            [](Brick* r, int k) { return (void*)((k == 0 ? r->type.p : r->orig.p) + r->nstay); });
+        run_ops(ops);
+        for (size_t k = 0; k < bricks.size(); k++) {
+            bricks[k]->Nlocal = bricks[k]->nstay + nin[k];
+            bricks[k]->Natoms = bricks[k]->Nlocal;
+            bricks[k]->Nghost = 0;
+        }
+    }
+
+    // ------------------------------------------------------------------ driver flow (verletlist/main.c)
+    void setup(bool adjust) override // main.c:58-72
+    {
+        for (Brick* b : bricks) {
+            b->setupNeighbor();
+            b->thermo_ready = false;
+            b->derive_dtforce();
+            b->setupThermo();
+        }
+        if (adjust) adjustThermo();
+        for (Brick* b : bricks) b->sort_atoms();
+        setupGhosts();
+        forward();
+        for (Brick* b : bricks) b->buildNeighbor();
+    }
+    void reneighbour() override // main.c:76-95
+    {
+        migrate();
+        for (Brick* b : bricks) b->sort_atoms();
+        setupGhosts();
+        forward();
+        for (Brick* b : bricks) b->buildNeighbor();
+    }
+    void force()
+    {
+        if (G.force_field == MDB_FF_EAM) { // force_eam.c: density -> fp of the images -> force
+            for (Brick* b : bricks) b->eam_density();
+            for (Brick* b : bricks) b->brick_pack_fp();
+            run_ops(fp_ops);
+            for (Brick* b : bricks) { b->eam_force(); b->force_launches++; }
+        } else {
+            for (Brick* b : bricks) b->launch_force(FORCE_DISPATCH);
+        }
+    }
+    void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) override // main.c:244-288
+    {
+        for (Brick* b : bricks)
+            if (!b->thermo_ready) b->setupThermo();
+        const int nstat = G.nstat > 0 ? G.nstat : nsteps + 1;
+        const int every = G.reneigh_every > 0 ? G.reneigh_every : nsteps + 1;
+        const size_t maxrec = nsteps / nstat + 3;
+        if (4 * maxrec * bricks.size() > 2048) throw Error("run: too many thermo records");
+        for (Brick* b : bricks) b->d_thermo.ensure(4 * maxrec, false, stream);
+        std::vector<int> rec_step;
+        auto record = [&](int step) {
+            for (Brick* b : bricks) b->vel_sums(b->d_thermo.p + 4 * rec_step.size());
+            rec_step.push_back(step);
+        };
+        double f0 = 0, n0 = 0;
+        for (Brick* b : bricks) { f0 += b->force_ms; n0 += b->neigh_ms; }
+        record(0);
+        force();
+        MDB_CUDA(cudaEventRecord(ev[0], stream)); // TOTAL starts after the first force, main.c:252
+        bool initial_done = false;
+        for (int n = 0; n < nsteps; n++) {
+            const bool reneigh = (n + 1) % every == 0;
+            if (!initial_done)
+                for (Brick* b : bricks) b->initialIntegrate();
+            if (reneigh) reneighbour();
+            else forward();
+            force();
+            const bool rec = !((n + 1) % nstat) && (n + 1) < nsteps;
+            if (rec || n + 1 == nsteps || !bricks[0]->fuse_integrate) {
+                for (Brick* b : bricks) b->finalIntegrate();
+                initial_done = false;
+                if (rec) record(n + 1);
+            } else {
+                for (Brick* b : bricks) b->finalInitialIntegrate();
+                initial_done = true;
+            }
+        }
+        MDB_CUDA(cudaEventRecord(ev[1], stream));
+        record(nsteps);
+        const size_t nr4 = 4 * rec_step.size();
+        for (size_t k = 0; k < bricks.size(); k++)
+            MDB_CUDA(cudaMemcpyAsync(h_sum + 2048 + k * nr4, bricks[k]->d_thermo.p, nr4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        for (size_t q = 0; q < nr4; q++) {
+            h_sum[q] = 0;
+            for (size_t k = 0; k < bricks.size(); k++) h_sum[q] += h_sum[2048 + k * nr4 + q];
+        }
+        sum_over_procs(h_sum, (int)nr4);
+        float ms = 0;
+        MDB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+        int nr = 0;
+        for (size_t r = 0; r < rec_step.size(); r++)
+            if (thermo_out && nr < max_records) {
+                thermo_out[3 * nr] = rec_step[r];
+                bricks[0]->thermo_from_sum(h_sum[4 * r + 3], &thermo_out[3 * nr + 1], &thermo_out[3 * nr + 2]);
+                nr++;
+            }
+        if (nrecords) *nrecords = nr;
+        if (timers) {
+            double f1 = 0, n1 = 0;
+            for (Brick* b : bricks) { f1 += b->force_ms; n1 += b->neigh_ms; }
+            timers[0] = ms * 1e-3;
+            timers[1] = (f1 - f0) * 1e-3;
+            timers[2] = (n1 - n0) * 1e-3;
+        }
+    }
+
+    // ------------------------------------------------------------------ accessors
+    void getCounts(long long* v) override // global atoms, this process: local atoms, ghosts, largest maxneighs, bricks
+    {
+        v[0] = gNatoms; v[1] = v[2] = v[3] = 0;
+        for (Brick* b : bricks) {
+            v[1] += b->Nlocal;
+            v[2] += b->Nghost;
+            v[3] = std::max<long long>(v[3], b->maxneighs);
+        }
+        v[4] = (long long)bricks.size();
+    }
+    void getAtoms(int which, int* tags, void* ax, void* ay, void* az) override // slot order of the bricks, global frame
+    {
+        size_t off = 0;
+        for (Brick* b : bricks) {
+            const size_t n = b->Nlocal;
+            const real *p, *q, *r;
+            if (which == 'x') { p = b->x.p; q = b->y.p; r = b->z.p; }
+            else if (which == 'v') { p = b->vx.p; q = b->vy.p; r = b->vz.p; }
+            else if (which == 'f') { p = b->fx.p; q = b->fy.p; r = b->fz.p; }
+            else throw Error("getAtoms: which must be 'x', 'v' or 'f'");
+            if (which == 'x') {
+                b->tx.ensure(n, false, stream); b->ty.ensure(n, false, stream); b->tz.ensure(n, false, stream);
+                MDB_LAUNCH(launches, k_dd_to_global<real>, grid_for(n, 256), 256, 0, stream, (int)n,
+                    (real)(b->bcoord[0] * b->xprd), (real)(b->bcoord[1] * b->yprd), (real)(b->bcoord[2] * b->zprd), p, q, r,
+                    b->tx.p, b->ty.p, b->tz.p);
+                p = b->tx.p; q = b->ty.p; r = b->tz.p;
+            }
+            MDB_CUDA(cudaMemcpyAsync((real*)ax + off, p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync((real*)ay + off, q, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync((real*)az + off, r, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
+            if (tags) MDB_CUDA(cudaMemcpyAsync(tags + off, b->orig.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            off += n;
+        }
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    void getNeighborTags(int* tags, int* nn, int* rows, int stride) override
+    {
+        size_t off = 0;
+        for (Brick* b : bricks) {
+            const size_t n = b->Nlocal;
+            if (b->nstride == 0) throw Error("getNeighborTags: no neighbor list");
+            b->rows.ensure(n * stride, false, stream);
+            MDB_LAUNCH(launches, k_dd_rows_as_tags, grid_for(n, 128), 128, 0, stream, (int)n, stride, b->LL, b->numneigh.p,
+                b->neighbors.p, b->orig.p, b->rows.p);
+            MDB_CUDA(cudaMemcpyAsync(rows + off * stride, b->rows.p, n * stride * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(nn + off, b->numneigh.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaMemcpyAsync(tags + off, b->orig.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            off += n;
+        }
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    void saveState() override
+    {
+        for (Brick* b : bricks) b->brick_save();
+    }
+    void restoreState() override
+    {
+        for (Brick* b : bricks) b->brick_restore();
+    }
+    void setOption(const char* name, double v) override
+    {
+        for (Brick* b : bricks) b->setOption(name, v);
+    }
+    void setTiming(bool on) override
+    {
+        timing = on;
+        for (Brick* b : bricks) b->timing = on;
+    }
+    void stats(double* force_ms, long long* force_launches, double* neigh_ms, long long* neigh_launches, long long* nl,
+        double* cms, bool reset) override
+    {
+        double f = 0, n = 0;
+        long long fl = 0, nbl = 0, l = launches;
+        for (Brick* b : bricks) {
+            f += b->force_ms; n += b->neigh_ms; fl += b->force_launches; nbl += b->neigh_launches; l += b->launches;
+            if (reset) { b->force_ms = b->neigh_ms = 0; b->force_launches = b->neigh_launches = b->launches = 0; }
+        }
+        if (force_ms) *force_ms = f;
+        if (force_launches) *force_launches = fl;
+        if (neigh_ms) *neigh_ms = n;
+        if (neigh_launches) *neigh_launches = nbl;
+        if (nl) *nl = l;
+        if (cms) *cms = comm_ms;
+        if (reset) { launches = 0; comm_ms = 0; }
+    }
+};
+
+DDBase* make_dd(const mdb_params& g, const int grid[3], int nprocs, int proc, const void* nccl_id, int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw Error("mdb_dd_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) throw Error(fmt("mdb_dd_create: device %d out of range (%d devices)", device, ndev));
+    if (g.precision == MDB_DP) return new DomainGroup<double>(g, grid, nprocs, proc, nccl_id, device);
+    if (g.precision == MDB_SP) return new DomainGroup<float>(g, grid, nprocs, proc, nccl_id, device);
+    throw Error("mdb_dd_create: precision must be MDB_SP or MDB_DP");
+}

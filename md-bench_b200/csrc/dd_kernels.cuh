@@ -5,18 +5,28 @@
 // neighbor brick in that direction instead of the box itself.  With one brick per axis the neighbor
 // is the brick itself and the scheme reduces to the reference's setupPbc/updatePbc.
 // Image index b in [0,26) uses the reference's ADDGHOST ladder (c_img in vl_kernels.cuh):
-// s_b = c_img[b] is the image shift; the atom is SENT in direction -s_b and appears at x + s_b*ext.
+// s_b = c_img[b] is the image shift; the atom is SENT to the brick at coords - s_b and appears there
+// at x + s_b*ext.  See dd_topo.h for the slot / peer-segment order both sides agree on.
 #pragma once
 #include "mdb_util.cuh"
 
 namespace mdb {
 
-struct DirTable {
-    int off[27]; // off[b] .. off[b+1]: entries of direction b
+// What a brick sends, by send slot (valid directions ordered by (receiving brick, direction)).
+// Entries [off[s], off[s+1]) of the send list belong to slot s; consecutive slots with the same
+// receiver form a peer segment [pstart, pstart+plen), stored in the send buffer as W arrays of plen
+// (SoA per peer), so the receiver takes each array with one contiguous transfer straight into place.
+struct SendTable {
+    int nslots;
+    int dir[26];
+    int off[27];
+    int pstart[26];
+    int plen[26];
 };
 
 // createAtom (atom.c:67-187) restricted to one brick: one thread per FCC site of the brick, global
 // emission index (closed form, see k_create_atoms) kept as the atom's tag, position brick-local.
+// Atoms are stored in x-fastest site order of the brick.
 template <class real>
 __global__ void k_dd_create_atoms(int gnx, int gny, int gnz, int lnx, int lny, int lnz, int cx, int cy, int cz,
     real alat, real* __restrict__ x, real* __restrict__ y, real* __restrict__ z, real* __restrict__ vx,
@@ -56,29 +66,35 @@ __global__ void k_dd_create_atoms(int gnx, int gny, int gnz, int lnx, int lny, i
 // ---- migration: atoms that left the brick (the decomposed updateAtomsPbc, pbc.c:59-84) -------------
 // dest[i] = ladder index of the image shift that brings the atom into the receiving brick's local
 // frame (x + s*ext), or -1 if it stays.  Axes with a single brick wrap in place like the reference.
+// s2b[27]: shift triple -> ladder index (-1 for no shift or a direction without a neighbor brick).
+struct ShiftMap {
+    signed char b[27];
+};
 template <class real>
-__global__ void k_dd_dest(int nlocal, real ex, real ey, real ez, int px, int py, int pz, const signed char* __restrict__ s2b,
-    real* __restrict__ x, real* __restrict__ y, real* __restrict__ z, int* __restrict__ dest, int* __restrict__ leave)
+__global__ void k_dd_dest(int nlocal, real ex, real ey, real ez, int px, int py, int pz, int perx, int pery, int perz,
+    ShiftMap s2b, real* __restrict__ x, real* __restrict__ y, real* __restrict__ z, int* __restrict__ dest,
+    int* __restrict__ leave)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlocal) return;
-    int s[3]   = { 0, 0, 0 };
-    real* c[3] = { x, y, z };
+    int s[3]        = { 0, 0, 0 };
+    real* c[3]      = { x, y, z };
     const real e[3] = { ex, ey, ez };
     const int p[3]  = { px, py, pz };
+    const int per[3] = { perx, pery, perz };
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        real v = c[a][i];
+        const real v = c[a][i];
         if (p[a] == 1) {
-            c[a][i] = wrap1(v, e[a]);
+            if (per[a]) c[a][i] = wrap1(v, e[a]);
         } else {
-            if (v < (real)0.0) s[a] = +1;       // receiver sees x + ext
-            else if (v >= e[a]) s[a] = -1;      // receiver sees x - ext
+            if (v < (real)0.0) s[a] = +1;  // receiver sees x + ext
+            else if (v >= e[a]) s[a] = -1; // receiver sees x - ext
         }
     }
-    const int b = s2b[(s[0] + 1) + 3 * (s[1] + 1) + 9 * (s[2] + 1)];
-    dest[i]  = b;
-    leave[i] = b >= 0;
+    const int b = s2b.b[(s[0] + 1) + 3 * (s[1] + 1) + 9 * (s[2] + 1)];
+    dest[i]     = b;
+    leave[i]    = b >= 0;
 }
 // compact: stayers keep their relative order at the front, leavers are listed in ascending order
 __global__ void k_dd_split(int nlocal, const int* __restrict__ leave, const int* __restrict__ leave_scan,
@@ -90,38 +106,44 @@ __global__ void k_dd_split(int nlocal, const int* __restrict__ leave, const int*
     if (leave[i]) leavers[l] = i;
     else stay_src[i - l] = i;
 }
-// flags[b*nb + q] = 1 if border/leaver atom q goes to direction b
-__global__ void k_dd_flags_mask(int nb, const int* __restrict__ list, const unsigned* __restrict__ mask, int* __restrict__ flags)
+// flags[s*nb + q] = 1 if border atom list[q] has image dir[s]
+__global__ void k_dd_flags_mask(int nb, SendTable T, const int* __restrict__ list, const unsigned* __restrict__ mask,
+    int* __restrict__ flags)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 26LL * nb) return;
-    const int b = (int)(t / nb), q = (int)(t % nb);
-    flags[t]    = (mask[list[q]] >> b) & 1u;
+    if (t >= (long long)T.nslots * nb) return;
+    const int s = (int)(t / nb), q = (int)(t % nb);
+    flags[t]    = (mask[list[q]] >> T.dir[s]) & 1u;
 }
-__global__ void k_dd_flags_dest(int nb, const int* __restrict__ list, const int* __restrict__ dest, int* __restrict__ flags)
+__global__ void k_dd_flags_dest(int nb, SendTable T, const int* __restrict__ list, const int* __restrict__ dest,
+    int* __restrict__ flags)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 26LL * nb) return;
-    const int b = (int)(t / nb), q = (int)(t % nb);
-    flags[t]    = dest[list[q]] == b;
+    if (t >= (long long)T.nslots * nb) return;
+    const int s = (int)(t / nb), q = (int)(t % nb);
+    flags[t]    = dest[list[q]] == T.dir[s];
 }
-// sendlist[scan[t]] = list[q] for set flags: direction blocks come out contiguous and ascending
-__global__ void k_dd_fill_sendlist(int nb, const int* __restrict__ list, const int* __restrict__ flags,
+// sendlist[scan[t]] = list[q] for set flags: slot blocks come out contiguous, ascending inside
+__global__ void k_dd_fill_sendlist(int nb, int nslots, const int* __restrict__ list, const int* __restrict__ flags,
     const int* __restrict__ scan, int* __restrict__ sendlist)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 26LL * nb) return;
+    if (t >= (long long)nslots * nb) return;
     if (flags[t]) sendlist[scan[t]] = list[(int)(t % nb)];
 }
-__global__ void k_dd_block_offsets(int nb, const int* __restrict__ scan, int* __restrict__ off)
+// off[s] = first entry of slot s (off[nslots] = total is written by the scan itself)
+__global__ void k_dd_block_offsets(int nb, int nslots, const int* __restrict__ scan, int* __restrict__ off)
 {
-    const int b = threadIdx.x;
-    if (b < 26) off[b] = scan[(long long)b * nb];
+    const int s = threadIdx.x;
+    if (s < nslots) off[s] = scan[(long long)s * nb];
 }
-__global__ void k_flag_nonzero(int n, const unsigned* __restrict__ mask, int* __restrict__ flag)
+__global__ void k_dd_flag_border(int n, unsigned valid, unsigned* __restrict__ mask, int* __restrict__ flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = mask[i] != 0;
+    if (i >= n) return;
+    const unsigned m = mask[i] & valid;
+    mask[i]          = m;
+    flag[i]          = m != 0;
 }
 __global__ void k_compact(int n, const int* __restrict__ flag, const int* __restrict__ scan, int* __restrict__ list)
 {
@@ -129,54 +151,52 @@ __global__ void k_compact(int n, const int* __restrict__ flag, const int* __rest
     if (i < n && flag[i]) list[scan[i]] = i;
 }
 
-// pack W arrays of the listed atoms, direction segment b laid out as [a0 | a1 | ...], each cnt_b long;
-// the first three arrays (positions) get the image shift x + s_b*ext as ONE fma like updatePbc (F11)
-template <class real, int W>
-__global__ void k_dd_pack(int total, DirTable T, const int* __restrict__ sendlist, real ex, real ey, real ez,
+__device__ __forceinline__ int dd_slot_of(const SendTable& T, int t)
+{
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < 26; k++) s += (k < T.nslots && t >= T.off[k]);
+    return s;
+}
+// pack W arrays of the listed atoms into per-peer SoA segments; with SHIFT the first three arrays
+// (positions) get the image shift x + s_b*ext as ONE fma like updatePbc
+template <class real, int W, bool SHIFT>
+__global__ void k_dd_pack(int total, SendTable T, const int* __restrict__ sendlist, real ex, real ey, real ez,
     const real* __restrict__ a0, const real* __restrict__ a1, const real* __restrict__ a2, const real* __restrict__ a3,
     const real* __restrict__ a4, const real* __restrict__ a5, real* __restrict__ out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    int b = 0;
-#pragma unroll
-    for (int k = 1; k < 26; k++) b += (t >= T.off[k]);
-    const int cnt = T.off[b + 1] - T.off[b], q = t - T.off[b], i = sendlist[t];
-    real* o = out + (size_t)W * T.off[b] + q;
-    o[0]               = fma_rn((real)c_img[b][0], ex, a0[i]);
-    o[cnt]             = fma_rn((real)c_img[b][1], ey, a1[i]);
-    o[2 * (size_t)cnt] = fma_rn((real)c_img[b][2], ez, a2[i]);
+    const int s = dd_slot_of(T, t), b = T.dir[s];
+    const size_t pl = T.plen[s];
+    const int i     = sendlist[t];
+    real* o         = out + (size_t)W * T.pstart[s] + (t - T.pstart[s]);
+    if (SHIFT) {
+        o[0] = fma_rn((real)c_img[b][0], ex, a0[i]);
+        if (W > 1) o[pl] = fma_rn((real)c_img[b][1], ey, a1[i]);
+        if (W > 2) o[2 * pl] = fma_rn((real)c_img[b][2], ez, a2[i]);
+    } else {
+        o[0] = a0[i];
+        if (W > 1) o[pl] = a1[i];
+        if (W > 2) o[2 * pl] = a2[i];
+    }
     if (W > 3) {
-        o[3 * (size_t)cnt] = a3[i];
-        o[4 * (size_t)cnt] = a4[i];
-        o[5 * (size_t)cnt] = a5[i];
+        o[3 * pl] = a3[i];
+        o[4 * pl] = a4[i];
+        o[5 * pl] = a5[i];
     }
 }
-__global__ void k_dd_pack_int(int total, const int* __restrict__ sendlist, const int* __restrict__ a, int* __restrict__ out)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < total) out[t] = a[sendlist[t]];
-}
-// unpack W arrays received for block b into dst arrays starting at `base`
-template <class real, int W>
-__global__ void k_dd_unpack(int total, DirTable T, int base, const real* __restrict__ in, real* __restrict__ a0,
-    real* __restrict__ a1, real* __restrict__ a2, real* __restrict__ a3, real* __restrict__ a4, real* __restrict__ a5)
+// two int arrays (type, tag) in the same per-peer segment layout
+__global__ void k_dd_pack_int2(int total, SendTable T, const int* __restrict__ sendlist, const int* __restrict__ a0,
+    const int* __restrict__ a1, int* __restrict__ out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    int b = 0;
-#pragma unroll
-    for (int k = 1; k < 26; k++) b += (t >= T.off[k]);
-    const int cnt = T.off[b + 1] - T.off[b], q = t - T.off[b];
-    const real* s = in + (size_t)W * T.off[b] + q;
-    a0[base + t] = s[0];
-    a1[base + t] = s[cnt];
-    a2[base + t] = s[2 * (size_t)cnt];
-    if (W > 3) {
-        a3[base + t] = s[3 * (size_t)cnt];
-        a4[base + t] = s[4 * (size_t)cnt];
-        a5[base + t] = s[5 * (size_t)cnt];
-    }
+    const int s = dd_slot_of(T, t);
+    const int i = sendlist[t];
+    int* o      = out + (size_t)2 * T.pstart[s] + (t - T.pstart[s]);
+    o[0]            = a0[i];
+    o[T.plen[s]]    = a1[i];
 }
 // gather the stayers to the front (like k_permute_atoms but without forces)
 template <class real>
@@ -193,6 +213,24 @@ __global__ void k_dd_gather_stay(int n, const int* __restrict__ src, const real*
     nvx[q] = vx[o]; nvy[q] = vy[o]; nvz[q] = vz[o];
     ntype[q] = type[o];
     ntag[q]  = tag[o];
+}
+// neighbor rows as global tags (parity read-back): out[i*stride + k] = tag[neighbor k of i]
+__global__ void k_dd_rows_as_tags(int nlocal, int stride, NbLayout L, const int* __restrict__ numneigh,
+    const int* __restrict__ neighbors, const int* __restrict__ tag, int* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const int n = min(numneigh[i], stride);
+    for (int k = 0; k < n; k++) out[(size_t)i * stride + k] = tag[neighbors[L.base(i) + (size_t)k * L.sk]];
+}
+// brick-local -> global coordinates for read-back
+template <class real>
+__global__ void k_dd_to_global(int n, real ox, real oy, real oz, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, real* __restrict__ gx, real* __restrict__ gy, real* __restrict__ gz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gx[i] = x[i] + ox; gy[i] = y[i] + oy; gz[i] = z[i] + oz;
 }
 
 } // namespace mdb

@@ -10,6 +10,7 @@
 #pragma once
 #include <algorithm>
 #include <utility>
+#include <vector>
 
 namespace mdb {
 
@@ -75,5 +76,52 @@ struct Topo {
         return m;
     }
 };
+
+// One contiguous transfer of an exchange: `len` entries from entry `src_start` of brick `src`'s send list
+// to entry `dst_start` of what brick `dst` receives.  kind: 0 = both bricks in this process (device copy),
+// 1 = this process sends, 2 = this process receives.
+struct Xfer {
+    int kind, src, dst, src_start, dst_start, len, peer_proc;
+};
+// The schedule of one exchange as process `proc` executes it, from cnt[brick*26 + direction] = number of
+// entries brick sends in that direction (known to every process after the allgather).  Receiving bricks
+// ascending, then sending bricks ascending: both ends of a pair of processes enumerate their common
+// transfers in the same order, which is what NCCL's in-order matching of send/recv needs.
+inline void dd_schedule(const Topo& t, int proc, const int* cnt, std::vector<Xfer>& out)
+{
+    out.clear();
+    // first entry of the segment S sends to R: S's send slots are ordered by (receiver, direction)
+    auto send_start = [&](int S, int R) {
+        int dir[26], peer[26];
+        const int ns = t.slots(S, true, dir, peer);
+        int off      = 0;
+        for (int k = 0; k < ns && peer[k] < R; k++) off += cnt[S * 26 + dir[k]];
+        return off;
+    };
+    for (int R = 0; R < t.nbricks; R++) {
+        int dir[26], peer[26];
+        const int ns = t.slots(R, false, dir, peer);
+        int total    = 0;
+        for (int k = 0; k < ns;) {
+            int e = k, len = 0;
+            while (e < ns && peer[e] == peer[k]) len += cnt[peer[e] * 26 + dir[e]], e++;
+            const int S   = peer[k];
+            const bool ms = t.owner(S) == proc, mr = t.owner(R) == proc;
+            if (len && (ms || mr)) {
+                Xfer x;
+                x.kind      = ms && mr ? 0 : (ms ? 1 : 2);
+                x.src       = S;
+                x.dst       = R;
+                x.src_start = send_start(S, R);
+                x.dst_start = total;
+                x.len       = len;
+                x.peer_proc = ms && mr ? proc : (ms ? t.owner(R) : t.owner(S));
+                out.push_back(x);
+            }
+            total += len;
+            k = e;
+        }
+    }
+}
 
 } // namespace mdb

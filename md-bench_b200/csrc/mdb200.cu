@@ -193,3 +193,136 @@ int mdb_setOption(mdb_ctx* c, const char* name, double value) { MDB_TRY(c->sim->
 int mdb_countPairs(mdb_ctx* c, long long* listed, long long* in_cutoff) { MDB_TRY(c->sim->countPairs(listed, in_cutoff)) }
 
 } // extern "C"
+
+// ---- spatial decomposition (include/mdb200.h, "multi-GPU") -----------------------------------------
+#include "dd_topo.h"
+#include "nccl_dl.h"
+
+struct mdb_dd {
+    DDBase* g;
+};
+
+#define MDB_DD_TRY(body)                                                                         \
+    try {                                                                                        \
+        if (!d || !d->g) throw Error("null mdb_dd");                                             \
+        body;                                                                                    \
+        return 0;                                                                                \
+    } catch (const std::exception& e) {                                                          \
+        g_err = e.what();                                                                        \
+        return -1;                                                                               \
+    }
+
+extern "C" {
+
+int mdb_dd_uniqueIdBytes(void) { return (int)sizeof(NcclApi::unique_id); }
+int mdb_dd_getUniqueId(void* id)
+{
+    try {
+        NcclApi& N = nccl_api();
+        N.load();
+        MDB_NCCL(N.GetUniqueId((NcclApi::unique_id*)id));
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+int mdb_dd_plan(int gx, int gy, int gz, int perx, int pery, int perz, int nprocs, int brick, int send, int dir[26],
+    int peer[26], int owner[26])
+{
+    Topo t;
+    t.g[0] = gx; t.g[1] = gy; t.g[2] = gz;
+    t.periodic[0] = perx; t.periodic[1] = pery; t.periodic[2] = perz;
+    t.nbricks = gx * gy * gz;
+    t.nprocs  = nprocs;
+    if (t.nbricks < 1 || nprocs < 1 || t.nbricks % nprocs || brick < 0 || brick >= t.nbricks) {
+        g_err = "mdb_dd_plan: bad brick grid / process count";
+        return -1;
+    }
+    const int n = t.slots(brick, send != 0, dir, peer);
+    for (int k = 0; k < n; k++) owner[k] = t.owner(peer[k]);
+    return n;
+}
+int mdb_dd_schedule(int gx, int gy, int gz, int perx, int pery, int perz, int nprocs, int proc, const int* cnt,
+    int max_ops, int* ops)
+{
+    Topo t;
+    t.g[0] = gx; t.g[1] = gy; t.g[2] = gz;
+    t.periodic[0] = perx; t.periodic[1] = pery; t.periodic[2] = perz;
+    t.nbricks = gx * gy * gz;
+    t.nprocs  = nprocs;
+    if (t.nbricks < 1 || nprocs < 1 || t.nbricks % nprocs || proc < 0 || proc >= nprocs || !cnt) {
+        g_err = "mdb_dd_schedule: bad brick grid / process";
+        return -1;
+    }
+    std::vector<Xfer> plan;
+    dd_schedule(t, proc, cnt, plan);
+    for (size_t k = 0; k < plan.size() && (int)k < max_ops; k++) {
+        const Xfer& x = plan[k];
+        const int v[7] = { x.kind, x.src, x.dst, x.src_start, x.dst_start, x.len, x.peer_proc };
+        memcpy(ops + 7 * k, v, sizeof v);
+    }
+    return (int)plan.size();
+}
+mdb_dd* mdb_dd_create(const mdb_params* p, int gx, int gy, int gz, int nprocs, int proc, const void* nccl_id, int device)
+{
+    try {
+        if (!p) throw Error("mdb_dd_create: null params");
+        if (p->ntypes != 1) throw Error("mdb_dd_create: only ntypes == 1 is supported (EXPLICIT_TYPES off)");
+        const int grid[3] = { gx, gy, gz };
+        mdb_dd* d = new mdb_dd;
+        d->g      = make_dd(*p, grid, nprocs, proc, nccl_id, device);
+        return d;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void mdb_dd_destroy(mdb_dd* d)
+{
+    if (!d) return;
+    delete d->g;
+    delete d;
+}
+int mdb_dd_setStream(mdb_dd* d, void* s) { MDB_DD_TRY(d->g->setStream((cudaStream_t)s)) }
+int mdb_dd_sync(mdb_dd* d) { MDB_DD_TRY(d->g->sync()) }
+long long mdb_dd_createAtom(mdb_dd* d)
+{
+    try {
+        if (!d || !d->g) throw Error("null mdb_dd");
+        return d->g->createAtom();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+int mdb_dd_setEam(mdb_dd* d, int nrho, double drho, int nr, double dr, double cut, double mass, const double* frho,
+    const double* zr, const double* rhor)
+{
+    MDB_DD_TRY(d->g->setEam(nrho, drho, nr, dr, cut, mass, frho, zr, rhor))
+}
+int mdb_dd_setup(mdb_dd* d, int adjust) { MDB_DD_TRY(d->g->setup(adjust != 0)) }
+int mdb_dd_reneighbour(mdb_dd* d) { MDB_DD_TRY(d->g->reneighbour()) }
+int mdb_dd_run(mdb_dd* d, int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers)
+{
+    MDB_DD_TRY(d->g->run(nsteps, thermo_out, max_records, nrecords, timers))
+}
+int mdb_dd_computeThermo(mdb_dd* d, double* T, double* P) { MDB_DD_TRY(d->g->computeThermo(T, P)) }
+int mdb_dd_getCounts(mdb_dd* d, long long v[5]) { MDB_DD_TRY(d->g->getCounts(v)) }
+int mdb_dd_getAtoms(mdb_dd* d, int which, int* tags, void* x, void* y, void* z) { MDB_DD_TRY(d->g->getAtoms(which, tags, x, y, z)) }
+int mdb_dd_getNeighborTags(mdb_dd* d, int* tags, int* numneigh, int* rows, int stride)
+{
+    MDB_DD_TRY(d->g->getNeighborTags(tags, numneigh, rows, stride))
+}
+int mdb_dd_saveState(mdb_dd* d) { MDB_DD_TRY(d->g->saveState()) }
+int mdb_dd_restoreState(mdb_dd* d) { MDB_DD_TRY(d->g->restoreState()) }
+int mdb_dd_setOption(mdb_dd* d, const char* name, double v) { MDB_DD_TRY(d->g->setOption(name, v)) }
+int mdb_dd_setTiming(mdb_dd* d, int on) { MDB_DD_TRY(d->g->setTiming(on != 0)) }
+int mdb_dd_getKernelStats(mdb_dd* d, double* force_ms, long long* force_launches, double* neigh_ms,
+    long long* neigh_launches, long long* total_launches, double* comm_ms)
+{
+    MDB_DD_TRY(d->g->stats(force_ms, force_launches, neigh_ms, neigh_launches, total_launches, comm_ms, false))
+}
+int mdb_dd_resetKernelStats(mdb_dd* d) { MDB_DD_TRY(d->g->stats(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true)) }
+
+} // extern "C"

@@ -59,4 +59,29 @@ enum { FORCE_DISPATCH = 0, FORCE_LJ_FULL = 1, FORCE_LJ_HALF = 2, FORCE_EAM = 3 }
 
 SimBase* make_sim(const mdb_params& p, int device);
 
+// a spatially decomposed box: the bricks of this process + the transport between bricks (dd_group.cuh)
+struct DDBase {
+    virtual ~DDBase() {}
+    virtual void setStream(cudaStream_t s)                                                                   = 0;
+    virtual void sync()                                                                                      = 0;
+    virtual long long createAtom()                                                                           = 0;
+    virtual void setup(bool adjust)                                                                          = 0;
+    virtual void reneighbour()                                                                               = 0;
+    virtual void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers)         = 0;
+    virtual void computeThermo(double* T, double* P)                                                         = 0;
+    virtual void getCounts(long long* v)                                                                     = 0;
+    virtual void getAtoms(int which, int* tags, void* x, void* y, void* z)                                   = 0;
+    virtual void getNeighborTags(int* tags, int* numneigh, int* rows, int stride)                            = 0;
+    virtual void saveState()                                                                                 = 0;
+    virtual void restoreState()                                                                              = 0;
+    virtual void setOption(const char* name, double v)                                                       = 0;
+    virtual void setTiming(bool on)                                                                          = 0;
+    virtual void stats(double* force_ms, long long* force_launches, double* neigh_ms, long long* neigh_launches,
+        long long* launches, double* comm_ms, bool reset)                                                    = 0;
+    virtual void setEam(int nrho, double drho, int nr, double dr, double cut, double mass, const double* frho,
+        const double* zr, const double* rhor)                                                                = 0;
+};
+
+DDBase* make_dd(const mdb_params& global, const int grid[3], int nprocs, int proc, const void* nccl_id, int device);
+
 } // namespace mdb

@@ -9,6 +9,9 @@
 #include "scan.cuh"
 #include "vl_kernels.cuh"
 #include "eam_kernels.cuh"
+#include "dd_topo.h"
+#include "dd_kernels.cuh"
+#include "nccl_dl.h"
 
 namespace mdb {
 
@@ -291,17 +294,19 @@ template <class real> struct Sim final : SimBase {
     // ------------------------------------------------------------------ thermo
     void setupThermo() override // common/thermo.c:30-53
     {
-        const long long natoms = Natoms;
+        const long long natoms = brick ? gNatoms : Natoms;
+        // brick mode: the thermo scales are those of the whole box (bgrid bricks of xprd x yprd x zprd)
+        const double gx = (double)xprd * bgrid[0], gy = (double)yprd * bgrid[1], gz = (double)zprd * bgrid[2];
         if (P.force_field == MDB_FF_LJ) {
             mvv2e     = (real)1.0;
             dof_boltz = (real)(natoms * 3 - 3);
             t_scale   = mvv2e / dof_boltz;
-            p_scale   = (real)(1.0 / 3 / (double)xprd / (double)yprd / (double)zprd);
+            p_scale   = (real)(1.0 / 3 / gx / gy / gz);
         } else {
             mvv2e     = (real)1.036427e-04;
             dof_boltz = (real)((double)(natoms * 3 - 3) * 8.617343e-05);
             t_scale   = mvv2e / dof_boltz;
-            p_scale   = (real)(1.602176e+06 / 3 / (double)xprd / (double)yprd / (double)zprd);
+            p_scale   = (real)(1.602176e+06 / 3 / gx / gy / gz);
             if (!thermo_ready) dtforce = dtforce / mvv2e; // thermo.c:51 (once per setup)
         }
         thermo_ready = true;
@@ -741,19 +746,26 @@ template <class real> struct Sim final : SimBase {
             force_ms += ms;
         }
     }
-    void launch_eam()
+    void eam_density() // force_eam.c:49-112
     {
         if (!eam.ready) throw Error("computeForceEam: no EAM tables (call mdb_setEam first)");
         fp.ensure((size_t)Nlocal + Nghost, false, stream);
-        const real cfsq = cutforce * cutforce;
-        MDB_LAUNCH(launches, k_eam_density<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cfsq, eam,
-            rhor_spline.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fp.p);
-        if (Nghost)
+        MDB_LAUNCH(launches, k_eam_density<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
+            eam, rhor_spline.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fp.p);
+    }
+    void eam_force() // force_eam.c:127-224
+    {
+        MDB_LAUNCH(launches, k_eam_force<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
+            eam, rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+    }
+    void launch_eam()
+    {
+        if (brick) throw Error("computeForceEam on a brick goes through the decomposition (fp exchange)");
+        eam_density();
+        if (Nghost) // force_eam.c:118-120
             MDB_LAUNCH(launches, k_eam_ghost_fp<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost,
                 border_map.p, fp.p);
-        MDB_LAUNCH(launches, k_eam_force<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cfsq, eam,
-            rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p,
-            fz.p);
+        eam_force();
     }
     // ComputeForceFunction: returns elapsed seconds like the reference (force.h:16)
     double computeForce(int which) override
@@ -780,6 +792,14 @@ template <class real> struct Sim final : SimBase {
         MDB_LAUNCH(launches, k_final_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, dtforce,
             vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
+
+    void finalInitialIntegrate() // finalIntegrate(n) + initialIntegrate(n+1) in one pass
+    {
+        MDB_LAUNCH(launches, k_final_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
+            dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
+    }
+
+#include "dd_brick.inc"
 
     // ------------------------------------------------------------------ driver flow
     void setup(bool adjust) override // verletlist/main.c:58-72
@@ -835,9 +855,8 @@ template <class real> struct Sim final : SimBase {
                 finalIntegrate();
                 initial_done = false;
                 if (rec) record(n + 1);
-            } else { // finalIntegrate(n) + initialIntegrate(n+1) in one pass
-                MDB_LAUNCH(launches, k_final_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
-                    dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
+            } else {
+                finalInitialIntegrate();
                 initial_done = true;
             }
         }
@@ -1013,5 +1032,7 @@ SimBase* make_sim(const mdb_params& p, int device)
     if (p.precision == MDB_SP) return new Sim<float>(p, device);
     throw Error("mdb_create: precision must be MDB_SP or MDB_DP");
 }
+
+#include "dd_group.cuh"
 
 } // namespace mdb
