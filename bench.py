@@ -174,14 +174,18 @@ def reference_arm(args, rank, world):
     return 0
 
 
-def workload_config(args, world):
+def workload_config(args, world, grid=(1, 1, 1)):
     return {"workload": "Cu FCC %dx%dx%d unit cells per GPU (%d atoms/GPU), LJ sigma=eps=1 rc=2.5 skin=0.3, reneigh 20, "
                         "verletlist full neighbor lists, %s, %d timesteps per bench step (BASELINE config 1 physics at config 5 per-GPU size)"
                         % (args.nx, args.nx, args.nx, 4 * args.nx ** 3, args.precision.upper(), args.ntimes),
             "nx_per_gpu": args.nx, "ntimes": args.ntimes, "precision": args.precision,
             "l2": "inputs larger than L2 (neighbor list %.1f GB + positions %.2f GB per GPU vs 126 MB L2)"
                   % (4 * args.nx ** 3 * 100 * 4 / 1e9, 4 * args.nx ** 3 * 24 / 1e9),
-            "parallelism": "1 domain per GPU" if world == 1 else "replicas x%d (independent domains, no collective)" % world}
+            "global_box": "%dx%dx%d unit cells = %d atoms" % (args.nx * grid[0], args.nx * grid[1], args.nx * grid[2],
+                                                             4 * args.nx ** 3 * grid[0] * grid[1] * grid[2]),
+            "parallelism": "1 domain" if grid == (1, 1, 1) else
+            "spatial decomposition %dx%dx%d bricks over %d GPU(s), ghost exchange %s"
+            % (grid[0], grid[1], grid[2], world, "by NCCL send/recv over NVLink" if world > 1 else "by device copies")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -199,7 +203,8 @@ def main():
     ap.add_argument("--ref-ntimes", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-sort", action="store_true", help="A/B: keep the reference atom order internally")
+    ap.add_argument("--sort", action="store_true", help="A/B: re-sort the atoms by bin at every rebuild (SORT_ATOMS)")
+    ap.add_argument("--bricks", default=None, help="gx,gy,gz: run a decomposed box on ONE GPU (debug / A-B)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,16 +222,30 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m = importlib.import_module("md-bench_b200")
     dp = args.precision == "dp"
-    P = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx,
-                         ntimes=args.ntimes, half_neigh=args.half)
-    sim = m.Simulation(P, device=local)
-    sim.setStream(torch.cuda.current_stream().cuda_stream)
-    if args.no_sort:
-        sim.setOption("sort_atoms", 0)
-    natoms = sim.createAtom()
+    decomposed = world > 1 or args.bricks is not None
+    stream = torch.cuda.current_stream().cuda_stream
+    if decomposed:
+        # spatial decomposition: one brick per GPU (or --bricks gx,gy,gz on one GPU), ghosts over NCCL/NVLink
+        grid = tuple(int(v) for v in args.bricks.split(",")) if args.bricks else m.dd_grid(world)
+        uid = [m.dd_unique_id() if (rank == 0 and world > 1) else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0)
+        P = m.default_params(precision=m.DP if dp else m.SP, nx=args.nx * grid[0], ny=args.nx * grid[1],
+                             nz=args.nx * grid[2], ntimes=args.ntimes, half_neigh=args.half)
+        sim = m.Decomposition(P, grid, nprocs=world, proc=rank, nccl_id=uid[0], device=local)
+    else:
+        grid = (1, 1, 1)
+        P = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx,
+                             ntimes=args.ntimes, half_neigh=args.half)
+        sim = m.Simulation(P, device=local)
+    sim.setStream(stream)
+    if args.sort:
+        sim.setOption("sort_atoms", 1)
+    natoms = sim.createAtom()          # atoms of the WHOLE job
+    nlocal0 = sim.counts()["Nlocal"]   # atoms on this rank
     sim.setup(adjust=True)
     sim.saveState()
-    listed0, inside0 = sim.countPairs()
+    listed0, inside0 = (0, 0) if decomposed else sim.countPairs()
 
     def one_step():
         sim.restoreState()
@@ -257,8 +276,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     launches = sim.kernelStats()["launches"]
-    listed1, inside1 = sim.countPairs()
-    value = natoms * world * args.ntimes * args.steps / (ms * 1e-3)
+    listed1, inside1 = (0, 0) if decomposed else sim.countPairs()
+    value = natoms * args.ntimes * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (LJ force): CUDA-event time per launch, measured live ----
     sim.setTiming(True)
@@ -267,15 +286,16 @@ def main():
     ks = sim.kernelStats()
     sim.setTiming(False)
     f_ms = ks["force_ms"] / max(1, ks["force_launches"])
+    per_launch_atoms = nlocal0 / (grid[0] * grid[1] * grid[2] // world)   # atoms one force launch covers
     peak_tf = m.measure_fma_peak(m.DP if dp else m.SP, local)
-    ach_tf = FLOP_PER_ATOM_STEP * natoms / (f_ms * 1e-3) * 1e-12
+    ach_tf = FLOP_PER_ATOM_STEP * per_launch_atoms / (f_ms * 1e-3) * 1e-12
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
         hbm_src = "measured (MEASURED_PEAKS.json)"
     except Exception:
         pass
-    ach_gbs = BYTES_PER_ATOM_STEP[args.precision] * natoms / (f_ms * 1e-3) * 1e-9
+    ach_gbs = BYTES_PER_ATOM_STEP[args.precision] * per_launch_atoms / (f_ms * 1e-3) * 1e-9
     roofline = {"kernel": "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
                 "bound": "fp64" if dp else "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
@@ -285,8 +305,10 @@ def main():
                         "bytes_per_atom_step": BYTES_PER_ATOM_STEP[args.precision], "peak_source": hbm_src},
                 "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
                 "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"]),
-                "pairs_per_atom": {"listed_t0": listed0 / natoms, "in_cutoff_t0": inside0 / natoms,
-                                   "listed_end": listed1 / natoms, "in_cutoff_end": inside1 / natoms}}
+                "halo_ms_per_step": (ks["comm_ms"] / args.ntimes) if decomposed else None,
+                "pairs_per_atom": None if decomposed else
+                {"listed_t0": listed0 / natoms, "in_cutoff_t0": inside0 / natoms,
+                 "listed_end": listed1 / natoms, "in_cutoff_end": inside1 / natoms}}
 
     # ---- e2e: same metric through the C ABI with HOST buffers, copies inside the timed region ----
     e2e = None
@@ -294,30 +316,49 @@ def main():
         sim.restoreState()
         real = np.float64 if dp else np.float32
         tdt = torch.float64 if dp else torch.float32
-        hx = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
-        hv = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
-        ox = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
-        ov = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
-        sim.get("x", out=hx.numpy())
-        sim.get("v", out=hv.numpy())
         ksteps = max(1, min(args.steps, 3))
+        if decomposed:
+            cap = nlocal0 + nlocal0 // 8 + 1024     # atoms migrate between ranks during a run
+            htag = torch.empty(nlocal0, dtype=torch.int32, pin_memory=True)
+            hx = torch.empty((3, nlocal0), dtype=tdt, pin_memory=True)
+            hv = torch.empty((3, nlocal0), dtype=tdt, pin_memory=True)
+            otag = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+            ox = torch.empty((3, cap), dtype=tdt, pin_memory=True)
+            ov = torch.empty((3, cap), dtype=tdt, pin_memory=True)
+            sim.get_into("x", htag.numpy(), hx.numpy())
+            sim.get_into("v", None, hv.numpy())
+        else:
+            hx = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+            hv = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+            ox = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+            ov = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+            sim.get("x", out=hx.numpy())
+            sim.get("v", out=hv.numpy())
         for it in range(1 + ksteps):
             if it == 1:
                 barrier()
                 t0 = time.perf_counter()
-            sim.setAtoms(hx.numpy(), hv.numpy())      # H2D from pinned host memory
-            sim.setup(adjust=False)
-            rec_e, _ = sim.run(args.ntimes)            # thermo records come back D2H
-            sim.get("x", out=ox.numpy())               # D2H of the final state
-            sim.get("v", out=ov.numpy())
+            if decomposed:
+                sim.setAtoms(htag.numpy(), hx.numpy(), hv.numpy())   # H2D from pinned host memory
+                sim.setup(adjust=False)
+                rec_e, _ = sim.run(args.ntimes)                      # thermo records come back D2H
+                assert sim.counts()["Nlocal"] <= cap
+                sim.get_into("x", otag.numpy(), ox.numpy())          # D2H of the final state
+                sim.get_into("v", None, ov.numpy())
+            else:
+                sim.setAtoms(hx.numpy(), hv.numpy())
+                sim.setup(adjust=False)
+                rec_e, _ = sim.run(args.ntimes)
+                sim.get("x", out=ox.numpy())
+                sim.get("v", out=ov.numpy())
         barrier()
         te = time.perf_counter() - t0
         tt = torch.tensor([te], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-        nb = natoms * 3 * np.dtype(real).itemsize
-        e2e = {"value": natoms * world * args.ntimes * ksteps / te, "unit": UNIT, "h2d_bytes_per_step": 2 * nb,
+        nb = natoms * 3 * np.dtype(real).itemsize + (natoms * 4 if decomposed else 0)   # whole job
+        e2e = {"value": natoms * args.ntimes * ksteps / te, "unit": UNIT, "h2d_bytes_per_step": 2 * nb,
                "d2h_bytes_per_step": 2 * nb + 8 * 3 * len(rec_e), "steps": ksteps,
                "final_T": float(rec_e[-1][1])}
 
@@ -328,7 +369,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64" if dp else "f32", "data": "synthetic", "config": workload_config(args, world),
+                "dtype": "f64" if dp else "f32", "data": "synthetic", "config": workload_config(args, world, grid),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
                 "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
         print(json.dumps(line))

@@ -208,6 +208,10 @@ void        mdb_dd_destroy(mdb_dd* d);
 int         mdb_dd_setStream(mdb_dd* d, void* cuda_stream);
 int         mdb_dd_sync(mdb_dd* d);
 long long   mdb_dd_createAtom(mdb_dd* d);               /* createAtom per brick; returns global Natoms */
+/* what the file readers (atom.c:199-562) hand over, decomposed: n atoms lying in THIS process's bricks,
+ * HOST SoA buffers of `precision` reals in the global frame, global tags; vx..vz may be NULL */
+int         mdb_dd_setAtoms(mdb_dd* d, long long n, const int* tags, const void* x, const void* y,
+                            const void* z, const void* vx, const void* vy, const void* vz);
 int         mdb_dd_setEam(mdb_dd* d, int nrho, double drho, int nr, double dr, double cut, double mass,
                           const double* frho, const double* zr, const double* rhor);
 int         mdb_dd_setup(mdb_dd* d, int adjust);        /* main.c:58-72 over all bricks */

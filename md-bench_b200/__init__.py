@@ -56,7 +56,7 @@ EXPORTS = [
     "mdb_getEamSplines", "mdb_getNeighbors", "mdb_getGhostMap", "mdb_getNeighborParams",
     "mdb_getStencil", "mdb_getBinCounts", "mdb_getEamFp", "mdb_countPairs", "mdb_measureFmaPeak",
     "mdb_dd_uniqueIdBytes", "mdb_dd_getUniqueId", "mdb_dd_plan", "mdb_dd_schedule", "mdb_dd_create", "mdb_dd_destroy",
-    "mdb_dd_setStream", "mdb_dd_sync", "mdb_dd_createAtom", "mdb_dd_setEam", "mdb_dd_setup",
+    "mdb_dd_setStream", "mdb_dd_sync", "mdb_dd_createAtom", "mdb_dd_setAtoms", "mdb_dd_setEam", "mdb_dd_setup",
     "mdb_dd_reneighbour", "mdb_dd_run", "mdb_dd_computeThermo", "mdb_dd_getCounts", "mdb_dd_getAtoms",
     "mdb_dd_getNeighborTags", "mdb_dd_saveState", "mdb_dd_restoreState", "mdb_dd_setOption",
     "mdb_dd_setTiming", "mdb_dd_getKernelStats", "mdb_dd_resetKernelStats",
@@ -438,6 +438,18 @@ class Decomposition:
         if n < 0:
             raise MdbError(self.L.mdb_last_error().decode())
         return n
+
+    def setAtoms(self, tags, x, v=None):
+        """x, v: (3, n) arrays (one row per coordinate, e.g. views of pinned memory) in the global frame"""
+        tags = np.ascontiguousarray(tags, dtype=np.int32)
+        n = len(tags)
+        assert x.shape == (3, n) and x.dtype == self.np_real and x.flags["C_CONTIGUOUS"]
+        cols = [x[k] for k in range(3)] + ([v[k] for k in range(3)] if v is not None else [None] * 3)
+        self._ck(self.L.mdb_dd_setAtoms(self.h, C.c_longlong(n), _vp(tags), *[_vp(q) for q in cols]))
+
+    def get_into(self, what, tags, out):
+        """like get(), into preallocated (3, n) C-contiguous `out` and (n,) int32 `tags` (may be None)"""
+        self._ck(self.L.mdb_dd_getAtoms(self.h, ord(what), _vp(tags), *[_vp(out[k]) for k in range(3)]))
 
     def setEam(self, nrho, drho, nr, dr, cut, mass, frho, zr, rhor):
         a = [np.ascontiguousarray(t, dtype=np.float64) for t in (frho, zr, rhor)]

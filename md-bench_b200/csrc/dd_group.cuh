@@ -88,6 +88,8 @@ template <class real> struct DomainGroup final : DDBase {
         for (Brick* b : bricks) { b->brick_release(); delete b; }
         d_off_all.release();
         d_sum.release();
+        for (auto& b : st) b.release();
+        st_tag.release(); st_flag.release(); st_scan.release();
         cudaFreeHost(h_off_all);
         cudaFreeHost(h_sum);
         for (auto& e : ev) cudaEventDestroy(e);
@@ -189,6 +191,51 @@ template <class real> struct DomainGroup final : DDBase {
     {
         for (Brick* b : bricks) b->brick_createAtom();
         return gNatoms;
+    }
+    // what an input reader hands over (atom.c:199-562), decomposed: n atoms of THIS process's bricks from
+    // host SoA buffers in the global frame, with their global tags; each is dealt to the brick it lies in
+    DBuf<real> st[6];
+    DBuf<int> st_tag, st_flag, st_scan;
+    void setAtoms(long long n, const int* tags, const void* ax, const void* ay, const void* az, const void* avx,
+        const void* avy, const void* avz) override
+    {
+        if (n < 0 || n > 2000000000LL || !tags || !ax || !ay || !az) throw Error("mdb_dd_setAtoms: bad arguments");
+        const void* h[6] = { ax, ay, az, avx, avy, avz };
+        const bool has_v = avx && avy && avz;
+        for (int k = 0; k < (has_v ? 6 : 3); k++) {
+            st[k].ensure(n + 1, false, stream);
+            MDB_CUDA(cudaMemcpyAsync(st[k].p, h[k], n * sizeof(real), cudaMemcpyHostToDevice, stream));
+        }
+        st_tag.ensure(n + 1, false, stream);
+        st_flag.ensure(n + 1, false, stream);
+        st_scan.ensure(n + 2, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(st_tag.p, tags, n * sizeof(int), cudaMemcpyHostToDevice, stream));
+        long long taken = 0;
+        for (Brick* b : bricks) {
+            b->derive();
+            MDB_LAUNCH(launches, k_dd_select<real>, grid_for(n, 256), 256, 0, stream, (int)n, b->xprd, b->yprd, b->zprd,
+                topo.g[0], topo.g[1], topo.g[2], b->bcoord[0], b->bcoord[1], b->bcoord[2], st[0].p, st[1].p, st[2].p,
+                st_flag.p);
+            b->scanner.exclusive(st_flag.p, st_scan.p, n, st_scan.p + n, stream);
+            int cntb = 0;
+            MDB_CUDA(cudaMemcpyAsync(&cntb, st_scan.p + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaStreamSynchronize(stream));
+            b->Nlocal = cntb;
+            b->Natoms = cntb;
+            b->Nghost = 0;
+            b->ensure_atoms((size_t)cntb + cntb / 4 + 1024, false);
+            if (cntb)
+                MDB_LAUNCH(launches, k_dd_take<real>, grid_for(n, 256), 256, 0, stream, (int)n, st_flag.p, st_scan.p, b->xprd,
+                    b->yprd, b->zprd, topo.g[0], topo.g[1], topo.g[2], b->bcoord[0], b->bcoord[1], b->bcoord[2], st[0].p,
+                    st[1].p, st[2].p, has_v ? st[3].p : (const real*)nullptr, has_v ? st[4].p : (const real*)nullptr,
+                    has_v ? st[5].p : (const real*)nullptr, st_tag.p, b->x.p, b->y.p, b->z.p, b->vx.p, b->vy.p, b->vz.p,
+                    b->type.p, b->orig.p);
+            b->zero3(b->fx.p, b->fy.p, b->fz.p, cntb);
+            b->neigh_ready = false;
+            taken += cntb;
+        }
+        MDB_CUDA(cudaStreamSynchronize(stream)); // host buffers may be reused by the caller
+        if (taken != n) throw Error(fmt("mdb_dd_setAtoms: %lld of %lld atoms lie outside this process's bricks", n - taken, n));
     }
     void setEam(int nrho, double drho, int nr, double dr, double cut, double mass, const double* frho, const double* zr,
         const double* rhor) override

@@ -233,4 +233,37 @@ __global__ void k_dd_to_global(int n, real ox, real oy, real oz, const real* __r
     gx[i] = x[i] + ox; gy[i] = y[i] + oy; gz[i] = z[i] + oz;
 }
 
+// ---- scatter by brick: atoms handed over in the global frame (input readers, bench restarts) ------
+// flag[i] = atom i (wrapped into the box once, like updateAtomsPbc) lies in brick (cx,cy,cz)
+template <class real>
+__global__ void k_dd_select(int n, real ex, real ey, real ez, int gx, int gy, int gz, int cx, int cy, int cz,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, int* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const real X = wrap1(x[i], ex * gx), Y = wrap1(y[i], ey * gy), Z = wrap1(z[i], ez * gz);
+    const int a = min(gx - 1, max(0, (int)floor(X / ex))), b = min(gy - 1, max(0, (int)floor(Y / ey))),
+              c = min(gz - 1, max(0, (int)floor(Z / ez)));
+    flag[i] = a == cx && b == cy && c == cz;
+}
+template <class real>
+__global__ void k_dd_take(int n, const int* __restrict__ flag, const int* __restrict__ scan, real ex, real ey, real ez,
+    int gx, int gy, int gz, int cx, int cy, int cz, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, const real* __restrict__ vx, const real* __restrict__ vy, const real* __restrict__ vz,
+    const int* __restrict__ tag, real* __restrict__ ox, real* __restrict__ oy, real* __restrict__ oz, real* __restrict__ ovx,
+    real* __restrict__ ovy, real* __restrict__ ovz, int* __restrict__ otype, int* __restrict__ otag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const int q = scan[i];
+    ox[q]    = wrap1(x[i], ex * gx) - cx * ex;
+    oy[q]    = wrap1(y[i], ey * gy) - cy * ey;
+    oz[q]    = wrap1(z[i], ez * gz) - cz * ez;
+    ovx[q]   = vx ? vx[i] : (real)0;
+    ovy[q]   = vy ? vy[i] : (real)0;
+    ovz[q]   = vz ? vz[i] : (real)0;
+    otype[q] = 0;
+    otag[q]  = tag[i];
+}
+
 } // namespace mdb

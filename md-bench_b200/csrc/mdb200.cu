@@ -296,6 +296,11 @@ long long mdb_dd_createAtom(mdb_dd* d)
         return -1;
     }
 }
+int mdb_dd_setAtoms(mdb_dd* d, long long n, const int* tags, const void* x, const void* y, const void* z, const void* vx,
+    const void* vy, const void* vz)
+{
+    MDB_DD_TRY(d->g->setAtoms(n, tags, x, y, z, vx, vy, vz))
+}
 int mdb_dd_setEam(mdb_dd* d, int nrho, double drho, int nr, double dr, double cut, double mass, const double* frho,
     const double* zr, const double* rhor)
 {

@@ -65,6 +65,8 @@ struct DDBase {
     virtual void setStream(cudaStream_t s)                                                                   = 0;
     virtual void sync()                                                                                      = 0;
     virtual long long createAtom()                                                                           = 0;
+    virtual void setAtoms(long long n, const int* tags, const void* x, const void* y, const void* z, const void* vx,
+        const void* vy, const void* vz)                                                                      = 0;
     virtual void setup(bool adjust)                                                                          = 0;
     virtual void reneighbour()                                                                               = 0;
     virtual void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers)         = 0;

@@ -318,3 +318,19 @@ def test_dd_save_restore_is_bit_reproducible():
     t2, x2 = d.get("x")
     assert np.array_equal(r1, r2) and np.array_equal(t1, t2) and np.array_equal(x1, x2)
     d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid", [(2, 1, 1), (2, 2, 2)])
+def test_dd_nccl_processes(grid):
+    """one process per GPU, bricks exchange by NCCL send/recv (needs >= 2 GPUs; skipped on a 1-GPU box)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29650 + grid[1]), os.path.join(here, "dd_nccl_worker.py")] + [str(g) for g in grid] + ["12", "60"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DD_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
