@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sort", action="store_true", help="A/B: re-sort the atoms by bin at every rebuild (SORT_ATOMS)")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for mdb_setOption (A/B)")
     ap.add_argument("--bricks", default=None, help="gx,gy,gz: run a decomposed box on ONE GPU (debug / A-B)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +242,9 @@ def main():
     sim.setStream(stream)
     if args.sort:
         sim.setOption("sort_atoms", 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        sim.setOption(k, float(v))
     natoms = sim.createAtom()          # atoms of the WHOLE job
     nlocal0 = sim.counts()["Nlocal"]   # atoms on this rank
     sim.setup(adjust=True)

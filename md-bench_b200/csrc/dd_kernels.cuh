@@ -26,7 +26,16 @@ struct SendTable {
 
 // createAtom (atom.c:67-187) restricted to one brick: one thread per FCC site of the brick, global
 // emission index (closed form, see k_create_atoms) kept as the atom's tag, position brick-local.
-// Atoms are stored in x-fastest site order of the brick.
+// Inside the brick the atoms are stored in the same 8x8x8 sub-box order the reference's generator uses
+// for the whole box: 32 consecutive atoms = one lattice plane of a sub-box, a compact patch whose
+// neighbor gathers share cache lines (x-fastest rows were 1.4x slower in the force kernel, profiles/r1_ab2.txt).
+__device__ __forceinline__ long long fcc_emission_index(int i, int j, int k, int nx, int ny, int nz)
+{
+    const int ox = i >> 3, sx = i & 7, oy = j >> 3, sy = j & 7, oz = k >> 3, sz = k & 7;
+    const int bx = min(8, 2 * nx - 8 * ox), by = min(8, 2 * ny - 8 * oy), bz = min(8, 2 * nz - 8 * oz);
+    const long long sites = 8LL * oz * (2LL * nx) * (2LL * ny) + (2LL * nx) * (8LL * oy) * bz + (8LL * ox) * by * bz;
+    return sites / 2 + (long long)sz * (bx * by / 2) + (long long)sy * (bx / 2) + (((sy + sz) & 1) ? sx / 2 : (sx + 1) / 2);
+}
 template <class real>
 __global__ void k_dd_create_atoms(int gnx, int gny, int gnz, int lnx, int lny, int lnz, int cx, int cy, int cz,
     real alat, real* __restrict__ x, real* __restrict__ y, real* __restrict__ z, real* __restrict__ vx,
@@ -41,11 +50,8 @@ __global__ void k_dd_create_atoms(int gnx, int gny, int gnz, int lnx, int lny, i
     const int j = jl + 2 * lny * cy, k = kl + 2 * lnz * cz;
     const int il = 2 * ihl + ((j + k) & 1);
     const int i  = il + 2 * lnx * cx;
-    const int ox = i >> 3, sx = i & 7, oy = j >> 3, sy = j & 7, oz = k >> 3, sz = k & 7;
-    const int bx = min(8, 2 * gnx - 8 * ox), by = min(8, 2 * gny - 8 * oy), bz = min(8, 2 * gnz - 8 * oz);
-    const long long sites = 8LL * oz * (2LL * gnx) * (2LL * gny) + (2LL * gnx) * (8LL * oy) * bz + (8LL * ox) * by * bz;
-    const long long a = sites / 2 + (long long)sz * (bx * by / 2) + (long long)sy * (bx / 2) +
-                        (((sy + sz) & 1) ? sx / 2 : (sx + 1) / 2);
+    const long long a = fcc_emission_index(i, j, k, gnx, gny, gnz);     // global tag
+    const long long q = fcc_emission_index(il, jl, kl, lnx, lny, lnz); // slot inside the brick
     int n = k * (2 * gny) * (2 * gnx) + j * (2 * gnx) + i + 1;
     double v[3];
 #pragma unroll
@@ -53,14 +59,14 @@ __global__ void k_dd_create_atoms(int gnx, int gny, int gnz, int lnx, int lny, i
         for (int m = 0; m < 5; m++) park_miller(n);
         v[c] = park_miller(n);
     }
-    x[t]    = (real)(0.5 * (double)alat * il);
-    y[t]    = (real)(0.5 * (double)alat * jl);
-    z[t]    = (real)(0.5 * (double)alat * kl);
-    vx[t]   = (real)v[0];
-    vy[t]   = (real)v[1];
-    vz[t]   = (real)v[2];
-    type[t] = 0;
-    tag[t]  = (int)a;
+    x[q]    = (real)(0.5 * (double)alat * il);
+    y[q]    = (real)(0.5 * (double)alat * jl);
+    z[q]    = (real)(0.5 * (double)alat * kl);
+    vx[q]   = (real)v[0];
+    vy[q]   = (real)v[1];
+    vz[q]   = (real)v[2];
+    type[q] = 0;
+    tag[q]  = (int)a;
 }
 
 // ---- migration: atoms that left the brick (the decomposed updateAtomsPbc, pbc.c:59-84) -------------

@@ -42,7 +42,7 @@ template <class real> struct Sim final : SimBase {
     // atoms).  Turn it on (mdb_setOption "sort_atoms") for long runs of diffusing systems.
     bool sort_enabled = false, extmap_valid = false;
     int force_variant = 1, neigh_variant = 3, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
-    bool fuse_integrate = true;
+    bool fuse_integrate = true, sort_rows = false;
     int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
     bool bin_rank_ready = false;
     DBuf<int> bin_rank;
@@ -690,6 +690,8 @@ template <class real> struct Sim final : SimBase {
             }
             break;
         }
+        if (sort_rows)
+            MDB_LAUNCH(launches, k_sort_rows, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, LL, numneigh.p, neighbors.p);
         if (timing) {
             MDB_CUDA(cudaEventRecord(evB, stream));
             MDB_CUDA(cudaEventSynchronize(evB));
@@ -1017,6 +1019,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "list_layout")) list_layout = (int)v;
         else if (!strcmp(name, "sort_order")) sort_order = (int)v;
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
+        else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

@@ -431,6 +431,32 @@ __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, Bi
     if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
 }
 
+// Rows in ascending neighbor index (in place).  The ORDER of a row is free (parity is on index sets);
+// ascending order makes the k-th entries of the 32 atoms of a warp point at nearby / consecutive
+// atoms whenever consecutive atoms are spatial neighbors, so the position gathers of the force kernel
+// touch few 128-byte lines.  Rows arrive nearly sorted (stencil order walks z, y, x), so a plain
+// insertion sort does ~n + inversions steps; the 32 rows of a tile are walked in lockstep, each access
+// one coalesced line.
+__global__ void __launch_bounds__(128) k_sort_rows(int nlocal, NbLayout L, const int* __restrict__ numneigh,
+    int* __restrict__ neighbors)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const int n     = numneigh[i];
+    int* a          = neighbors + L.base(i);
+    const size_t sk = L.sk;
+    for (int k = 1; k < n; k++) {
+        const int v = a[k * sk];
+        int j       = k - 1;
+        int w;
+        while (j >= 0 && (w = a[j * sk]) > v) {
+            a[(j + 1) * sk] = w;
+            j--;
+        }
+        a[(j + 1) * sk] = v;
+    }
+}
+
 // ---- v2 list build --------------------------------------------------------------------------------
 // The membership test must be the reference's exact expression, but 87% of the ~604 candidates per
 // atom are far outside the cutoff.  For DP a single-precision pre-test on float copies of the
