@@ -49,6 +49,7 @@ template <class real> struct Sim final : SimBase {
     NbLayout LL { 0, 0, 0 };                                    // element (i,k) at neighbors[LL.base(i) + k*LL.sk]
     DBuf<float> xf, yf, zf;
     DBuf<float4> pk;
+    DBuf<char> pos4; // packed positions {x,y,z,-} for the p4 force kernel
     DBuf<int> run_off, run_len;
     int nruns = 0;
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
@@ -105,6 +106,7 @@ template <class real> struct Sim final : SimBase {
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
             b->release();
         ghost_msk.release();
+        pos4.release();
         xf.release(); yf.release(); zf.release(); pk.release(); run_off.release(); run_len.release();
         d_partial.release();
         d_red.release();
@@ -724,6 +726,18 @@ template <class real> struct Sim final : SimBase {
                     else
                         MDB_LAUNCH(launches, (k_force_lj_full_v3<real, 8, 2>), grid_for(nthr, 128), 128, 0, stream,
                             Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL.tile_stride, fx.p, fy.p, fz.p);
+                } else if (force_variant == 6 || force_variant == 7) { // packed positions, one gather per neighbor
+                    typedef typename PosOf<real>::type P4;
+                    const int nall = Nlocal + Nghost;
+                    pos4.ensure((size_t)nall * sizeof(P4), false, stream);
+                    MDB_LAUNCH(launches, k_pack_pos4<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, z.p,
+                        (P4*)pos4.p);
+                    if (force_variant == 6)
+                        MDB_LAUNCH(launches, (k_force_lj_full_p4<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                            c2, (const P4*)pos4.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                    else
+                        MDB_LAUNCH(launches, (k_force_lj_full_p4<real, 8>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                            c2, (const P4*)pos4.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
                 } else if (force_variant == 0)
                     MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
                         x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);

@@ -830,6 +830,104 @@ __global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<r
     fz[i] = fiz;
 }
 
+// ---- p4: packed positions ----------------------------------------------------------------------------
+// ncu r1_s2 (profiles/r1_s2_force_raw.txt): the v2 kernel is bound by L1 (l1tex 87%): three 64-bit gathers per
+// neighbor, ~17 sectors per request.  Here the positions are ALSO kept as one 32-byte record {x,y,z,-} per
+// atom (DP; 16 bytes for SP): ONE gather request per neighbor, exactly one sector per lane, fetched with
+// a single 256-bit load (LDG.E.256, new on sm_100).
+struct __align__(32) PosD {
+    double x, y, z, w;
+};
+template <class real> struct PosOf;
+template <> struct PosOf<double> { typedef PosD type; };
+template <> struct PosOf<float> { typedef float4 type; };
+__device__ __forceinline__ void ld_pos(const PosD* p, double& x, double& y, double& z)
+{
+    double w;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+}
+__device__ __forceinline__ void ld_pos(const float4* p, float& x, float& y, float& z)
+{
+    const float4 v = __ldg(p);
+    x = v.x; y = v.y; z = v.z;
+}
+__device__ __forceinline__ void st_pos(PosD* p, double x, double y, double z)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(0.0) : "memory");
+}
+__device__ __forceinline__ void st_pos(float4* p, float x, float y, float z) { *p = make_float4(x, y, z, 0.f); }
+
+template <class real>
+__global__ void k_pack_pos4(int n, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    typename PosOf<real>::type* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_pos(out + i, x[i], y[i], z[i]);
+}
+
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_force_lj_full_p4(int nlocal, LJConst2<real> c,
+    const typename PosOf<real>::type* __restrict__ pos, const int* __restrict__ numneigh, const int* __restrict__ nbT,
+    NbLayout L, real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    real xt, yt, zt;
+    ld_pos(pos + i, xt, yt, zt);
+    const int nn  = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    const int* nb   = nbT + L.base(i);
+    const int nfull = nn - nn % U;
+    int j[U], jn[U];
+    if (nfull > 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = __ldg(nb + (size_t)u * L.sk);
+    }
+    for (int k = 0; k < nfull; k += U) {
+        real dx[U], dy[U], dz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            real xj, yj, zj;
+            ld_pos(pos + j[u], xj, yj, zj);
+            dx[u] = xt - xj; dy[u] = yt - yj; dz[u] = zt - zj;
+        }
+        nb += (size_t)U * L.sk;
+        if (k + U < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = __ldg(nb + (size_t)u * L.sk);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+            if (rsq < c.cutforcesq) {
+                const real f = lj_pair2(rsq, c);
+                fix += dx[u] * f;
+                fiy += dy[u] * f;
+                fiz += dz[u] * f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = jn[u];
+    }
+    for (int k = nfull; k < nn; k++) {
+        const int jj = __ldg(nb);
+        nb += L.sk;
+        real xj, yj, zj;
+        ld_pos(pos + jj, xj, yj, zj);
+        const real dx = xt - xj, dy = yt - yj, dz = zt - zj;
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < c.cutforcesq) {
+            const real f = lj_pair2(rsq, c);
+            fix += dx * f;
+            fiy += dy * f;
+            fiz += dz * f;
+        }
+    }
+    fx[i] = fix;
+    fy[i] = fiy;
+    fz[i] = fiz;
+}
+
 // ---- v3: LPA lanes per atom, row-major list ---------------------------------------------------------
 // With one thread per atom every lane gathers a DIFFERENT neighbor, ~22 distinct 32-byte sectors per
 // 64-bit request, and the L1 data pipe (bank conflicts) becomes the limiter (ncu r1_v2: l1tex 89%,
