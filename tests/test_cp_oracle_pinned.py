@@ -1,0 +1,197 @@
+"""Pins the clusterpair restatement (oracle/cp_oracle.c) to the reference's own clusterpair builds
+(oracle/_ref, built from /root/reference by oracle/Makefile):
+  * cp_dp_aos / cp_sp_aos: the UNMODIFIED AVX-512 builds (M x N = 4 x 8): clusters, bounding boxes, ghost
+    clusters, cluster-pair lists bit for bit (their SIMD force kernels use rcp14, so forces only to 1e-3);
+  * cpref44_* / cpref48_*: the reference's scalar kernel computeForceLJRef with M = 4 (see oracle/Makefile):
+    the same structural checks plus forces and 60-step trajectories to rounding.
+Skipped where the prebuilt reference libraries are absent or the CPU lacks AVX-512 (they are -march=x86-64-v4).
+"""
+import numpy as np
+import pytest
+
+from conftest import ref_usable
+from cpbind import OracleCP, RefCP, initial_atoms, refcp_available
+
+VARIANTS = ["cp_dp_aos", "cp_sp_aos", "cpref44_sp", "cpref44_dp", "cpref48_dp", "cpref48_sp"]
+
+
+def usable(variant):
+    return refcp_available(variant) and ref_usable("vl_dp_aos")
+
+
+def make_pair(variant, nx, half=0):
+    r = RefCP(variant)
+    r.configure(nx=nx, half_neigh=half)
+    r.setup(upto="atoms")
+    # vector width of the build decides the dummy padding of the lists (neighbor.c:395-403)
+    vw = {"cp_dp_aos": 8, "cp_sp_aos": 16}.get(variant, r.N)
+    o = OracleCP(r.dp, r.N, vw)
+    o.configure(nx=nx, half_neigh=half)
+    # identical input bits: the atoms the reference generated (createAtom + adjustThermo)
+    o.set_atoms(r.atoms("x"), r.atoms("v"))
+    return r, o
+
+
+def assert_same_structure(r, o, lists=True, tol=0.0):
+    """tol = 0: identical input bits -> everything bit for bit.  tol > 0 (after some steps of two independent
+    trajectories): coordinates to rounding, all integer structure (membership, ghost maps, lists) still exact."""
+    def same(a, b):
+        if tol == 0.0:
+            return np.array_equal(a, b)
+        fin = np.isfinite(a)
+        return np.array_equal(fin, np.isfinite(b)) and np.abs(a[fin] - b[fin]).max() <= tol * max(1.0, np.abs(a[fin]).max())
+    for k in ("Nlocal", "Nghost", "Nclusters_local", "Nclusters_ghost", "dummy_cj"):
+        assert r.geti(k) == o.geti(k), k
+    rn, rb = r.iclusters()
+    on, ob = o.iclusters()
+    assert np.array_equal(rn, on) and same(rb, ob), "i-clusters differ"
+    rn, rb = r.jclusters()
+    on, ob = o.jclusters()
+    assert np.array_equal(rn, on), "j-cluster sizes differ"
+    live = rn > 0
+    assert same(rb[live], ob[live]), "j-cluster bounding boxes differ"
+    assert np.array_equal(r.icluster_bin(), o.icluster_bin())
+    gm_r, gm_o = r.ghost_map(), o.ghost_map()
+    for k in gm_r:
+        assert np.array_equal(gm_r[k], gm_o[k]), k
+    xr, xo = r.cl("x"), o.cl("x")
+    assert same(xr, xo), "cluster positions (incl. ghost tiles, inf padding) differ"
+    if lists:
+        nr, mr, rr = r.cluster_lists()
+        no, mo, ro = o.cluster_lists()
+        assert np.array_equal(nr, no) and np.array_equal(mr, mo), "list lengths differ"
+        assert all(np.array_equal(a, b) for a, b in zip(rr, ro)), "cluster-pair lists differ as sorted index sets"
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("half", [0, 1])
+def test_setup_structures_bit_exact(variant, half):
+    if not usable(variant):
+        pytest.skip("reference library %s not runnable here" % variant)
+    if half and variant.startswith("cp_"):
+        pytest.skip("half lists of the SIMD builds are exercised through the scalar builds")
+    r, o = make_pair(variant, 6, half)
+    r.buildClusters(); r.defineJClusters(); r.setupPbc(); r.binClusters(); r.buildNeighbor()
+    o.setup()
+    assert_same_structure(r, o)
+    # the t=0 lattice has many equal z per column: the cluster contents only agree if the selection sort's
+    # tie order is reproduced (SURVEY hard part 3)
+    assert np.array_equal(r.cl("v"), o.cl("v"))
+
+
+@pytest.mark.parametrize("variant", ["cpref44_sp", "cpref44_dp", "cpref48_dp", "cpref48_sp"])
+@pytest.mark.parametrize("half", [0, 1])
+def test_forces_and_trajectory_vs_scalar_reference(variant, half):
+    if not usable(variant):
+        pytest.skip("reference library %s not runnable here" % variant)
+    r, o = make_pair(variant, 6, half)
+    r.buildClusters(); r.defineJClusters(); r.setupPbc(); r.binClusters(); r.buildNeighbor()
+    o.setup()
+    r.computeForce(); o.computeForce()
+    tol = 1e-10 if r.dp else 1e-4
+    fr, fo = r.cl("f"), o.cl("f")
+    # t=0 lattice forces are cancellation noise: judge against the largest pair term (~1)
+    assert np.abs(np.nan_to_num(fr) - np.nan_to_num(fo)).max() <= tol * max(1.0, np.abs(np.nan_to_num(fr)).max())
+    for n in range(45):   # two rebuilds (steps 20, 40): clusters are re-sorted and atoms permuted
+        a, b = r.step(n), o.step(n)
+        assert a == b
+        if a:
+            assert_same_structure(r, o, tol=tol)
+    r.updateSingleAtoms(); o.updateSingleAtoms()
+    xr, xo = r.atoms("x"), o.atoms("x")
+    assert np.abs(xr - xo).max() <= tol * np.abs(xr).max()
+    assert np.abs(r.atoms("v") - o.atoms("v")).max() <= (1e-9 if r.dp else 1e-3) * np.abs(r.atoms("v")).max()
+    Tr, Pr = r.thermo()
+    To, Po = o.thermo()
+    assert abs(Tr - To) <= tol * Tr and abs(Pr - Po) <= tol * Pr
+
+
+@pytest.mark.parametrize("variant", ["cp_dp_aos", "cp_sp_aos"])
+def test_simd_builds_rebuild_structures(variant):
+    """unmodified 4x8 builds through two rebuilds: the oracle is stepped with the REFERENCE's positions at each
+    rebuild (their rcp14 forces differ from exact division at 1e-4), so every rebuild sees identical input bits"""
+    if not usable(variant):
+        pytest.skip("reference library %s not runnable here" % variant)
+    r, o = make_pair(variant, 6)
+    r.buildClusters(); r.defineJClusters(); r.setupPbc(); r.binClusters(); r.buildNeighbor()
+    o.setup()
+    r.computeForce()
+    for n in range(40):
+        if r.step(n):
+            # hand the oracle the reference's atoms as they were when its reneighbour() started
+            # (after updateSingleAtoms + updateAtomsPbc the atom arrays are exactly what buildClusters consumed)
+            o2 = OracleCP(r.dp, r.N, o.geti("N") if False else {"cp_dp_aos": 8, "cp_sp_aos": 16}[variant])
+            o2.configure(nx=6)
+            o2.set_atoms(r.atoms("x"), r.atoms("v"))
+            o2.setup()
+            # cluster ORDER inside the reference comes from re-binning its own permuted atoms; o2 bins the same
+            # atom arrays (updateSingleAtoms wrote them in cluster order before the rebuild) -> identical structures
+            assert_same_structure(r, o2)
+
+
+def test_cluster_geometry_matches_survey_goldens():
+    """SURVEY 8c structural goldens of BASELINE config 2 (Cu FCC 32^3, 4x4): 32x32 columns of 128 atoms,
+    32768 full i-clusters, 13900 ghost clusters, 1 849 584 cluster pairs (min 47, max 89), 32768 masked"""
+    x, v = initial_atoms(False, 32)
+    o = OracleCP(False, 4)
+    o.configure(nx=32)
+    o.set_atoms(x, v)
+    o.setup()
+    p = o.neigh_params()
+    assert (p["nbinx"], p["nbiny"]) == (32, 32)
+    assert o.geti("Nclusters_local") == 32768 and o.geti("Nclusters_ghost") == 13900 and o.geti("Nghost") == 55600
+    assert o.geti("dummy_cj") == 46668
+    nn, nm, rows = o.cluster_lists()
+    assert int(nn.sum()) == 1849584 and nn.min() == 47 and nn.max() == 89 and int(nm.sum()) == 32768
+    nat, _ = o.iclusters()
+    assert np.all(nat == 4)
+
+
+class _Fixture:
+    """a committed reference snapshot (tests/golden/cp*.npz, generator make_golden_cp.py) behind the accessor
+    names of RefCP, so assert_same_structure() can compare anything against it"""
+
+    def __init__(self, g, tag="t0"):
+        self.g, self.t = g, tag
+        self.N = int(g["N"])
+
+    def geti(self, k):
+        names = ("Nlocal", "Nghost", "Nclusters_local", "Nclusters_ghost", "dummy_cj")
+        return int(self.g[self.t + "_counts"][names.index(k)])
+
+    def iclusters(self): return self.g[self.t + "_inat"], self.g[self.t + "_ibb"]
+    def jclusters(self): return self.g[self.t + "_jnat"], self.g[self.t + "_jbb"]
+    def icluster_bin(self): return self.g[self.t + "_ibin"]
+    def ghost_map(self): return {k: self.g[self.t + "_" + k] for k in ("border_map", "PBCx", "PBCy", "PBCz")}
+    def cl(self, what): return self.g[self.t + "_cl" + what]
+
+    def cluster_lists(self):
+        nnz = self.g[self.t + "_nnz"]
+        off = np.concatenate([[0], np.cumsum(nnz)])
+        flat = self.g[self.t + "_nbr_flat"]
+        return self.g[self.t + "_numneigh"], self.g[self.t + "_numneigh_masked"], [flat[off[i]:off[i + 1]] for i in range(len(nnz))]
+
+
+@pytest.mark.parametrize("name,vw", [("cp44_sp_nx6", 4), ("cp44_dp_nx6", 4), ("cp44_dp_half_nx6", 4), ("cp48ref_dp_nx6", 8),
+                                     ("cp48_dp_nx6", 8), ("cp48_sp_nx6", 16)])
+def test_oracle_matches_golden_fixture(golden_dir, name, vw):
+    """runs everywhere (no reference library needed): the restatement against the committed reference snapshots"""
+    import os
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    dp = g["x0"].dtype == np.float64
+    o = OracleCP(dp, int(g["N"]), vw)
+    o.configure(nx=int(g["nx"]), half_neigh=int(g["half"]))
+    o.set_atoms(g["x0"], g["v0"])
+    o.setup()
+    assert_same_structure(_Fixture(g), o)
+    assert np.array_equal(g["t0_clv"], o.cl("v"))
+    if "t0_clf" in g:
+        tol = 1e-10 if dp else 1e-4
+        o.computeForce()
+        assert np.abs(np.nan_to_num(g["t0_clf"]) - np.nan_to_num(o.cl("f"))).max() <= tol
+        for n in range(int(g["nsteps"])):
+            o.step(n)
+        o.updateSingleAtoms()
+        assert np.abs(g["tN_x"] - o.atoms("x")).max() <= tol * np.abs(g["tN_x"]).max()
+        T, P = o.thermo()
+        assert abs(T - g["tN_thermo"][0]) <= tol * T
