@@ -76,7 +76,8 @@ def test_setup_structures_bit_exact(variant, half):
     assert_same_structure(r, o)
     # the t=0 lattice has many equal z per column: the cluster contents only agree if the selection sort's
     # tie order is reproduced (SURVEY hard part 3)
-    assert np.array_equal(r.cl("v"), o.cl("v"))
+    real_lane = np.isfinite(o.cl("x")[:len(o.cl("v"))])   # padding lanes of cl_v are uninitialised memory
+    assert np.array_equal(r.cl("v")[real_lane], o.cl("v")[real_lane])
 
 
 @pytest.mark.parametrize("variant", ["cpref44_sp", "cpref44_dp", "cpref48_dp", "cpref48_sp"])
@@ -184,7 +185,8 @@ def test_oracle_matches_golden_fixture(golden_dir, name, vw):
     o.set_atoms(g["x0"], g["v0"])
     o.setup()
     assert_same_structure(_Fixture(g), o)
-    assert np.array_equal(g["t0_clv"], o.cl("v"))
+    real_lane = np.isfinite(o.cl("x")[:len(o.cl("v"))])   # padding lanes of cl_v are uninitialised in the reference too
+    assert np.array_equal(g["t0_clv"][real_lane], o.cl("v")[real_lane])
     if "t0_clf" in g:
         tol = 1e-10 if dp else 1e-4
         o.computeForce()
