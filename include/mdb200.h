@@ -235,6 +235,77 @@ int         mdb_dd_getKernelStats(mdb_dd* d, double* force_ms, long long* force_
                                   long long* neigh_launches, long long* total_launches, double* comm_ms);
 int         mdb_dd_resetKernelStats(mdb_dd* d);
 
+/* ---- clusterpair scheme (reference src/clusterpair/, OPT_SCHEME=clusterpair) --------------------- */
+/* GROMACS-style M x N cluster pairs with M = 4 i-atoms per cluster (force.h:48) and cluster_n = 4 or 8
+ * j-atoms per cluster (the reference fixes N at compile time through VECTOR_WIDTH, force.h:50-58; here
+ * it is chosen at create time).  The driver of this scheme (clusterpair/main.c:40-93, 225-300) calls
+ * plain functions buildClusters / defineJClusters / binClusters / updateSingleAtoms (neighbor.h:42-50)
+ * next to the function pointers computeForce (force.h), buildNeighbor (neighbor.h:40),
+ * initialIntegrate / finalIntegrate (integrate.h:14), updatePbc / updateAtomsPbc (pbc.h); one entry
+ * point per function below.  Cluster data use the reference's layout (force.h:62-91): tile t of
+ * cluster_n atoms stored as [x0..x(N-1) | y0.. | z0..]; tile t is j-cluster t and, for N = 8, also
+ * the i-clusters 2t (lanes 0-3) and 2t+1 (lanes 4-7); ghost j-clusters follow the local ones and the
+ * last tile (dummy_cj) is all +infinity.  p->layout applies to atom positions only, velocities are
+ * always SoA (clusterpair/atom.h:66-92).  pbc_x/y/z are ignored like in the reference (pbc.c:183-323). */
+typedef struct mdb_cp mdb_cp;
+mdb_cp*     mdb_cp_create(const mdb_params* p, int cluster_n, int device);
+void        mdb_cp_destroy(mdb_cp* c);
+int         mdb_cp_setStream(mdb_cp* c, void* cuda_stream);
+int         mdb_cp_sync(mdb_cp* c);
+int         mdb_cp_setOption(mdb_cp* c, const char* name, double value);
+long long   mdb_cp_createAtom(mdb_cp* c);                         /* clusterpair/atom.c:49-180 */
+int         mdb_cp_setAtoms(mdb_cp* c, long long n, const void* x, const void* y, const void* z,
+                            const void* vx, const void* vy, const void* vz);
+/* atom arrays as they are (refreshed by updateSingleAtoms only, like the reference's); which = 'x'|'v';
+ * tag (may be NULL) = index each atom had when it was handed over (the reference does not track it) */
+int         mdb_cp_getAtoms(mdb_cp* c, int which, void* x, void* y, void* z, int* tag);
+/* v = {Natoms, Nlocal, Nghost (atoms), Nclusters_local, Nclusters_ghost, dummy_cj, maxneighs,
+ *      local j-clusters (= local tiles)} */
+int         mdb_cp_getCounts(mdb_cp* c, long long v[8]);
+int         mdb_cp_setupThermo(mdb_cp* c);
+int         mdb_cp_adjustThermo(mdb_cp* c);
+int         mdb_cp_computeThermo(mdb_cp* c, double* T, double* P); /* reads the ATOM arrays, thermo.c:55-80 */
+int         mdb_cp_setupNeighbor(mdb_cp* c);                      /* neighbor.c:70-172 */
+int         mdb_cp_buildClusters(mdb_cp* c);                      /* neighbor.c:663-753 (+binAtoms, sortAtomsByZCoord) */
+int         mdb_cp_defineJClusters(mdb_cp* c);                    /* neighbor.c:755-873 */
+int         mdb_cp_setupPbc(mdb_cp* c);                           /* pbc.c:183-323 (incl. updatePbc(first)) */
+int         mdb_cp_binClusters(mdb_cp* c);                        /* neighbor.c:875-1021 */
+int         mdb_cp_buildNeighbor(mdb_cp* c);                      /* buildNeighborCPU, neighbor.c:262-481 */
+int         mdb_cp_pruneNeighbor(mdb_cp* c);                      /* pruneNeighborCPU, neighbor.c:483-531 */
+int         mdb_cp_updateSingleAtoms(mdb_cp* c);                  /* neighbor.c:1023-1049 */
+int         mdb_cp_updateAtomsPbc(mdb_cp* c);                     /* updateAtomsPbcCPU, pbc.c:117-144 */
+int         mdb_cp_updatePbc(mdb_cp* c, int first);               /* updatePbcCPU, pbc.c:45-114 */
+double      mdb_cp_computeForce(mdb_cp* c);                       /* computeForceLJ 4xN / 2xNN / Ref, force_lj.c:47-164 */
+int         mdb_cp_initialIntegrate(mdb_cp* c);                   /* integrate.c:23-44 */
+int         mdb_cp_finalIntegrate(mdb_cp* c);                     /* integrate.c:46-63 */
+int         mdb_cp_setup(mdb_cp* c, int adjust);                  /* clusterpair/main.c:40-76 after the atoms exist */
+int         mdb_cp_reneighbour(mdb_cp* c);                        /* clusterpair/main.c:78-93 */
+/* clusterpair/main.c:225-300; thermo records are taken from the atom arrays exactly when the reference
+ * takes them (so an intermediate record shows the velocities of the last rebuild) */
+int         mdb_cp_run(mdb_cp* c, int nsteps, double* thermo_out, int max_records, int* nrecords,
+                       double* timers);
+int         mdb_cp_saveState(mdb_cp* c);                          /* atom arrays x, v kept on the device */
+int         mdb_cp_restoreState(mdb_cp* c);
+int         mdb_cp_setTiming(mdb_cp* c, int on);
+int         mdb_cp_getKernelStats(mdb_cp* c, double* force_ms, long long* force_launches, double* neigh_ms,
+                                  long long* neigh_launches, long long* total_launches);
+int         mdb_cp_resetKernelStats(mdb_cp* c);
+/* cluster pairs listed, atom pairs inside the force cutoff (clusterpair/stats.h equivalents) */
+int         mdb_cp_countPairs(mdb_cp* c, long long* cluster_pairs, long long* atom_pairs_in_cutoff);
+/* parity accessors: which = 'i' (Nclusters_local entries) | 'j' (local + ghost j-clusters):
+ * Cluster.natoms and the bounding box {minx,maxx,miny,maxy,minz,maxz} (atom.h:19-24) */
+int         mdb_cp_getClusters(mdb_cp* c, int which, int* natoms, void* bbox);
+/* cl_x / cl_v / cl_f ('x' | 'v' | 'f') as tiles x 3 x cluster_n reals; 'x': local + ghost tiles, else local */
+int         mdb_cp_getClusterData(mdb_cp* c, int which, void* out);
+int         mdb_cp_getClusterTags(mdb_cp* c, int* tags);          /* (local + ghost tiles) x cluster_n, -1 = padding */
+int         mdb_cp_getClusterBins(mdb_cp* c, int* icluster_bin);  /* Atom.icluster_bin */
+/* Neighbor.numneigh / numneigh_masked / neighbors (row-major rows of row_stride ints), neighbor.h:31-40 */
+int         mdb_cp_getLists(mdb_cp* c, int* numneigh, int* numneigh_masked, int* neighbors, int row_stride);
+int         mdb_cp_getGhostMap(mdb_cp* c, int* border_map, int* PBCx, int* PBCy, int* PBCz);
+/* ints {nbinx,nbiny,mbinx,mbiny,mbins,mbinxlo,mbinylo,nstencil}, reals {binsizex,binsizey,bininvx,
+ * bininvy,cutneighsq,cutneigh,xprd,yprd,zprd,rbb_sq}; stencil (may be NULL) nstencil ints */
+int         mdb_cp_getNeighborParams(mdb_cp* c, int ints[8], double reals[10], int* stencil);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* FMA issue-rate micro-benchmark on `device`: dense FP32 (MDB_SP) or FP64 (MDB_DP) vector peak in
  * TFLOP/s (FMA = 2 flop).  The roofline denominator for the force kernels. */

@@ -60,6 +60,15 @@ EXPORTS = [
     "mdb_dd_reneighbour", "mdb_dd_run", "mdb_dd_computeThermo", "mdb_dd_getCounts", "mdb_dd_getAtoms",
     "mdb_dd_getNeighborTags", "mdb_dd_saveState", "mdb_dd_restoreState", "mdb_dd_setOption",
     "mdb_dd_setTiming", "mdb_dd_getKernelStats", "mdb_dd_resetKernelStats",
+    "mdb_cp_create", "mdb_cp_destroy", "mdb_cp_setStream", "mdb_cp_sync", "mdb_cp_setOption", "mdb_cp_createAtom",
+    "mdb_cp_setAtoms", "mdb_cp_getAtoms", "mdb_cp_getCounts", "mdb_cp_setupThermo", "mdb_cp_adjustThermo",
+    "mdb_cp_computeThermo", "mdb_cp_setupNeighbor", "mdb_cp_buildClusters", "mdb_cp_defineJClusters", "mdb_cp_setupPbc",
+    "mdb_cp_binClusters", "mdb_cp_buildNeighbor", "mdb_cp_pruneNeighbor", "mdb_cp_updateSingleAtoms",
+    "mdb_cp_updateAtomsPbc", "mdb_cp_updatePbc", "mdb_cp_computeForce", "mdb_cp_initialIntegrate",
+    "mdb_cp_finalIntegrate", "mdb_cp_setup", "mdb_cp_reneighbour", "mdb_cp_run", "mdb_cp_saveState",
+    "mdb_cp_restoreState", "mdb_cp_setTiming", "mdb_cp_getKernelStats", "mdb_cp_resetKernelStats", "mdb_cp_countPairs",
+    "mdb_cp_getClusters", "mdb_cp_getClusterData", "mdb_cp_getClusterTags", "mdb_cp_getClusterBins", "mdb_cp_getLists",
+    "mdb_cp_getGhostMap", "mdb_cp_getNeighborParams",
 ]
 
 _lib = None
@@ -91,6 +100,12 @@ def load_library(build=True):
     L.mdb_dd_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.mdb_dd_createAtom.restype = C.c_longlong
     L.mdb_dd_createAtom.argtypes = [C.c_void_p]
+    L.mdb_cp_create.restype = C.c_void_p
+    L.mdb_cp_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int]
+    L.mdb_cp_createAtom.restype = C.c_longlong
+    L.mdb_cp_createAtom.argtypes = [C.c_void_p]
+    L.mdb_cp_computeForce.restype = C.c_double
+    L.mdb_cp_computeForce.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -507,3 +522,222 @@ class Decomposition:
                                               C.byref(tl), C.byref(cm)))
         return dict(force_ms=fm.value, force_launches=fl.value, neigh_ms=nm.value, neigh_launches=nl.value,
                     launches=tl.value, comm_ms=cm.value)
+
+
+class ClusterSimulation:
+    """One CLUSTERPAIR simulation domain on one GPU (opaque mdb_cp): the reference's OPT_SCHEME=clusterpair with
+    M = 4 and cluster_n = 4 | 8 (src/clusterpair/).  Method names are the reference driver's
+    (clusterpair/main.c:40-93, neighbor.h:42-50); the accessors return what the reference keeps in
+    Atom / Neighbor (cluster tiles as (tiles, 3, N) arrays)."""
+
+    M = 4
+
+    def __init__(self, params=None, cluster_n=4, device=0, **kw):
+        self.L = load_library()
+        self.params = params if params is not None else default_params(**kw)
+        self.dp = self.params.precision == DP
+        self.aos = self.params.layout == AOS
+        self.np_real = np.float64 if self.dp else np.float32
+        self.N = cluster_n
+        h = self.L.mdb_cp_create(C.byref(self.params), cluster_n, device)
+        if not h:
+            raise MdbError(self.L.mdb_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mdb_cp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+
+    # ---- atoms ----
+    def createAtom(self):
+        n = self.L.mdb_cp_createAtom(self.h)
+        if n < 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+        return n
+
+    def setAtoms(self, x, v=None):
+        """x, v: (n,3) arrays; positions go over in this ctx's layout, velocities always SoA"""
+        n = x.shape[0]
+        x = np.ascontiguousarray(x, dtype=self.np_real)
+        bx = [x, None, None] if self.aos else [np.ascontiguousarray(x[:, k]) for k in range(3)]
+        bv = [None] * 3 if v is None else [np.ascontiguousarray(np.asarray(v, dtype=self.np_real)[:, k]) for k in range(3)]
+        self._ck(self.L.mdb_cp_setAtoms(self.h, C.c_longlong(n), *[_vp(b) for b in bx], *[_vp(b) for b in bv]))
+
+    set_atoms = setAtoms
+
+    def counts(self):
+        v = (C.c_longlong * 8)()
+        self._ck(self.L.mdb_cp_getCounts(self.h, v))
+        k = ("Natoms", "Nlocal", "Nghost", "Nclusters_local", "Nclusters_ghost", "dummy_cj", "maxneighs", "ncj")
+        return dict(zip(k, [int(q) for q in v]))
+
+    def geti(self, k):
+        if k in ("reneigh_every", "nstat", "half_neigh"):
+            return getattr(self.params, k)
+        return self.counts()[k]
+
+    def atoms(self, what, tags=False):
+        n = self.counts()["Nlocal"]
+        t = np.empty(n, np.int32) if tags else None
+        if what == "x" and self.aos:
+            a = np.empty((n, 3), self.np_real)
+            self._ck(self.L.mdb_cp_getAtoms(self.h, ord("x"), _vp(a), None, None, _vp(t)))
+        else:
+            cols = [np.empty(n, self.np_real) for _ in range(3)]
+            self._ck(self.L.mdb_cp_getAtoms(self.h, ord(what), *[_vp(q) for q in cols], _vp(t)))
+            a = np.stack(cols, axis=1)
+        return (a, t) if tags else a
+
+    def setOption(self, name, value): self._ck(self.L.mdb_cp_setOption(self.h, name.encode(), C.c_double(value)))
+    def saveState(self): self._ck(self.L.mdb_cp_saveState(self.h))
+    def restoreState(self): self._ck(self.L.mdb_cp_restoreState(self.h))
+    def setStream(self, stream_ptr): self._ck(self.L.mdb_cp_setStream(self.h, C.c_void_p(stream_ptr)))
+    def sync(self): self._ck(self.L.mdb_cp_sync(self.h))
+
+    # ---- operators ----
+    def setupNeighbor(self): self._ck(self.L.mdb_cp_setupNeighbor(self.h))
+    def setupThermo(self): self._ck(self.L.mdb_cp_setupThermo(self.h))
+    def adjustThermo(self): self._ck(self.L.mdb_cp_adjustThermo(self.h))
+    def buildClusters(self): self._ck(self.L.mdb_cp_buildClusters(self.h))
+    def defineJClusters(self): self._ck(self.L.mdb_cp_defineJClusters(self.h))
+    def setupPbc(self): self._ck(self.L.mdb_cp_setupPbc(self.h))
+    def binClusters(self): self._ck(self.L.mdb_cp_binClusters(self.h))
+    def buildNeighbor(self): self._ck(self.L.mdb_cp_buildNeighbor(self.h))
+    def pruneNeighbor(self): self._ck(self.L.mdb_cp_pruneNeighbor(self.h))
+    def updateSingleAtoms(self): self._ck(self.L.mdb_cp_updateSingleAtoms(self.h))
+    def updateAtomsPbc(self): self._ck(self.L.mdb_cp_updateAtomsPbc(self.h))
+    def updatePbc(self, first=False): self._ck(self.L.mdb_cp_updatePbc(self.h, int(first)))
+    def initialIntegrate(self): self._ck(self.L.mdb_cp_initialIntegrate(self.h))
+    def finalIntegrate(self): self._ck(self.L.mdb_cp_finalIntegrate(self.h))
+    def reneighbour(self): self._ck(self.L.mdb_cp_reneighbour(self.h))
+    def setup(self, adjust=False): self._ck(self.L.mdb_cp_setup(self.h, int(adjust)))
+
+    def computeForce(self):
+        t = self.L.mdb_cp_computeForce(self.h)
+        if t < 0:
+            raise MdbError(self.L.mdb_last_error().decode())
+        return t
+
+    def thermo(self):
+        T, P = C.c_double(), C.c_double()
+        self._ck(self.L.mdb_cp_computeThermo(self.h, C.byref(T), C.byref(P)))
+        return T.value, P.value
+
+    computeThermo = thermo
+
+    def step(self, n):
+        """one iteration of the reference loop, clusterpair/main.c:246-266 (operator by operator)"""
+        reneigh = (n + 1) % self.params.reneigh_every == 0
+        self.initialIntegrate()
+        if reneigh:
+            self.reneighbour()
+        else:
+            self.updatePbc(False)
+        self.computeForce()
+        self.finalIntegrate()
+        return reneigh
+
+    def run(self, nsteps):
+        nstat = max(1, self.params.nstat)
+        out = np.zeros(3 * (nsteps // nstat + 4))
+        nrec = C.c_int()
+        tm = (C.c_double * 3)()
+        self._ck(self.L.mdb_cp_run(self.h, nsteps, _vp(out), len(out) // 3, C.byref(nrec), tm))
+        return out[:3 * nrec.value].reshape(-1, 3), dict(TOTAL=tm[0], FORCE=tm[1], NEIGH=tm[2])
+
+    def setTiming(self, on): self._ck(self.L.mdb_cp_setTiming(self.h, int(on)))
+
+    def kernelStats(self):
+        fm, nm = C.c_double(), C.c_double()
+        fl, nl, tl = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        self._ck(self.L.mdb_cp_getKernelStats(self.h, C.byref(fm), C.byref(fl), C.byref(nm), C.byref(nl), C.byref(tl)))
+        return dict(force_ms=fm.value, force_launches=fl.value, neigh_ms=nm.value, neigh_launches=nl.value,
+                    launches=tl.value)
+
+    def resetKernelStats(self): self._ck(self.L.mdb_cp_resetKernelStats(self.h))
+
+    def countPairs(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        self._ck(self.L.mdb_cp_countPairs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- parity accessors (same names as the checker's bindings use for the reference) ----
+    def tiles(self):
+        c = self.counts()
+        return c["ncj"], c["Nclusters_ghost"]
+
+    def _clusters(self, which, n):
+        nat = np.empty(n, np.int32)
+        bb = np.empty((n, 6), self.np_real)
+        self._ck(self.L.mdb_cp_getClusters(self.h, ord(which), _vp(nat), _vp(bb)))
+        return nat, bb
+
+    def iclusters(self): return self._clusters("i", self.counts()["Nclusters_local"])
+
+    def jclusters(self):
+        ncj, ngh = self.tiles()
+        return self._clusters("j", ncj + ngh)
+
+    def cl(self, what):
+        ncj, ngh = self.tiles()
+        nt = ncj + (ngh if what == "x" else 0)
+        a = np.empty((nt, 3, self.N), self.np_real)
+        self._ck(self.L.mdb_cp_getClusterData(self.h, ord(what), _vp(a)))
+        return a
+
+    def cluster_tags(self):
+        ncj, ngh = self.tiles()
+        a = np.empty((ncj + ngh, self.N), np.int32)
+        self._ck(self.L.mdb_cp_getClusterTags(self.h, _vp(a)))
+        return a
+
+    def icluster_bin(self):
+        a = np.empty(self.counts()["Nclusters_local"], np.int32)
+        self._ck(self.L.mdb_cp_getClusterBins(self.h, _vp(a)))
+        return a
+
+    def cluster_lists(self, strip_dummy=True):
+        """numneigh, numneigh_masked, [sorted j-cluster ids per i-cluster]"""
+        c = self.counts()
+        ncl, mx = c["Nclusters_local"], c["maxneighs"]
+        nn, nm = np.empty(ncl, np.int32), np.empty(ncl, np.int32)
+        nb = np.empty((ncl, mx), np.int32)
+        self._ck(self.L.mdb_cp_getLists(self.h, _vp(nn), _vp(nm), _vp(nb), mx))
+        return nn, nm, [np.sort(nb[ci, :nn[ci]]) for ci in range(ncl)]
+
+    def raw_lists(self):
+        c = self.counts()
+        ncl, mx = c["Nclusters_local"], c["maxneighs"]
+        nn, nm = np.empty(ncl, np.int32), np.empty(ncl, np.int32)
+        nb = np.empty((ncl, mx), np.int32)
+        self._ck(self.L.mdb_cp_getLists(self.h, _vp(nn), _vp(nm), _vp(nb), mx))
+        return nn, nm, nb
+
+    def ghost_map(self):
+        ng = self.counts()["Nclusters_ghost"]
+        a = [np.empty(ng, np.int32) for _ in range(4)]
+        self._ck(self.L.mdb_cp_getGhostMap(self.h, *[_vp(q) for q in a]))
+        return dict(border_map=a[0], PBCx=a[1], PBCy=a[2], PBCz=a[3])
+
+    def neigh_params(self):
+        iv = (C.c_int * 8)()
+        rv = (C.c_double * 10)()
+        self._ck(self.L.mdb_cp_getNeighborParams(self.h, iv, rv, None))
+        d = dict(zip(("nbinx", "nbiny", "mbinx", "mbiny", "mbins", "mbinxlo", "mbinylo", "nstencil"), [int(q) for q in iv]))
+        d.update(zip(("binsizex", "binsizey", "bininvx", "bininvy", "cutneighsq", "cutneigh", "xprd", "yprd", "zprd",
+                      "rbb_sq"), [float(q) for q in rv]))
+        st = np.empty(d["nstencil"], np.int32)
+        self._ck(self.L.mdb_cp_getNeighborParams(self.h, iv, rv, _vp(st)))
+        d["stencil"] = st
+        return d

@@ -1,0 +1,674 @@
+// cp_kernels.cuh -- sm_100a kernels of the CLUSTERPAIR scheme (GROMACS-style M x N cluster pairs;
+// reference src/clusterpair/).  M = 4 i-atoms per cluster like every CPU build of the reference
+// (force.h:48); N = 4 or 8 is a template parameter.
+//
+// Data layout in HBM = the reference's cluster layout (force.h:62-91), because it is
+// already what a GPU wants: a TILE of W = N atoms stored as [x0..x(W-1) | y0.. | z0..], tiles
+// consecutive.  Tile t is j-cluster t; for N = 8 it also holds the two i-clusters 2t (lanes 0-3) and
+// 2t+1 (lanes 4-7).  Ghost j-clusters follow the local ones, then one all-infinity dummy tile.
+// A j-cluster is fetched with three (N = 4) or six (N = 8) 256-bit loads in DP, three float4 loads in
+// SP, all lanes of an i-cluster reading the same addresses (broadcast): no gathers, which is what
+// bounds the verletlist kernel.
+#pragma once
+#include <cmath>
+
+#include "mdb_util.cuh"
+
+namespace mdb {
+
+constexpr int CP_M = 4;
+
+// geometry of clusterpair/neighbor.c:26-45 (2-D bins = columns along z)
+template <class real> struct CpGeom {
+    real xprd, yprd, zprd, bininvx, bininvy, cutneigh, cutneighsq, rbb_sq;
+    int nbinx, nbiny, mbinxlo, mbinylo, mbinx, mbiny, mbins;
+};
+
+// coord2bin2D, clusterpair/neighbor.c:601-618: single rounded multiplies, truncation like C's (int)
+template <class real> __device__ __forceinline__ void cp_coord2bin2D(const CpGeom<real>& g, real x, real y, int& ix, int& iy)
+{
+    ix = axis2bin(x, g.xprd, g.bininvx, g.nbinx, g.mbinxlo);
+    iy = axis2bin(y, g.yprd, g.bininvy, g.nbiny, g.mbinylo);
+}
+template <class real> __device__ __forceinline__ int cp_coord2bin(const CpGeom<real>& g, real x, real y)
+{
+    int ix, iy;
+    cp_coord2bin2D(g, x, y, ix, iy);
+    const int b = iy * g.mbinx + ix + 1; // neighbor.c:599 (with its "+ 1")
+    return b < 0 ? 0 : (b >= g.mbins ? g.mbins - 1 : b);
+}
+
+// ---- index helpers: force.h:62-91 with M = 4 ---------------------------------------------------------
+template <int N> __device__ __host__ __forceinline__ int cp_cj0(int ci) { return N == CP_M ? ci : ci >> 1; }
+template <int N> __device__ __host__ __forceinline__ size_t cp_ci_base3(int ci) // CI_VECTOR_BASE_INDEX
+{
+    return N == CP_M ? (size_t)ci * N * 3 : (size_t)(ci >> 1) * N * 3 + (ci & 1) * (N >> 1);
+}
+template <int N> __device__ __host__ __forceinline__ size_t cp_ci_base1(int ci) // CI_SCALAR_BASE_INDEX
+{
+    return N == CP_M ? (size_t)ci * N : (size_t)(ci >> 1) * N + (ci & 1) * (N >> 1);
+}
+
+// ---- binAtoms (neighbor.c:620-651): histogram / fill; bins then sorted inside k_cp_sort_emit ----------
+template <class real>
+__global__ void k_cp_bin_count(int n, CpGeom<real> g, const real* __restrict__ x, const real* __restrict__ y,
+    int* __restrict__ atom_bin, int* __restrict__ bincount)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = cp_coord2bin(g, x[i], y[i]);
+    atom_bin[i] = b;
+    atomicAdd(&bincount[b], 1);
+}
+// clusters per bin (neighbor.c:687-690): ceil(c / M), made even when N > M
+template <int N> __global__ void k_cp_clusters_per_bin(int mbins, const int* __restrict__ bincount, int* __restrict__ ncl,
+    int* __restrict__ maxcount)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int c       = 0;
+    if (b < mbins) {
+        c     = bincount[b];
+        int k = (c + CP_M - 1) / CP_M;
+        if (N > CP_M && (k & 1)) k++;
+        ncl[b] = k;
+    }
+    c = __reduce_max_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c > 0) atomicMax(maxcount, c);
+}
+
+// One block per bin: order the bin's atoms like binAtoms + sortAtomsByZCoord (neighbor.c:620-683) and emit the
+// bin's clusters (buildClusters, neighbor.c:685-775).
+//   binAtoms appends atoms in ascending index; sortAtomsByZCoord is a selection sort with strict '<' and
+//   SWAP, so among equal z the final order is not that of a stable sort (SURVEY hard part 3).  If all z
+//   of the bin are distinct the result is simply the sorted order (rank sort); otherwise the selection sort
+//   is replayed: one parallel arg-min (lowest position wins ties) + swap per round.
+template <class real, int N>
+__global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __restrict__ binstart, const int* __restrict__ binatoms_in,
+    const int* __restrict__ clbase, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const real* __restrict__ vx, const real* __restrict__ vy, const real* __restrict__ vz, const int* __restrict__ tag,
+    real* __restrict__ cl_x, real* __restrict__ cl_v, int* __restrict__ cl_tag, int* __restrict__ inat,
+    real* __restrict__ ibb, int* __restrict__ ibin)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int bin = blockIdx.x;
+    const int s0 = binstart[bin], c = binstart[bin + 1] - s0;
+    if (c == 0) return;
+    real* sz  = reinterpret_cast<real*>(smem_raw);        // z of the atom at each position
+    int* sid  = reinterpret_cast<int*>(sz + c);           // atom index at each position
+    int* sout = sid + c;                                  // result order
+    __shared__ int s_ties;
+    __shared__ real s_minz[4];
+    __shared__ int s_minp[4];
+    const int t = threadIdx.x;
+    if (t == 0) s_ties = 0;
+    // ascending atom index = the order binAtoms filled the bin (rank sort on the unique indices)
+    for (int k = t; k < c; k += blockDim.x) sout[k] = binatoms_in[s0 + k];
+    __syncthreads();
+    for (int k = t; k < c; k += blockDim.x) {
+        const int v = sout[k];
+        int r       = 0;
+        for (int q = 0; q < c; q++) r += sout[q] < v;
+        sid[r] = v;
+        sz[r]  = z[v];
+    }
+    __syncthreads();
+    // rank by (z, position); detect ties
+    for (int k = t; k < c; k += blockDim.x) {
+        const real zk = sz[k];
+        int r = 0, tie = 0;
+        for (int q = 0; q < c; q++) {
+            const real zq = sz[q];
+            r += (zq < zk) || (zq == zk && q < k);
+            tie |= (zq == zk && q != k);
+        }
+        sout[r] = sid[k];
+        if (tie) s_ties = 1;
+    }
+    __syncthreads();
+    if (s_ties) { // replay the selection sort on (sz, sid)
+        for (int a = 0; a < c - 1; a++) {
+            real mz = INFINITY;
+            int mp  = 0x7fffffff;
+            for (int k = a + t; k < c; k += blockDim.x) {
+                const real zk = sz[k];
+                if (zk < mz) { mz = zk; mp = k; } // ascending k: first position wins
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const real oz = __shfl_down_sync(0xffffffffu, mz, d);
+                const int op  = __shfl_down_sync(0xffffffffu, mp, d);
+                if (oz < mz || (oz == mz && op < mp)) { mz = oz; mp = op; }
+            }
+            if ((t & 31) == 0) { s_minz[t >> 5] = mz; s_minp[t >> 5] = mp; }
+            __syncthreads();
+            if (t == 0) {
+                for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+                    if (s_minz[w] < mz || (s_minz[w] == mz && s_minp[w] < mp)) { mz = s_minz[w]; mp = s_minp[w]; }
+                if (mp >= c) mp = a; // non-finite z (blown-up run): keep the element in place
+                // neighbor.c:676-677: bin_ptr[ac_i] = min_idx; bin_ptr[min_ac] = i
+                const int ia = sid[a];
+                const real za = sz[a];
+                sid[a] = sid[mp]; sz[a] = sz[mp];
+                sid[mp] = ia; sz[mp] = za;
+            }
+            __syncthreads();
+        }
+        for (int k = t; k < c; k += blockDim.x) sout[k] = sid[k];
+        __syncthreads();
+    }
+    // emit clusters of this bin
+    int ncl = (c + CP_M - 1) / CP_M;
+    if (N > CP_M && (ncl & 1)) ncl++;
+    const int base = clbase[bin];
+    for (int k = t; k < ncl; k += blockDim.x) {
+        const int ci = base + k;
+        real* cx = cl_x + cp_ci_base3<N>(ci);
+        real* cv = cl_v + cp_ci_base3<N>(ci);
+        int* ct  = cl_tag + cp_ci_base1<N>(ci);
+        real lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        int nat = 0;
+#pragma unroll
+        for (int cii = 0; cii < CP_M; cii++) {
+            const int ac = k * CP_M + cii;
+            if (ac < c) {
+                const int i = sout[ac];
+                const real p[3] = { x[i], y[i], z[i] };
+                cx[cii] = p[0]; cx[N + cii] = p[1]; cx[2 * N + cii] = p[2];
+                cv[cii] = vx[i]; cv[N + cii] = vy[i]; cv[2 * N + cii] = vz[i];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    if (lo[d] > p[d]) lo[d] = p[d];
+                    if (hi[d] < p[d]) hi[d] = p[d];
+                }
+                ct[cii] = tag[i];
+                nat++;
+            } else {
+                cx[cii] = INFINITY; cx[N + cii] = INFINITY; cx[2 * N + cii] = INFINITY;
+                cv[cii] = 0; cv[N + cii] = 0; cv[2 * N + cii] = 0;
+                ct[cii] = -1;
+            }
+        }
+        inat[ci] = nat;
+        ibin[ci] = bin;
+        real* bb = ibb + (size_t)ci * 6;
+        bb[0] = lo[0]; bb[1] = hi[0]; bb[2] = lo[1]; bb[3] = hi[1]; bb[4] = lo[2]; bb[5] = hi[2];
+    }
+}
+
+// defineJClusters, neighbor.c:777-895 (M == N: copy; 2M == N: union of the two i-clusters of the tile)
+template <class real, int N>
+__global__ void k_cp_define_j(int ncj, const int* __restrict__ inat, const real* __restrict__ ibb, int* __restrict__ jnat,
+    real* __restrict__ jbb)
+{
+    const int cj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cj >= ncj) return;
+    real* o = jbb + (size_t)cj * 6;
+    if (N == CP_M) {
+        const real* a = ibb + (size_t)cj * 6;
+#pragma unroll
+        for (int k = 0; k < 6; k++) o[k] = a[k];
+        jnat[cj] = inat[cj];
+    } else {
+        const real *a = ibb + (size_t)(2 * cj) * 6, *b = ibb + (size_t)(2 * cj + 1) * 6;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            o[2 * d]     = a[2 * d] < b[2 * d] ? a[2 * d] : b[2 * d];             // MIN
+            o[2 * d + 1] = a[2 * d + 1] > b[2 * d + 1] ? a[2 * d + 1] : b[2 * d + 1]; // MAX
+        }
+        jnat[cj] = inat[2 * cj] + inat[2 * cj + 1];
+    }
+}
+
+// ---- setupPbc (pbc.c:183-323): ghost j-clusters by bounding box, ADDGHOST ladder order ---------------------
+template <class real>
+__global__ void k_cp_ghost_count(int ncj, PbcGeom<real> g, const int* __restrict__ jnat, const real* __restrict__ jbb,
+    unsigned* __restrict__ mask, int* __restrict__ count)
+{
+    const int cj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cj >= ncj) return;
+    unsigned m = 0;
+    if (jnat[cj] > 0) {
+        const real* b = jbb + (size_t)cj * 6;
+        const bool lo[3] = { b[0] < g.cutneigh, b[2] < g.cutneigh, b[4] < g.cutneigh };
+        const bool hi[3] = { b[1] >= g.xhi_cut, b[3] >= g.yhi_cut, b[5] >= g.zhi_cut };
+#pragma unroll
+        for (int q = 0; q < 26; q++) {
+            bool ok = true;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const int d = c_img[q][a];
+                if (d > 0) ok = ok && lo[a];
+                if (d < 0) ok = ok && hi[a];
+            }
+            if (ok) m |= 1u << q;
+        }
+    }
+    mask[cj]  = m;
+    count[cj] = __popc(m);
+}
+template <int N>
+__global__ void k_cp_ghost_fill(int ncj, const unsigned* __restrict__ mask, const int* __restrict__ offset,
+    const int* __restrict__ cl_tag_in, int* __restrict__ border_map, int* __restrict__ code, int* __restrict__ jnat,
+    int* __restrict__ cl_tag)
+{
+    const int cj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cj >= ncj) return;
+    unsigned m = mask[cj];
+    int g      = offset[cj];
+    const int nat = jnat[cj];
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        border_map[g]  = cj;
+        code[g]        = (c_img[b][0] + 1) | ((c_img[b][1] + 1) << 2) | ((c_img[b][2] + 1) << 4);
+        jnat[ncj + g]  = nat;
+        for (int q = 0; q < N; q++) cl_tag[(size_t)(ncj + g) * N + q] = q < nat ? cl_tag_in[(size_t)cj * N + q] : -1;
+        g++;
+    }
+}
+// updatePbcCPU, pbc.c:45-114: one thread per ghost tile lane; image = fma(PBC, prd, source) (ONE fma);
+// first != 0 also pads the tile with infinity and computes the bounding box (one thread per tile then)
+template <class real, int N>
+__global__ void k_cp_update_pbc(int ncj, int nghost, real xprd, real yprd, real zprd, const int* __restrict__ border_map,
+    const int* __restrict__ code, const int* __restrict__ jnat, real* __restrict__ cl_x)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nghost * N) return;
+    const int g = t / N, q = t % N;
+    const int cj = ncj + g;
+    if (q >= jnat[cj]) return;
+    const int c = code[g];
+    const real* s = cl_x + (size_t)border_map[g] * N * 3;
+    real* d       = cl_x + (size_t)cj * N * 3;
+    d[q]         = fma_rn((real)((c & 3) - 1), xprd, s[q]);
+    d[N + q]     = fma_rn((real)(((c >> 2) & 3) - 1), yprd, s[N + q]);
+    d[2 * N + q] = fma_rn((real)(((c >> 4) & 3) - 1), zprd, s[2 * N + q]);
+}
+template <class real, int N>
+__global__ void k_cp_update_pbc_first(int ncj, int nghost, real xprd, real yprd, real zprd, const int* __restrict__ border_map,
+    const int* __restrict__ code, const int* __restrict__ jnat, real* __restrict__ cl_x, real* __restrict__ jbb)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > nghost) return;
+    const int cj = ncj + g;
+    real* d = cl_x + (size_t)cj * N * 3;
+    if (g == nghost) { // the dummy cluster at the end, pbc.c:304-311
+        for (int q = 0; q < 3 * N; q++) d[q] = INFINITY;
+        return;
+    }
+    const int c = code[g], nat = jnat[cj];
+    const real* s = cl_x + (size_t)border_map[g] * N * 3;
+    const real sh[3] = { (real)((c & 3) - 1), (real)(((c >> 2) & 3) - 1), (real)(((c >> 4) & 3) - 1) };
+    const real prd[3] = { xprd, yprd, zprd };
+    real* bb = jbb + (size_t)cj * 6;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        real lo = INFINITY, hi = -INFINITY;
+        for (int q = 0; q < N; q++) {
+            if (q < nat) {
+                const real v = fma_rn(sh[a], prd[a], s[a * N + q]);
+                d[a * N + q] = v;
+                if (lo > v) lo = v;
+                if (hi < v) hi = v;
+            } else d[a * N + q] = INFINITY;
+        }
+        bb[2 * a] = lo; bb[2 * a + 1] = hi;
+    }
+}
+
+// ---- binClusters (neighbor.c:897-1043): bin of every j-cluster ------------------------------------------------
+// local j-cluster: the bin of its i-cluster(s); ghost: the bin of its INNERMOST atom (neighbor.c:957-985)
+template <class real, int N>
+__global__ void k_cp_cluster_bin(int ncj, int nghost, CpGeom<real> g, const int* __restrict__ ibin, const int* __restrict__ code,
+    const int* __restrict__ jnat, const real* __restrict__ cl_x, int* __restrict__ cbin, int* __restrict__ cbincount)
+{
+    const int cj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cj >= ncj + nghost) return;
+    int bin = -1;
+    if (cj < ncj) {
+        bin = ibin[N == CP_M ? cj : 2 * cj];
+    } else if (jnat[cj] > 0) {
+        const int c = code[cj - ncj];
+        const int px = (c & 3) - 1, py = ((c >> 2) & 3) - 1;
+        const real* p = cl_x + (size_t)cj * N * 3;
+        int ix, iy;
+        cp_coord2bin2D(g, p[0], p[N], ix, iy);
+        ix = max(min(ix, g.mbinx - 1), 0);
+        iy = max(min(iy, g.mbiny - 1), 0);
+        for (int q = 1; q < jnat[cj]; q++) {
+            int nix, niy;
+            cp_coord2bin2D(g, p[q], p[N + q], nix, niy);
+            nix = max(min(nix, g.mbinx - 1), 0);
+            niy = max(min(niy, g.mbiny - 1), 0);
+            if (px > 0 && ix > nix) ix = nix;
+            if (px < 0 && ix < nix) ix = nix;
+            if (py > 0 && iy > niy) iy = niy;
+            if (py < 0 && iy < niy) iy = niy;
+        }
+        bin = iy * g.mbinx + ix + 1;
+        bin = bin >= g.mbins ? g.mbins - 1 : bin;
+    }
+    cbin[cj] = bin;
+    if (bin >= 0) atomicAdd(&cbincount[bin], 1);
+}
+static __global__ void k_cp_cluster_fill(int n, const int* __restrict__ cbin, const int* __restrict__ cbinstart, int* __restrict__ cursor,
+    int* __restrict__ cbinlist)
+{
+    const int cj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cj >= n) return;
+    const int b = cbin[cj];
+    if (b >= 0) cbinlist[cbinstart[b] + atomicAdd(&cursor[b], 1)] = cj;
+}
+// per bin: clusters ascending in (bbminz, id) -- the reference keeps its bins z-sorted too (neighbor.c:989-1012; the
+// ORDER inside a bin does not change the neighbor SETS) -- plus the running maximum of bbmaxz, which lets the list
+// build binary-search the first cluster that can be in z-range.  One warp per bin, rank sort.
+template <class real>
+__global__ void __launch_bounds__(128) k_cp_cluster_sort(int mbins, const int* __restrict__ cbinstart,
+    const int* __restrict__ cbinlist_in, int* cbinlist, const real* __restrict__ jbb, real* __restrict__ pmaxz)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= mbins) return;
+    const int s = cbinstart[b], c = cbinstart[b + 1] - s;
+    for (int k = lane; k < c; k += 32) {
+        const int v   = cbinlist_in[s + k];
+        const real zv = jbb[(size_t)v * 6 + 4];
+        int r         = 0;
+        for (int q = 0; q < c; q++) {
+            const int u   = cbinlist_in[s + q];
+            const real zu = jbb[(size_t)u * 6 + 4];
+            r += (zu < zv) || (zu == zv && u < v);
+        }
+        cbinlist[s + r] = v;
+    }
+    __syncwarp();
+    for (int k = lane; k < c; k += 32) {
+        real m = -INFINITY;
+        for (int q = 0; q <= k; q++) {
+            const real zmax = jbb[(size_t)cbinlist[s + q] * 6 + 5];
+            m               = zmax > m ? zmax : m;
+        }
+        pmaxz[s + k] = m;
+    }
+}
+
+// ---- buildNeighborCPU (neighbor.c:262-481): cluster-pair list -------------------------------------------------------
+// One thread per i-cluster.  Set semantics of the reference: every j-cluster of the stencil bins with
+// d_bb_sq < cutneighsq and (d_bb_sq < rbb_sq or some atom pair closer than cutneigh); half lists keep cj >= CJ1(ci);
+// the diagonal entry (cj == CJ0(ci)) is moved to the front and counted in numneigh_masked (neighbor.c:374-385).
+// d_bb_sq accumulates z, y, x with the contraction of the reference build; atomDistanceInRange is
+// fma(dz,dz,fma(dx,dx,dy*dy)) < cutneighsq (disassembly of the reference build).
+template <class real, int N>
+__global__ void __launch_bounds__(128) k_cp_build_neighbor(int ncl, int half, CpGeom<real> g, const int* __restrict__ stencil,
+    int nstencil, const int* __restrict__ ibin, const int* __restrict__ inat, const real* __restrict__ ibb,
+    const int* __restrict__ jnat, const real* __restrict__ jbb, const real* __restrict__ cl_x, const int* __restrict__ cbinstart,
+    const int* __restrict__ cbinlist, const real* __restrict__ pmaxz, int maxneighs, int* __restrict__ numneigh,
+    int* __restrict__ numneigh_masked, int* __restrict__ neighbors, int* __restrict__ max_n)
+{
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = 0;
+    if (ci < ncl) {
+        const real* I = ibb + (size_t)ci * 6;
+        const real ixlo = I[0], ixhi = I[1], iylo = I[2], iyhi = I[3], izlo = I[4], izhi = I[5];
+        const int bin = ibin[ci], nati = inat[ci], self = cp_cj0<N>(ci);
+        const real* xi = cl_x + cp_ci_base3<N>(ci);
+        real px[CP_M], py[CP_M], pz[CP_M];
+#pragma unroll
+        for (int q = 0; q < CP_M; q++) { px[q] = xi[q]; py[q] = xi[N + q]; pz[q] = xi[2 * N + q]; }
+        int* row = neighbors + (size_t)ci * maxneighs;
+        int nmasked = 0;
+        const real zlo_need = izlo - g.cutneigh; // clusters entirely below this cannot be in range
+        for (int k = 0; k < nstencil; k++) {
+            const int jb = bin + __ldg(stencil + k);
+            if (jb < 0 || jb >= g.mbins) continue;
+            const int s = __ldg(cbinstart + jb), e = __ldg(cbinstart + jb + 1);
+            // first position whose running max of bbmaxz reaches zlo_need (conservative: the exact test follows)
+            int lo = s, hi = e;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(pmaxz + mid) < zlo_need - (real)1e-3) lo = mid + 1;
+                else hi = mid;
+            }
+            for (int m = lo; m < e; m++) {
+                const int cj = __ldg(cbinlist + m);
+                const real* J = jbb + (size_t)cj * 6;
+                const real jzlo = __ldg(J + 4);
+                if (jzlo - izhi > g.cutneigh + (real)1e-3) break; // sorted by bbminz: nothing further can be in range
+                if (half && self > cj) continue;                  // neighbor.c:318: ci_cj1 > cj
+                real dl, dh, dm, d2;
+                dl = izlo - __ldg(J + 5); dh = jzlo - izhi; dm = fmax(fmax(dl, dh), (real)0);
+                d2 = mul_rn(dm, dm);
+                dl = iylo - __ldg(J + 3); dh = __ldg(J + 2) - iyhi; dm = fmax(fmax(dl, dh), (real)0);
+                d2 = fma_rn(dm, dm, d2);
+                dl = ixlo - __ldg(J + 1); dh = __ldg(J + 0) - ixhi; dm = fmax(fmax(dl, dh), (real)0);
+                d2 = fma_rn(dm, dm, d2);
+                if (!(d2 < g.cutneighsq)) continue;
+                bool in = d2 < g.rbb_sq;
+                if (!in) { // atomDistanceInRange, neighbor.c:216-234
+                    const real* xj = cl_x + (size_t)cj * N * 3;
+                    const int natj = __ldg(jnat + cj);
+                    for (int b = 0; b < natj && !in; b++) {
+                        const real xb = __ldg(xj + b), yb = __ldg(xj + N + b), zb = __ldg(xj + 2 * N + b);
+#pragma unroll
+                        for (int a = 0; a < CP_M; a++) {
+                            if (a < nati) {
+                                const real dx = sub_rn(px[a], xb), dy = sub_rn(py[a], yb), dz = sub_rn(pz[a], zb);
+                                in = in || (fma_rn(dz, dz, fma_rn(dx, dx, mul_rn(dy, dy))) < g.cutneighsq);
+                            }
+                        }
+                    }
+                }
+                if (in) {
+                    if (n < maxneighs) {
+                        if (cj != self) row[n] = cj;
+                        else { row[n] = row[nmasked]; row[nmasked] = cj; nmasked++; }
+                    }
+                    n++;
+                }
+            }
+        }
+        numneigh[ci]        = n;
+        numneigh_masked[ci] = nmasked;
+    }
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
+// pruneNeighbor (neighbor.c:483-531): drop listed cluster pairs without any atom pair inside cutneigh (the pairs
+// the bounding-box shortcut d_bb_sq < rbb_sq admitted), compacting each row exactly like the reference (the last
+// entry moves into the hole; numneigh_masked shrinks when the hole is in the masked prefix).
+template <class real, int N>
+__global__ void __launch_bounds__(128) k_cp_prune(int ncl, real cutsq, const int* __restrict__ inat, const int* __restrict__ jnat,
+    const real* __restrict__ cl_x, int maxneighs, int* __restrict__ numneigh, int* __restrict__ numneigh_masked,
+    int* __restrict__ neighbors)
+{
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= ncl) return;
+    const real* xi = cl_x + cp_ci_base3<N>(ci);
+    const int nati = inat[ci];
+    real px[CP_M], py[CP_M], pz[CP_M];
+#pragma unroll
+    for (int q = 0; q < CP_M; q++) { px[q] = xi[q]; py[q] = xi[N + q]; pz[q] = xi[2 * N + q]; }
+    int* row = neighbors + (size_t)ci * maxneighs;
+    int n = numneigh[ci], nm = numneigh_masked[ci], k = 0;
+    while (k < n) {
+        const int cj   = row[k];
+        const real* xj = cl_x + (size_t)cj * N * 3;
+        const int natj = jnat[cj];
+        bool in        = false;
+        for (int b = 0; b < natj && !in; b++) {
+            const real xb = xj[b], yb = xj[N + b], zb = xj[2 * N + b];
+#pragma unroll
+            for (int a = 0; a < CP_M; a++)
+                if (a < nati) {
+                    const real dx = sub_rn(px[a], xb), dy = sub_rn(py[a], yb), dz = sub_rn(pz[a], zb);
+                    in = in || (fma_rn(dz, dz, fma_rn(dx, dx, mul_rn(dy, dy))) < cutsq);
+                }
+        }
+        if (in) k++;
+        else {
+            n--;
+            if (k < nm) nm--;
+            row[k] = row[n];
+        }
+    }
+    numneigh[ci]        = n;
+    numneigh_masked[ci] = nm;
+}
+
+// ---- force: computeForceLJRef semantics (force_lj.c:47-164) ---------------------------------------------------------
+// One lane per i-atom slot; the 4 lanes of an i-cluster walk the same list row and fetch each j-cluster tile
+// with 256-bit (DP) / 128-bit (SP) loads from identical addresses (broadcast).  Each lane evaluates its atom against
+// the N atoms of the tile in registers.  Exclusion on the diagonal tile: full lists skip j == own lane, half lists
+// keep j > own lane (force_lj.c:99-113).  Padding lanes sit at +infinity: rsq is inf / NaN and fails the cutoff
+// test (no fast-math anywhere in this library).
+template <class real> struct CpTileLoad;
+template <> struct CpTileLoad<double> {
+    template <int N> static __device__ __forceinline__ void load(const double* p, double (&v)[N])
+    {
+#pragma unroll
+        for (int q = 0; q < N; q += 4)
+            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[q]), "=d"(v[q + 1]), "=d"(v[q + 2]), "=d"(v[q + 3]) : "l"(p + q));
+    }
+    // positions change between force calls inside one graph of kernels: plain (coherent) loads for the half kernel's
+    // force tiles are not needed; positions are read-only during a force kernel, so .nc is valid.
+};
+template <> struct CpTileLoad<float> {
+    template <int N> static __device__ __forceinline__ void load(const float* p, float (&v)[N])
+    {
+#pragma unroll
+        for (int q = 0; q < N; q += 4) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(p + q));
+            v[q] = f.x; v[q + 1] = f.y; v[q + 2] = f.z; v[q + 3] = f.w;
+        }
+    }
+};
+
+template <class real, int N, bool HALF>
+__global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<real> c, const real* __restrict__ cl_x,
+    const int* __restrict__ numneigh, const int* __restrict__ neighbors, int maxneighs, real* __restrict__ cl_f)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci  = tid >> 2, cii = tid & 3;
+    const bool valid = ci < ncl;
+    const int cic = valid ? ci : ncl - 1;
+    const size_t ib = cp_ci_base3<N>(cic);
+    const real xt = cl_x[ib + cii], yt = cl_x[ib + N + cii], zt = cl_x[ib + 2 * N + cii];
+    const int self = cp_cj0<N>(cic);
+    const int ii   = N == CP_M ? cii : cii + CP_M * (cic & 1); // own lane inside the diagonal tile
+    const int nn   = valid ? numneigh[cic] : 0;
+    const int* row = neighbors + (size_t)cic * maxneighs;
+    real fix = 0, fiy = 0, fiz = 0;
+    int cjn = nn > 0 ? __ldg(row) : 0;
+    for (int k = 0; k < nn; k++) {
+        const int cj = cjn;
+        if (k + 1 < nn) cjn = __ldg(row + k + 1);
+        const real* t = cl_x + (size_t)cj * N * 3;
+        real xj[N], yj[N], zj[N];
+        CpTileLoad<real>::template load<N>(t, xj);
+        CpTileLoad<real>::template load<N>(t + N, yj);
+        CpTileLoad<real>::template load<N>(t + 2 * N, zj);
+        const bool diag = cj == self;
+        real rx[N], ry[N], rz[N];
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            const real dx = xt - xj[q], dy = yt - yj[q], dz = zt - zj[q];
+            const real rsq = dx * dx + dy * dy + dz * dz;
+            const bool excl = diag && (HALF ? !(ii < q) : (ii == q));
+            // padding lanes are at +inf: dx is inf/NaN there, so nothing may be accumulated unless the pair is in range
+            real px = 0, py = 0, pz = 0;
+            if (rsq < c.cutforcesq && !excl) {
+                const real f = lj_pair2(rsq, c);
+                px = dx * f; py = dy * f; pz = dz * f;
+            }
+            fix += px; fiy += py; fiz += pz;
+            if (HALF) { rx[q] = px; ry[q] = py; rz[q] = pz; }
+        }
+        // reaction on the j tile: sum over the 4 lanes of the i-cluster, then one atomic per j atom.  The reference also
+        // subtracts from ghost tiles (its HALF_NEIGHBOR_LISTS_CHECK_CJ guard is ineffective) but never
+        // reads them back; skipping cj >= ncj leaves every local force unchanged.
+        if (HALF && cj < ncj) {
+            real* fj = cl_f + (size_t)cj * N * 3;
+#pragma unroll
+            for (int q = 0; q < N; q++) {
+                real sx = rx[q], sy = ry[q], sz = rz[q];
+                sx += __shfl_xor_sync(0xffffffffu, sx, 1); sy += __shfl_xor_sync(0xffffffffu, sy, 1); sz += __shfl_xor_sync(0xffffffffu, sz, 1);
+                sx += __shfl_xor_sync(0xffffffffu, sx, 2); sy += __shfl_xor_sync(0xffffffffu, sy, 2); sz += __shfl_xor_sync(0xffffffffu, sz, 2);
+                if (cii == (q & 3) && (sx != 0 || sy != 0 || sz != 0)) {
+                    atomicAdd(fj + q, -sx); atomicAdd(fj + N + q, -sy); atomicAdd(fj + 2 * N + q, -sz);
+                }
+            }
+        }
+    }
+    if (!valid) return;
+    if (HALF) {
+        atomicAdd(cl_f + ib + cii, fix); atomicAdd(cl_f + ib + N + cii, fiy); atomicAdd(cl_f + ib + 2 * N + cii, fiz);
+    } else {
+        cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
+    }
+}
+
+// ---- integrate (clusterpair/integrate.c:23-63): one thread per i-atom slot, padding lanes untouched ------------------
+template <class real, int N, int MODE> // MODE 0: initial, 1: final, 2: final(n) + initial(n+1)
+__global__ void k_cp_integrate(int ncl, real dtforce, real dt, const int* __restrict__ inat, real* __restrict__ cl_x,
+    real* __restrict__ cl_v, const real* __restrict__ cl_f)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci  = tid >> 2, cii = tid & 3;
+    if (ci >= ncl || cii >= inat[ci]) return;
+    const size_t b = cp_ci_base3<N>(ci) + cii;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const size_t s = b + (size_t)a * N;
+        const real f = cl_f[s];
+        real v = cl_v[s] + dtforce * f;
+        if (MODE == 2) v = v + dtforce * f;
+        cl_v[s] = v;
+        if (MODE != 1) cl_x[s] = cl_x[s] + dt * v;
+    }
+}
+// updateSingleAtoms (neighbor.c:1045-1071): cluster data back to the atom arrays, compacted in cluster order
+template <class real, int N>
+__global__ void k_cp_update_single_atoms(int ncl, const int* __restrict__ inat, const int* __restrict__ atom_off,
+    const real* __restrict__ cl_x, const real* __restrict__ cl_v, const int* __restrict__ cl_tag, real* __restrict__ x,
+    real* __restrict__ y, real* __restrict__ z, real* __restrict__ vx, real* __restrict__ vy, real* __restrict__ vz, int* __restrict__ tag)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci  = tid >> 2, cii = tid & 3;
+    if (ci >= ncl || cii >= inat[ci]) return;
+    const size_t b = cp_ci_base3<N>(ci) + cii;
+    const int i    = atom_off[ci] + cii;
+    x[i] = cl_x[b]; y[i] = cl_x[b + N]; z[i] = cl_x[b + 2 * N];
+    vx[i] = cl_v[b]; vy[i] = cl_v[b + N]; vz[i] = cl_v[b + 2 * N];
+    tag[i] = cl_tag[cp_ci_base1<N>(ci) + cii];
+}
+template <class real> __global__ void k_cp_zero(size_t n, real* __restrict__ a)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = 0;
+}
+// pairs for the roofline: listed cluster pairs x M x N and atom pairs inside the cutoff
+template <class real, int N>
+__global__ void k_cp_count_pairs(int ncl, real cutforcesq, const real* __restrict__ cl_x, const int* __restrict__ numneigh,
+    const int* __restrict__ neighbors, int maxneighs, unsigned long long* __restrict__ out)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci  = tid >> 2, cii = tid & 3;
+    unsigned long long listed = 0, inside = 0;
+    if (ci < ncl) {
+        const size_t ib = cp_ci_base3<N>(ci);
+        const real xt = cl_x[ib + cii], yt = cl_x[ib + N + cii], zt = cl_x[ib + 2 * N + cii];
+        const int nn = numneigh[ci];
+        if (cii == 0) listed = nn;
+        for (int k = 0; k < nn; k++) {
+            const real* t = cl_x + (size_t)neighbors[(size_t)ci * maxneighs + k] * N * 3;
+            for (int q = 0; q < N; q++) {
+                const real dx = xt - t[q], dy = yt - t[N + q], dz = zt - t[2 * N + q];
+                inside += (dx * dx + dy * dy + dz * dz) < cutforcesq;
+            }
+        }
+    }
+    atomicAdd(out, listed);
+    atomicAdd(out + 1, inside);
+}
+
+} // namespace mdb

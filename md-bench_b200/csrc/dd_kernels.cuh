@@ -103,7 +103,7 @@ __global__ void k_dd_dest(int nlocal, real ex, real ey, real ez, int px, int py,
     leave[i]    = b >= 0;
 }
 // compact: stayers keep their relative order at the front, leavers are listed in ascending order
-__global__ void k_dd_split(int nlocal, const int* __restrict__ leave, const int* __restrict__ leave_scan,
+static __global__ void k_dd_split(int nlocal, const int* __restrict__ leave, const int* __restrict__ leave_scan,
     int* __restrict__ stay_src, int* __restrict__ leavers)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,7 +113,7 @@ __global__ void k_dd_split(int nlocal, const int* __restrict__ leave, const int*
     else stay_src[i - l] = i;
 }
 // flags[s*nb + q] = 1 if border atom list[q] has image dir[s]
-__global__ void k_dd_flags_mask(int nb, SendTable T, const int* __restrict__ list, const unsigned* __restrict__ mask,
+static __global__ void k_dd_flags_mask(int nb, SendTable T, const int* __restrict__ list, const unsigned* __restrict__ mask,
     int* __restrict__ flags)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,7 +121,7 @@ __global__ void k_dd_flags_mask(int nb, SendTable T, const int* __restrict__ lis
     const int s = (int)(t / nb), q = (int)(t % nb);
     flags[t]    = (mask[list[q]] >> T.dir[s]) & 1u;
 }
-__global__ void k_dd_flags_dest(int nb, SendTable T, const int* __restrict__ list, const int* __restrict__ dest,
+static __global__ void k_dd_flags_dest(int nb, SendTable T, const int* __restrict__ list, const int* __restrict__ dest,
     int* __restrict__ flags)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,7 +130,7 @@ __global__ void k_dd_flags_dest(int nb, SendTable T, const int* __restrict__ lis
     flags[t]    = dest[list[q]] == T.dir[s];
 }
 // sendlist[scan[t]] = list[q] for set flags: slot blocks come out contiguous, ascending inside
-__global__ void k_dd_fill_sendlist(int nb, int nslots, const int* __restrict__ list, const int* __restrict__ flags,
+static __global__ void k_dd_fill_sendlist(int nb, int nslots, const int* __restrict__ list, const int* __restrict__ flags,
     const int* __restrict__ scan, int* __restrict__ sendlist)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,12 +138,12 @@ __global__ void k_dd_fill_sendlist(int nb, int nslots, const int* __restrict__ l
     if (flags[t]) sendlist[scan[t]] = list[(int)(t % nb)];
 }
 // off[s] = first entry of slot s (off[nslots] = total is written by the scan itself)
-__global__ void k_dd_block_offsets(int nb, int nslots, const int* __restrict__ scan, int* __restrict__ off)
+static __global__ void k_dd_block_offsets(int nb, int nslots, const int* __restrict__ scan, int* __restrict__ off)
 {
     const int s = threadIdx.x;
     if (s < nslots) off[s] = scan[(long long)s * nb];
 }
-__global__ void k_dd_flag_border(int n, unsigned valid, unsigned* __restrict__ mask, int* __restrict__ flag)
+static __global__ void k_dd_flag_border(int n, unsigned valid, unsigned* __restrict__ mask, int* __restrict__ flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -151,7 +151,7 @@ __global__ void k_dd_flag_border(int n, unsigned valid, unsigned* __restrict__ m
     mask[i]          = m;
     flag[i]          = m != 0;
 }
-__global__ void k_compact(int n, const int* __restrict__ flag, const int* __restrict__ scan, int* __restrict__ list)
+static __global__ void k_compact(int n, const int* __restrict__ flag, const int* __restrict__ scan, int* __restrict__ list)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) list[scan[i]] = i;
@@ -193,7 +193,7 @@ __global__ void k_dd_pack(int total, SendTable T, const int* __restrict__ sendli
     }
 }
 // two int arrays (type, tag) in the same per-peer segment layout
-__global__ void k_dd_pack_int2(int total, SendTable T, const int* __restrict__ sendlist, const int* __restrict__ a0,
+static __global__ void k_dd_pack_int2(int total, SendTable T, const int* __restrict__ sendlist, const int* __restrict__ a0,
     const int* __restrict__ a1, int* __restrict__ out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,7 +221,7 @@ __global__ void k_dd_gather_stay(int n, const int* __restrict__ src, const real*
     ntag[q]  = tag[o];
 }
 // neighbor rows as global tags (parity read-back): out[i*stride + k] = tag[neighbor k of i]
-__global__ void k_dd_rows_as_tags(int nlocal, int stride, NbLayout L, const int* __restrict__ numneigh,
+static __global__ void k_dd_rows_as_tags(int nlocal, int stride, NbLayout L, const int* __restrict__ numneigh,
     const int* __restrict__ neighbors, const int* __restrict__ tag, int* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -10,6 +10,9 @@ struct mdb_ctx {
 };
 
 static thread_local std::string g_err;
+namespace mdb {
+void set_last_error(const char* msg) { g_err = msg; } // for the other translation units of the C ABI (cp_sim.cu)
+}
 
 #define MDB_TRY(body)                                                                            \
     try {                                                                                        \

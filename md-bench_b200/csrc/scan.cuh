@@ -9,7 +9,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS   = 8;
 constexpr int SCAN_TILE    = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile(
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile(
     const int* __restrict__ in, int* __restrict__ out, int* __restrict__ tile_sums, size_t n)
 {
     __shared__ int warp_sums[SCAN_THREADS / 32];
@@ -50,13 +50,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile(
     }
 }
 
-__global__ void k_scan_add(int* __restrict__ out, const int* __restrict__ tile_off, size_t n)
+static __global__ void k_scan_add(int* __restrict__ out, const int* __restrict__ tile_off, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] += tile_off[i / SCAN_TILE];
 }
 
-__global__ void k_scan_total(const int* __restrict__ tile_sums, int* __restrict__ dst)
+static __global__ void k_scan_total(const int* __restrict__ tile_sums, int* __restrict__ dst)
 {
     *dst = tile_sums[0];
 }

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_vel_partial(int n, const real* 
     }
 }
 // out[0..3] = sums over blocks
-__global__ void __launch_bounds__(RED_THREADS) k_vel_final(int nblocks, const double* __restrict__ partial, double* __restrict__ out)
+static __global__ void __launch_bounds__(RED_THREADS) k_vel_final(int nblocks, const double* __restrict__ partial, double* __restrict__ out)
 {
     for (int c = 0; c < 4; c++) {
         double s = 0;
@@ -254,7 +254,7 @@ __global__ void k_ghost_count(int nlocal, PbcGeom<real> g, const real* __restric
 }
 // setupPbc pass 2: ghost index = exclusive scan of the counts in atom order + rank of the image in
 // the ladder, i.e. exactly the reference's Nghost++ order.  code = (dx+1) | (dy+1)<<2 | (dz+1)<<4.
-__global__ void k_ghost_fill(int nlocal, const unsigned* __restrict__ mask,
+static __global__ void k_ghost_fill(int nlocal, const unsigned* __restrict__ mask,
     const int* __restrict__ offset, int* __restrict__ border_map, int* __restrict__ code,
     int* __restrict__ type)
 {
@@ -321,7 +321,7 @@ __global__ void k_bin_count(int nall, BinGeom<real> g, const real* __restrict__ 
     atom_bin[i] = b;
     atomicAdd(&bincount[b], 1);
 }
-__global__ void k_bin_fill(int nall, const int* __restrict__ atom_bin, const int* __restrict__ binstart,
+static __global__ void k_bin_fill(int nall, const int* __restrict__ atom_bin, const int* __restrict__ binstart,
     int* __restrict__ cursor, int* __restrict__ binatoms)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -329,7 +329,7 @@ __global__ void k_bin_fill(int nall, const int* __restrict__ atom_bin, const int
     const int b                          = atom_bin[i];
     binatoms[binstart[b] + atomicAdd(&cursor[b], 1)] = i;
 }
-__global__ void k_bin_sort(int nbins, const int* __restrict__ binstart, int* __restrict__ binatoms,
+static __global__ void k_bin_sort(int nbins, const int* __restrict__ binstart, int* __restrict__ binatoms,
     const int* __restrict__ key, int* __restrict__ maxcount)
 {
     // key == nullptr: ascending atom index; else ascending key[atom] (the atom's reference index)
@@ -373,7 +373,7 @@ __global__ void k_permute_atoms(int n, const int* __restrict__ perm, const real*
     ntype[q] = type[o];
     norig[q] = orig[o];
 }
-__global__ void k_iota(int n, int* __restrict__ a)
+static __global__ void k_iota(int n, int* __restrict__ a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = i;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, Bi
 // touch few 128-byte lines.  Rows arrive nearly sorted (stencil order walks z, y, x), so a plain
 // insertion sort does ~n + inversions steps; the 32 rows of a tile are walked in lockstep, each access
 // one coalesced line.
-__global__ void __launch_bounds__(128) k_sort_rows(int nlocal, NbLayout L, const int* __restrict__ numneigh,
+static __global__ void __launch_bounds__(128) k_sort_rows(int nlocal, NbLayout L, const int* __restrict__ numneigh,
     int* __restrict__ neighbors)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half,
 
 // parity read-back: transposed list in internal numbering -> the reference's row-major rows in the
 // reference's numbering (extmap: internal index -> reference index, locals and ghosts)
-__global__ void k_untranspose(int nlocal, int row_stride, NbLayout L, const int* __restrict__ numneigh,
+static __global__ void k_untranspose(int nlocal, int row_stride, NbLayout L, const int* __restrict__ numneigh,
     const int* __restrict__ nbT, const int* __restrict__ extmap, int* __restrict__ rows,
     int* __restrict__ numneigh_ext)
 {

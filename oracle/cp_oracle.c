@@ -573,6 +573,30 @@ EXPORT void ocp_build_neighbor(OCP* o)
         }
     }
 }
+/* neighbor.c:483-531 pruneNeighbor: drops listed cluster pairs without an atom pair inside cutneigh (NOT cutforce:
+ * the reference's own comment line 486-487); the hole is filled with the row's last entry */
+EXPORT void ocp_prune_neighbor(OCP* o)
+{
+    const int N = o->N;
+    for (int ci = 0; ci < o->Nclusters_local; ci++) {
+        int* neighs = &o->neighbors[(size_t)ci * o->maxneighs];
+        int numneighs = o->numneigh[ci], numneighs_masked = o->numneigh_masked[ci], k = 0;
+        if (N < o->vector_width)
+            while (numneighs > 0 && neighs[numneighs - 1] == o->dummy_cj) numneighs--;
+        while (k < numneighs) {
+            if (atom_distance_in_range(o, ci, neighs[k], o->cutneighsq)) k++;
+            else {
+                numneighs--;
+                if (k < numneighs_masked) numneighs_masked--;
+                neighs[k] = neighs[numneighs];
+            }
+        }
+        if (N < o->vector_width)
+            while (numneighs % (o->vector_width / N)) neighs[numneighs++] = o->dummy_cj;
+        o->numneigh[ci] = numneighs;
+        o->numneigh_masked[ci] = numneighs_masked;
+    }
+}
 /* neighbor.c:1023-1049 updateSingleAtoms: cluster data back to the atom arrays, compacted in cluster order */
 EXPORT void ocp_update_single_atoms(OCP* o)
 {

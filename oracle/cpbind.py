@@ -73,6 +73,12 @@ class _Common:
             rows.append(np.sort(r))
         return nn, nm, rows
 
+    def raw_lists(self):
+        """numneigh, numneigh_masked, rows (ncl, maxneighs) in list order"""
+        ncl, mx = self.geti("Nclusters_local"), self.geti("maxneighs")
+        return (self._arr("numneigh", ncl, np.int32).copy(), self._arr("numneigh_masked", ncl, np.int32).copy(),
+                self._arr("neighbors", ncl * mx, np.int32).reshape(ncl, mx).copy())
+
     def ghost_map(self):
         ngh = self.geti("Nclusters_ghost")
         return {k: self._arr(k, ngh, np.int32).copy() for k in ("border_map", "PBCx", "PBCy", "PBCz")}
@@ -139,6 +145,7 @@ class OracleCP(_Common):
     def setupPbc(self): self._call("ocp_setup_pbc")
     def binClusters(self): self._call("ocp_bin_clusters")
     def buildNeighbor(self): self._call("ocp_build_neighbor")
+    def pruneNeighbor(self): self._call("ocp_prune_neighbor")
     def updateSingleAtoms(self): self._call("ocp_update_single_atoms")
     def updateAtomsPbc(self): self._call("ocp_update_atoms_pbc")
     def updatePbc(self, first=False): self._call("ocp_update_pbc", int(first))
@@ -288,6 +295,7 @@ class RefCP(_Common):
     def setupPbc(self): self.lib.setupPbc(C.byref(self.atom), C.byref(self.param))
     def binClusters(self): self.lib.binClusters(C.byref(self.atom))
     def buildNeighbor(self): self.lib.buildNeighborCPU(C.byref(self.atom), C.byref(self.neighbor))
+    def pruneNeighbor(self): self.lib.pruneNeighbor(C.byref(self.param), C.byref(self.atom), C.byref(self.neighbor))
     def updateSingleAtoms(self): self.lib.updateSingleAtoms(C.byref(self.atom))
     def updateAtomsPbc(self): self.lib.updateAtomsPbcCPU(C.byref(self.atom), C.byref(self.param), C.c_bool(False))
     def updatePbc(self, first=False): self.lib.updatePbcCPU(C.byref(self.atom), C.byref(self.param), C.c_bool(first))

@@ -130,6 +130,34 @@ def test_simd_builds_rebuild_structures(variant):
             assert_same_structure(r, o2)
 
 
+@pytest.mark.parametrize("variant", ["cpref44_dp", "cpref48_sp", "cp_dp_aos"])
+def test_prune_neighbor_matches_reference(variant):
+    """pruneNeighbor (neighbor.c:483-531) 15 steps after the build: the reference's list in ITS row order and its
+    cluster positions are handed to the restatement (list order inside a bin is not pinned; the SIMD builds' rcp14
+    trajectories differ), both prune, rows must agree entry by entry"""
+    if not usable(variant):
+        pytest.skip("reference library %s not runnable here" % variant)
+    r, o = make_pair(variant, 6)
+    r.buildClusters(); r.defineJClusters(); r.setupPbc(); r.binClusters(); r.buildNeighbor()
+    o.setup()
+    r.computeForce()
+    for n in range(15):
+        r.step(n)
+    nn, nm, nb = r.raw_lists()
+    assert o.geti("maxneighs") == r.geti("maxneighs")
+    xr = r.cl("x")
+    o._arr("cl_x", xr.size, o.np_real)[:] = xr.reshape(-1)
+    o._arr("numneigh", len(nn), np.int32)[:] = nn
+    o._arr("numneigh_masked", len(nn), np.int32)[:] = nm
+    o._arr("neighbors", nb.size, np.int32)[:] = nb.reshape(-1)
+    r.pruneNeighbor(); o.pruneNeighbor()
+    a, b = r.raw_lists(), o.raw_lists()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0].sum() < nn.sum(), "nothing was pruned: the test does not exercise the removal path"
+    for ci in range(len(nn)):
+        assert np.array_equal(a[2][ci, :a[0][ci]], b[2][ci, :b[0][ci]])
+
+
 def test_cluster_geometry_matches_survey_goldens():
     """SURVEY 8c structural goldens of BASELINE config 2 (Cu FCC 32^3, 4x4): 32x32 columns of 128 atoms,
     32768 full i-clusters, 13900 ghost clusters, 1 849 584 cluster pairs (min 47, max 89), 32768 masked"""

@@ -1,0 +1,286 @@
+"""GPU parity tests of the CLUSTERPAIR scheme (BASELINE config 2): the CUDA path through the C ABI (mdb_cp_*, via
+the ctypes mirror ClusterSimulation) against the checker (cpbind.OracleCP) on the same inputs, against the golden
+fixtures produced by the reference's clusterpair builds, and at full size through size-independent properties.
+
+Tolerances: clusters (membership, order, bounding boxes), ghost clusters, ghost maps, cluster bins and cluster-pair
+lists (as sorted index sets) bit-exact; forces / x / v / thermo DP rel 1e-10, SP rel 1e-4 (relative to the largest
+magnitude of the compared array; the t = 0 lattice forces are cancellation noise)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_pkg
+from cpbind import OracleCP, initial_atoms
+from test_cp_oracle_pinned import _Fixture, assert_same_structure
+
+pytestmark = pytest.mark.gpu
+
+TOL = {True: 1e-10, False: 1e-4}
+
+
+def make_cp(dp, N, nx, ny=None, nz=None, half=0, aos=True, **kw):
+    m = load_pkg()
+    p = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS if aos else m.SOA, nx=nx, ny=ny or nx, nz=nz or nx,
+                         half_neigh=half, **kw)
+    return m.ClusterSimulation(p, cluster_n=N)
+
+
+def make_oracle(dp, N, nx, ny=None, nz=None, half=0, **kw):
+    o = OracleCP(dp, N, N)   # vector width = N: no dummy padding, like the device lists
+    o.configure(nx=nx, ny=ny, nz=nz, half_neigh=half, **kw)
+    return o
+
+
+def jittered(dp, nx, ny, nz, amp=0.08, seed=3):
+    """lattice atoms displaced by up to `amp` and wrapped: no equal z inside a column (rank-sort path), partially filled
+    clusters at the column ends, atoms on both sides of every periodic face"""
+    x, v = initial_atoms(dp, nx, ny, nz)
+    r = np.random.default_rng(seed)
+    real = np.float64 if dp else np.float32
+    lat = real((4.0 / 0.8442) ** (1.0 / 3.0))
+    prd = np.array([real(nx * lat), real(ny * lat), real(nz * lat)], real)
+    x = (x + r.uniform(-amp, amp, x.shape)).astype(real)
+    x = np.where(x < 0, x + prd, x)
+    x = np.where(x >= prd, x - prd, x).astype(real)
+    return x, v
+
+
+def max_rel(a, b):
+    a, b = np.nan_to_num(np.asarray(a, np.float64), posinf=0, neginf=0), np.nan_to_num(np.asarray(b, np.float64), posinf=0, neginf=0)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def check_forces(s, o, dp, floor=1.0):
+    fs, fo = np.nan_to_num(s.cl("f")), np.nan_to_num(o.cl("f"))
+    real_lane = np.isfinite(o.cl("x")[:len(fo)])
+    d = np.abs(fs - fo)[real_lane].max()
+    assert d <= TOL[dp] * max(floor, np.abs(fo[real_lane]).max()), d
+
+
+@pytest.mark.parametrize("half", [0, 1])
+@pytest.mark.parametrize("N", [4, 8])
+@pytest.mark.parametrize("dp", [True, False])
+def test_structures_forces_trajectory_vs_oracle(dp, N, half):
+    """lattice input (every column is full of z ties: the selection-sort replay decides the cluster contents),
+    operator by operator through two rebuilds"""
+    x, v = initial_atoms(dp, 6)
+    s, o = make_cp(dp, N, 6, half=half), make_oracle(dp, N, 6, half=half)
+    s.setAtoms(x, v); o.set_atoms(x, v)
+    s.setupNeighbor(); s.setupThermo()
+    s.buildClusters(); s.defineJClusters(); s.setupPbc(); s.binClusters(); s.buildNeighbor()
+    o.setup()
+    a, b = s.neigh_params(), o.neigh_params()
+    for k in ("nbinx", "nbiny", "mbinx", "mbiny", "mbins", "mbinxlo", "mbinylo", "nstencil"):
+        assert a[k] == b[k], k
+    for k in ("binsizex", "binsizey", "bininvx", "bininvy", "cutneighsq", "xprd"):
+        assert a[k] == b[k], k
+    assert np.array_equal(a["stencil"], b["stencil"])
+    assert_same_structure(o, s)
+    real_lane = np.isfinite(o.cl("x")[:len(o.cl("v"))])
+    assert np.array_equal(o.cl("v")[real_lane], s.cl("v")[real_lane])
+    assert np.array_equal(o.tags()[1].reshape(-1, N)[:len(s.cluster_tags())], s.cluster_tags())
+    s.computeForce(); o.computeForce()
+    check_forces(s, o, dp)
+    for n in range(45):
+        ra, rb = s.step(n), o.step(n)
+        assert ra == rb
+        if ra:   # independent trajectories: coordinates to rounding, all integer structure still exact
+            assert_same_structure(o, s, tol=TOL[dp])
+    check_forces(s, o, dp, floor=0.0)
+    s.updateSingleAtoms(); o.updateSingleAtoms()
+    xs, ts = s.atoms("x", tags=True)
+    assert np.array_equal(ts, o.tags()[0])
+    assert max_rel(xs, o.atoms("x")) <= TOL[dp]
+    assert max_rel(s.atoms("v"), o.atoms("v")) <= (1e-9 if dp else 1e-3)
+    (Ts, Ps), (To, Po) = s.thermo(), o.thermo()
+    assert abs(Ts - To) <= TOL[dp] * To and abs(Ps - Po) <= TOL[dp] * Po
+    s.close()
+
+
+@pytest.mark.parametrize("aos", [True, False])
+@pytest.mark.parametrize("N", [4, 8])
+@pytest.mark.parametrize("dp", [True, False])
+def test_jittered_noncubic_box_bit_exact(dp, N, aos):
+    """non-cubic box, no z ties, ragged columns (partially filled clusters, odd cluster counts padded for N = 8)"""
+    nx, ny, nz = 5, 7, 6
+    x, v = jittered(dp, nx, ny, nz)
+    s, o = make_cp(dp, N, nx, ny, nz, aos=aos), make_oracle(dp, N, nx, ny, nz)
+    s.setAtoms(x, v); o.set_atoms(x, v)
+    s.setup(adjust=False); o.setup()
+    assert_same_structure(o, s)
+    nat, _ = s.iclusters()
+    assert nat.min() < 4, "the case is meant to contain partially filled clusters"
+    s.computeForce(); o.computeForce()
+    check_forces(s, o, dp, floor=0.0)
+    # wrap + rebuild from moved atoms
+    for n in range(20):
+        s.step(n); o.step(n)
+    assert_same_structure(o, s, tol=TOL[dp])
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["cp44_sp_nx6", "cp44_dp_nx6", "cp44_dp_half_nx6", "cp48ref_dp_nx6", "cp48_dp_nx6", "cp48_sp_nx6"])
+def test_cuda_matches_golden_fixture(golden_dir, name):
+    """the committed snapshots of the REFERENCE's clusterpair builds (tests/golden/make_golden_cp.py)"""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    dp, N, nx, half = g["x0"].dtype == np.float64, int(g["N"]), int(g["nx"]), int(g["half"])
+    s = make_cp(dp, N, nx, half=half)
+    s.setAtoms(g["x0"], g["v0"])
+    s.setup(adjust=False)
+    f = _Fixture(g)
+    if name == "cp48_sp_nx6":   # AVX-512 SP build: rows are padded with dummy entries to its vector width (16 / 8)
+        nn, nm, rows = s.cluster_lists()
+        assert np.array_equal(nn, g["t0_nnz"]) and np.array_equal(nm, g["t0_numneigh_masked"])
+        assert all(np.array_equal(a, b) for a, b in zip(f.cluster_lists()[2], rows))
+        assert_same_structure(f, s, lists=False)
+    else:
+        assert_same_structure(f, s)
+    real_lane = np.isfinite(g["t0_clx"][:len(g["t0_clv"])])
+    assert np.array_equal(g["t0_clv"][real_lane], s.cl("v")[real_lane])
+    if "t0_clf" in g:
+        s.computeForce()
+        fr = np.nan_to_num(g["t0_clf"])
+        assert np.abs(fr - np.nan_to_num(s.cl("f")))[real_lane].max() <= TOL[dp]
+        for n in range(int(g["nsteps"])):
+            s.step(n)
+        s.updateSingleAtoms()
+        assert max_rel(s.atoms("x"), g["tN_x"]) <= TOL[dp]
+        T, P = s.thermo()
+        assert abs(T - g["tN_thermo"][0]) <= TOL[dp] * T and abs(P - g["tN_thermo"][1]) <= TOL[dp] * P
+    s.close()
+
+
+@pytest.mark.parametrize("dp", [True, False])
+def test_createAtom_adjustThermo_on_device(dp):
+    for (nx, ny, nz) in [(6, 6, 6), (5, 7, 3)]:
+        s = make_cp(dp, 4, nx, ny, nz)
+        assert s.createAtom() == 4 * nx * ny * nz
+        x, v = initial_atoms(dp, nx, ny, nz)
+        assert np.array_equal(s.atoms("x"), x)
+        s.setupThermo(); s.adjustThermo()
+        assert max_rel(s.atoms("v"), v) <= (1e-12 if dp else 1e-5)
+        s.close()
+
+
+@pytest.mark.parametrize("N,half", [(4, 0), (8, 0), (4, 1)])
+def test_run_loop_equals_operator_by_operator(N, half):
+    """mdb_cp_run (device-resident loop, fused final+initial integrate) == the same operators called one by one"""
+    x, v = jittered(True, 6, 6, 6, amp=0.1)
+    a, b = make_cp(True, N, 6, half=half, nstat=25), make_cp(True, N, 6, half=half, nstat=25)
+    for s in (a, b):
+        s.setAtoms(x, v)
+        s.setup(adjust=False)
+    rec, _ = a.run(60)
+    recs = [(0,) + b.thermo()]
+    b.computeForce()
+    for n in range(60):
+        b.step(n)
+        if (n + 1) % 25 == 0 and n + 1 < 60:
+            recs.append((n + 1,) + b.thermo())
+    b.updateSingleAtoms()
+    recs.append((60,) + b.thermo())
+    assert np.array_equal(rec[:, 0], [q[0] for q in recs])
+    if half:   # reaction forces are accumulated with atomics: summation order is not fixed
+        assert np.allclose(rec, np.array(recs), rtol=1e-12)
+        assert max_rel(a.atoms("x"), b.atoms("x")) < 1e-12
+    else:
+        assert np.array_equal(rec, np.array(recs))
+        assert np.array_equal(a.atoms("x"), b.atoms("x")) and np.array_equal(a.atoms("v"), b.atoms("v"))
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("dp,N", [(True, 4), (False, 8)])
+def test_prune_neighbor_vs_oracle(dp, N):
+    """pruneNeighbor 15 steps after the build: the device's list (its row order) and cluster positions are handed to
+    the checker, both prune, rows agree entry by entry; forces from the pruned list equal those from the full list"""
+    x, v = initial_atoms(dp, 6)
+    s, o = make_cp(dp, N, 6), make_oracle(dp, N, 6)
+    s.setAtoms(x, v); o.set_atoms(x, v)
+    s.setup(adjust=False); o.setup()
+    s.computeForce()
+    for n in range(15):
+        s.step(n)
+    nn, nm, nb = s.raw_lists()
+    assert o.geti("maxneighs") == s.counts()["maxneighs"]
+    o._arr("numneigh", len(nn), np.int32)[:] = nn
+    o._arr("numneigh_masked", len(nn), np.int32)[:] = nm
+    o._arr("neighbors", nb.size, np.int32)[:] = nb.reshape(-1)
+    xs = s.cl("x")
+    o._arr("cl_x", xs.size, o.np_real)[:] = xs.reshape(-1)
+    s.computeForce()
+    f_full = s.cl("f").copy()
+    s.pruneNeighbor(); o.pruneNeighbor()
+    a, b = s.raw_lists(), o.raw_lists()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0].sum() < nn.sum()
+    for ci in range(len(nn)):
+        assert np.array_equal(a[2][ci, :a[0][ci]], b[2][ci, :b[0][ci]])
+    s.computeForce()
+    assert max_rel(s.cl("f"), f_full) <= (1e-12 if dp else 1e-5)
+    s.close()
+
+
+def test_config2_structural_goldens_and_thermo(golden_dir):
+    """BASELINE config 2: Cu FCC 32^3, clusterpair 4x4 SP, 200 steps.  Structure at t = 0 (32x32 columns,
+    32768 full i-clusters, 13900 ghost clusters, 1 849 584 cluster pairs, min 47, max 89, 32768 masked) and the thermo
+    records of the reference's scalar 4x4 SP build (tests/golden/thermo_cp.json)."""
+    s = make_cp(False, 4, 32)
+    s.createAtom()
+    s.setup(adjust=True)
+    c = s.counts()
+    p = s.neigh_params()
+    assert (p["nbinx"], p["nbiny"]) == (32, 32)
+    assert (c["Nclusters_local"], c["Nclusters_ghost"], c["Nghost"], c["dummy_cj"]) == (32768, 13900, 55600, 46668)
+    nn, nm, _ = s.raw_lists()
+    assert int(nn.sum()) == 1849584 and nn.min() == 47 and nn.max() == 89 and int(nm.sum()) == 32768
+    assert np.all(s.iclusters()[0] == 4)
+    rec, tm = s.run(200)
+    gold = [q for q in json.load(open(os.path.join(golden_dir, "thermo_cp.json"))) if q["variant"] == "cpref44_sp"][0]
+    assert np.array_equal(rec[:, 0], [q[0] for q in gold["records"]])
+    for got, want in zip(rec, gold["records"]):
+        assert abs(got[1] - want[1]) <= 1e-4 * want[1] and abs(got[2] - want[2]) <= 1e-4 * want[2], (got, want)
+    # SP trajectories agree to 1e-4 only: a bounding box may end up on the other side of the ghost cutoff
+    assert abs(s.counts()["Nclusters_ghost"] - gold["nclusters_ghost"]) <= 0.005 * gold["nclusters_ghost"]
+    assert tm["TOTAL"] > 0
+    s.close()
+
+
+@pytest.mark.parametrize("dp,N,half", [(True, 4, 0), (False, 4, 1), (True, 8, 0)])
+def test_config2_dp_thermo_and_properties(golden_dir, dp, N, half):
+    """size-independent properties at 32^3: every atom in exactly one cluster slot, zero net force at the end (the
+    last step follows a rebuild), momentum conserved over 200 steps for M = N.  (With N = 2M the lists are not
+    symmetric -- a 4-atom i-cluster against an 8-atom j-cluster -- so an atom that outruns the skin between two
+    rebuilds leaves a one-sided pair and the reference's 4x8 scheme itself does not conserve momentum at T = 1.44:
+    the checker shows the same drift, profiles/dbg_cp.py.)"""
+    s = make_cp(dp, N, 32, half=half)
+    s.createAtom()
+    s.setup(adjust=True)
+    tags = s.cluster_tags()[:s.counts()["ncj"]].reshape(-1)
+    assert np.array_equal(np.sort(tags[tags >= 0]), np.arange(131072))
+    v0 = s.atoms("v").astype(np.float64).sum(axis=0)
+    rec, _ = s.run(200)
+    f = np.nan_to_num(s.cl("f").astype(np.float64))
+    fmax = np.abs(f).max()
+    assert fmax > 1.0
+    assert np.all(np.abs(f.sum(axis=(0, 2))) <= (1e-9 if dp else 2e-2) * fmax)
+    v1 = s.atoms("v").astype(np.float64).sum(axis=0)
+    if N == 4:
+        assert np.all(np.abs(v1 - v0) <= (1e-9 if dp else 5e-2))
+    if dp and N == 4 and not half:
+        gold = [q for q in json.load(open(os.path.join(golden_dir, "thermo_cp.json"))) if q["variant"] == "cpref44_dp"][0]
+        for got, want in zip(rec, gold["records"]):
+            assert abs(got[1] - want[1]) <= 1e-9 * want[1] and abs(got[2] - want[2]) <= 1e-9 * want[2], (got, want)
+    s.close()
+
+
+def test_maxneighs_overflow_resize():
+    """rows longer than maxneighs (100): the build is repeated with 1.2 x the longest row (neighbor.c:412-428)"""
+    x, v = initial_atoms(True, 6)
+    s, o = make_cp(True, 4, 6, skin=1.6), make_oracle(True, 4, 6, skin=1.6)
+    s.setAtoms(x, v); o.set_atoms(x, v)
+    s.setup(adjust=False); o.setup()
+    assert s.counts()["maxneighs"] == o.geti("maxneighs") > 100
+    assert_same_structure(o, s)
+    s.close()
