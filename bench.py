@@ -29,6 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 METRIC = "atom-steps/sec (LJ Cu FCC, verletlist, full neighbor lists)"
+METRIC_CP = "atom-steps/sec (LJ Cu FCC, clusterpair %dx%d)"
 UNIT = "atom-steps/s"
 # algorithmic work of the LJ full-list force kernel per atom-step
 FLOP_PER_ATOM_STEP = 1429.0           # 8*L + 15*C, L = 76.035 listed, C = 54.74 inside the cutoff
@@ -176,8 +177,12 @@ def reference_arm(args, rank, world):
 
 def workload_config(args, world, grid=(1, 1, 1)):
     return {"workload": "Cu FCC %dx%dx%d unit cells per GPU (%d atoms/GPU), LJ sigma=eps=1 rc=2.5 skin=0.3, reneigh 20, "
-                        "verletlist full neighbor lists, %s, %d timesteps per bench step (BASELINE config 1 physics at config 5 per-GPU size)"
-                        % (args.nx, args.nx, args.nx, 4 * args.nx ** 3, args.precision.upper(), args.ntimes),
+                        "%s, %s, %d timesteps per bench step (BASELINE config 1 physics at config 5 per-GPU size)"
+                        % (args.nx, args.nx, args.nx, 4 * args.nx ** 3,
+                           ("clusterpair 4x%d %s cluster-pair lists" % (args.cluster_n, "half" if args.half else "full"))
+                           if getattr(args, "scheme", "verletlist") == "clusterpair"
+                           else "verletlist %s neighbor lists" % ("half" if args.half else "full"),
+                           args.precision.upper(), args.ntimes),
             "nx_per_gpu": args.nx, "ntimes": args.ntimes, "precision": args.precision,
             "l2": "inputs larger than L2 (neighbor list %.1f GB + positions %.2f GB per GPU vs 126 MB L2)"
                   % (4 * args.nx ** 3 * 100 * 4 / 1e9, 4 * args.nx ** 3 * 24 / 1e9),
@@ -206,6 +211,9 @@ def main():
     ap.add_argument("--sort", action="store_true", help="A/B: re-sort the atoms by bin at every rebuild (SORT_ATOMS)")
     ap.add_argument("--opt", action="append", default=[], help="name=value for mdb_setOption (A/B)")
     ap.add_argument("--bricks", default=None, help="gx,gy,gz: run a decomposed box on ONE GPU (debug / A-B)")
+    ap.add_argument("--scheme", default="verletlist", choices=["verletlist", "clusterpair"],
+                    help="OPT_SCHEME of the reference; clusterpair = GROMACS-style 4 x N cluster pairs (one GPU)")
+    ap.add_argument("--cluster-n", type=int, default=4, choices=[4, 8])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,7 +233,15 @@ def main():
     dp = args.precision == "dp"
     decomposed = world > 1 or args.bricks is not None
     stream = torch.cuda.current_stream().cuda_stream
-    if decomposed:
+    cp = args.scheme == "clusterpair"
+    if cp and decomposed:
+        raise SystemExit("bench.py: the clusterpair scheme runs one domain per GPU (no decomposition yet)")
+    if cp:
+        grid = (1, 1, 1)
+        P = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx,
+                             ntimes=args.ntimes, half_neigh=args.half)
+        sim = m.ClusterSimulation(P, cluster_n=args.cluster_n, device=local)
+    elif decomposed:
         # spatial decomposition: one brick per GPU (or --bricks gx,gy,gz on one GPU), ghosts over NCCL/NVLink
         grid = tuple(int(v) for v in args.bricks.split(",")) if args.bricks else m.dd_grid(world)
         uid = [m.dd_unique_id() if (rank == 0 and world > 1) else None]
@@ -240,7 +256,7 @@ def main():
                              ntimes=args.ntimes, half_neigh=args.half)
         sim = m.Simulation(P, device=local)
     sim.setStream(stream)
-    if args.sort:
+    if args.sort and not cp:
         sim.setOption("sort_atoms", 1)
     for kv in args.opt:
         k, v = kv.split("=")
@@ -292,7 +308,12 @@ def main():
     f_ms = ks["force_ms"] / max(1, ks["force_launches"])
     per_launch_atoms = nlocal0 / (grid[0] * grid[1] * grid[2] // world)   # atoms one force launch covers
     peak_tf = m.measure_fma_peak(m.DP if dp else m.SP, local)
-    ach_tf = FLOP_PER_ATOM_STEP * per_launch_atoms / (f_ms * 1e-3) * 1e-12
+    flop_per_atom = FLOP_PER_ATOM_STEP
+    if cp:
+        # 8 flop per evaluated atom pair (every listed cluster pair = M x N atom pairs) + 15 more per pair
+        # inside the cutoff; counts taken live from the current list (mean of the first and the last list of a run)
+        flop_per_atom = (8.0 * 0.5 * (listed0 + listed1) * 4 * args.cluster_n + 15.0 * 0.5 * (inside0 + inside1)) / natoms
+    ach_tf = flop_per_atom * per_launch_atoms / (f_ms * 1e-3) * 1e-12
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -300,17 +321,20 @@ def main():
     except Exception:
         pass
     ach_gbs = BYTES_PER_ATOM_STEP[args.precision] * per_launch_atoms / (f_ms * 1e-3) * 1e-9
-    roofline = {"kernel": "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
+    roofline = {"kernel": ("k_cp_force_lj<%s,%d,%s>" % ("double" if dp else "float", args.cluster_n, "half" if args.half else "full")) if cp
+                else "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
                 "bound": "fp64" if dp else "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
                 "peak_source": "measured in this run: FMA issue micro-benchmark (md-bench_b200/csrc/peaks.cu)",
-                "ms_per_launch": f_ms, "flop_per_atom_step": FLOP_PER_ATOM_STEP,
+                "ms_per_launch": f_ms, "flop_per_atom_step": flop_per_atom,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "bytes_per_atom_step": BYTES_PER_ATOM_STEP[args.precision], "peak_source": hbm_src},
                 "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
                 "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"]),
                 "halo_ms_per_step": (ks["comm_ms"] / args.ntimes) if decomposed else None,
                 "pairs_per_atom": None if decomposed else
+                {"cluster_pairs_per_atom_t0": listed0 / natoms, "in_cutoff_t0": inside0 / natoms,
+                 "cluster_pairs_per_atom_end": listed1 / natoms, "in_cutoff_end": inside1 / natoms} if cp else
                 {"listed_t0": listed0 / natoms, "in_cutoff_t0": inside0 / natoms,
                  "listed_end": listed1 / natoms, "in_cutoff_end": inside1 / natoms}}
 
@@ -331,6 +355,13 @@ def main():
             ov = torch.empty((3, cap), dtype=tdt, pin_memory=True)
             sim.get_into("x", htag.numpy(), hx.numpy())
             sim.get_into("v", None, hv.numpy())
+        elif cp:   # positions AoS, velocities SoA (clusterpair/atom.h:66-92)
+            hx = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+            hv = torch.empty((3, natoms), dtype=tdt, pin_memory=True)
+            ox = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
+            ov = torch.empty((3, natoms), dtype=tdt, pin_memory=True)
+            sim.get("x", out=hx.numpy())
+            sim.get("v", out=hv.numpy())
         else:
             hx = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
             hv = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
@@ -349,6 +380,12 @@ def main():
                 assert sim.counts()["Nlocal"] <= cap
                 sim.get_into("x", otag.numpy(), ox.numpy())          # D2H of the final state
                 sim.get_into("v", None, ov.numpy())
+            elif cp:
+                sim.setAtomsRaw(hx.numpy(), hv.numpy())
+                sim.setup(adjust=False)
+                rec_e, _ = sim.run(args.ntimes)   # ends with updateSingleAtoms: the atom arrays hold the final state
+                sim.get("x", out=ox.numpy())
+                sim.get("v", out=ov.numpy())
             else:
                 sim.setAtoms(hx.numpy(), hv.numpy())
                 sim.setup(adjust=False)
@@ -371,7 +408,7 @@ def main():
         cpu = cpu_baseline()
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": (METRIC_CP % (4, args.cluster_n)) if cp else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64" if dp else "f32", "data": "synthetic", "config": workload_config(args, world, grid),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,

@@ -599,6 +599,26 @@ class ClusterSimulation:
             a = np.stack(cols, axis=1)
         return (a, t) if tags else a
 
+    def get(self, what, out=None):
+        """x / v of the atom arrays as (n,3); `out`: preallocated C-contiguous (n,3) array for 'x' in the AOS layout
+        (e.g. a view of pinned host memory), or a (3,n) array for SoA data"""
+        n = self.counts()["Nlocal"]
+        if what == "x" and self.aos:
+            a = out if out is not None else np.empty((n, 3), self.np_real)
+            assert a.shape == (n, 3) and a.dtype == self.np_real and a.flags["C_CONTIGUOUS"]
+            self._ck(self.L.mdb_cp_getAtoms(self.h, ord("x"), _vp(a), None, None, None))
+            return a
+        a = out if out is not None else np.empty((3, n), self.np_real)
+        assert a.shape == (3, n) and a.dtype == self.np_real and a.flags["C_CONTIGUOUS"]
+        self._ck(self.L.mdb_cp_getAtoms(self.h, ord(what), _vp(a[0]), _vp(a[1]), _vp(a[2]), None))
+        return a
+
+    def setAtomsRaw(self, x_aos, v_soa):
+        """x: (n,3) C-contiguous (AOS layout ctx), v: (3,n) C-contiguous -- no host-side repacking (bench e2e leg)"""
+        n = x_aos.shape[0]
+        self._ck(self.L.mdb_cp_setAtoms(self.h, C.c_longlong(n), _vp(x_aos), None, None, _vp(v_soa[0]), _vp(v_soa[1]),
+                                        _vp(v_soa[2])))
+
     def setOption(self, name, value): self._ck(self.L.mdb_cp_setOption(self.h, name.encode(), C.c_double(value)))
     def saveState(self): self._ck(self.L.mdb_cp_saveState(self.h))
     def restoreState(self): self._ck(self.L.mdb_cp_restoreState(self.h))

@@ -17,6 +17,12 @@
 namespace mdb {
 
 constexpr int CP_M = 4;
+// Padding lanes of partially filled tiles, and the dummy tile: the reference stores +INFINITY there and relies on
+// inf/NaN failing `rsq < cutforcesq`.  The device arrays hold a large FINITE sentinel instead, so
+// the force kernels can run branch-free (a masked pair contributes 0 * finite, never 0 * inf); the accessor that
+// hands cl_x back to the caller turns the sentinel into +INFINITY again.  Real coordinates are < 1e6.
+#define CP_PAD ((real)1.0e15)
+#define CP_PAD_MIN ((real)1.0e14)
 
 // geometry of clusterpair/neighbor.c:26-45 (2-D bins = columns along z)
 template <class real> struct CpGeom {
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
                 ct[cii] = tag[i];
                 nat++;
             } else {
-                cx[cii] = INFINITY; cx[N + cii] = INFINITY; cx[2 * N + cii] = INFINITY;
+                cx[cii] = CP_PAD; cx[N + cii] = CP_PAD; cx[2 * N + cii] = CP_PAD;
                 cv[cii] = 0; cv[N + cii] = 0; cv[2 * N + cii] = 0;
                 ct[cii] = -1;
             }
@@ -293,7 +299,7 @@ __global__ void k_cp_update_pbc_first(int ncj, int nghost, real xprd, real yprd,
     const int cj = ncj + g;
     real* d = cl_x + (size_t)cj * N * 3;
     if (g == nghost) { // the dummy cluster at the end, pbc.c:304-311
-        for (int q = 0; q < 3 * N; q++) d[q] = INFINITY;
+        for (int q = 0; q < 3 * N; q++) d[q] = CP_PAD;
         return;
     }
     const int c = code[g], nat = jnat[cj];
@@ -310,7 +316,7 @@ __global__ void k_cp_update_pbc_first(int ncj, int nghost, real xprd, real yprd,
                 d[a * N + q] = v;
                 if (lo > v) lo = v;
                 if (hi < v) hi = v;
-            } else d[a * N + q] = INFINITY;
+            } else d[a * N + q] = CP_PAD;
         }
         bb[2 * a] = lo; bb[2 * a + 1] = hi;
     }
@@ -522,6 +528,14 @@ __global__ void __launch_bounds__(128) k_cp_prune(int ncl, real cutsq, const int
 // keep j > own lane (force_lj.c:99-113).  Padding lanes sit at +infinity: rsq is inf / NaN and fails the cutoff
 // test (no fast-math anywhere in this library).
 template <class real> struct CpTileLoad;
+__device__ __forceinline__ float rcp_fast(float a);
+__device__ __forceinline__ double rcp_fast(double a);
+template <class real> __device__ __forceinline__ real lj_pair_fast(real rsq, const LJConst2<real>& c)
+{
+    const real s  = rcp_fast(rsq);
+    const real s3 = s * s * s;
+    return (s * s3) * (c.A * s3 - c.B);
+}
 template <> struct CpTileLoad<double> {
     template <int N> static __device__ __forceinline__ void load(const double* p, double (&v)[N])
     {
@@ -543,65 +557,95 @@ template <> struct CpTileLoad<float> {
     }
 };
 
+// reciprocal for the pair kernels: SP = MUFU.RCP + one Newton step (2 FFMA, ~1 ulp), DP = rcp_nr (vl_kernels.cuh)
+__device__ __forceinline__ float rcp_fast(float a)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    const float e = fmaf(-a, y, 1.0f);
+    return fmaf(y, e, y);
+}
+__device__ __forceinline__ double rcp_fast(double a) { return rcp_nr(a); }
+
+// one j tile against the lane's i-atom, branch-free.  DIAG: the tile is the i-cluster's own j-cluster.
+template <class real, int N, bool HALF, bool DIAG>
+__device__ __forceinline__ void cp_tile(const real* __restrict__ t, const LJConst2<real>& c, real xt, real yt, real zt, int ii,
+    int cii, bool react, real* __restrict__ fj, real& fix, real& fiy, real& fiz)
+{
+    real xj[N], yj[N], zj[N];
+    CpTileLoad<real>::template load<N>(t, xj);
+    CpTileLoad<real>::template load<N>(t + N, yj);
+    CpTileLoad<real>::template load<N>(t + 2 * N, zj);
+    real rx[N], ry[N], rz[N];
+#pragma unroll
+    for (int q = 0; q < N; q++) {
+        const real dx = xt - xj[q], dy = yt - yj[q], dz = zt - zj[q];
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        bool in = rsq < c.cutforcesq;
+        if (DIAG) in = in && (HALF ? (ii < q) : (ii != q)); // force_lj.c:99-113
+        real f = lj_pair_fast(rsq, c);
+        f      = in ? f : (real)0; // rsq == 0 on the excluded self pair gives inf/NaN: discarded here, never multiplied
+        if (HALF) {
+            rx[q] = dx * f; ry[q] = dy * f; rz[q] = dz * f;
+            fix += rx[q]; fiy += ry[q]; fiz += rz[q];
+        } else {
+            fix = fma(dx, f, fix); fiy = fma(dy, f, fiy); fiz = fma(dz, f, fiz);
+        }
+    }
+    if (HALF) { // reaction on the j tile: sum over the 4 lanes of the i-cluster, then one atomic per j atom and lane
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            real sx = rx[q], sy = ry[q], sz = rz[q];
+            sx += __shfl_xor_sync(0xffffffffu, sx, 1); sy += __shfl_xor_sync(0xffffffffu, sy, 1); sz += __shfl_xor_sync(0xffffffffu, sz, 1);
+            sx += __shfl_xor_sync(0xffffffffu, sx, 2); sy += __shfl_xor_sync(0xffffffffu, sy, 2); sz += __shfl_xor_sync(0xffffffffu, sz, 2);
+            if (react && cii == (q & 3) && (sx != 0 || sy != 0 || sz != 0)) {
+                atomicAdd(fj + q, -sx); atomicAdd(fj + N + q, -sy); atomicAdd(fj + 2 * N + q, -sz);
+            }
+        }
+    }
+}
+
 template <class real, int N, bool HALF>
 __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<real> c, const real* __restrict__ cl_x,
-    const int* __restrict__ numneigh, const int* __restrict__ neighbors, int maxneighs, real* __restrict__ cl_f)
+    const int* __restrict__ numneigh, const int* __restrict__ numneigh_masked, const int* __restrict__ neighbors, int maxneighs,
+    real* __restrict__ cl_f)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int ci  = tid >> 2, cii = tid & 3;
     const bool valid = ci < ncl;
     const int cic = valid ? ci : ncl - 1;
     const size_t ib = cp_ci_base3<N>(cic);
-    const real xt = cl_x[ib + cii], yt = cl_x[ib + N + cii], zt = cl_x[ib + 2 * N + cii];
+    real xt = cl_x[ib + cii], yt = cl_x[ib + N + cii], zt = cl_x[ib + 2 * N + cii];
+    const bool pad_i = xt >= CP_PAD_MIN;
+    if (pad_i) xt = yt = zt = -CP_PAD; // far from every real atom AND from the +CP_PAD padding lanes of the j tiles
     const int self = cp_cj0<N>(cic);
     const int ii   = N == CP_M ? cii : cii + CP_M * (cic & 1); // own lane inside the diagonal tile
     const int nn   = valid ? numneigh[cic] : 0;
+    const int nm   = valid ? numneigh_masked[cic] : 0; // the list build keeps the diagonal entries in front (neighbor.c:374-385)
     const int* row = neighbors + (size_t)cic * maxneighs;
     real fix = 0, fiy = 0, fiz = 0;
     int cjn = nn > 0 ? __ldg(row) : 0;
-    for (int k = 0; k < nn; k++) {
+    int k   = 0;
+    for (; k < nm; k++) {
         const int cj = cjn;
         if (k + 1 < nn) cjn = __ldg(row + k + 1);
         const real* t = cl_x + (size_t)cj * N * 3;
-        real xj[N], yj[N], zj[N];
-        CpTileLoad<real>::template load<N>(t, xj);
-        CpTileLoad<real>::template load<N>(t + N, yj);
-        CpTileLoad<real>::template load<N>(t + 2 * N, zj);
-        const bool diag = cj == self;
-        real rx[N], ry[N], rz[N];
-#pragma unroll
-        for (int q = 0; q < N; q++) {
-            const real dx = xt - xj[q], dy = yt - yj[q], dz = zt - zj[q];
-            const real rsq = dx * dx + dy * dy + dz * dz;
-            const bool excl = diag && (HALF ? !(ii < q) : (ii == q));
-            // padding lanes are at +inf: dx is inf/NaN there, so nothing may be accumulated unless the pair is in range
-            real px = 0, py = 0, pz = 0;
-            if (rsq < c.cutforcesq && !excl) {
-                const real f = lj_pair2(rsq, c);
-                px = dx * f; py = dy * f; pz = dz * f;
-            }
-            fix += px; fiy += py; fiz += pz;
-            if (HALF) { rx[q] = px; ry[q] = py; rz[q] = pz; }
-        }
-        // reaction on the j tile: sum over the 4 lanes of the i-cluster, then one atomic per j atom.  The reference also
-        // subtracts from ghost tiles (its HALF_NEIGHBOR_LISTS_CHECK_CJ guard is ineffective) but never
-        // reads them back; skipping cj >= ncj leaves every local force unchanged.
-        if (HALF && cj < ncj) {
-            real* fj = cl_f + (size_t)cj * N * 3;
-#pragma unroll
-            for (int q = 0; q < N; q++) {
-                real sx = rx[q], sy = ry[q], sz = rz[q];
-                sx += __shfl_xor_sync(0xffffffffu, sx, 1); sy += __shfl_xor_sync(0xffffffffu, sy, 1); sz += __shfl_xor_sync(0xffffffffu, sz, 1);
-                sx += __shfl_xor_sync(0xffffffffu, sx, 2); sy += __shfl_xor_sync(0xffffffffu, sy, 2); sz += __shfl_xor_sync(0xffffffffu, sz, 2);
-                if (cii == (q & 3) && (sx != 0 || sy != 0 || sz != 0)) {
-                    atomicAdd(fj + q, -sx); atomicAdd(fj + N + q, -sy); atomicAdd(fj + 2 * N + q, -sz);
-                }
-            }
-        }
+        real* fj      = cl_f + (size_t)cj * N * 3;
+        // the reference also subtracts from ghost tiles (its HALF_NEIGHBOR_LISTS_CHECK_CJ guard is ineffective, SURVEY 8a
+        // a16) but never reads them back; skipping cj >= ncj leaves every local force unchanged.
+        if (cj == self) cp_tile<real, N, HALF, true>(t, c, xt, yt, zt, ii, cii, cj < ncj, fj, fix, fiy, fiz);
+        else cp_tile<real, N, HALF, false>(t, c, xt, yt, zt, ii, cii, cj < ncj, fj, fix, fiy, fiz);
+    }
+    for (; k < nn; k++) {
+        const int cj = cjn;
+        if (k + 1 < nn) cjn = __ldg(row + k + 1);
+        cp_tile<real, N, HALF, false>(cl_x + (size_t)cj * N * 3, c, xt, yt, zt, ii, cii, cj < ncj, cl_f + (size_t)cj * N * 3, fix,
+            fiy, fiz);
     }
     if (!valid) return;
+    if (pad_i) fix = fiy = fiz = 0;
     if (HALF) {
-        atomicAdd(cl_f + ib + cii, fix); atomicAdd(cl_f + ib + N + cii, fiy); atomicAdd(cl_f + ib + 2 * N + cii, fiz);
+        if (!pad_i) { atomicAdd(cl_f + ib + cii, fix); atomicAdd(cl_f + ib + N + cii, fiy); atomicAdd(cl_f + ib + 2 * N + cii, fiz); }
     } else {
         cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
     }
@@ -656,7 +700,8 @@ __global__ void k_cp_count_pairs(int ncl, real cutforcesq, const real* __restric
     unsigned long long listed = 0, inside = 0;
     if (ci < ncl) {
         const size_t ib = cp_ci_base3<N>(ci);
-        const real xt = cl_x[ib + cii], yt = cl_x[ib + N + cii], zt = cl_x[ib + 2 * N + cii];
+        real xt = cl_x[ib + cii], yt = cl_x[ib + N + cii], zt = cl_x[ib + 2 * N + cii];
+        if (xt >= CP_PAD_MIN) xt = yt = zt = -CP_PAD;
         const int nn = numneigh[ci];
         if (cii == 0) listed = nn;
         for (int k = 0; k < nn; k++) {

@@ -561,10 +561,10 @@ template <class real, int N> struct CpSim final : CpBase {
         if (P.half_neigh) {
             MDB_CUDA(cudaMemsetAsync(cl_f.p, 0, (size_t)ncj * 3 * N * sizeof(real), stream));
             MDB_LAUNCH(launches, (k_cp_force_lj<real, N, true>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
-                neighbors.p, maxneighs, cl_f.p);
+                numneigh_masked.p, neighbors.p, maxneighs, cl_f.p);
         } else {
             MDB_LAUNCH(launches, (k_cp_force_lj<real, N, false>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
-                neighbors.p, maxneighs, cl_f.p);
+                numneigh_masked.p, neighbors.p, maxneighs, cl_f.p);
         }
         force_launches++;
         if (timing) {
@@ -727,11 +727,17 @@ template <class real, int N> struct CpSim final : CpBase {
     }
     void getClusterData(int which, void* out) override
     {
-        if (which == 'x') d2h(out, cl_x.p, (size_t)(ncj + nghost) * 3 * N * sizeof(real));
+        const size_t nx = (size_t)(ncj + nghost) * 3 * N;
+        if (which == 'x') d2h(out, cl_x.p, nx * sizeof(real));
         else if (which == 'v') d2h(out, cl_v.p, (size_t)ncj * 3 * N * sizeof(real));
         else if (which == 'f') d2h(out, cl_f.p, (size_t)ncj * 3 * N * sizeof(real));
         else throw Error("mdb_cp_getClusterData: which must be 'x', 'v' or 'f'");
         MDB_CUDA(cudaStreamSynchronize(stream));
+        if (which == 'x') { // padding lanes: device sentinel -> the reference's +INFINITY (cp_kernels.cuh, CP_PAD)
+            real* o = (real*)out;
+            for (size_t k = 0; k < nx; k++)
+                if (o[k] >= CP_PAD_MIN) o[k] = INFINITY;
+        }
     }
     void getClusterTags(int* tags) override
     {
