@@ -605,6 +605,116 @@ __device__ __forceinline__ void cp_tile(const real* __restrict__ t, const LJCons
     }
 }
 
+// ---- SP, full lists: the same tile with PACKED FP32 arithmetic (sm_100 add/mul/fma.f32x2 -> FADD2 / FMUL2 / FFMA2).
+// The scalar kernel is bound by instruction issue (ncu: issue 81 %, FMA pipe 55 %, profiles/r1_s3_cp_force_raw.txt).
+// A packed instruction does two lanes' worth of work for one issue slot (measured: FFMA2 reaches the same 72.7 TFLOP/s
+// as FFMA at half the issue rate and keeps it with integer work mixed in, profiles/ubench_ffma2.cu), so evaluating
+// j atoms (q, q+1) together moves the bound from issue to the FMA pipe itself.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+struct CpPackedConst {
+    f32x2 A, negB, one;
+    float cutforcesq;
+};
+template <int N, bool DIAG>
+__device__ __forceinline__ void cp_tile_packed(const float* __restrict__ t, const CpPackedConst& c, f32x2 xt, f32x2 yt, f32x2 zt,
+    int ii, f32x2& fx, f32x2& fy, f32x2& fz)
+{
+    f32x2 xj[N / 2], yj[N / 2], zj[N / 2];
+#pragma unroll
+    for (int q = 0; q < N / 2; q += 2) { // one 128-bit load = two packed pairs
+        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(xj[q]), "=l"(xj[q + 1]) : "l"(t + 2 * q));
+        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(yj[q]), "=l"(yj[q + 1]) : "l"(t + N + 2 * q));
+        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(zj[q]), "=l"(zj[q + 1]) : "l"(t + 2 * N + 2 * q));
+    }
+#pragma unroll
+    for (int q = 0; q < N / 2; q++) {
+        const f32x2 dx = sub2(xt, xj[q]), dy = sub2(yt, yj[q]), dz = sub2(zt, zj[q]);
+        const f32x2 rsq = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+        float r0, r1, y0, y1;
+        upk2(rsq, r0, r1);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(r0));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(r1));
+        bool in0 = r0 < c.cutforcesq, in1 = r1 < c.cutforcesq;
+        if (DIAG) { in0 = in0 && ii != 2 * q; in1 = in1 && ii != 2 * q + 1; }
+        f32x2 y        = pk2(y0, y1);
+        const f32x2 nr = sub2(c.one, mul2(rsq, y)); // Newton step: y += y * (1 - rsq * y)
+        y              = fma2(y, nr, y);
+        const f32x2 s3 = mul2(mul2(y, y), y);
+        f32x2 f        = mul2(mul2(y, s3), fma2(c.A, s3, c.negB));
+        float f0, f1;
+        upk2(f, f0, f1);
+        f  = pk2(in0 ? f0 : 0.0f, in1 ? f1 : 0.0f); // excluded self pair: rsq = 0 gives inf/NaN, discarded here
+        fx = fma2(dx, f, fx); fy = fma2(dy, f, fy); fz = fma2(dz, f, fz);
+    }
+}
+template <int N>
+__global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, LJConst2<float> c, const float* __restrict__ cl_x,
+    const int* __restrict__ numneigh, const int* __restrict__ numneigh_masked, const int* __restrict__ neighbors, int maxneighs,
+    float* __restrict__ cl_f)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci  = tid >> 2, cii = tid & 3;
+    const bool valid = ci < ncl;
+    const int cic = valid ? ci : ncl - 1;
+    const size_t ib = cp_ci_base3<N>(cic);
+    float x0 = cl_x[ib + cii], y0 = cl_x[ib + N + cii], z0 = cl_x[ib + 2 * N + cii];
+    const bool pad_i = x0 >= 1.0e14f;
+    if (pad_i) x0 = y0 = z0 = -1.0e15f;
+    const f32x2 xt = pk2(x0, x0), yt = pk2(y0, y0), zt = pk2(z0, z0);
+    CpPackedConst pc { pk2(c.A, c.A), pk2(-c.B, -c.B), pk2(1.0f, 1.0f), c.cutforcesq };
+    const int self = cp_cj0<N>(cic);
+    const int ii   = N == CP_M ? cii : cii + CP_M * (cic & 1);
+    const int nn   = valid ? numneigh[cic] : 0;
+    const int nm   = valid ? numneigh_masked[cic] : 0;
+    const int* row = neighbors + (size_t)cic * maxneighs;
+    f32x2 fx = pk2(0.f, 0.f), fy = fx, fz = fx;
+    int cjn = nn > 0 ? __ldg(row) : 0;
+    int k   = 0;
+    for (; k < nm; k++) {
+        const int cj = cjn;
+        if (k + 1 < nn) cjn = __ldg(row + k + 1);
+        const float* t = cl_x + (size_t)cj * N * 3;
+        if (cj == self) cp_tile_packed<N, true>(t, pc, xt, yt, zt, ii, fx, fy, fz);
+        else cp_tile_packed<N, false>(t, pc, xt, yt, zt, ii, fx, fy, fz);
+    }
+    for (; k < nn; k++) {
+        const int cj = cjn;
+        if (k + 1 < nn) cjn = __ldg(row + k + 1);
+        cp_tile_packed<N, false>(cl_x + (size_t)cj * N * 3, pc, xt, yt, zt, ii, fx, fy, fz);
+    }
+    if (!valid) return;
+    float a, b;
+    upk2(fx, a, b); const float fix = pad_i ? 0.f : a + b;
+    upk2(fy, a, b); const float fiy = pad_i ? 0.f : a + b;
+    upk2(fz, a, b); const float fiz = pad_i ? 0.f : a + b;
+    cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
+}
+
 template <class real, int N, bool HALF>
 __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<real> c, const real* __restrict__ cl_x,
     const int* __restrict__ numneigh, const int* __restrict__ numneigh_masked, const int* __restrict__ neighbors, int maxneighs,
@@ -648,6 +758,189 @@ __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<
         if (!pad_i) { atomicAdd(cl_f + ib + cii, fix); atomicAdd(cl_f + ib + N + cii, fiy); atomicAdd(cl_f + ib + 2 * N + cii, fiz); }
     } else {
         cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
+    }
+}
+
+// ---- force, generation 2: one WARP per i-cluster, one LANE per j atom ---------------------------------------------------
+// ncu of the lane-per-i-atom kernels above: every j tile costs ~3 L1 wavefronts per cluster pair (three 128-bit row loads,
+// eight different tiles per warp instruction), as many cycles as the arithmetic of its 16 atom pairs -- and with packed
+// FP32 math halving the issue slots the kernel simply became L1-bound (0.211 vs 0.220 ms, profiles/r1_ab3.txt).
+// Here a warp walks ONE list row, 32 / N tiles per iteration: lane (t, q) fetches atom q of tile t with a single 128-bit
+// (SP) / 256-bit (DP) load from an {x, y, z, -} copy of the cluster positions (k_cp_pack_j) -- one wavefront per cluster
+// pair -- and evaluates it against the four i atoms, which are warp-uniform registers.  The 12 i-force sums are
+// reduced over the warp once per row with a halving butterfly (12 -> 6 -> 3 values, then 3 full steps).
+template <class real, int N>
+__global__ void k_cp_pack_j(size_t nslots, const real* __restrict__ cl_x, typename PosOf<real>::type* __restrict__ out)
+{
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const size_t t = s / N, q = s % N;
+    const real* p  = cl_x + t * N * 3 + q;
+    st_pos(out + s, p[0], p[N], p[2 * N]);
+}
+
+template <class real> struct CpPairMath;
+template <> struct CpPairMath<double> { // scalar FP64
+    double xi[4], yi[4], zi[4], fx[4], fy[4], fz[4];
+    double cut, A, B;
+    __device__ __forceinline__ void init(const double* px, const double* py, const double* pz, const LJConst2<double>& c)
+    {
+#pragma unroll
+        for (int m = 0; m < 4; m++) { xi[m] = px[m]; yi[m] = py[m]; zi[m] = pz[m]; fx[m] = fy[m] = fz[m] = 0; }
+        cut = c.cutforcesq; A = c.A; B = c.B;
+    }
+    // pairs (i atom m, this lane's j atom) for m = 0..3; ok[m] = pair allowed (exclusions, list padding);
+    // returns the reaction sum for the j atom in (rx, ry, rz)
+    template <bool HALF>
+    __device__ __forceinline__ void tile(double xj, double yj, double zj, const bool (&ok)[4], double& rx, double& ry, double& rz)
+    {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const double dx = xi[m] - xj, dy = yi[m] - yj, dz = zi[m] - zj;
+            const double rsq = dx * dx + dy * dy + dz * dz;
+            const double s = rcp_nr(rsq), s3 = s * s * s;
+            double f = (s * s3) * (A * s3 - B);
+            f        = (rsq < cut && ok[m]) ? f : 0.0;
+            fx[m] = fma(dx, f, fx[m]); fy[m] = fma(dy, f, fy[m]); fz[m] = fma(dz, f, fz[m]);
+            if (HALF) { rx = fma(dx, f, rx); ry = fma(dy, f, ry); rz = fma(dz, f, rz); }
+        }
+    }
+    __device__ __forceinline__ void sums(double (&v)[12])
+    {
+#pragma unroll
+        for (int m = 0; m < 4; m++) { v[3 * m] = fx[m]; v[3 * m + 1] = fy[m]; v[3 * m + 2] = fz[m]; }
+    }
+};
+template <> struct CpPairMath<float> { // packed FP32: i atoms (0,1) and (2,3) share an instruction
+    f32x2 xi[2], yi[2], zi[2], fx[2], fy[2], fz[2], A, negB, one;
+    float cut;
+    __device__ __forceinline__ void init(const float* px, const float* py, const float* pz, const LJConst2<float>& c)
+    {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            xi[h] = pk2(px[2 * h], px[2 * h + 1]); yi[h] = pk2(py[2 * h], py[2 * h + 1]); zi[h] = pk2(pz[2 * h], pz[2 * h + 1]);
+            fx[h] = fy[h] = fz[h] = pk2(0.f, 0.f);
+        }
+        A = pk2(c.A, c.A); negB = pk2(-c.B, -c.B); one = pk2(1.f, 1.f);
+        cut = c.cutforcesq;
+    }
+    template <bool HALF>
+    __device__ __forceinline__ void tile(float xj, float yj, float zj, const bool (&ok)[4], float& rx, float& ry, float& rz)
+    {
+        const f32x2 xj2 = pk2(xj, xj), yj2 = pk2(yj, yj), zj2 = pk2(zj, zj);
+        f32x2 r2x = pk2(0.f, 0.f), r2y = r2x, r2z = r2x;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const f32x2 dx = sub2(xi[h], xj2), dy = sub2(yi[h], yj2), dz = sub2(zi[h], zj2);
+            const f32x2 rsq = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float r0, r1, y0, y1;
+            upk2(rsq, r0, r1);
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(r0));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(r1));
+            const bool in0 = r0 < cut && ok[2 * h], in1 = r1 < cut && ok[2 * h + 1];
+            f32x2 y        = pk2(y0, y1);
+            y              = fma2(y, sub2(one, mul2(rsq, y)), y); // Newton step
+            const f32x2 s3 = mul2(mul2(y, y), y);
+            f32x2 f        = mul2(mul2(y, s3), fma2(A, s3, negB));
+            float f0, f1;
+            upk2(f, f0, f1);
+            f     = pk2(in0 ? f0 : 0.0f, in1 ? f1 : 0.0f);
+            fx[h] = fma2(dx, f, fx[h]); fy[h] = fma2(dy, f, fy[h]); fz[h] = fma2(dz, f, fz[h]);
+            if (HALF) { r2x = fma2(dx, f, r2x); r2y = fma2(dy, f, r2y); r2z = fma2(dz, f, r2z); }
+        }
+        if (HALF) {
+            float a, b;
+            upk2(r2x, a, b); rx += a + b;
+            upk2(r2y, a, b); ry += a + b;
+            upk2(r2z, a, b); rz += a + b;
+        }
+    }
+    __device__ __forceinline__ void sums(float (&v)[12])
+    {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            upk2(fx[h], v[6 * h], v[6 * h + 3]);
+            upk2(fy[h], v[6 * h + 1], v[6 * h + 4]);
+            upk2(fz[h], v[6 * h + 2], v[6 * h + 5]);
+        }
+    }
+};
+
+template <class real, int N, bool HALF>
+__global__ void __launch_bounds__(128) k_cp_force_jl(int ncl, int ncj, int dummy_cj, LJConst2<real> c, const real* __restrict__ cl_x,
+    const typename PosOf<real>::type* __restrict__ pos, const int* __restrict__ numneigh, const int* __restrict__ neighbors,
+    int maxneighs, real* __restrict__ cl_f)
+{
+    constexpr int TPW = 32 / N; // tiles per warp iteration
+    const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ci >= ncl) return; // whole warp
+    const int lane = threadIdx.x & 31, t = lane / N, q = lane % N;
+    const size_t ib = cp_ci_base3<N>(ci);
+    real px[4], py[4], pz[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        px[m] = cl_x[ib + m]; py[m] = cl_x[ib + N + m]; pz[m] = cl_x[ib + 2 * N + m];
+        if (px[m] >= CP_PAD_MIN) px[m] = py[m] = pz[m] = -CP_PAD; // padding i lane: far from everything, j padding included
+    }
+    CpPairMath<real> M;
+    M.init(px, py, pz, c);
+    const int self = cp_cj0<N>(ci);
+    const int ioff = N == CP_M ? 0 : CP_M * (ci & 1); // lane of i atom 0 inside the diagonal tile
+    const int nn   = numneigh[ci];
+    const int* row = neighbors + (size_t)ci * maxneighs;
+    // software pipeline: list entries two iterations ahead, positions one iteration ahead
+    int cj_next = t < nn ? __ldg(row + t) : dummy_cj;
+    int cj_nn   = TPW + t < nn ? __ldg(row + TPW + t) : dummy_cj;
+    real xj, yj, zj;
+    ld_pos(pos + (size_t)cj_next * N + q, xj, yj, zj);
+    for (int k0 = 0; k0 < nn; k0 += TPW) {
+        const int cj = cj_next;
+        const real x = xj, y = yj, z = zj;
+        cj_next = cj_nn;
+        cj_nn   = k0 + 2 * TPW + t < nn ? __ldg(row + k0 + 2 * TPW + t) : dummy_cj;
+        ld_pos(pos + (size_t)cj_next * N + q, xj, yj, zj);
+        const bool diag = cj == self;
+        bool ok[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) ok[m] = !diag || (HALF ? (ioff + m < q) : (ioff + m != q)); // force_lj.c:99-113
+        real rx = 0, ry = 0, rz = 0;
+        M.template tile<HALF>(x, y, z, ok, rx, ry, rz);
+        // reaction on local j atoms.  The reference also subtracts from ghost tiles (its HALF_NEIGHBOR_LISTS_CHECK_CJ guard is
+        // ineffective) but never reads them back; skipping cj >= ncj leaves every local force unchanged.
+        if (HALF && cj < ncj && (rx != 0 || ry != 0 || rz != 0)) {
+            real* fj = cl_f + (size_t)cj * N * 3 + q;
+            atomicAdd(fj, -rx); atomicAdd(fj + N, -ry); atomicAdd(fj + 2 * N, -rz);
+        }
+    }
+    // warp reduction of v[3 m + comp]: 12 -> 6 (xor 16) -> 3 (xor 8) -> full sums over xor 4, 2, 1
+    real v[12];
+    M.sums(v);
+    const bool h1 = lane & 16, h2 = lane & 8;
+    real w[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const real send = h1 ? v[j] : v[j + 6];
+        const real keep = h1 ? v[j + 6] : v[j];
+        w[j]            = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    real u[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const real send = h2 ? w[j] : w[j + 3];
+        const real keep = h2 ? w[j + 3] : w[j];
+        u[j]            = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1)
+#pragma unroll
+        for (int j = 0; j < 3; j++) u[j] += __shfl_xor_sync(0xffffffffu, u[j], d);
+    if ((lane & 7) == 0) {
+        const int m = (h1 ? 2 : 0) + (h2 ? 1 : 0); // i atom whose three components this lane group holds
+        if (cl_x[ib + m] < CP_PAD_MIN) { // padding i lanes keep their zero
+            real* f = cl_f + ib + m;
+            if (HALF) { atomicAdd(f, u[0]); atomicAdd(f + N, u[1]); atomicAdd(f + 2 * N, u[2]); }
+            else { f[0] = u[0]; f[N] = u[1]; f[2 * N] = u[2]; }
+        } else if (!HALF) { cl_f[ib + m] = 0; cl_f[ib + N + m] = 0; cl_f[ib + 2 * N + m] = 0; }
     }
 }
 

@@ -95,6 +95,7 @@ template <class real, int N> struct CpSim final : CpBase {
     // ---- lists (clusterpair/neighbor.h:31-40) ----
     int maxneighs = 100; // neighbor.c:65
     DBuf<int> numneigh, numneigh_masked, neighbors;
+    DBuf<char> pos4; // {x, y, z, -} per cluster slot for the force kernel (k_cp_pack_j)
     bool lists_ready = false;
     // ---- scratch ----
     Scanner scanner;
@@ -137,6 +138,7 @@ template <class real, int N> struct CpSim final : CpBase {
                  &goff, &border_map, &code, &numneigh, &numneigh_masked, &neighbors, &d_flags })
             b->release();
         gmask.release();
+        pos4.release();
         d_partial.release(); d_red.release(); d_thermo.release(); d_cnt.release();
         scanner.release();
         cudaFreeHost(h_flags);
@@ -558,10 +560,31 @@ template <class real, int N> struct CpSim final : CpBase {
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
         const unsigned grid = grid_for((size_t)ncl * CP_M, 128);
-        if (P.half_neigh) {
+        // force_variant 0 (default) picks the fastest measured kernel per case (profiles/r1_ab3.txt): full lists -> lane per
+        // i atom (packed FP32 in SP), half lists -> warp per i-cluster / lane per j atom (its reaction forces need no
+        // shuffles).  1 = lane per i atom, scalar; 2 = lane per i atom, packed FP32 (SP full only); 3 = warp per i-cluster.
+        int fv = force_variant;
+        if (fv == 0) fv = P.half_neigh ? 3 : (sizeof(real) == 4 ? 2 : 1);
+        if (fv == 2 && (sizeof(real) != 4 || P.half_neigh)) fv = 1;
+        if (fv == 3) {
+            typedef typename PosOf<real>::type P4;
+            const size_t nslots = (size_t)(ncj + nghost + 1) * N;
+            pos4.ensure(nslots * sizeof(P4), false, stream);
+            MDB_LAUNCH(launches, (k_cp_pack_j<real, N>), grid_for(nslots, 256), 256, 0, stream, nslots, cl_x.p, (P4*)pos4.p);
+            if (P.half_neigh) {
+                MDB_CUDA(cudaMemsetAsync(cl_f.p, 0, (size_t)ncj * 3 * N * sizeof(real), stream));
+                MDB_LAUNCH(launches, (k_cp_force_jl<real, N, true>), grid_for(ncl, 4), 128, 0, stream, ncl, ncj, dummy_cj, c2,
+                    cl_x.p, (const P4*)pos4.p, numneigh.p, neighbors.p, maxneighs, cl_f.p);
+            } else {
+                MDB_LAUNCH(launches, (k_cp_force_jl<real, N, false>), grid_for(ncl, 4), 128, 0, stream, ncl, ncj, dummy_cj, c2,
+                    cl_x.p, (const P4*)pos4.p, numneigh.p, neighbors.p, maxneighs, cl_f.p);
+            }
+        } else if (P.half_neigh) {
             MDB_CUDA(cudaMemsetAsync(cl_f.p, 0, (size_t)ncj * 3 * N * sizeof(real), stream));
             MDB_LAUNCH(launches, (k_cp_force_lj<real, N, true>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
                 numneigh_masked.p, neighbors.p, maxneighs, cl_f.p);
+        } else if (fv == 2) {
+            launch_packed(grid, c2);
         } else {
             MDB_LAUNCH(launches, (k_cp_force_lj<real, N, false>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
                 numneigh_masked.p, neighbors.p, maxneighs, cl_f.p);
@@ -575,6 +598,12 @@ template <class real, int N> struct CpSim final : CpBase {
             force_ms += ms;
         }
     }
+    void launch_packed(unsigned grid, const LJConst2<float>& c2)
+    {
+        MDB_LAUNCH(launches, k_cp_force_lj_sp_packed<N>, grid, 128, 0, stream, ncl, c2, (const float*)cl_x.p, numneigh.p,
+            numneigh_masked.p, neighbors.p, maxneighs, (float*)cl_f.p);
+    }
+    void launch_packed(unsigned, const LJConst2<double>&) {}
     double computeForce() override // returns elapsed seconds like the reference's ComputeForceFunction
     {
         const bool t        = timing;

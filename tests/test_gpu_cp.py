@@ -284,3 +284,30 @@ def test_maxneighs_overflow_resize():
     assert s.counts()["maxneighs"] == o.geti("maxneighs") > 100
     assert_same_structure(o, s)
     s.close()
+
+
+# ---- the C driver of the clusterpair scheme: reference command line and report ---------------------------------------
+def _cp_driver():
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "md-bench_b200", "driver", "MDBench-CP-B200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    return exe
+
+
+@pytest.mark.parametrize("extra,variant,tol", [([], "cpref44_sp", 1e-4), (["--operators"], "cpref44_sp", 1e-4),
+                                               (["--precision", "dp"], "cpref44_dp", 1e-6)])
+def test_cp_driver_default_run_prints_reference_report(golden_dir, extra, variant, tol):
+    """MDBench-CP-B200 with the reference's defaults = BASELINE config 2 (Cu FCC 32^3, 4x4, 200 steps): the
+    step/temp/pressure lines of the reference's scalar 4x4 build (thermo_cp.json; the printed 7 digits in DP)"""
+    import re
+    import subprocess
+    gold = [q for q in json.load(open(os.path.join(golden_dir, "thermo_cp.json"))) if q["variant"] == variant][0]
+    out = subprocess.run([_cp_driver()] + extra, capture_output=True, text=True, timeout=300).stdout
+    lines = [(int(a), float(b), float(c)) for a, b, c in re.findall(r"^(-?\d+)\t(\S+)\t(\S+)$", out, flags=re.M)]
+    assert [l[0] for l in lines] == [0, 100, 200], out
+    for (st, T, P), (gs, gT, gP) in zip(lines, gold["records"]):
+        assert abs(T - gT) <= tol * gT and abs(P - gP) <= tol * gP, (st, T, P, gT, gP)
+    assert re.search(r"System: 131072 atoms \d+ ghost atoms, Steps: 200", out)
+    assert "million atom updates per second" in out and "TOTAL" in out and "Kernel: CUDA sm_100a 4x4" in out
