@@ -640,27 +640,32 @@ struct CpPackedConst {
     f32x2 A, negB, one;
     float cutforcesq;
 };
-template <int N, bool DIAG>
-__device__ __forceinline__ void cp_tile_packed(const float* __restrict__ t, const CpPackedConst& c, f32x2 xt, f32x2 yt, f32x2 zt,
-    int ii, f32x2& fx, f32x2& fy, f32x2& fz)
-{
-    f32x2 xj[N / 2], yj[N / 2], zj[N / 2];
+template <int N> struct CpTileRegs {
+    f32x2 x[N / 2], y[N / 2], z[N / 2];
+    __device__ __forceinline__ void load(const float* __restrict__ t)
+    {
 #pragma unroll
-    for (int q = 0; q < N / 2; q += 2) { // one 128-bit load = two packed pairs
-        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(xj[q]), "=l"(xj[q + 1]) : "l"(t + 2 * q));
-        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(yj[q]), "=l"(yj[q + 1]) : "l"(t + N + 2 * q));
-        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(zj[q]), "=l"(zj[q + 1]) : "l"(t + 2 * N + 2 * q));
+        for (int q = 0; q < N / 2; q += 2) { // one 128-bit load = two packed pairs
+            asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(x[q]), "=l"(x[q + 1]) : "l"(t + 2 * q));
+            asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(y[q]), "=l"(y[q + 1]) : "l"(t + N + 2 * q));
+            asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(z[q]), "=l"(z[q + 1]) : "l"(t + 2 * N + 2 * q));
+        }
     }
+};
+// iq = the lane's own slot inside this tile if the tile is the i-cluster's own j-cluster, else -1
+template <int N>
+__device__ __forceinline__ void cp_tile_packed(const CpTileRegs<N>& T, const CpPackedConst& c, f32x2 xt, f32x2 yt, f32x2 zt, int iq,
+    f32x2& fx, f32x2& fy, f32x2& fz)
+{
 #pragma unroll
     for (int q = 0; q < N / 2; q++) {
-        const f32x2 dx = sub2(xt, xj[q]), dy = sub2(yt, yj[q]), dz = sub2(zt, zj[q]);
+        const f32x2 dx = sub2(xt, T.x[q]), dy = sub2(yt, T.y[q]), dz = sub2(zt, T.z[q]);
         const f32x2 rsq = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
         float r0, r1, y0, y1;
         upk2(rsq, r0, r1);
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(r0));
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(r1));
-        bool in0 = r0 < c.cutforcesq, in1 = r1 < c.cutforcesq;
-        if (DIAG) { in0 = in0 && ii != 2 * q; in1 = in1 && ii != 2 * q + 1; }
+        const bool in0 = r0 < c.cutforcesq && iq != 2 * q, in1 = r1 < c.cutforcesq && iq != 2 * q + 1; // force_lj.c:99-113
         f32x2 y        = pk2(y0, y1);
         const f32x2 nr = sub2(c.one, mul2(rsq, y)); // Newton step: y += y * (1 - rsq * y)
         y              = fma2(y, nr, y);
@@ -673,9 +678,8 @@ __device__ __forceinline__ void cp_tile_packed(const float* __restrict__ t, cons
     }
 }
 template <int N>
-__global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, LJConst2<float> c, const float* __restrict__ cl_x,
-    const int* __restrict__ numneigh, const int* __restrict__ numneigh_masked, const int* __restrict__ neighbors, int maxneighs,
-    float* __restrict__ cl_f)
+__global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, int dummy_cj, LJConst2<float> c, const float* __restrict__ cl_x,
+    const int* __restrict__ numneigh, const int* __restrict__ neighbors, int maxneighs, float* __restrict__ cl_f)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int ci  = tid >> 2, cii = tid & 3;
@@ -689,23 +693,20 @@ __global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, LJConst2
     CpPackedConst pc { pk2(c.A, c.A), pk2(-c.B, -c.B), pk2(1.0f, 1.0f), c.cutforcesq };
     const int self = cp_cj0<N>(cic);
     const int ii   = N == CP_M ? cii : cii + CP_M * (cic & 1);
-    const int nn   = valid ? numneigh[cic] : 0;
-    const int nm   = valid ? numneigh_masked[cic] : 0;
     const int* row = neighbors + (size_t)cic * maxneighs;
+    const int nn   = valid ? numneigh[cic] : 0;
     f32x2 fx = pk2(0.f, 0.f), fy = fx, fz = fx;
-    int cjn = nn > 0 ? __ldg(row) : 0;
-    int k   = 0;
-    for (; k < nm; k++) {
-        const int cj = cjn;
-        if (k + 1 < nn) cjn = __ldg(row + k + 1);
-        const float* t = cl_x + (size_t)cj * N * 3;
-        if (cj == self) cp_tile_packed<N, true>(t, pc, xt, yt, zt, ii, fx, fy, fz);
-        else cp_tile_packed<N, false>(t, pc, xt, yt, zt, ii, fx, fy, fz);
-    }
-    for (; k < nn; k++) {
-        const int cj = cjn;
-        if (k + 1 < nn) cjn = __ldg(row + k + 1);
-        cp_tile_packed<N, false>(cl_x + (size_t)cj * N * 3, pc, xt, yt, zt, ii, fx, fy, fz);
+    // software pipeline: list entry two tiles ahead, tile positions one tile ahead (the dummy tile past the end)
+    int cj = nn > 0 ? __ldg(row) : dummy_cj, cj1 = nn > 1 ? __ldg(row + 1) : dummy_cj;
+    CpTileRegs<N> A, B;
+    A.load(cl_x + (size_t)cj * N * 3);
+    for (int k = 0; k < nn; k++) {
+        const int cj2 = k + 2 < nn ? __ldg(row + k + 2) : dummy_cj;
+        B.load(cl_x + (size_t)cj1 * N * 3);
+        cp_tile_packed<N>(A, pc, xt, yt, zt, cj == self ? ii : -1, fx, fy, fz);
+        A   = B;
+        cj  = cj1;
+        cj1 = cj2;
     }
     if (!valid) return;
     float a, b;
@@ -886,11 +887,13 @@ __global__ void __launch_bounds__(128) k_cp_force_jl(int ncl, int ncj, int dummy
     M.init(px, py, pz, c);
     const int self = cp_cj0<N>(ci);
     const int ioff = N == CP_M ? 0 : CP_M * (ci & 1); // lane of i atom 0 inside the diagonal tile
-    const int nn   = numneigh[ci];
     const int* row = neighbors + (size_t)ci * maxneighs;
+    const int nn   = numneigh[ci];
     // software pipeline: list entries two iterations ahead, positions one iteration ahead
-    int cj_next = t < nn ? __ldg(row + t) : dummy_cj;
-    int cj_nn   = TPW + t < nn ? __ldg(row + TPW + t) : dummy_cj;
+    // rows are maxneighs (>= 2 TPW) wide: the first entries are fetched without waiting for the row length
+    int cj_next = __ldg(row + t), cj_nn = __ldg(row + TPW + t);
+    if (t >= nn) cj_next = dummy_cj;
+    if (TPW + t >= nn) cj_nn = dummy_cj;
     real xj, yj, zj;
     ld_pos(pos + (size_t)cj_next * N + q, xj, yj, zj);
     for (int k0 = 0; k0 < nn; k0 += TPW) {

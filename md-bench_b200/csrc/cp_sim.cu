@@ -600,8 +600,8 @@ template <class real, int N> struct CpSim final : CpBase {
     }
     void launch_packed(unsigned grid, const LJConst2<float>& c2)
     {
-        MDB_LAUNCH(launches, k_cp_force_lj_sp_packed<N>, grid, 128, 0, stream, ncl, c2, (const float*)cl_x.p, numneigh.p,
-            numneigh_masked.p, neighbors.p, maxneighs, (float*)cl_f.p);
+        MDB_LAUNCH(launches, k_cp_force_lj_sp_packed<N>, grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p, numneigh.p,
+            neighbors.p, maxneighs, (float*)cl_f.p);
     }
     void launch_packed(unsigned, const LJConst2<double>&) {}
     double computeForce() override // returns elapsed seconds like the reference's ComputeForceFunction
