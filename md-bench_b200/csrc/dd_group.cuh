@@ -494,6 +494,7 @@ template <class real> struct DomainGroup final : DDBase {
         for (Brick* b : bricks) {
             const size_t n = b->Nlocal;
             if (b->nstride == 0) throw Error("getNeighborTags: no neighbor list");
+            b->ensure_per_atom();
             b->rows.ensure(n * stride, false, stream);
             MDB_LAUNCH(launches, k_dd_rows_as_tags, grid_for(n, 128), 128, 0, stream, (int)n, stride, b->LL, b->numneigh.p,
                 b->neighbors.p, b->orig.p, b->rows.p);

@@ -50,8 +50,18 @@ template <class real> struct Sim final : SimBase {
     DBuf<float> xf, yf, zf;
     DBuf<float4> pk;
     DBuf<char> pos4; // packed positions {x,y,z,-} for the p4 force kernel
-    DBuf<int> run_off, run_len;
+    DBuf<int> run_off, run_len, run_i0, run_dj, run_dk;
     int nruns = 0;
+    // merged lists (k_build_neighbor_m2): one row per atom pair (2t, 2t+1) with membership bits; LJ full lists only.
+    // "merge" option: 0 (default) off -- one row per atom, the reference's structure; 2 on.  Measured SLOWER
+    // (force 1.86 vs 1.53 ms DP, 1.31 vs 1.13 ms SP at 8.4M atoms, profiles/r1_ab3.txt): the union rows cost 1.43x the
+    // FP64 work and the lanes of a warp now span 64 atoms, so the gathers touch more lines per request.  Kept as an
+    // A/B variant.  With merge on, numneigh / neighbors are materialised on demand (ensure_per_atom).
+    int merge = 0, mcap = 0, st_Ry = 0, st_Rz = 0;
+    bool merged_built = false, pa_valid = true;
+    DBuf<int> mneigh, mnum, numneigh_atom;
+    DBuf<StencilRow> st_tab;
+    NbLayout LLm { 0, 0, 0 };
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
     DBuf<unsigned> ghost_msk;
     int saved_n = 0;
@@ -108,6 +118,8 @@ template <class real> struct Sim final : SimBase {
         ghost_msk.release();
         pos4.release();
         xf.release(); yf.release(); zf.release(); pk.release(); run_off.release(); run_len.release();
+        run_i0.release(); run_dj.release(); run_dk.release(); mneigh.release(); mnum.release(); numneigh_atom.release();
+        st_tab.release();
         d_partial.release();
         d_red.release();
         d_thermo.release();
@@ -438,17 +450,34 @@ template <class real> struct Sim final : SimBase {
         if (!P.from_input) { xprd = bx; yprd = by; zprd = bz; }
         stencil.ensure(nstencil, false, stream);
         MDB_CUDA(cudaMemcpyAsync(stencil.p, h_stencil.data(), nstencil * sizeof(int), cudaMemcpyHostToDevice, stream));
-        // runs of consecutive offsets (x-adjacent bins, adjacent in the CSR) for k_build_neighbor_v3
-        std::vector<int> ro, rl;
-        for (int k = 0; k < nstencil; k++) {
-            if (!ro.empty() && h_stencil[k] == ro.back() + rl.back()) rl.back()++;
-            else { ro.push_back(h_stencil[k]); rl.push_back(1); }
-        }
+        // runs of consecutive offsets (x-adjacent bins, adjacent in the CSR) for k_build_neighbor_v3/v4/m2, with their
+        // row (dj, dk) and first x offset, and the same runs as a (dj, dk) -> StencilRow table
+        std::vector<int> ro, rl, ri, rj, rk;
+        st_Ry = nexty; st_Rz = nextz;
+        std::vector<StencilRow> tab((size_t)(2 * nexty + 1) * (2 * nextz + 1), StencilRow { 0, 0 });
+        for (int k = -nextz; k <= nextz; k++)
+            for (int j = -nexty; j <= nexty; j++) {
+                int i0 = 0, len = 0;
+                for (int i = -nextx; i <= nextx; i++)
+                    if (bindist(i, j, k) < cutneighsq) {
+                        if (len == 0) i0 = i;
+                        else if (i != i0 + len) throw Error("setupNeighbor: stencil row is not one run");
+                        len++;
+                    }
+                if (len == 0) continue;
+                ro.push_back(k * bg.mbiny * bg.mbinx + j * bg.mbinx + i0);
+                rl.push_back(len); ri.push_back(i0); rj.push_back(j); rk.push_back(k);
+                tab[(size_t)(k + nextz) * (2 * nexty + 1) + (j + nexty)] = StencilRow { i0, len };
+            }
         nruns = (int)ro.size();
-        run_off.ensure(nruns, false, stream);
-        run_len.ensure(nruns, false, stream);
+        for (DBuf<int>* b : { &run_off, &run_len, &run_i0, &run_dj, &run_dk }) b->ensure(nruns, false, stream);
+        st_tab.ensure(tab.size(), false, stream);
         MDB_CUDA(cudaMemcpyAsync(run_off.p, ro.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(run_len.p, rl.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(run_i0.p, ri.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(run_dj.p, rj.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(run_dk.p, rk.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(st_tab.p, tab.data(), tab.size() * sizeof(StencilRow), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
         bincount.ensure(bg.mbins + 2, false, stream);
         binstart.ensure(bg.mbins + 3, false, stream);
@@ -634,12 +663,74 @@ template <class real> struct Sim final : SimBase {
         hi = (float)((double)cutneighsq + m);
         if (sizeof(real) == 4) { lo = -1.0f; } // SP: always run the exact (float) expression
     }
+    bool use_merged() const { return merge == 2 && P.force_field == MDB_FF_LJ && !P.half_neigh; }
+    void build_merged() // one row per atom pair, see k_build_neighbor_m2 (vl_kernels.cuh)
+    {
+        const int nall = Nlocal + Nghost, npairs = (Nlocal + 1) / 2;
+        pk.ensure(nall, false, stream);
+        MDB_LAUNCH(launches, k_pack_binned<real>, grid_for(nall, 256), 256, 0, stream, nall, binatoms.p, x.p, y.p, z.p, pk.p);
+        nstride = round_up((size_t)Nlocal, 32);
+        const size_t pstride = round_up((size_t)npairs, 32);
+        mnum.ensure(pstride, false, stream);
+        numneigh_atom.ensure(nstride, false, stream);
+        if (mcap == 0) mcap = maxneighs + maxneighs / 2; // union of two overlapping rows
+        float lo, hi;
+        list_margin(lo, hi);
+        for (;;) {
+            const size_t rowlen = round_up((size_t)mcap, 8);
+            LLm = NbLayout { 32 * rowlen, 32, 5 };
+            mneigh.ensure(rowlen * pstride, false, stream);
+            MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
+            MDB_CUDA(cudaMemsetAsync(d_flags.p + 4, 0, sizeof(int), stream));
+            MDB_LAUNCH(launches, k_build_neighbor_m2<real>, grid_for(npairs, 128), 128, 0, stream, Nlocal, bg, cutneighsq, lo, hi,
+                x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p, run_i0.p, run_dj.p, run_dk.p, nruns, st_tab.p, st_Ry,
+                st_Rz, mcap, LLm, mnum.p, numneigh_atom.p, mneigh.p, d_flags.p + 4, d_flags.p + 1);
+            neigh_launches++;
+            MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            MDB_CUDA(cudaStreamSynchronize(stream));
+            max_bin_count = h_flags[2];
+            if (h_flags[1] >= maxneighs) maxneighs = (int)(h_flags[1] * 1.2); // the reference's row capacity, neighbor.c:247-262
+            if (h_flags[4] > mcap) {
+                mcap = (int)(h_flags[4] * 1.2);
+                continue;
+            }
+            break;
+        }
+        merged_built = true;
+        pa_valid     = false;
+    }
+    // the reference's per-atom rows from the merged ones (accessors, counters, kernels without a merged variant)
+    void ensure_per_atom()
+    {
+        if (!merged_built || pa_valid) return;
+        const size_t rowlen = round_up((size_t)maxneighs, 8);
+        if (list_layout == 1) LL = NbLayout { rowlen, 1, 0 };
+        else if (list_layout == 2) LL = NbLayout { 32 * rowlen, 32, 5 };
+        else LL = NbLayout { 0, nstride, 31 };
+        numneigh.ensure(nstride, false, stream);
+        neighbors.ensure(rowlen * nstride, false, stream);
+        MDB_LAUNCH(launches, k_unmerge_m2, grid_for((Nlocal + 1) / 2, 128), 128, 0, stream, Nlocal, LLm, mnum.p, mneigh.p, maxneighs,
+            LL, numneigh.p, neighbors.p);
+        pa_valid = true;
+    }
     void buildNeighbor() override // verletlist/neighbor.c:186-264
     {
         if (!neigh_ready) setupNeighbor();
         float ms = 0;
         if (timing) MDB_CUDA(cudaEventRecord(evA, stream));
         bin_atoms();
+        if (use_merged()) {
+            build_merged();
+            if (timing) {
+                MDB_CUDA(cudaEventRecord(evB, stream));
+                MDB_CUDA(cudaEventSynchronize(evB));
+                MDB_CUDA(cudaEventElapsedTime(&ms, evA, evB));
+                neigh_ms += ms;
+            }
+            return;
+        }
+        merged_built = false;
+        pa_valid     = true;
         if (neigh_variant >= 2) { // candidates packed in CSR order
             const int nall = Nlocal + Nghost;
             pk.ensure(nall, false, stream);
@@ -707,12 +798,23 @@ template <class real> struct Sim final : SimBase {
     {
         if (which == FORCE_DISPATCH)
             which = P.force_field == MDB_FF_EAM ? FORCE_EAM : (P.half_neigh ? FORCE_LJ_HALF : FORCE_LJ_FULL);
+        if (merged_built && which != FORCE_LJ_FULL) ensure_per_atom();
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         if (which == FORCE_EAM) {
             launch_eam();
         } else {
             LJConst<real> c { cutforce * cutforce, sigma6, epsilon };
-            if (which == FORCE_LJ_FULL) {
+            if (which == FORCE_LJ_FULL && merged_built) {
+                LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6,
+                    (real)24.0 * epsilon * sigma6 };
+                const int npairs = (Nlocal + 1) / 2;
+                if (force_variant == 2)
+                    MDB_LAUNCH(launches, (k_force_lj_full_m2<real, 4>), grid_for(npairs, 128), 128, 0, stream, Nlocal, c2, x.p, y.p,
+                        z.p, mnum.p, mneigh.p, LLm, fx.p, fy.p, fz.p);
+                else
+                    MDB_LAUNCH(launches, (k_force_lj_full_m2<real, 2>), grid_for(npairs, 128), 128, 0, stream, Nlocal, c2, x.p, y.p,
+                        z.p, mnum.p, mneigh.p, LLm, fx.p, fy.p, fz.p);
+            } else if (which == FORCE_LJ_FULL) {
                 LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6,
                     (real)24.0 * epsilon * sigma6 };
                 if (force_variant >= 3 && LL.sk == 1) { // lanes-per-atom kernels need row-major rows
@@ -909,6 +1011,7 @@ template <class real> struct Sim final : SimBase {
     void getNeighbors(int* nn, int* nb, int row_stride) override
     {
         if (nstride == 0) throw Error("getNeighbors: no neighbor list");
+        ensure_per_atom();
         build_extmap();
         nn_ext.ensure(Nlocal, false, stream);
         if (nb) rows.ensure((size_t)Nlocal * row_stride, false, stream);
@@ -955,6 +1058,7 @@ template <class real> struct Sim final : SimBase {
     }
     void countPairs(long long* listed, long long* inside) override
     {
+        ensure_per_atom();
         MDB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), stream));
         MDB_LAUNCH(launches, k_count_pairs<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
             cutforce * cutforce, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, d_cnt.p);
@@ -1034,6 +1138,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "sort_order")) sort_order = (int)v;
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
+        else if (!strcmp(name, "merge")) merge = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

@@ -662,6 +662,172 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half,
     if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
 }
 
+// ---- merged lists: ONE row for the atom pair (2t, 2t+1) -------------------------------------------------------------
+// ncu (profiles/r1_s2_force_raw.txt): the full-list force kernel is bound by the L1 data pipe -- three 64-bit gathers
+// per listed neighbor, ~19 sectors per warp request -- while the FP64 pipe idles at 45 %.  Two atoms that are adjacent
+// in memory are close in space (the generator emits atoms along x at distance 1.68; after a spatial sort they share a
+// bin), so their lists overlap by ~55 %.  One thread therefore owns the pair (2t, 2t+1) and a row holding the UNION of
+// the two reference rows, each entry tagged with two membership bits (bit 30: neighbor of atom 2t, bit 31: of 2t+1).
+// Every gathered position serves both atoms: ~0.7 gathers per listed pair instead of 1.  Membership bits keep the
+// result EXACTLY the reference's: a pair is evaluated iff it is in that atom's reference list (an atom that outruns
+// the skin between two rebuilds must not interact earlier than in the reference).
+//
+// Candidates: the stencil of atom 2t's bin is walked testing both atoms; if atom 2t+1 sits in another bin, the bins of
+// its stencil that are not part of the first stencil are walked for it alone (bins outside an atom's stencil cannot
+// hold a neighbor of it, neighbor.c:107-124, so testing both atoms there would only cost time).
+struct StencilRow { // x-run of the stencil in the bin row (dj, dk): offsets [i0, i0 + len)
+    int i0, len;
+};
+template <class real>
+__device__ __forceinline__ void m2_walk(int s, int e, bool both, int ia, int ib, bool has_b, real xa, real ya, real za, real xb,
+    real yb, real zb, real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, const float4* __restrict__ pk, int mcap, size_t sk, int*& out, int& n, int& na, int& nb)
+{
+    const float xas = (float)xa, yas = (float)ya, zas = (float)za, xbs = (float)xb, ybs = (float)yb, zbs = (float)zb;
+    const float cut = (float)cutneighsq;
+    for (int c0 = s; c0 < e; c0 += 32) {
+        const float4* p = pk + c0;
+        const int cnt   = min(32, e - c0);
+        unsigned pa = 0, ua = 0, pb = 0, ub = 0;
+#pragma unroll 8
+        for (int t = 0; t < cnt; t++) {
+            const float4 c = __ldg(p + t);
+            if (sizeof(real) == 4) { // SP: the reference's own expression
+                float dx = __fsub_rn(xas, c.x), dy = __fsub_rn(yas, c.y), dz = __fsub_rn(zas, c.z);
+                pa |= (__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))) <= cut ? 1u : 0u) << t;
+                dx = __fsub_rn(xbs, c.x); dy = __fsub_rn(ybs, c.y); dz = __fsub_rn(zbs, c.z);
+                pb |= (__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))) <= cut ? 1u : 0u) << t;
+            } else { // DP: float pre-test with an error margin, exact FP64 only in the uncertain band
+                float dx = xas - c.x, dy = yas - c.y, dz = zas - c.z;
+                float rs = dx * dx + dy * dy + dz * dz;
+                pa |= (rs < lo ? 1u : 0u) << t;
+                ua |= ((rs >= lo && rs <= hi) ? 1u : 0u) << t;
+                dx = xbs - c.x; dy = ybs - c.y; dz = zbs - c.z;
+                rs = dx * dx + dy * dy + dz * dz;
+                pb |= (rs < lo ? 1u : 0u) << t;
+                ub |= ((rs >= lo && rs <= hi) ? 1u : 0u) << t;
+            }
+        }
+        if (!both) pa = ua = 0;
+        if (!has_b) pb = ub = 0;
+        unsigned todo = pa | ua | pb | ub;
+        while (todo) {
+            const int t = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int j = __float_as_int(__ldg(&p[t].w));
+            bool ma = ((pa | ua) >> t) & 1u, mb = ((pb | ub) >> t) & 1u;
+            if (j == ia) ma = false;
+            if (j == ib) mb = false;
+            if (((ua | ub) >> t) & 1u) { // the reference's exact FP64 expression
+                const real xj = x[j], yj = y[j], zj = z[j];
+                if (ma && ((ua >> t) & 1u)) {
+                    const real dx = sub_rn(xa, xj), dy = sub_rn(ya, yj), dz = sub_rn(za, zj);
+                    ma = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq;
+                }
+                if (mb && ((ub >> t) & 1u)) {
+                    const real dx = sub_rn(xb, xj), dy = sub_rn(yb, yj), dz = sub_rn(zb, zj);
+                    mb = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq;
+                }
+            }
+            if (!(ma || mb)) continue;
+            if (n < mcap) *out = j | (ma ? 0x40000000 : 0) | (mb ? (int)0x80000000 : 0);
+            out += sk;
+            n++;
+            na += ma;
+            nb += mb;
+        }
+    }
+}
+__device__ __forceinline__ void bin3(int b, int mbinx, int mbiny, int& ix, int& iy, int& iz)
+{
+    const int l = b > 0 ? b - 1 : 0; // coord2bin's "+ 1"
+    ix = l % mbinx;
+    iy = (l / mbinx) % mbiny;
+    iz = l / (mbinx * mbiny);
+}
+template <class real>
+__global__ void __launch_bounds__(128) k_build_neighbor_m2(int nlocal, BinGeom<real> g, real cutneighsq, float lo, float hi,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float4* __restrict__ pk,
+    const int* __restrict__ binstart, const int* __restrict__ run_off, const int* __restrict__ run_len,
+    const int* __restrict__ run_i0, const int* __restrict__ run_dj, const int* __restrict__ run_dk, int nruns,
+    const StencilRow* __restrict__ st_tab, int Ry, int Rz, int mcap, NbLayout L, int* __restrict__ mnum,
+    int* __restrict__ numneigh_atom, int* __restrict__ mneigh, int* __restrict__ max_union, int* __restrict__ max_atom)
+{
+    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ia = 2 * t;
+    int n = 0, na = 0, nb = 0;
+    if (ia < nlocal) {
+        const bool has_b = ia + 1 < nlocal;
+        const int ib     = has_b ? ia + 1 : ia;
+        const real xa = x[ia], ya = y[ia], za = z[ia], xb = x[ib], yb = y[ib], zb = z[ib];
+        const int ba = coord2bin(g, xa, ya, za), bb = has_b ? coord2bin(g, xb, yb, zb) : ba;
+        int* out = mneigh + L.base(t);
+        for (int r = 0; r < nruns; r++) {
+            int b0 = ba + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
+            b0 = max(b0, 0);
+            b1 = min(b1, g.mbins + 1);
+            if (b1 <= b0) continue;
+            m2_walk<real>(__ldg(&binstart[b0]), __ldg(&binstart[b1]), true, ia, has_b ? ib : -1, has_b, xa, ya, za, xb, yb, zb,
+                cutneighsq, lo, hi, x, y, z, pk, mcap, L.sk, out, n, na, nb);
+        }
+        if (bb != ba) { // the part of atom b's stencil that atom a's stencil does not cover
+            int ax, ay, az, bx, by, bz;
+            bin3(ba, g.mbinx, g.mbiny, ax, ay, az);
+            bin3(bb, g.mbinx, g.mbiny, bx, by, bz);
+            const int ddx = bx - ax, ddy = by - ay, ddz = bz - az;
+            for (int r = 0; r < nruns; r++) {
+                const int len = __ldg(&run_len[r]);
+                int b0 = bb + __ldg(&run_off[r]), b1 = b0 + len;
+                // the same bins seen from atom a's bin: row (dj, dk), x offsets [xs, xs + len)
+                const int dj = __ldg(&run_dj[r]) + ddy, dk = __ldg(&run_dk[r]) + ddz, xs = __ldg(&run_i0[r]) + ddx;
+                int c0 = b0, c1 = b0; // covered sub-range [c0, c1) in flattened bin indices
+                if (dj >= -Ry && dj <= Ry && dk >= -Rz && dk <= Rz) {
+                    const StencilRow sr = st_tab[(dk + Rz) * (2 * Ry + 1) + (dj + Ry)];
+                    const int o0 = max(xs, sr.i0), o1 = min(xs + len, sr.i0 + sr.len);
+                    if (o1 > o0) { c0 = b0 + (o0 - xs); c1 = b0 + (o1 - xs); }
+                }
+                // [b0, c0) and [c1, b1)
+                int s0 = max(b0, 0), e0 = min(c0, g.mbins + 1);
+                if (e0 > s0)
+                    m2_walk<real>(__ldg(&binstart[s0]), __ldg(&binstart[e0]), false, ia, ib, true, xa, ya, za, xb, yb, zb, cutneighsq,
+                        lo, hi, x, y, z, pk, mcap, L.sk, out, n, na, nb);
+                s0 = max(c1, 0); e0 = min(b1, g.mbins + 1);
+                if (e0 > s0)
+                    m2_walk<real>(__ldg(&binstart[s0]), __ldg(&binstart[e0]), false, ia, ib, true, xa, ya, za, xb, yb, zb, cutneighsq,
+                        lo, hi, x, y, z, pk, mcap, L.sk, out, n, na, nb);
+            }
+        }
+        mnum[t]           = n;
+        numneigh_atom[ia] = na;
+        if (has_b) numneigh_atom[ib] = nb;
+    }
+    n = __reduce_max_sync(0xffffffffu, n);
+    na = __reduce_max_sync(0xffffffffu, max(na, nb));
+    if ((threadIdx.x & 31) == 0) { atomicMax(max_union, n); atomicMax(max_atom, na); }
+}
+
+// merged rows -> the reference's per-atom rows (parity read-back, pair counters, tag lists): entries keep their order
+static __global__ void k_unmerge_m2(int nlocal, NbLayout Lm, const int* __restrict__ mnum, const int* __restrict__ mneigh, int maxneighs,
+    NbLayout L, int* __restrict__ numneigh, int* __restrict__ neighbors)
+{
+    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ia = 2 * t;
+    if (ia >= nlocal) return;
+    const bool has_b = ia + 1 < nlocal;
+    const int* in    = mneigh + Lm.base(t);
+    int* oa          = neighbors + L.base(ia);
+    int* ob          = neighbors + L.base(has_b ? ia + 1 : ia);
+    int na = 0, nb = 0;
+    const int nn = mnum[t];
+    for (int k = 0; k < nn; k++) {
+        const int e = in[(size_t)k * Lm.sk], j = e & 0x3fffffff;
+        if (e & 0x40000000) { if (na < maxneighs) oa[(size_t)na * L.sk] = j; na++; }
+        if (has_b && e < 0) { if (nb < maxneighs) ob[(size_t)nb * L.sk] = j; nb++; }
+    }
+    numneigh[ia] = na;
+    if (has_b) numneigh[ia + 1] = nb;
+}
+
 // parity read-back: transposed list in internal numbering -> the reference's row-major rows in the
 // reference's numbering (extmap: internal index -> reference index, locals and ghosts)
 static __global__ void k_untranspose(int nlocal, int row_stride, NbLayout L, const int* __restrict__ numneigh,
@@ -828,6 +994,86 @@ __global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<r
     fx[i] = fix;
     fy[i] = fiy;
     fz[i] = fiz;
+}
+
+// ---- m2: merged rows, two atoms per thread (see k_build_neighbor_m2) ---------------------------------------------------
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_force_lj_full_m2(int nlocal, LJConst2<real> c, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ mnum, const int* __restrict__ mneigh,
+    NbLayout L, real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
+{
+    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ia = 2 * t;
+    if (ia >= nlocal) return;
+    const bool has_b = ia + 1 < nlocal;
+    const int ib     = has_b ? ia + 1 : ia;
+    const real xa = x[ia], ya = y[ia], za = z[ia], xb = x[ib], yb = y[ib], zb = z[ib];
+    const int nn  = mnum[t];
+    real fax = 0, fay = 0, faz = 0, fbx = 0, fby = 0, fbz = 0;
+    const int* nb   = mneigh + L.base(t);
+    const int nfull = nn - nn % U;
+    int e[U], en[U];
+    if (nfull > 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) e[u] = __ldg(nb + (size_t)u * L.sk);
+    }
+    for (int k = 0; k < nfull; k += U) {
+        real xj[U], yj[U], zj[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = e[u] & 0x3fffffff;
+            xj[u] = __ldg(x + j); yj[u] = __ldg(y + j); zj[u] = __ldg(z + j);
+        }
+        nb += (size_t)U * L.sk;
+        if (k + U < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; u++) en[u] = __ldg(nb + (size_t)u * L.sk);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            {
+                const real dx = xa - xj[u], dy = ya - yj[u], dz = za - zj[u];
+                const real rsq = dx * dx + dy * dy + dz * dz;
+                if ((e[u] & 0x40000000) && rsq < c.cutforcesq) {
+                    const real f = lj_pair2(rsq, c);
+                    fax += dx * f; fay += dy * f; faz += dz * f;
+                }
+            }
+            {
+                const real dx = xb - xj[u], dy = yb - yj[u], dz = zb - zj[u];
+                const real rsq = dx * dx + dy * dy + dz * dz;
+                if (e[u] < 0 && rsq < c.cutforcesq) {
+                    const real f = lj_pair2(rsq, c);
+                    fbx += dx * f; fby += dy * f; fbz += dz * f;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) e[u] = en[u];
+    }
+    for (int k = nfull; k < nn; k++) {
+        const int ee = __ldg(nb), j = ee & 0x3fffffff;
+        nb += L.sk;
+        const real xj = __ldg(x + j), yj = __ldg(y + j), zj = __ldg(z + j);
+        {
+            const real dx = xa - xj, dy = ya - yj, dz = za - zj;
+            const real rsq = dx * dx + dy * dy + dz * dz;
+            if ((ee & 0x40000000) && rsq < c.cutforcesq) {
+                const real f = lj_pair2(rsq, c);
+                fax += dx * f; fay += dy * f; faz += dz * f;
+            }
+        }
+        {
+            const real dx = xb - xj, dy = yb - yj, dz = zb - zj;
+            const real rsq = dx * dx + dy * dy + dz * dz;
+            if (ee < 0 && rsq < c.cutforcesq) {
+                const real f = lj_pair2(rsq, c);
+                fbx += dx * f; fby += dy * f; fbz += dz * f;
+            }
+        }
+    }
+    fx[ia] = fax; fy[ia] = fay; fz[ia] = faz;
+    if (has_b) { fx[ib] = fbx; fy[ib] = fby; fz[ib] = fbz; }
 }
 
 // ---- p4: packed positions ----------------------------------------------------------------------------

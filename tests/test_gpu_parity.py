@@ -401,3 +401,32 @@ def test_driver_eam_funcfl_file(golden_dir, tmp_path):
     for (st, T, P), (gs, gT, gP) in zip(lines, g["records"]):
         assert abs(float(T) - gT) <= 2e-6 * gT and abs(float(P) - gP) <= 2e-6 * gP, (st, T, gT)
     assert "Force field: eam" in out
+
+
+@pytest.mark.parametrize("dp", [True, False])
+def test_merged_pair_rows_variant_gives_the_reference_lists(dp):
+    """mdb_setOption("merge", 2): one list row per atom pair with membership bits (an A/B variant, slower, off by
+    default).  Per-atom rows reconstructed from it equal the per-atom build as sets (row by row identical for the
+    first atom of every pair), and the trajectory is the same to rounding."""
+    x = None
+    sims = []
+    for merge in (0, 2):
+        s = make_sim(dp, True, False, nx=7, ny=5, nz=6)
+        s.setOption("merge", merge)
+        s.createAtom()
+        s.setup(adjust=True)
+        sims.append(s)
+    a, b = sims
+    nna, nba = a.neighbors()
+    nnb, nbb = b.neighbors()
+    assert np.array_equal(nna, nnb)
+    for i in range(len(nna)):
+        assert np.array_equal(np.sort(nba[i, :nna[i]]), np.sort(nbb[i, :nnb[i]])), i
+        if i % 2 == 0:
+            assert np.array_equal(nba[i, :nna[i]], nbb[i, :nnb[i]]), i
+    assert a.countPairs() == b.countPairs()
+    ra, _ = a.run(45)
+    rb, _ = b.run(45)
+    assert np.allclose(ra, rb, rtol=1e-12 if dp else 1e-5)
+    assert rel_err(a.get("x"), b.get("x")) < (1e-12 if dp else 1e-5)
+    a.close(); b.close()
