@@ -15,7 +15,12 @@ template <class real> struct DomainGroup final : DDBase {
     int proc = 0, first = 0, nlocal_bricks = 0, device = 0;
     mdb_params G; // global parameters
     std::vector<Brick*> bricks;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
+    // option "overlap_halo": exchange the halo while the atoms without ghost neighbors are computed.  Off by default: at 2
+    // GPUs the halo is 0.11 ms of a 2.4 ms step and the split (two launches over index lists) costs more than it hides
+    // (6.84 vs 7.09 G atom-steps/s, profiles/r1_ab3.txt)
+    bool overlap = false;
     NcclApi::comm_t comm = nullptr;
     long long gNatoms = 0, launches = 0;
     bool timing = false;
@@ -53,6 +58,11 @@ template <class real> struct DomainGroup final : DDBase {
         first         = proc * nlocal_bricks;
         MDB_CUDA(cudaSetDevice(device));
         MDB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0; // the transfers must not queue behind the force kernel's blocks
+        MDB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        MDB_CUDA(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_hi));
+        MDB_CUDA(cudaEventCreateWithFlags(&ev_packed, cudaEventDisableTiming));
+        MDB_CUDA(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
         stream = own_stream;
         for (auto& e : ev) MDB_CUDA(cudaEventCreate(&e));
         MDB_CUDA(cudaMallocHost(&h_off_all, (size_t)topo.nbricks * 32 * sizeof(int)));
@@ -69,6 +79,10 @@ template <class real> struct DomainGroup final : DDBase {
             b->brick_init(&topo, first + k, gn, gNatoms);
             b->d_off = d_off_all.p + (size_t)(first + k) * 32;
             b->setStream(stream);
+            // several bricks: re-sort the atoms by bin at every rebuild.  Unlike the single domain (where the generator's
+            // order stays the better one) a brick's force kernel slows down by 20 % within 100 steps without it, and its
+            // list build by 27 % (profiles/r1_ab3.txt, dd_case)
+            if (topo.nbricks > 1) b->sort_enabled = true;
             bricks.push_back(b);
         }
         if (nprocs > 1) {
@@ -93,6 +107,9 @@ template <class real> struct DomainGroup final : DDBase {
         cudaFreeHost(h_off_all);
         cudaFreeHost(h_sum);
         for (auto& e : ev) cudaEventDestroy(e);
+        cudaEventDestroy(ev_packed);
+        cudaEventDestroy(ev_halo);
+        cudaStreamDestroy(comm_stream);
         cudaStreamDestroy(own_stream);
     }
     void setStream(cudaStream_t s) override
@@ -162,17 +179,18 @@ template <class real> struct DomainGroup final : DDBase {
             }
         }
     }
-    void run_ops(const std::vector<Op>& ops)
+    void run_ops(const std::vector<Op>& ops) { run_ops(ops, stream); }
+    void run_ops(const std::vector<Op>& ops, cudaStream_t st)
     {
         NcclApi& N = nccl_api();
         bool grouped = false;
         for (const Op& o : ops) {
             if (o.kind == COPY) {
-                MDB_CUDA(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToDevice, stream));
+                MDB_CUDA(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToDevice, st));
             } else {
                 if (!grouped) { MDB_NCCL(N.GroupStart()); grouped = true; }
-                if (o.kind == SEND) MDB_NCCL(N.Send(o.src, o.bytes, NcclApi::Int8, o.peer, comm, stream));
-                else MDB_NCCL(N.Recv(o.dst, o.bytes, NcclApi::Int8, o.peer, comm, stream));
+                if (o.kind == SEND) MDB_NCCL(N.Send(o.src, o.bytes, NcclApi::Int8, o.peer, comm, st));
+                else MDB_NCCL(N.Recv(o.dst, o.bytes, NcclApi::Int8, o.peer, comm, st));
             }
         }
         if (grouped) MDB_NCCL(N.GroupEnd());
@@ -365,6 +383,13 @@ template <class real> struct DomainGroup final : DDBase {
         setupGhosts();
         forward();
         for (Brick* b : bricks) b->buildNeighbor();
+        split_lists();
+    }
+    void split_lists() // interior / boundary atom lists for the overlapped steps
+    {
+        if (!overlap || G.force_field != MDB_FF_LJ) return;
+        for (Brick* b : bricks)
+            if (b->gflag_valid && !b->merged_built) b->build_split_lists();
     }
     void reneighbour() override // main.c:76-95
     {
@@ -373,6 +398,7 @@ template <class real> struct DomainGroup final : DDBase {
         setupGhosts();
         forward();
         for (Brick* b : bricks) b->buildNeighbor();
+        split_lists();
     }
     void force()
     {
@@ -384,6 +410,30 @@ template <class real> struct DomainGroup final : DDBase {
         } else {
             for (Brick* b : bricks) b->launch_force(FORCE_DISPATCH);
         }
+    }
+    // updatePbc + computeForce of a step between two rebuilds with the halo in flight during the force of the atoms that list
+    // no ghost atom: pack on the main stream, transfers (device copies / NCCL send-recv into the ghost range of x, y, z) on
+    // comm_stream, interior force on the main stream, then the boundary atoms once the halo has landed.  The interior launch
+    // reads local positions only and the transfers write ghost positions only.  All NCCL calls stay serialised: the transfers
+    // start after everything issued earlier on the main stream (ev_packed) and the main stream waits for them (ev_halo)
+    // before it issues anything else.  Not used while per-phase timing is on (the phases would overlap).
+    bool can_overlap() const
+    {
+        if (!overlap || timing || G.force_field != MDB_FF_LJ) return false;
+        for (Brick* b : bricks)
+            if (!b->can_split_force()) return false;
+        return true;
+    }
+    void forward_and_force_overlapped()
+    {
+        for (Brick* b : bricks) b->brick_pack_pos();
+        MDB_CUDA(cudaEventRecord(ev_packed, stream));
+        MDB_CUDA(cudaStreamWaitEvent(comm_stream, ev_packed, 0));
+        run_ops(pos_ops, comm_stream);
+        MDB_CUDA(cudaEventRecord(ev_halo, comm_stream));
+        for (Brick* b : bricks) b->launch_force_part(0);
+        MDB_CUDA(cudaStreamWaitEvent(stream, ev_halo, 0));
+        for (Brick* b : bricks) b->launch_force_part(1);
     }
     void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) override // main.c:244-288
     {
@@ -409,9 +459,15 @@ template <class real> struct DomainGroup final : DDBase {
             const bool reneigh = (n + 1) % every == 0;
             if (!initial_done)
                 for (Brick* b : bricks) b->initialIntegrate();
-            if (reneigh) reneighbour();
-            else forward();
-            force();
+            if (reneigh) {
+                reneighbour();
+                force();
+            } else if (can_overlap()) {
+                forward_and_force_overlapped();
+            } else {
+                forward();
+                force();
+            }
             const bool rec = !((n + 1) % nstat) && (n + 1) < nsteps;
             if (rec || n + 1 == nsteps || !bricks[0]->fuse_integrate) {
                 for (Brick* b : bricks) b->finalIntegrate();
@@ -515,6 +571,7 @@ template <class real> struct DomainGroup final : DDBase {
     }
     void setOption(const char* name, double v) override
     {
+        if (!strcmp(name, "overlap_halo")) { overlap = v != 0; return; }
         for (Brick* b : bricks) b->setOption(name, v);
     }
     void setTiming(bool on) override

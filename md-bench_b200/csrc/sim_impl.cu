@@ -116,6 +116,8 @@ template <class real> struct Sim final : SimBase {
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
             b->release();
         ghost_msk.release();
+        gflag.release();
+        split_tmp.release(); split_pos.release(); idx_interior.release(); idx_boundary.release();
         pos4.release();
         xf.release(); yf.release(); zf.release(); pk.release(); run_off.release(); run_len.release();
         run_i0.release(); run_dj.release(); run_dk.release(); mneigh.release(); mnum.release(); numneigh_atom.release();
@@ -663,6 +665,44 @@ template <class real> struct Sim final : SimBase {
         hi = (float)((double)cutneighsq + m);
         if (sizeof(real) == 4) { lo = -1.0f; } // SP: always run the exact (float) expression
     }
+    // decomposed runs: gflag[i] = 1 if atom i lists a ghost atom (set by k_build_neighbor_v4); the force is then launched
+    // in two parts so that the halo exchange overlaps the part that needs no ghosts (DomainGroup::run)
+    DBuf<unsigned char> gflag;
+    bool gflag_valid = false;
+    unsigned char* gflag_ptr()
+    {
+        if (!brick) return nullptr;
+        gflag.ensure(round_up((size_t)Nlocal, 32), false, stream);
+        gflag_valid = true;
+        return gflag.p;
+    }
+    bool can_split_force() const
+    {
+        return brick && gflag_valid && n_boundary >= 0 && !merged_built && P.force_field == MDB_FF_LJ && !P.half_neigh && force_variant == 1 &&
+               neigh_variant == 3;
+    }
+    DBuf<int> split_tmp, split_pos, idx_interior, idx_boundary;
+    int n_boundary = -1;
+    void build_split_lists() // after buildNeighbor, once per rebuild
+    {
+        const int n = Nlocal;
+        for (DBuf<int>* b : { &split_tmp, &split_pos, &idx_interior, &idx_boundary }) b->ensure((size_t)n + 1, false, stream);
+        MDB_LAUNCH(launches, k_flag_to_int, grid_for(n, 256), 256, 0, stream, n, gflag.p, split_tmp.p);
+        scanner.exclusive(split_tmp.p, split_pos.p, n, d_flags.p + 5, stream);
+        MDB_LAUNCH(launches, k_split_by_flag, grid_for(n, 256), 256, 0, stream, n, gflag.p, split_pos.p, idx_interior.p, idx_boundary.p);
+        MDB_CUDA(cudaMemcpyAsync(h_flags + 5, d_flags.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        n_boundary = h_flags[5];
+    }
+    void launch_force_part(int want) // 0: atoms without ghost neighbors, 1: the others
+    {
+        LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
+        const int n = want ? n_boundary : Nlocal - n_boundary;
+        if (n > 0)
+            MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 4>), grid_for(n, 128), 128, 0, stream, n, c2, x.p, y.p, z.p, numneigh.p,
+                neighbors.p, LL, fx.p, fy.p, fz.p, (const int*)(want ? idx_boundary.p : idx_interior.p), want);
+        if (want == 1) force_launches++;
+    }
     bool use_merged() const { return merge == 2 && P.force_field == MDB_FF_LJ && !P.half_neigh; }
     void build_merged() // one row per atom pair, see k_build_neighbor_m2 (vl_kernels.cuh)
     {
@@ -731,6 +771,8 @@ template <class real> struct Sim final : SimBase {
         }
         merged_built = false;
         pa_valid     = true;
+        gflag_valid  = false;
+        n_boundary   = -1;
         if (neigh_variant >= 2) { // candidates packed in CSR order
             const int nall = Nlocal + Nghost;
             pk.ensure(nall, false, stream);
@@ -765,7 +807,7 @@ template <class real> struct Sim final : SimBase {
                 else
                     MDB_LAUNCH(launches, k_build_neighbor_v4<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
                         P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p,
-                        nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+                        nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1, gflag_ptr());
             } else {
                 float lo, hi;
                 list_margin(lo, hi);
@@ -845,10 +887,12 @@ template <class real> struct Sim final : SimBase {
                         x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
                 else if (force_variant == 2)
                     MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 8>), grid_for(Nlocal, 128), 128, 0, stream,
-                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p,
+                        (const int*)nullptr, 0);
                 else
                     MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 4>), grid_for(Nlocal, 128), 128, 0, stream,
-                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p,
+                        (const int*)nullptr, 0);
             } else {
                 zero3(fx.p, fy.p, fz.p, Nlocal);
                 MDB_LAUNCH(launches, k_force_lj_half<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,

@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half,
     const real* __restrict__ z, const float4* __restrict__ pk, const int* __restrict__ binstart,
     const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs,
     NbLayout L, const int* __restrict__ orig, int* __restrict__ numneigh,
-    int* __restrict__ neighbors, int* __restrict__ max_n)
+    int* __restrict__ neighbors, int* __restrict__ max_n, unsigned char* __restrict__ gflag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n       = 0;
@@ -612,6 +612,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half,
         const real xt = x[i], yt = y[i], zt = z[i];
         const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
         const float cut = (float)cutneighsq;
+        bool ghost = false; // some listed neighbor is a ghost atom (decomposed runs: boundary atoms wait for the halo)
         const int oi   = half ? orig[i] : 0;
         const int ibin = coord2bin(g, xt, yt, zt);
         int* out       = neighbors + L.base(i);
@@ -653,13 +654,30 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half,
                     if (n < maxneighs) *out = j;
                     out += L.sk;
                     n++;
+                    ghost = ghost || j >= nlocal;
                 }
             }
         }
         numneigh[i] = n;
+        if (gflag) gflag[i] = ghost ? 1 : 0;
     }
     n = __reduce_max_sync(0xffffffffu, n);
     if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
+// gflag (k_build_neighbor_v4) -> interior[] / boundary[] index lists, ascending; pos = exclusive scan of gflag
+static __global__ void k_split_by_flag(int n, const unsigned char* __restrict__ gflag, const int* __restrict__ pos, int* __restrict__ interior,
+    int* __restrict__ boundary)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (gflag[i]) boundary[pos[i]] = i;
+    else interior[i - pos[i]] = i;
+}
+static __global__ void k_flag_to_int(int n, const unsigned char* __restrict__ gflag, int* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = gflag[i];
 }
 
 // ---- merged lists: ONE row for the atom pair (2t, 2t+1) -------------------------------------------------------------
@@ -939,10 +957,13 @@ template <class real, int U>
 __global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<real> c,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
     const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
-    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
+    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz, const int* __restrict__ sel, int want)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nlocal) return;
+    // decomposed runs: one launch for the atoms without ghost neighbors while the halo is in flight, one for the rest
+    // afterwards; sel = the (ascending) list of atom indices of this launch, nlocal its length.  sel == nullptr: every atom
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlocal) return;
+    const int i = sel ? sel[t] : t;
     const real xt = x[i], yt = y[i], zt = z[i];
     const int nn  = numneigh[i];
     real fix = 0, fiy = 0, fiz = 0;
