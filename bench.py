@@ -184,13 +184,66 @@ def workload_config(args, world, grid=(1, 1, 1)):
                            else "verletlist %s neighbor lists" % ("half" if args.half else "full"),
                            args.precision.upper(), args.ntimes),
             "nx_per_gpu": args.nx, "ntimes": args.ntimes, "precision": args.precision,
-            "l2": "inputs larger than L2 (neighbor list %.1f GB + positions %.2f GB per GPU vs 126 MB L2)"
-                  % (4 * args.nx ** 3 * 100 * 4 / 1e9, 4 * args.nx ** 3 * 24 / 1e9),
+            "l2": ("inputs larger than L2 (cluster-pair list %.1f GB + cluster data %.2f GB per GPU vs 126 MB L2)"
+                   % (args.nx ** 3 * 100 * 4 / 1e9, 4 * args.nx ** 3 * 36 / 1e9))
+            if getattr(args, "scheme", "verletlist") == "clusterpair" else
+            "inputs larger than L2 (neighbor list %.1f GB + positions %.2f GB per GPU vs 126 MB L2)"
+            % (4 * args.nx ** 3 * 100 * 4 / 1e9, 4 * args.nx ** 3 * 24 / 1e9),
             "global_box": "%dx%dx%d unit cells = %d atoms" % (args.nx * grid[0], args.nx * grid[1], args.nx * grid[2],
                                                              4 * args.nx ** 3 * grid[0] * grid[1] * grid[2]),
             "parallelism": "1 domain" if grid == (1, 1, 1) else
             "spatial decomposition %dx%dx%d bricks over %d GPU(s), ghost exchange %s"
             % (grid[0], grid[1], grid[2], world, "by NCCL send/recv over NVLink" if world > 1 else "by device copies")}
+
+
+def clusterpair_secondary(m, args, local, stream, steps=2):
+    """the same box with the reference's OTHER scheme, as BASELINE config 2 runs it (clusterpair 4x4, SP, full lists):
+    device-resident throughput (state restore + cluster build + list build + first force inside the timed region, like the
+    primary) and the force kernel's time per launch against the measured FP32 FMA peak"""
+    import torch
+    P = m.default_params(precision=m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx, ntimes=args.ntimes)
+    c = m.ClusterSimulation(P, cluster_n=4, device=local)
+    c.setStream(stream)
+    natoms = c.createAtom()
+    c.setup(adjust=True)
+    c.updateSingleAtoms()
+    c.saveState()
+    cp0, in0 = c.countPairs()
+
+    def one():
+        c.restoreState()
+        c.setup(adjust=False)
+        return c.run(args.ntimes)
+
+    one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        rec, _ = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    cp1, in1 = c.countPairs()
+    c.setTiming(True)
+    c.resetKernelStats()
+    _, tm = one()
+    ks = c.kernelStats()
+    c.setTiming(False)
+    f_ms = ks["force_ms"] / max(1, ks["force_launches"])
+    flop = (8.0 * 0.5 * (cp0 + cp1) * 16 + 15.0 * 0.5 * (in0 + in1)) / natoms
+    peak = m.measure_fma_peak(m.SP, local)
+    ach = flop * natoms / (f_ms * 1e-3) * 1e-12
+    out = {"metric": METRIC_CP % (4, 4), "config": "BASELINE config 2 physics (clusterpair 4x4, SP, full lists) at %d^3 unit cells" % args.nx,
+           "value": natoms * args.ntimes * steps / (ms * 1e-3), "unit": UNIT, "dtype": "f32", "steps": steps,
+           "ms_per_step": ms / steps,
+           "roofline": {"kernel": "k_cp_force_lj_sp_packed<4>", "bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak if peak else None, "ms_per_launch": f_ms, "flop_per_atom_step": flop,
+                        "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
+                        "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"])},
+           "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
+    c.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -214,6 +267,8 @@ def main():
     ap.add_argument("--scheme", default="verletlist", choices=["verletlist", "clusterpair"],
                     help="OPT_SCHEME of the reference; clusterpair = GROMACS-style 4 x N cluster pairs (one GPU)")
     ap.add_argument("--cluster-n", type=int, default=4, choices=[4, 8])
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary measurement (BASELINE config 2 physics: clusterpair 4x4 SP at the same box)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -407,14 +462,23 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
 
+    # ---- secondary: BASELINE config 2 physics (clusterpair 4x4, SP) at the same per-GPU box, N = 1 only ----
+    secondary = None
+    if world == 1 and not decomposed and not cp and not args.no_secondary:
+        sim.close()
+        sim = None
+        secondary = clusterpair_secondary(m, args, local, stream)
+
     if rank == 0:
         line = {"metric": (METRIC_CP % (4, args.cluster_n)) if cp else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64" if dp else "f32", "data": "synthetic", "config": workload_config(args, world, grid),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "secondary": secondary,
+                "gpu_launches": int(launches), "clocks": clk,
                 "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
         print(json.dumps(line))
-    sim.close()
+    if sim is not None:
+        sim.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
