@@ -376,10 +376,19 @@ def main():
     except Exception:
         pass
     ach_gbs = BYTES_PER_ATOM_STEP[args.precision] * per_launch_atoms / (f_ms * 1e-3) * 1e-9
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes of one launch from the committed ncu --set full capture of this very configuration, if there is one
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        te = tj.get("%s/%s/%d" % (args.scheme, args.precision, args.nx))
+        if te and not args.half and not decomposed and (not cp or args.cluster_n == 4):
+            traffic, traffic_src = te["bytes"], te["source"]
+    except Exception:
+        pass
     roofline = {"kernel": ("k_cp_force_lj<%s,%d,%s>" % ("double" if dp else "float", args.cluster_n, "half" if args.half else "full")) if cp
                 else "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
                 "bound": "fp64" if dp else "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_ATOM_STEP[args.precision] * per_launch_atoms if not cp else None,
                 "peak_source": "measured in this run: FMA issue micro-benchmark (md-bench_b200/csrc/peaks.cu)",
                 "ms_per_launch": f_ms, "flop_per_atom_step": flop_per_atom,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
