@@ -41,7 +41,7 @@ template <class real> struct Sim final : SimBase {
     // consecutive atoms (A/B in profiles/r1_ab.txt: force 1.49 ms unsorted vs 1.67 ms sorted at 8.4M
     // atoms).  Turn it on (mdb_setOption "sort_atoms") for long runs of diffusing systems.
     bool sort_enabled = false, extmap_valid = false;
-    int force_variant = 1, neigh_variant = 3, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
+    int force_variant = 1, neigh_variant = 4, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
     bool fuse_integrate = true, sort_rows = false;
     int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
     bool bin_rank_ready = false;
@@ -49,6 +49,8 @@ template <class real> struct Sim final : SimBase {
     NbLayout LL { 0, 0, 0 };                                    // element (i,k) at neighbors[LL.base(i) + k*LL.sk]
     DBuf<float> xf, yf, zf;
     DBuf<float4> pk;
+    DBuf<float> cxs, cys, czs; // candidates in CSR order, SoA (k_build_neighbor_v5)
+    DBuf<int> cids;
     DBuf<char> pos4; // packed positions {x,y,z,-} for the p4 force kernel
     DBuf<int> run_off, run_len, run_i0, run_dj, run_dk;
     int nruns = 0;
@@ -119,6 +121,7 @@ template <class real> struct Sim final : SimBase {
         gflag.release();
         split_tmp.release(); split_pos.release(); idx_interior.release(); idx_boundary.release();
         pos4.release();
+        cxs.release(); cys.release(); czs.release(); cids.release();
         xf.release(); yf.release(); zf.release(); pk.release(); run_off.release(); run_len.release();
         run_i0.release(); run_dj.release(); run_dk.release(); mneigh.release(); mnum.release(); numneigh_atom.release();
         st_tab.release();
@@ -679,7 +682,7 @@ template <class real> struct Sim final : SimBase {
     bool can_split_force() const
     {
         return brick && gflag_valid && n_boundary >= 0 && !merged_built && P.force_field == MDB_FF_LJ && !P.half_neigh && force_variant == 1 &&
-               neigh_variant == 3;
+               neigh_variant >= 3;
     }
     DBuf<int> split_tmp, split_pos, idx_interior, idx_boundary;
     int n_boundary = -1;
@@ -773,7 +776,13 @@ template <class real> struct Sim final : SimBase {
         pa_valid     = true;
         gflag_valid  = false;
         n_boundary   = -1;
-        if (neigh_variant >= 2) { // candidates packed in CSR order
+        if (neigh_variant == 4) { // candidates in CSR order as SoA float arrays, padded to a multiple of 4
+            const int nall = Nlocal + Nghost, npad = (int)round_up((size_t)nall + 4, 4);
+            for (DBuf<float>* b : { &cxs, &cys, &czs }) b->ensure(npad, false, stream);
+            cids.ensure(npad, false, stream);
+            MDB_LAUNCH(launches, k_pack_binned_soa<real>, grid_for(npad, 256), 256, 0, stream, nall, npad, binatoms.p, x.p, y.p,
+                z.p, cxs.p, cys.p, czs.p, cids.p);
+        } else if (neigh_variant >= 2) { // candidates packed in CSR order
             const int nall = Nlocal + Nghost;
             pk.ensure(nall, false, stream);
             MDB_LAUNCH(launches, k_pack_binned<real>, grid_for(nall, 256), 256, 0, stream, nall, binatoms.p, x.p, y.p,
@@ -800,7 +809,11 @@ template <class real> struct Sim final : SimBase {
             } else if (neigh_variant >= 2) {
                 float lo, hi;
                 list_margin(lo, hi);
-                if (neigh_variant == 2)
+                if (neigh_variant == 4)
+                    MDB_LAUNCH(launches, k_build_neighbor_v5<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                        P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p,
+                        run_len.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1, gflag_ptr());
+                else if (neigh_variant == 2)
                     MDB_LAUNCH(launches, k_build_neighbor_v3<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
                         P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p,
                         nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);

@@ -665,6 +665,116 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half,
     if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
 }
 
+// ---- v5 list build: v4 with the candidates as SoA float arrays and PACKED FP32 distance tests ------------------------
+// ncu of v4 (profiles/r1_s2_neigh_raw.txt): 35 executed instructions per candidate, issue 73 %, L1 83 %.  Here one
+// 128-bit load fetches a coordinate of FOUR consecutive candidates (3 loads per 4 instead of 4 per 4), the distance of two
+// candidates is one FADD2/FMUL2/FFMA2 sequence (bit-identical to the scalar round-to-nearest operations), and the
+// threshold tests are two more packed subtractions whose SIGN bits are shifted into the pass / maybe masks with one
+// funnel shift each (rs < T  <=>  sign(rs - T): the subtraction is monotone and exact in sign).  ~7 instructions per
+// candidate in phase 1; phase 2 (append, exact FP64 in the uncertain band) is v4's.
+template <class real>
+__global__ void k_pack_binned_soa(int nall, int npad, const int* __restrict__ binatoms, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, float* __restrict__ cx, float* __restrict__ cy, float* __restrict__ cz,
+    int* __restrict__ cid)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= npad) return;
+    if (m < nall) {
+        const int j = binatoms[m];
+        cx[m] = (float)x[j]; cy[m] = (float)y[j]; cz[m] = (float)z[j];
+        cid[m] = j;
+    } else { // alignment padding behind the last candidate: never in range
+        cx[m] = cy[m] = cz[m] = 1.0e30f;
+        cid[m] = -1;
+    }
+}
+__device__ __forceinline__ void ld2x2(const float* p, f32x2& a, f32x2& b)
+{
+    asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+template <class real>
+__global__ void __launch_bounds__(128) k_build_neighbor_v5(int nlocal, int half, BinGeom<real> g, real cutneighsq, float lo, float hi,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float* __restrict__ cx,
+    const float* __restrict__ cy, const float* __restrict__ cz, const int* __restrict__ cid, const int* __restrict__ binstart,
+    const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs, NbLayout L,
+    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n,
+    unsigned char* __restrict__ gflag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n       = 0;
+    if (i < nlocal) {
+        const real xt = x[i], yt = y[i], zt = z[i];
+        const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
+        const f32x2 xs2 = pk2(xs, xs), ys2 = pk2(ys, ys), zs2 = pk2(zs, zs);
+        // flagged iff rs < T.  SP: pass == maybe == (rs <= cutneighsq), the reference's own expression.
+        // DP: pass = rs < lo (certainly inside), maybe = rs <= hi (not certainly outside), exact FP64 in between.
+        const float tpass = sizeof(real) == 4 ? nextafterf((float)cutneighsq, INFINITY) : lo;
+        const float tmay  = sizeof(real) == 4 ? tpass : nextafterf(hi, INFINITY);
+        const f32x2 tp2 = pk2(tpass, tpass), tm2 = pk2(tmay, tmay);
+        const int oi   = half ? orig[i] : 0;
+        const int ibin = coord2bin(g, xt, yt, zt);
+        int* out       = neighbors + L.base(i);
+        bool ghost     = false;
+        for (int r = 0; r < nruns; r++) {
+            int b0 = ibin + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
+            b0 = max(b0, 0);
+            b1 = min(b1, g.mbins + 1);
+            if (b1 <= b0) continue;
+            const int s = __ldg(&binstart[b0]), e = __ldg(&binstart[b1]);
+            for (int c0 = s & ~3; c0 < e;) {
+                const int ng = min(8, (e - c0 + 3) >> 2); // groups of 4 candidates in this flush
+                unsigned mp = 0, mm = 0;
+                for (int q = 0; q < ng; q++) {
+                    f32x2 X0, X1, Y0, Y1, Z0, Z1;
+                    ld2x2(cx + c0 + 4 * q, X0, X1);
+                    ld2x2(cy + c0 + 4 * q, Y0, Y1);
+                    ld2x2(cz + c0 + 4 * q, Z0, Z1);
+                    f32x2 dx = sub2(xs2, X0), dy = sub2(ys2, Y0), dz = sub2(zs2, Z0);
+                    const f32x2 r0 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+                    dx = sub2(xs2, X1); dy = sub2(ys2, Y1); dz = sub2(zs2, Z1);
+                    const f32x2 r1 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+                    float a, b;
+                    upk2(sub2(r0, tm2), a, b);
+                    mm = __funnelshift_l(__float_as_uint(a), mm, 1); mm = __funnelshift_l(__float_as_uint(b), mm, 1);
+                    upk2(sub2(r1, tm2), a, b);
+                    mm = __funnelshift_l(__float_as_uint(a), mm, 1); mm = __funnelshift_l(__float_as_uint(b), mm, 1);
+                    if (sizeof(real) == 8) {
+                        upk2(sub2(r0, tp2), a, b);
+                        mp = __funnelshift_l(__float_as_uint(a), mp, 1); mp = __funnelshift_l(__float_as_uint(b), mp, 1);
+                        upk2(sub2(r1, tp2), a, b);
+                        mp = __funnelshift_l(__float_as_uint(a), mp, 1); mp = __funnelshift_l(__float_as_uint(b), mp, 1);
+                    }
+                }
+                if (sizeof(real) == 4) mp = mm;
+                // candidate t of this flush (position c0 + t) sits at bit k-1-t; valid ones: s <= c0 + t < e
+                const int k = 4 * ng, tlo = max(s - c0, 0), thi = min(e - c0, k);
+                const unsigned vmask = (unsigned)((1ull << (k - tlo)) - 1ull) & ~(unsigned)((1ull << (k - thi)) - 1ull);
+                unsigned todo = mm & vmask;
+                while (todo) {
+                    const int p = 31 - __clz(todo); // highest bit first = ascending candidate position (the reference's order)
+                    todo &= ~(1u << p);
+                    const int j = __ldg(cid + c0 + (k - 1 - p));
+                    if (j == i) continue;
+                    if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
+                    if (!((mp >> p) & 1u)) { // uncertain band: the reference's exact FP64 expression
+                        const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
+                        if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
+                    }
+                    if (n < maxneighs) *out = j;
+                    out += L.sk;
+                    n++;
+                    ghost = ghost || j >= nlocal;
+                }
+                c0 += k;
+            }
+        }
+        numneigh[i] = n;
+        if (gflag) gflag[i] = ghost ? 1 : 0;
+    }
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
 // gflag (k_build_neighbor_v4) -> interior[] / boundary[] index lists, ascending; pos = exclusive scan of gflag
 static __global__ void k_split_by_flag(int n, const unsigned char* __restrict__ gflag, const int* __restrict__ pos, int* __restrict__ interior,
     int* __restrict__ boundary)
