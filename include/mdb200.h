@@ -177,6 +177,13 @@ int         mdb_getEamFp(mdb_ctx* c, void* fp, int with_ghosts);   /* Eam.fp aft
  * current positions; computed on demand by a counting kernel */
 int         mdb_countPairs(mdb_ctx* c, long long* listed, long long* in_cutoff);
 
+/* ---- kernel micro-benchmark (reference src/verletlist/main-stub.c) ----------------------------------- */
+/* replaces createNeighbors (main-stub.c:62-106): a synthetic neighbor list for the atoms handed over with
+ * mdb_setAtoms -- pattern 0 "seq" (i+1, i+2, ...), 1 "fix" (0 .. nneighs-1 for every atom), 2 "rand" --
+ * nneighs entries replicated nreps times; mdb_computeForceLJFullNeigh / HalfNeigh then time the kernel alone */
+enum { MDB_STUB_SEQ = 0, MDB_STUB_FIX = 1, MDB_STUB_RAND = 2 };
+int         mdb_stubNeighbors(mdb_ctx* c, int pattern, int nneighs, int nreps, unsigned seed);
+
 /* ---- multi-GPU: spatial decomposition ----------------------------------------------- */
 /* The reference runs one domain ("replicas only").  Here a box may be cut into gx*gy*gz bricks, each
  * with a ghost shell of width cutneigh; what is generalised is the setupPbc / updatePbc /

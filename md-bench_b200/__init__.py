@@ -54,7 +54,7 @@ EXPORTS = [
     "mdb_finalIntegrate", "mdb_setup", "mdb_reneighbour", "mdb_run", "mdb_setTiming",
     "mdb_getKernelStats", "mdb_resetKernelStats", "mdb_setEam", "mdb_setEamSplines",
     "mdb_getEamSplines", "mdb_getNeighbors", "mdb_getGhostMap", "mdb_getNeighborParams",
-    "mdb_getStencil", "mdb_getBinCounts", "mdb_getEamFp", "mdb_countPairs", "mdb_measureFmaPeak",
+    "mdb_getStencil", "mdb_getBinCounts", "mdb_getEamFp", "mdb_countPairs", "mdb_measureFmaPeak", "mdb_stubNeighbors",
     "mdb_dd_uniqueIdBytes", "mdb_dd_getUniqueId", "mdb_dd_plan", "mdb_dd_schedule", "mdb_dd_create", "mdb_dd_destroy",
     "mdb_dd_setStream", "mdb_dd_sync", "mdb_dd_createAtom", "mdb_dd_setAtoms", "mdb_dd_setEam", "mdb_dd_setup",
     "mdb_dd_reneighbour", "mdb_dd_run", "mdb_dd_computeThermo", "mdb_dd_getCounts", "mdb_dd_getAtoms",
@@ -243,6 +243,10 @@ class Simulation:
         if t < 0:
             raise MdbError(self.L.mdb_last_error().decode())
         return t
+
+    def stubNeighbors(self, pattern, nneighs=76, nreps=1, seed=12345):
+        """synthetic list of the reference's kernel micro-benchmark (main-stub.c): pattern 'seq' | 'fix' | 'rand'"""
+        self._ck(self.L.mdb_stubNeighbors(self.h, {"seq": 0, "fix": 1, "rand": 2}[pattern], nneighs, nreps, C.c_uint(seed)))
 
     def computeForce(self): return self._force(self.L.mdb_computeForce)
     def computeForceLJFullNeigh(self): return self._force(self.L.mdb_computeForceLJFullNeigh)

@@ -194,6 +194,10 @@ int mdb_getBinCounts(mdb_ctx* c, int* bc) { MDB_TRY(c->sim->getBinCounts(bc)) }
 int mdb_getEamFp(mdb_ctx* c, void* fp, int with_ghosts) { MDB_TRY(c->sim->getEamFp(fp, with_ghosts != 0)) }
 int mdb_setOption(mdb_ctx* c, const char* name, double value) { MDB_TRY(c->sim->setOption(name, value)) }
 int mdb_countPairs(mdb_ctx* c, long long* listed, long long* in_cutoff) { MDB_TRY(c->sim->countPairs(listed, in_cutoff)) }
+int mdb_stubNeighbors(mdb_ctx* c, int pattern, int nneighs, int nreps, unsigned seed)
+{
+    MDB_TRY(c->sim->stubNeighbors(pattern, nneighs, nreps, seed))
+}
 
 } // extern "C"
 

@@ -49,6 +49,7 @@ struct SimBase {
         double* rdrho, void* rhor, void* frho, void* z2r)                                    = 0;
     virtual void getEamFp(void* fp, bool ghosts)                                             = 0;
     virtual void setOption(const char* name, double value)                                   = 0;
+    virtual void stubNeighbors(int pattern, int nneighs, int nreps, unsigned seed)           = 0;
 
     bool timing             = false;
     double force_ms         = 0, neigh_ms = 0;

@@ -1186,6 +1186,29 @@ template <class real> struct Sim final : SimBase {
         MDB_CUDA(cudaMemcpyAsync(out, tx.p, n * sizeof(real), cudaMemcpyDeviceToHost, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
     }
+    // synthetic lists of the reference's kernel micro-benchmark (main-stub.c:62-106) instead of a list build
+    void stubNeighbors(int pattern, int nneighs, int nreps, unsigned seed) override
+    {
+        if (Nlocal <= 0) throw Error("mdb_stubNeighbors: no atoms");
+        if (pattern < 0 || pattern > 2 || nneighs < 1 || nreps < 1) throw Error("mdb_stubNeighbors: bad pattern / counts");
+        if (pattern == 2 && Nlocal <= nneighs)
+            throw Error("When using random pattern, number of atoms should be higher than number of neighbors per atom!");
+        Nghost    = 0;
+        maxneighs = nneighs * nreps;
+        nstride   = round_up((size_t)Nlocal, 32);
+        const size_t rowlen = round_up((size_t)maxneighs, 8);
+        if (list_layout == 1) LL = NbLayout { rowlen, 1, 0 };
+        else if (list_layout == 2) LL = NbLayout { 32 * rowlen, 32, 5 };
+        else LL = NbLayout { 0, nstride, 31 };
+        numneigh.ensure(nstride, false, stream);
+        neighbors.ensure(rowlen * nstride, false, stream);
+        MDB_LAUNCH(launches, k_stub_neighbors, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, pattern, nneighs, nreps, seed, LL,
+            numneigh.p, neighbors.p);
+        merged_built = false;
+        pa_valid     = true;
+        gflag_valid  = false;
+        extmap_valid = false;
+    }
     void setOption(const char* name, double v) override
     {
         if (!strcmp(name, "sort_atoms")) sort_enabled = v != 0;

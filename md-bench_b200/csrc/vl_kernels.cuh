@@ -1432,6 +1432,36 @@ __global__ void k_count_pairs(int nlocal, real cutforcesq, const real* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Synthetic neighbor lists of the reference's kernel micro-benchmark (verletlist/main-stub.c:62-106 createNeighbors):
+// pattern 0 "seq": neighbors i+1, i+2, ... (mod Nlocal); 1 "fix": 0 .. nneighs-1 for every atom; 2 "rand": nneighs random
+// atoms != i (a hash stream per atom instead of rand(); the reference additionally rejects duplicates, which does not
+// change the access pattern).  The first nneighs entries are replicated nreps times.
+static __global__ void k_stub_neighbors(int nlocal, int pattern, int nneighs, int nreps, unsigned seed, NbLayout L, int* __restrict__ numneigh,
+    int* __restrict__ neighbors)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    int* out   = neighbors + L.base(i);
+    unsigned h = seed ^ (0x9e3779b9u * (unsigned)(i + 1));
+    int j      = pattern == 0 ? (i + 1) % nlocal : 0;
+    const int m = pattern == 0 ? nlocal : nneighs;
+    for (int k = 0; k < nneighs; k++) {
+        int v;
+        if (pattern == 2) {
+            do {
+                h ^= h << 13; h ^= h >> 17; h ^= h << 5; // xorshift32
+                v = (int)(h % (unsigned)nlocal);
+            } while (v == i && nlocal > 1);
+        } else {
+            v = j;
+            j = (j + 1) % m;
+        }
+        for (int r = 0; r < nreps; r++) out[(size_t)(r * nneighs + k) * L.sk] = v;
+    }
+    numneigh[i] = nneighs * nreps;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-layout conversion: AoS {x,y,z}* <-> SoA
 template <class real>
 __global__ void k_aos_to_soa(size_t n, const real* __restrict__ a, real* __restrict__ x,

@@ -430,3 +430,85 @@ def test_merged_pair_rows_variant_gives_the_reference_lists(dp):
     assert np.allclose(ra, rb, rtol=1e-12 if dp else 1e-5)
     assert rel_err(a.get("x"), b.get("x")) < (1e-12 if dp else 1e-5)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("pbc", [(1, 0, 1), (0, 0, 1), (0, 0, 0)])
+def test_open_boundaries_pbc_flags(pbc):
+    """param pbc_x/pbc_y/pbc_z = 0 (parameter.c:102-104; honoured by setupPbc, pbc.c:107-224): no images across an open
+    face -- ghost set, ghost coordinates and lists bit-exact against the checker, forces to tolerance"""
+    rng = np.random.default_rng(5)
+    nx, ny, nz = 6, 5, 7
+    o = OracleVL(True)
+    o.configure(nx=nx, ny=ny, nz=nz, pbc=pbc)
+    o.derive(); o.create_atoms(); o.setup_neighbor(); o.setup_thermo(); o.adjust_thermo()
+    x = (o.get("x") + rng.normal(0, 0.1, (o.geti("Nlocal"), 3)))
+    # keep every atom inside the box: an open face does not wrap (updateAtomsPbc wraps regardless of the flags)
+    prd = np.array([o.getr("xprd"), o.getr("yprd"), o.getr("zprd")])
+    x = np.clip(x, 1e-3, prd - 1e-3)
+    v = o.get("v")
+    o.set_atoms(x, v)
+    o.reneighbour()
+    o.computeForce()
+    s = make_sim(True, True, False, nx=nx, ny=ny, nz=nz, pbc_x=pbc[0], pbc_y=pbc[1], pbc_z=pbc[2])
+    s.setAtoms(x, v)
+    s.setupNeighbor(); s.setupThermo()
+    s.reneighbour()
+    s.computeForce()
+    assert s.counts()["Nghost"] == o.geti("Nghost")
+    if pbc == (0, 0, 0):
+        assert s.counts()["Nghost"] == 0
+    assert np.array_equal(s.get("x", ghosts=True), o.get("x", ghosts=True))
+    gm = s.ghostMap()
+    for k in ("border_map", "PBCx", "PBCy", "PBCz"):
+        assert np.array_equal(gm[k], o.get(k)), k
+    nn, nb = s.neighbors()
+    assert np.array_equal(nn, o.get("numneigh"))
+    onb = o.get("neighbors")
+    for i in range(len(nn)):
+        assert np.array_equal(nb[i, :nn[i]], onb[i, :nn[i]]), i
+    f, fo = s.get("f"), o.get("f")
+    assert np.abs(f - fo).max() <= 1e-10 * np.abs(fo).max()
+    s.close()
+
+
+@pytest.mark.parametrize("pattern", ["seq", "fix", "rand"])
+def test_stub_neighbor_patterns_and_force(pattern):
+    """the kernel micro-benchmark's synthetic lists (main-stub.c:62-106) and the force they give, against numpy"""
+    n, nn, nr = 300, 76, 2
+    m = load_pkg()
+    s = m.Simulation(m.default_params(layout=m.SOA, nx=1, ny=1, nz=1, cutforce=1.0e6, skin=0.0))
+    x = np.repeat((np.arange(n) * 1e-5)[:, None], 3, axis=1)
+    s.setAtoms(x, None)
+    s.stubNeighbors(pattern, nn, nr)
+    cnt, nb = s.neighbors()
+    assert np.all(cnt == nn * nr)
+    assert np.array_equal(nb[:, :nn], nb[:, nn:2 * nn])          # replicated nreps times
+    if pattern == "seq":
+        assert np.array_equal(nb[:, :nn], (np.arange(n)[:, None] + 1 + np.arange(nn)[None, :]) % n)
+    elif pattern == "fix":
+        assert np.array_equal(nb[:, :nn], np.repeat(np.arange(nn)[None, :], n, axis=0))
+    else:
+        assert nb.min() >= 0 and nb.max() < n and not np.any(nb == np.arange(n)[:, None])
+        assert len(np.unique(nb[:, :nn])) > n // 2               # spread over the atoms
+    if pattern != "fix":                                         # "fix" lists atom i itself for i < nneighs (r = 0)
+        s.computeForceLJFullNeigh()
+        f = s.get("f")
+        d = x[:, None, :] - x[nb]                                # (n, nn*nr, 3)
+        rsq = (d * d).sum(axis=2)
+        sr2 = 1.0 / rsq
+        sr6 = sr2 ** 3
+        ref = (d * (48.0 * sr6 * (sr6 - 0.5) * sr2)[:, :, None]).sum(axis=1)
+        assert np.abs(f - ref).max() <= 1e-10 * np.abs(ref).max()
+    s.close()
+
+
+def test_stub_driver_report():
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "md-bench_b200", "driver", "MDBench-VL-B200-stub")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    out = subprocess.run([exe, "-p", "rand", "-na", "20000", "-nn", "76", "-n", "20"], capture_output=True, text=True, timeout=120).stdout
+    assert "Pattern: rand" in out and "Number of atoms: 20000" in out and "Mega atom updates/s" in out
+    out = subprocess.run([exe, "-p", "seq", "-na", "4096", "--csv", "-n", "5"], capture_output=True, text=True, timeout=120).stdout
+    assert out.splitlines()[0].startswith("steps,pattern,natoms,nneighs,nreps") and out.splitlines()[1].startswith("5,seq,4096,76,1,")
