@@ -895,6 +895,13 @@ template <class real> struct Sim final : SimBase {
                     else
                         MDB_LAUNCH(launches, (k_force_lj_full_p4<real, 8>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
                             c2, (const P4*)pos4.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                } else if (force_variant == 8 || force_variant == 9) { // branch-free force block (v6), U = 4 / 2
+                    if (force_variant == 8)
+                        MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
+                            x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                    else
+                        MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
+                            x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
                 } else if (force_variant == 0)
                     MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
                         x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
@@ -902,7 +909,10 @@ template <class real> struct Sim final : SimBase {
                     MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 8>), grid_for(Nlocal, 128), 128, 0, stream,
                         Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p,
                         (const int*)nullptr, 0);
-                else
+                else if (sizeof(real) == 4) // default, SP: the branch-free kernel (1.00 vs 1.13 ms, profiles/r1_ab3.txt)
+                    MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
+                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                else // default, DP: v2 (the branch-free kernel pays 1.617 vs 1.537 ms for the FP64 work outside the cutoff)
                     MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 4>), grid_for(Nlocal, 128), 128, 0, stream,
                         Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p,
                         (const int*)nullptr, 0);

@@ -1127,6 +1127,66 @@ __global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<r
     fz[i] = fiz;
 }
 
+// ---- v6: v2 with the in-cutoff block made branch-free, so that the U pairs in flight interleave ---------------------------
+// SASS of v2: every pair's force block is a divergent region holding a 12-deep dependent DFMA/DMUL chain, executed pair
+// after pair; the micro-benchmark with perfectly coalesced lists ("seq") therefore reaches only 54 % of the FP64 issue
+// rate.  Here the force of all U pairs is computed unconditionally and selected to zero outside the cutoff (a listed pair
+// is never at distance 0, so the reciprocal is finite), which lets the scheduler interleave the U chains.
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_force_lj_full_v6(int nlocal, LJConst2<real> c, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
+    NbLayout L, real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    const int* nb   = nbT + L.base(i);
+    const int nfull = nn - nn % U;
+    int j[U], jn[U];
+    if (nfull > 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = __ldg(nb + (size_t)u * L.sk);
+    }
+    for (int k = 0; k < nfull; k += U) {
+        real dx[U], dy[U], dz[U], rsq[U], f[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            dx[u] = xt - __ldg(x + j[u]);
+            dy[u] = yt - __ldg(y + j[u]);
+            dz[u] = zt - __ldg(z + j[u]);
+        }
+        nb += (size_t)U * L.sk;
+        if (k + U < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = __ldg(nb + (size_t)u * L.sk);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+#pragma unroll
+        for (int u = 0; u < U; u++) f[u] = lj_pair2(rsq[u], c);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const real g = rsq[u] < c.cutforcesq ? f[u] : (real)0;
+            fix = fma(dx[u], g, fix); fiy = fma(dy[u], g, fiy); fiz = fma(dz[u], g, fiz);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = jn[u];
+    }
+    for (int k = nfull; k < nn; k++) {
+        const int jj  = __ldg(nb);
+        nb += L.sk;
+        const real dx = xt - __ldg(x + jj), dy = yt - __ldg(y + jj), dz = zt - __ldg(z + jj);
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        const real g   = rsq < c.cutforcesq ? lj_pair2(rsq, c) : (real)0;
+        fix = fma(dx, g, fix); fiy = fma(dy, g, fiy); fiz = fma(dz, g, fiz);
+    }
+    fx[i] = fix;
+    fy[i] = fiy;
+    fz[i] = fiz;
+}
+
 // ---- m2: merged rows, two atoms per thread (see k_build_neighbor_m2) ---------------------------------------------------
 template <class real, int U>
 __global__ void __launch_bounds__(128) k_force_lj_full_m2(int nlocal, LJConst2<real> c, const real* __restrict__ x,
