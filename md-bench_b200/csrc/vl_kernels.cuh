@@ -1064,9 +1064,9 @@ template <class real> __device__ __forceinline__ real lj_pair2(real rsq, const L
 }
 
 template <class real, int U>
-__global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<real> c,
+__device__ __forceinline__ void force_lj_full_v2_body(int nlocal, const LJConst2<real>& c,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, const NbLayout& L,
     real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz, const int* __restrict__ sel, int want)
 {
     // decomposed runs: one launch for the atoms without ghost neighbors while the halo is in flight, one for the rest
@@ -1127,6 +1127,14 @@ __global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<r
     fz[i] = fiz;
 }
 
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<real> c,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
+    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz, const int* __restrict__ sel, int want)
+{
+    force_lj_full_v2_body<real, U>(nlocal, c, x, y, z, numneigh, nbT, L, fx, fy, fz, sel, want);
+}
 // ---- v6: v2 with the in-cutoff block made branch-free, so that the U pairs in flight interleave ---------------------------
 // SASS of v2: every pair's force block is a divergent region holding a 12-deep dependent DFMA/DMUL chain, executed pair
 // after pair; the micro-benchmark with perfectly coalesced lists ("seq") therefore reaches only 54 % of the FP64 issue
