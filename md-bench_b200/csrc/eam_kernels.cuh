@@ -180,4 +180,150 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, real cutforcesq, 
     fz[i] = fiz;
 }
 
+// ---- generation 2 of the EAM passes ----------------------------------------------------------------------------------
+// The first kernels above spend their time in 4 (density) / 10 (force) scalar table gathers per pair, an IEEE square root
+// and a division.  Here the spline coefficients a pair needs are repacked into rows of 4 / 12 reals (k_eam_pack_tables)
+// and fetched with one / three vector loads; r and 1/r come from rsqrt.approx + Newton steps; two neighbors are in flight.
+// The arithmetic on the coefficients is unchanged (same Horner forms as force_eam.c:86-88, 170-180).
+template <class real>
+__global__ void k_eam_pack_tables(int rows, const real* __restrict__ rhor_spline, const real* __restrict__ z2r_spline,
+    real* __restrict__ rho4, real* __restrict__ frc12)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= rows) return;
+    const real *rs = rhor_spline + (size_t)m * 7, *zs = z2r_spline + (size_t)m * 7;
+    real* a = rho4 + (size_t)m * 4;
+    a[0] = rs[3]; a[1] = rs[4]; a[2] = rs[5]; a[3] = rs[6];
+    real* b = frc12 + (size_t)m * 12;
+    b[0] = rs[0]; b[1] = rs[1]; b[2] = rs[2]; b[3] = zs[0];
+    b[4] = zs[1]; b[5] = zs[2]; b[6] = zs[3]; b[7] = zs[4];
+    b[8] = zs[5]; b[9] = zs[6]; b[10] = 0; b[11] = 0;
+}
+__device__ __forceinline__ void ld4(const double* p, double& a, double& b, double& c, double& d)
+{
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld4(const float* p, float& a, float& b, float& c, float& d)
+{
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    a = v.x; b = v.y; c = v.z; d = v.w;
+}
+// 1 / sqrt(a) to working precision: approximation + Newton steps y <- y (1.5 - 0.5 a y^2)
+__device__ __forceinline__ double rsqrt_nr(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+__device__ __forceinline__ float rsqrt_nr(float a)
+{
+    float y = rsqrtf(a);
+    return y * fmaf(-0.5f * a * y, y, 1.5f);
+}
+
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_eam_density_v2(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ rho4,
+    const real* __restrict__ frho_spline, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* __restrict__ fp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    const int* nb = nbT + L.base(i);
+    real rhoi     = 0;
+    for (int k = 0; k < nn; k += U) {
+        int j[U];
+        real rsq[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = k + u < nn ? __ldg(nb + (size_t)(k + u) * L.sk) : i;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const real dx = xt - __ldg(x + j[u]), dy = yt - __ldg(y + j[u]), dz = zt - __ldg(z + j[u]);
+            rsq[u] = dx * dx + dy * dy + dz * dz;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rsq[u] < cutforcesq && k + u < nn) {
+                const real r = rsq[u] * rsqrt_nr(rsq[u]);
+                real p = r * t.rdr + (real)1.0;
+                int m  = (int)(p);
+                m      = m < t.nr - 1 ? m : t.nr - 1;
+                p -= m;
+                p = p < (real)1.0 ? p : (real)1.0;
+                real s3, s4, s5, s6;
+                ld4(rho4 + (size_t)m * 4, s3, s4, s5, s6);
+                rhoi += ((s3 * p + s4) * p + s5) * p + s6;
+            }
+        }
+    }
+    real p = (real)1.0 * rhoi * t.rdrho + (real)1.0;
+    int m  = (int)(p);
+    m      = max(1, min(m, t.nrho - 1));
+    p -= m;
+    p = min(p, (real)1.0);
+    const real* s = frho_spline + m * 7;
+    fp[i]         = (__ldg(s + 0) * p + __ldg(s + 1)) * p + __ldg(s + 2);
+}
+
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_eam_force_v2(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ frc12,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const real* __restrict__ fp,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* __restrict__ fx, real* __restrict__ fy,
+    real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i], fpi = fp[i];
+    const int nn  = numneigh[i];
+    const int* nb = nbT + L.base(i);
+    real fix = 0, fiy = 0, fiz = 0;
+    for (int k = 0; k < nn; k += U) {
+        int j[U];
+        real dx[U], dy[U], dz[U], rsq[U], fpj[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = k + u < nn ? __ldg(nb + (size_t)(k + u) * L.sk) : i;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            dx[u] = xt - __ldg(x + j[u]); dy[u] = yt - __ldg(y + j[u]); dz[u] = zt - __ldg(z + j[u]);
+            fpj[u] = __ldg(fp + j[u]);
+            rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rsq[u] < cutforcesq && k + u < nn) {
+                const real recip = rsqrt_nr(rsq[u]);
+                const real r     = rsq[u] * recip;
+                real p           = r * t.rdr + (real)1.0;
+                int m            = (int)(p);
+                m                = m < t.nr - 1 ? m : t.nr - 1;
+                p -= m;
+                p = p < (real)1.0 ? p : (real)1.0;
+                const real* row = frc12 + (size_t)m * 12;
+                real rs0, rs1, rs2, zs0, zs1, zs2, zs3, zs4, zs5, zs6, pad0, pad1;
+                ld4(row, rs0, rs1, rs2, zs0);
+                ld4(row + 4, zs1, zs2, zs3, zs4);
+                ld4(row + 8, zs5, zs6, pad0, pad1);
+                const real rhoip = (rs0 * p + rs1) * p + rs2;
+                const real z2p   = (zs0 * p + zs1) * p + zs2;
+                const real z2    = ((zs3 * p + zs4) * p + zs5) * p + zs6;
+                const real phi   = z2 * recip;
+                const real phip  = z2p * recip - phi * recip;
+                const real psip  = fpi * rhoip + fpj[u] * rhoip + phip;
+                const real fpair = -psip * recip;
+                fix += dx[u] * fpair;
+                fiy += dy[u] * fpair;
+                fiz += dz[u] * fpair;
+            }
+        }
+    }
+    fx[i] = fix;
+    fy[i] = fiy;
+    fz[i] = fiz;
+}
+
 } // namespace mdb

@@ -78,7 +78,8 @@ template <class real> struct Sim final : SimBase {
     Scanner scanner;
     // ---- eam ----
     EamTables<real> eam;
-    DBuf<real> fp, rhor_spline, frho_spline, z2r_spline;
+    DBuf<real> fp, rhor_spline, frho_spline, z2r_spline, eam_rho4, eam_frc12; // + repacked rows for the v2 kernels
+    int eam_variant = 1; // option "eam_variant": 0 = first kernels (scalar table gathers, IEEE sqrt / division), 1 = v2
     // ---- scratch ----
     int* h_flags      = nullptr; // pinned: [0] ghost total, [1] max neighbors, [2] max bin count
     DBuf<int> d_flags;
@@ -110,7 +111,7 @@ template <class real> struct Sim final : SimBase {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &fx, &fy, &fz, &sx, &sy, &sz, &svx, &svy,
-                 &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline, &x2, &y2, &z2, &vx2, &vy2,
+                 &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline, &eam_rho4, &eam_frc12, &x2, &y2, &z2, &vx2, &vy2,
                  &vz2, &fx2, &fy2, &fz2, &tx, &ty, &tz })
             b->release();
         for (DBuf<int>* b : { &orig, &orig2, &type2, &extmap, &nn_ext, &bin_rank }) b->release();
@@ -935,11 +936,19 @@ template <class real> struct Sim final : SimBase {
     {
         if (!eam.ready) throw Error("computeForceEam: no EAM tables (call mdb_setEam first)");
         fp.ensure((size_t)Nlocal + Nghost, false, stream);
+        if (eam_variant == 1)
+            MDB_LAUNCH(launches, (k_eam_density_v2<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
+                eam_rho4.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fp.p);
+        else
         MDB_LAUNCH(launches, k_eam_density<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
             eam, rhor_spline.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fp.p);
     }
     void eam_force() // force_eam.c:127-224
     {
+        if (eam_variant == 1)
+            MDB_LAUNCH(launches, (k_eam_force_v2<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
+                eam_frc12.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+        else
         MDB_LAUNCH(launches, k_eam_force<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
             eam, rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
     }
@@ -1145,6 +1154,11 @@ template <class real> struct Sim final : SimBase {
         MDB_CUDA(cudaMemcpyAsync(rhor_spline.p, rh.data(), rh.size() * sizeof(real), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(frho_spline.p, fr.data(), fr.size() * sizeof(real), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(z2r_spline.p, z2.data(), z2.size() * sizeof(real), cudaMemcpyHostToDevice, stream));
+        const int rows = (int)(rh.size() / 7); // rows the kernels can index: m <= nr - 1 < nr_tot / 7
+        eam_rho4.ensure((size_t)rows * 4, false, stream);
+        eam_frc12.ensure((size_t)rows * 12, false, stream);
+        MDB_LAUNCH(launches, k_eam_pack_tables<real>, grid_for(rows, 128), 128, 0, stream, rows, rhor_spline.p, z2r_spline.p,
+            eam_rho4.p, eam_frc12.p);
         MDB_CUDA(cudaStreamSynchronize(stream));
         h_rhor = rh; h_frho = fr; h_z2r = z2;
         eam.ready = true;
@@ -1229,6 +1243,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
         else if (!strcmp(name, "merge")) merge = (int)v;
+        else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };
