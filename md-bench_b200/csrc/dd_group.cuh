@@ -33,6 +33,22 @@ template <class real> struct DomainGroup final : DDBase {
     std::vector<int> cnt;     // [nbricks*26] entries per (sending brick, direction) of the last exchange
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 
+    // ---- halo by peer stores (dd_kernels.cuh, k_dd_push): one brick per process, several processes
+    bool push_wanted = true, push_ready = false; // option "halo_push" (0: NCCL send/recv on every step)
+    int epoch = 0;
+    int* sync_flags = nullptr;            // own flag words: [0,32) "ready" from p, [32,64) "done" from p, [96] error
+    PeerFlags peer_flags {};              // every process's flag buffer, mapped
+    struct IpcSlot {
+        cudaIpcMemHandle_t h[3];
+        void* base[3];
+        bool open[3];
+    };
+    std::vector<IpcSlot> peer_xyz;        // peers' x, y, z allocations as mapped here
+    DBuf<unsigned char> ipc_stage;        // device staging for the handle allgather
+    PushTable push_tab {};
+    unsigned push_to = 0, push_from = 0;  // processes this one pushes to / is pushed by
+    std::vector<Xfer> pos_plan;
+
     enum OpKind { COPY, SEND, RECV };
     struct Op {
         OpKind kind;
@@ -92,12 +108,142 @@ template <class real> struct DomainGroup final : DDBase {
             NcclApi::unique_id id;
             memcpy(&id, nccl_id, sizeof id);
             MDB_NCCL(N.CommInitRank(&comm, nprocs, id, proc));
+            if (nlocal_bricks == 1 && nprocs <= 32) init_push();
         }
+    }
+    // allgather of `bytes` bytes per process through NCCL (host buffers in, host buffers out)
+    void allgather_bytes(const void* mine, void* all, size_t bytes)
+    {
+        ipc_stage.ensure(bytes * topo.nprocs, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(ipc_stage.p + bytes * proc, mine, bytes, cudaMemcpyHostToDevice, stream));
+        MDB_NCCL(nccl_api().AllGather(ipc_stage.p + bytes * proc, ipc_stage.p, bytes, NcclApi::Int8, comm, stream));
+        MDB_CUDA(cudaMemcpyAsync(all, ipc_stage.p, bytes * topo.nprocs, cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    bool all_agree(bool ok) // every process must take the same path
+    {
+        double v = ok ? 0.0 : 1.0;
+        h_sum[0] = v;
+        sum_over_procs(h_sum, 1);
+        return h_sum[0] == 0.0;
+    }
+    void init_push() // flag words of every process, mapped once
+    {
+        bool ok = true;
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof mine);
+        if (cudaMalloc(&sync_flags, 128 * sizeof(int)) != cudaSuccess) { sync_flags = nullptr; ok = false; }
+        if (ok) {
+            MDB_CUDA(cudaMemsetAsync(sync_flags, 0, 128 * sizeof(int), stream));
+            MDB_CUDA(cudaStreamSynchronize(stream));
+            ok = cudaIpcGetMemHandle(&mine, sync_flags) == cudaSuccess;
+        }
+        std::vector<cudaIpcMemHandle_t> all(topo.nprocs);
+        allgather_bytes(&mine, all.data(), sizeof mine);
+        ok = all_agree(ok);
+        for (int p = 0; ok && p < topo.nprocs; p++) {
+            if (p == proc) { peer_flags.p[p] = sync_flags; continue; }
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+            peer_flags.p[p] = (int*)q;
+        }
+        push_ready = all_agree(ok);
+        peer_xyz.assign(topo.nprocs, IpcSlot {});
+    }
+    // per rebuild: where every process keeps x, y, z now (allocation handles + first ghost entry), then the segment table
+    void prepare_push()
+    {
+        if (!push_ready) return;
+        Brick* b = bricks[0];
+        struct Pub {
+            cudaIpcMemHandle_t h[3];
+            int nlocal, ok;
+        } mine;
+        memset(&mine, 0, sizeof mine);
+        mine.nlocal = b->Nlocal;
+        mine.ok     = 1;
+        real* arr[3] = { b->x.p, b->y.p, b->z.p };
+        for (int k = 0; k < 3; k++)
+            if (cudaIpcGetMemHandle(&mine.h[k], arr[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+        std::vector<Pub> all(topo.nprocs);
+        allgather_bytes(&mine, all.data(), sizeof mine);
+        bool ok = true;
+        for (int p = 0; p < topo.nprocs; p++) ok = ok && all[p].ok;
+        push_tab.nseg = 0;
+        push_to = push_from = 0;
+        for (const Xfer& t : pos_plan) {
+            if (!ok) break;
+            if (t.kind == 2) { push_from |= 1u << t.peer_proc; continue; }
+            if (t.len == 0) continue;
+            if (push_tab.nseg >= 32) { ok = false; break; }
+            PushSeg& sg = push_tab.seg[push_tab.nseg];
+            sg.src_start = t.src_start;
+            sg.len       = t.len;
+            void* base[3];
+            int nl;
+            if (t.kind == 0) { // this brick is its own neighbor along an axis with one brick
+                for (int k = 0; k < 3; k++) base[k] = arr[k];
+                nl = b->Nlocal;
+            } else {
+                const int p = t.peer_proc;
+                IpcSlot& ps = peer_xyz[p];
+                for (int k = 0; k < 3 && ok; k++) {
+                    if (ps.open[k] && memcmp(&ps.h[k], &all[p].h[k], sizeof(cudaIpcMemHandle_t)) == 0) continue;
+                    if (ps.open[k]) { cudaIpcCloseMemHandle(ps.base[k]); ps.open[k] = false; }
+                    void* q = nullptr;
+                    if (cudaIpcOpenMemHandle(&q, all[p].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+                    ps.base[k] = q; ps.h[k] = all[p].h[k]; ps.open[k] = true;
+                }
+                if (!ok) break;
+                for (int k = 0; k < 3; k++) base[k] = ps.base[k];
+                nl = all[p].nlocal;
+                push_to |= 1u << p;
+            }
+            sg.dx = (real*)base[0] + nl + t.dst_start;
+            sg.dy = (real*)base[1] + nl + t.dst_start;
+            sg.dz = (real*)base[2] + nl + t.dst_start;
+            push_tab.nseg++;
+        }
+        // segments ascending in src_start (k_dd_push locates an entry by counting the starts below it)
+        std::sort(push_tab.seg, push_tab.seg + push_tab.nseg, [](const PushSeg& a, const PushSeg& c) { return a.src_start < c.src_start; });
+        if (!all_agree(ok)) push_ready = false; // fall back to NCCL send/recv for good, on every process alike
+    }
+    void forward_push() // updatePbc (pbc.c:42-55) across GPUs by peer stores, see dd_kernels.cuh
+    {
+        Brick* b = bricks[0];
+        epoch++;
+        const unsigned long long timeout = 10ull * 1000 * 1000 * 1000;
+        // ready: my senders may overwrite my ghosts; wait until my receivers have released theirs
+        if (push_from) MDB_LAUNCH(launches, k_dd_signal, 1, 32, 0, stream, peer_flags, push_from, 0, proc, epoch);
+        if (push_to) MDB_LAUNCH(launches, k_dd_wait, 1, 32, 0, stream, sync_flags, push_to, 0, epoch, timeout);
+        if (b->n_gsend)
+            MDB_LAUNCH(launches, k_dd_push<real>, grid_for(b->n_gsend, 256), 256, 0, stream, b->n_gsend, b->gtab, push_tab, b->dd_gsend.p,
+                b->xprd, b->yprd, b->zprd, b->x.p, b->y.p, b->z.p);
+        // done: this epoch's positions have landed at my receivers; wait for the same from my senders
+        if (push_to) MDB_LAUNCH(launches, k_dd_signal, 1, 32, 0, stream, peer_flags, push_to, 1, proc, epoch);
+        if (push_from) MDB_LAUNCH(launches, k_dd_wait, 1, 32, 0, stream, sync_flags, push_from, 1, epoch, timeout);
+    }
+    void check_push_error()
+    {
+        if (!push_ready || !sync_flags) return;
+        int e = 0;
+        MDB_CUDA(cudaMemcpyAsync(&e, sync_flags + 96, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        if (e) throw Error("decomposition: a peer GPU did not answer the halo handshake within 10 s");
     }
     ~DomainGroup() override
     {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
+        for (size_t p = 0; p < peer_xyz.size(); p++)
+            for (int k = 0; k < 3; k++)
+                if (peer_xyz[p].open[k]) cudaIpcCloseMemHandle(peer_xyz[p].base[k]);
+        if (sync_flags) {
+            for (int p = 0; p < topo.nprocs && p < 32; p++)
+                if (p != proc && peer_flags.p[p]) cudaIpcCloseMemHandle(peer_flags.p[p]);
+            cudaFree(sync_flags);
+        }
+        ipc_stage.release();
         if (comm) nccl_api().CommDestroy(comm);
         for (Brick* b : bricks) { b->brick_release(); delete b; }
         d_off_all.release();
@@ -320,6 +466,10 @@ template <class real> struct DomainGroup final : DDBase {
         run_ops(int_ops);
         build_ops(pos_ops, 3, sizeof(real), false, [](Brick* s) { return (const void*)s->dd_sendbuf.p; },
             [](Brick* r, int k) { return (void*)((k == 0 ? r->x.p : (k == 1 ? r->y.p : r->z.p)) + r->Nlocal); });
+        if (push_ready) {
+            dd_schedule(topo, proc, cnt.data(), pos_plan);
+            prepare_push();
+        }
         if (G.force_field == MDB_FF_EAM)
             build_ops(fp_ops, 1, sizeof(real), false, [](Brick* s) { return (const void*)s->dd_sendbuf.p; },
                 [](Brick* r, int) { return (void*)(r->fp.p + r->Nlocal); });
@@ -327,8 +477,12 @@ template <class real> struct DomainGroup final : DDBase {
     void forward() // updatePbc (pbc.c:42-55): fresh positions of the border atoms to their images
     {
         if (timing) MDB_CUDA(cudaEventRecord(ev[2], stream));
-        for (Brick* b : bricks) b->brick_pack_pos();
-        run_ops(pos_ops);
+        if (push_ready && push_wanted) {
+            forward_push();
+        } else {
+            for (Brick* b : bricks) b->brick_pack_pos();
+            run_ops(pos_ops);
+        }
         if (timing) {
             float ms = 0;
             MDB_CUDA(cudaEventRecord(ev[3], stream));
@@ -480,6 +634,7 @@ template <class real> struct DomainGroup final : DDBase {
         }
         MDB_CUDA(cudaEventRecord(ev[1], stream));
         record(nsteps);
+        check_push_error();
         const size_t nr4 = 4 * rec_step.size();
         for (size_t k = 0; k < bricks.size(); k++)
             MDB_CUDA(cudaMemcpyAsync(h_sum + 2048 + k * nr4, bricks[k]->d_thermo.p, nr4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -572,6 +727,7 @@ template <class real> struct DomainGroup final : DDBase {
     void setOption(const char* name, double v) override
     {
         if (!strcmp(name, "overlap_halo")) { overlap = v != 0; return; }
+        if (!strcmp(name, "halo_push")) { push_wanted = v != 0; return; }
         for (Brick* b : bricks) b->setOption(name, v);
     }
     void setTiming(bool on) override

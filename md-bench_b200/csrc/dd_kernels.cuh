@@ -192,6 +192,76 @@ __global__ void k_dd_pack(int total, SendTable T, const int* __restrict__ sendli
         o[5 * pl] = a5[i];
     }
 }
+// ---- halo exchange by PEER STORES (one process per GPU, NVLink / NVSwitch peer memory) -------------------------------
+// updatePbc across bricks without NCCL on the per-step path: the kernel that computes the image positions stores them
+// straight into the ghost range of the RECEIVER's x, y, z arrays (mapped through CUDA IPC), segment by segment of the
+// transfer schedule; a brick that is its own neighbor along an axis is just another segment whose destination is local.
+// Ordering between the GPUs is a two-phase handshake on flag words in peer memory (k_dd_signal / k_dd_wait):
+//   ready:  every process tells its senders that it has finished reading the previous ghost positions, and waits for the
+//           same word from its receivers before it overwrites their ghosts;
+//   done:   after the push kernel (kernel boundary + system fence) every process tells its receivers that this epoch's
+//           positions have landed, and waits for the same word from its senders before anything reads its own ghosts.
+struct PushSeg {
+    int src_start, len; // entries [src_start, src_start + len) of the brick's send list
+    void *dx, *dy, *dz; // destination of entry src_start in the receiver's arrays
+};
+struct PushTable {
+    int nseg;
+    PushSeg seg[32];
+};
+template <class real>
+__global__ void k_dd_push(int total, SendTable T, PushTable P, const int* __restrict__ sendlist, real ex, real ey, real ez,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int b = T.dir[dd_slot_of(T, t)];
+    int g       = 0;
+#pragma unroll 4
+    for (int k = 1; k < 32; k++) g += (k < P.nseg && t >= P.seg[k].src_start);
+    const PushSeg sg = P.seg[g];
+    const int o      = t - sg.src_start;
+    const int i      = sendlist[t];
+    // the image shift as ONE fma like updatePbc
+    ((real*)sg.dx)[o] = fma_rn((real)c_img[b][0], ex, x[i]);
+    ((real*)sg.dy)[o] = fma_rn((real)c_img[b][1], ey, y[i]);
+    ((real*)sg.dz)[o] = fma_rn((real)c_img[b][2], ez, z[i]);
+}
+struct PeerFlags {
+    int* p[32]; // flag buffer of every process (own entry = own buffer)
+};
+// word `slot * 32 + me` of every process in `mask` := value (release at system scope: everything this GPU wrote before
+// is visible to the reader that acquires the word)
+static __global__ void k_dd_signal(PeerFlags F, unsigned mask, int slot, int me, int value)
+{
+    const int p = threadIdx.x;
+    if (p >= 32 || !((mask >> p) & 1u)) return;
+    __threadfence_system();
+    int* w = F.p[p] + slot * 32 + me;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(w), "r"(value) : "memory");
+}
+// spin until word `slot * 32 + p` of the own buffer reaches `value` for every p in `mask`; gives up after `timeout_ns`
+// and raises the error word (own[96]) instead of hanging the GPU
+static __global__ void k_dd_wait(int* own, unsigned mask, int slot, int value, unsigned long long timeout_ns)
+{
+    const int p = threadIdx.x;
+    if (p >= 32 || !((mask >> p) & 1u)) return;
+    const int* w = own + slot * 32 + p;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+        if (v >= value) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            atomicExch(own + 96, 1);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
 // two int arrays (type, tag) in the same per-peer segment layout
 static __global__ void k_dd_pack_int2(int total, SendTable T, const int* __restrict__ sendlist, const int* __restrict__ a0,
     const int* __restrict__ a1, int* __restrict__ out)
