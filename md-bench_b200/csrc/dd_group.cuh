@@ -38,12 +38,13 @@ template <class real> struct DomainGroup final : DDBase {
     int epoch = 0;
     int* sync_flags = nullptr;            // own flag words: [0,32) "ready" from p, [32,64) "done" from p, [96] error
     PeerFlags peer_flags {};              // every process's flag buffer, mapped
+    // peers' position allocations as mapped here.  A brick's x, y, z alternate between two allocations (the spatial sort
+    // and the migration swap buffers), so every mapping ever opened is kept: after the first rebuilds nothing is opened
+    // any more (cudaIpcOpenMemHandle of an 84 MB array costs milliseconds)
     struct IpcSlot {
-        cudaIpcMemHandle_t h[3];
-        void* base[3];
-        bool open[3];
+        std::vector<std::pair<cudaIpcMemHandle_t, void*>> open;
     };
-    std::vector<IpcSlot> peer_xyz;        // peers' x, y, z allocations as mapped here
+    std::vector<IpcSlot> peer_xyz;
     DBuf<unsigned char> ipc_stage;        // device staging for the handle allgather
     PushTable push_tab {};
     unsigned push_to = 0, push_from = 0;  // processes this one pushes to / is pushed by
@@ -188,14 +189,16 @@ template <class real> struct DomainGroup final : DDBase {
                 const int p = t.peer_proc;
                 IpcSlot& ps = peer_xyz[p];
                 for (int k = 0; k < 3 && ok; k++) {
-                    if (ps.open[k] && memcmp(&ps.h[k], &all[p].h[k], sizeof(cudaIpcMemHandle_t)) == 0) continue;
-                    if (ps.open[k]) { cudaIpcCloseMemHandle(ps.base[k]); ps.open[k] = false; }
+                    base[k] = nullptr;
+                    for (auto& e : ps.open)
+                        if (memcmp(&e.first, &all[p].h[k], sizeof(cudaIpcMemHandle_t)) == 0) base[k] = e.second;
+                    if (base[k]) continue;
                     void* q = nullptr;
                     if (cudaIpcOpenMemHandle(&q, all[p].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
-                    ps.base[k] = q; ps.h[k] = all[p].h[k]; ps.open[k] = true;
+                    ps.open.push_back(std::make_pair(all[p].h[k], q));
+                    base[k] = q;
                 }
                 if (!ok) break;
-                for (int k = 0; k < 3; k++) base[k] = ps.base[k];
                 nl = all[p].nlocal;
                 push_to |= 1u << p;
             }
@@ -236,8 +239,7 @@ template <class real> struct DomainGroup final : DDBase {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         for (size_t p = 0; p < peer_xyz.size(); p++)
-            for (int k = 0; k < 3; k++)
-                if (peer_xyz[p].open[k]) cudaIpcCloseMemHandle(peer_xyz[p].base[k]);
+            for (auto& e : peer_xyz[p].open) cudaIpcCloseMemHandle(e.second);
         if (sync_flags) {
             for (int p = 0; p < topo.nprocs && p < 32; p++)
                 if (p != proc && peer_flags.p[p]) cudaIpcCloseMemHandle(peer_flags.p[p]);
@@ -466,7 +468,7 @@ template <class real> struct DomainGroup final : DDBase {
         run_ops(int_ops);
         build_ops(pos_ops, 3, sizeof(real), false, [](Brick* s) { return (const void*)s->dd_sendbuf.p; },
             [](Brick* r, int k) { return (void*)((k == 0 ? r->x.p : (k == 1 ? r->y.p : r->z.p)) + r->Nlocal); });
-        if (push_ready) {
+        if (push_ready && push_wanted) {
             dd_schedule(topo, proc, cnt.data(), pos_plan);
             prepare_push();
         }
