@@ -70,13 +70,19 @@ void        mdb_default_params(mdb_params* p);
  * dtforce (parameter.c:115-120).  Returns NULL on failure. */
 mdb_ctx*    mdb_create(const mdb_params* p, int device);
 void        mdb_destroy(mdb_ctx* c);
-/* tuning switches (A/B measurements, debugging):
- *  "sort_atoms" (default 0, like the reference's SORT_ATOMS build option): re-sort the local atoms by
- *      neighbor bin at every rebuild (neighbor.c:360-426); the permutation is tracked, every accessor
+/* tuning switches (A/B measurements, debugging); defaults are the fastest measured variants (profiles/):
+ *  "sort_atoms" (default 0, like the reference's SORT_ATOMS build option; 1 for the bricks of a decomposed box): re-sort
+ *      the local atoms by neighbor bin at every rebuild (neighbor.c:360-426); the permutation is tracked, every accessor
  *      below still speaks the reference's atom numbering.
  *  "sort_order" 0 = the reference's x-fastest bin order, 1 = Morton order of the bins.
  *  "list_layout" 0 = transposed, 1 = row-major rows, 2 (default) = k-major tiles of 32 atoms.
- *  "force_variant", "neigh_variant": kernel generations kept for A/B. */
+ *  "neigh_variant" list-build kernel: 4 (default) packed-FP32 tests on SoA candidates, 3 = float4 candidates, 0-2 older.
+ *  "force_variant" LJ full-list kernel: 1 (default; DP: 4 neighbors in flight, SP: branch-free), 8/9 branch-free U=4/2,
+ *      0/2-7 older generations.
+ *  "merge" 2 = one list row per atom pair with membership bits (exact, slower; default 0).
+ *  "eam_variant" 1 (default) packed spline rows + rsqrt, 0 = first kernels.
+ *  "fuse_integrate" (default 1) finalIntegrate(n) + initialIntegrate(n+1) in one pass inside mdb_run.
+ *  "sort_rows" 1 = sort every neighbor row by index after the build (default 0). */
 int         mdb_setOption(mdb_ctx* c, const char* name, double value);
 /* run all work of this ctx on the given cudaStream_t (passed as void*); NULL = ctx-owned stream */
 int         mdb_setStream(mdb_ctx* c, void* cuda_stream);
@@ -191,7 +197,8 @@ int         mdb_stubNeighbors(mdb_ctx* c, int pattern, int nneighs, int nreps, u
  * neighbor brick in that direction (which is the brick itself along an axis with one brick, i.e. the
  * reference's scheme).  Bricks are dealt to processes in consecutive blocks (one process per GPU;
  * #bricks must be a multiple of #processes).  Bricks of one process exchange by device copies,
- * bricks of different processes by NCCL send/recv over NVLink (NCCL is dlopen()ed on first use).
+ * bricks of different processes over NVLink: per step by peer stores into the neighbor GPU's arrays (CUDA IPC + flag
+ * handshake, one brick per process), per rebuild by NCCL send/recv (NCCL is dlopen()ed on first use).
  * Atoms carry GLOBAL tags = the index createAtom (atom.c:67-187) gives them in the undecomposed box,
  * so results are comparable with a single-domain run atom by atom. */
 typedef struct mdb_dd mdb_dd;
@@ -236,6 +243,9 @@ int         mdb_dd_getAtoms(mdb_dd* d, int which, int* tags, void* x, void* y, v
 int         mdb_dd_getNeighborTags(mdb_dd* d, int* tags, int* numneigh, int* rows, int stride);
 int         mdb_dd_saveState(mdb_dd* d);
 int         mdb_dd_restoreState(mdb_dd* d);
+/* every mdb_setOption name (applied to all bricks of this process), plus "halo_push" (default 1: per-step ghost
+ * positions by peer stores into the IPC-mapped arrays of the neighbor GPUs; 0: NCCL send/recv) and "overlap_halo"
+ * (default 0; 1: exchange the halo while the atoms that list no ghost are computed).  Same value on every process. */
 int         mdb_dd_setOption(mdb_dd* d, const char* name, double value);
 int         mdb_dd_setTiming(mdb_dd* d, int on);
 int         mdb_dd_getKernelStats(mdb_dd* d, double* force_ms, long long* force_launches, double* neigh_ms,
@@ -259,6 +269,9 @@ mdb_cp*     mdb_cp_create(const mdb_params* p, int cluster_n, int device);
 void        mdb_cp_destroy(mdb_cp* c);
 int         mdb_cp_setStream(mdb_cp* c, void* cuda_stream);
 int         mdb_cp_sync(mdb_cp* c);
+/* "prune_every" (default 1000, common/parameter.c:40): pruneNeighbor period inside mdb_cp_run; "force_variant" 0 = auto
+ * (full lists: lane per i atom, packed FP32 in SP; half lists: warp per i-cluster), 1 = lane per i atom scalar,
+ * 2 = lane per i atom packed FP32 (SP full), 3 = warp per i-cluster / lane per j atom */
 int         mdb_cp_setOption(mdb_cp* c, const char* name, double value);
 long long   mdb_cp_createAtom(mdb_cp* c);                         /* clusterpair/atom.c:49-180 */
 int         mdb_cp_setAtoms(mdb_cp* c, long long n, const void* x, const void* y, const void* z,
