@@ -469,14 +469,20 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
+        try:
+            cpu = cpu_baseline()
+        except Exception as e:
+            cpu = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference", "sample": "failed: %s" % e}
 
     # ---- secondary: BASELINE config 2 physics (clusterpair 4x4, SP) at the same per-GPU box, N = 1 only ----
     secondary = None
     if world == 1 and not decomposed and not cp and not args.no_secondary:
         sim.close()
         sim = None
-        secondary = clusterpair_secondary(m, args, local, stream)
+        try:
+            secondary = clusterpair_secondary(m, args, local, stream)
+        except Exception as e:   # the primary line must not depend on the secondary measurement
+            secondary = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         line = {"metric": (METRIC_CP % (4, args.cluster_n)) if cp else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

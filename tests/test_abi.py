@@ -75,3 +75,17 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 m = bad.search(txt)
                 assert m is None, (os.path.join(dp, f), m.group(0))
+
+
+def test_no_cpu_fallback_clusterpair_and_decomposition():
+    """the other two handles of the C ABI fail just as loudly without a CUDA device"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = load_pkg()
+    with pytest.raises(m.MdbError) as e:
+        m.ClusterSimulation()
+    assert "CUDA" in str(e.value)
+    with pytest.raises(m.MdbError) as e:
+        m.Decomposition(m.default_params(nx=8, ny=8, nz=8), (2, 1, 1))
+    assert "CUDA" in str(e.value)
