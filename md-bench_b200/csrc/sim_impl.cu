@@ -79,6 +79,7 @@ template <class real> struct Sim final : SimBase {
     // ---- eam ----
     EamTables<real> eam;
     DBuf<real> fp, rhor_spline, frho_spline, z2r_spline, eam_rho4, eam_frc12; // + repacked rows for the v2 kernels
+    int half_variant = 2; // option "half_variant": 0 first kernel, 1 v2 with 2 neighbors in flight, 2 (default) 4 in flight
     int eam_variant = 1; // option "eam_variant": 0 = first kernels (scalar table gathers, IEEE sqrt / division), 1 = v2
     // ---- scratch ----
     int* h_flags      = nullptr; // pinned: [0] ghost total, [1] max neighbors, [2] max bin count
@@ -919,8 +920,17 @@ template <class real> struct Sim final : SimBase {
                         (const int*)nullptr, 0);
             } else {
                 zero3(fx.p, fy.p, fz.p, Nlocal);
-                MDB_LAUNCH(launches, k_force_lj_half<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
-                    x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6,
+                    (real)24.0 * epsilon * sigma6 };
+                if (half_variant == 0)
+                    MDB_LAUNCH(launches, k_force_lj_half<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
+                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                else if (half_variant == 2)
+                    MDB_LAUNCH(launches, (k_force_lj_half_v2<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
+                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                else
+                    MDB_LAUNCH(launches, (k_force_lj_half_v2<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
+                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
             }
         }
         force_launches++;
@@ -1244,6 +1254,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
         else if (!strcmp(name, "merge")) merge = (int)v;
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;
+        else if (!strcmp(name, "half_variant")) half_variant = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

@@ -1469,6 +1469,76 @@ __global__ void __launch_bounds__(128) k_force_lj_half(int nlocal, LJConst<real>
     atomicAdd(&fz[i], fiz);
 }
 
+// half lists, generation 2: the full-list kernel's structure (U neighbors in flight, next indices prefetched, reciprocal by
+// rcp.approx + Newton steps); the reaction on local j stays three native RED.ADD per pair
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_force_lj_half_v2(int nlocal, LJConst2<real> c, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
+    NbLayout L, real* fx, real* fy, real* fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    const int* nb   = nbT + L.base(i);
+    const int nfull = nn - nn % U;
+    int j[U], jn[U];
+    if (nfull > 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = __ldg(nb + (size_t)u * L.sk);
+    }
+    for (int k = 0; k < nfull; k += U) {
+        real dx[U], dy[U], dz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            dx[u] = xt - __ldg(x + j[u]);
+            dy[u] = yt - __ldg(y + j[u]);
+            dz[u] = zt - __ldg(z + j[u]);
+        }
+        nb += (size_t)U * L.sk;
+        if (k + U < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = __ldg(nb + (size_t)u * L.sk);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+            if (rsq < c.cutforcesq) {
+                const real f  = lj_pair2(rsq, c);
+                const real px = dx[u] * f, py = dy[u] * f, pz = dz[u] * f;
+                fix += px; fiy += py; fiz += pz;
+                if (j[u] < nlocal) { // force_lj.c:171-175
+                    atomicAdd(&fx[j[u]], -px);
+                    atomicAdd(&fy[j[u]], -py);
+                    atomicAdd(&fz[j[u]], -pz);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = jn[u];
+    }
+    for (int k = nfull; k < nn; k++) {
+        const int jj  = __ldg(nb);
+        nb += L.sk;
+        const real dx = xt - __ldg(x + jj), dy = yt - __ldg(y + jj), dz = zt - __ldg(z + jj);
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < c.cutforcesq) {
+            const real f  = lj_pair2(rsq, c);
+            const real px = dx * f, py = dy * f, pz = dz * f;
+            fix += px; fiy += py; fiz += pz;
+            if (jj < nlocal) {
+                atomicAdd(&fx[jj], -px);
+                atomicAdd(&fy[jj], -py);
+                atomicAdd(&fz[jj], -pz);
+            }
+        }
+    }
+    atomicAdd(&fx[i], fix);
+    atomicAdd(&fy[i], fiy);
+    atomicAdd(&fz[i], fiz);
+}
+
 // workload counters (the reference's Stats, verletlist/stats.h:13-18): listed pairs and pairs
 // inside the force cutoff for the current positions
 template <class real>
