@@ -234,11 +234,16 @@ def clusterpair_secondary(m, args, local, stream, steps=2):
     flop = (8.0 * 0.5 * (cp0 + cp1) * 16 + 15.0 * 0.5 * (in0 + in1)) / natoms
     peak = m.measure_fma_peak(m.SP, local)
     ach = flop * natoms / (f_ms * 1e-3) * 1e-12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("clusterpair/sp/%d" % args.nx, {}).get("bytes")
+    except Exception:
+        pass
     out = {"metric": METRIC_CP % (4, 4), "config": "BASELINE config 2 physics (clusterpair 4x4, SP, full lists) at %d^3 unit cells" % args.nx,
            "value": natoms * args.ntimes * steps / (ms * 1e-3), "unit": UNIT, "dtype": "f32", "steps": steps,
            "ms_per_step": ms / steps,
            "roofline": {"kernel": "k_cp_force_lj_sp_packed<4>", "bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak if peak else None, "ms_per_launch": f_ms, "flop_per_atom_step": flop,
+                        "frac": ach / peak if peak else None, "traffic": traffic, "ms_per_launch": f_ms, "flop_per_atom_step": flop,
                         "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
                         "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"])},
            "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
