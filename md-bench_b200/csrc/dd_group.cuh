@@ -215,7 +215,7 @@ template <class real> struct DomainGroup final : DDBase {
     {
         Brick* b = bricks[0];
         epoch++;
-        const unsigned long long timeout = 10ull * 1000 * 1000 * 1000;
+        const unsigned long long timeout = 30ull * 1000 * 1000 * 1000;
         // ready: my senders may overwrite my ghosts; wait until my receivers have released theirs
         if (push_from) MDB_LAUNCH(launches, k_dd_signal, 1, 32, 0, stream, peer_flags, push_from, 0, proc, epoch);
         if (push_to) MDB_LAUNCH(launches, k_dd_wait, 1, 32, 0, stream, sync_flags, push_to, 0, epoch, timeout);
@@ -232,7 +232,7 @@ template <class real> struct DomainGroup final : DDBase {
         int e = 0;
         MDB_CUDA(cudaMemcpyAsync(&e, sync_flags + 96, sizeof(int), cudaMemcpyDeviceToHost, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
-        if (e) throw Error("decomposition: a peer GPU did not answer the halo handshake within 10 s");
+        if (e) throw Error("decomposition: a peer GPU did not answer the halo handshake within 30 s");
     }
     ~DomainGroup() override
     {
@@ -549,6 +549,7 @@ template <class real> struct DomainGroup final : DDBase {
     }
     void reneighbour() override // main.c:76-95
     {
+        check_push_error();
         migrate();
         for (Brick* b : bricks) b->sort_atoms();
         setupGhosts();

@@ -241,12 +241,13 @@ static __global__ void k_dd_signal(PeerFlags F, unsigned mask, int slot, int me,
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(w), "r"(value) : "memory");
 }
 // spin until word `slot * 32 + p` of the own buffer reaches `value` for every p in `mask`; gives up after `timeout_ns`
-// and raises the error word (own[96]) instead of hanging the GPU
+// and raises the error word (own[96]) instead of hanging the GPU (the host checks it at every rebuild and after a run)
 static __global__ void k_dd_wait(int* own, unsigned mask, int slot, int value, unsigned long long timeout_ns)
 {
     const int p = threadIdx.x;
     if (p >= 32 || !((mask >> p) & 1u)) return;
     const int* w = own + slot * 32 + p;
+    if (*((volatile int*)own + 96)) return; // an earlier wait already gave up: do not stall every following step as well
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
