@@ -193,7 +193,9 @@ def workload_config(args, world, grid=(1, 1, 1)):
                                                              4 * args.nx ** 3 * grid[0] * grid[1] * grid[2]),
             "parallelism": "1 domain" if grid == (1, 1, 1) else
             "spatial decomposition %dx%dx%d bricks over %d GPU(s), ghost exchange %s"
-            % (grid[0], grid[1], grid[2], world, "by NCCL send/recv over NVLink" if world > 1 else "by device copies")}
+            % (grid[0], grid[1], grid[2], world,
+               "per step by peer stores into the neighbor GPUs' arrays over NVLink (CUDA IPC + flag handshake), per rebuild by NCCL send/recv"
+               if world > 1 else "by device copies")}
 
 
 def clusterpair_secondary(m, args, local, stream, steps=2):
