@@ -163,7 +163,13 @@ template <class real, int N> struct CpSim final : CpBase {
         cutforce = (real)P.cutforce;
         cutneigh = cutforce + skin;
         lattice  = (real)pow((4.0 / (double)rho), (1.0 / 3.0));
-        xprd = P.nx * lattice; yprd = P.ny * lattice; zprd = P.nz * lattice;
+        if (P.from_input) { // box of an input file: the readers set param->xprd = xhi - xlo, and setupNeighbor takes it
+            xprd = (real)P.xhi - (real)P.xlo; // (neighbor.c:78-82); the box is then treated as [0, prd) like the reference does
+            yprd = (real)P.yhi - (real)P.ylo;
+            zprd = (real)P.zhi - (real)P.zlo;
+        } else {
+            xprd = P.nx * lattice; yprd = P.ny * lattice; zprd = P.nz * lattice;
+        }
     }
     void setStream(cudaStream_t s) override
     {
@@ -820,7 +826,6 @@ static CpBase* make_cp(const mdb_params& p, int cluster_n, int device)
     if (device < 0 || device >= ndev) throw Error(fmt("mdb_cp_create: device %d out of range (%d devices)", device, ndev));
     if (p.force_field != MDB_FF_LJ) throw Error("mdb_cp_create: the clusterpair scheme has only the LJ kernels (force.c)");
     if (p.ntypes != 1) throw Error("mdb_cp_create: only ntypes == 1 is supported (EXPLICIT_TYPES off)");
-    if (p.from_input) throw Error("mdb_cp_create: boxes from input files are not supported by this scheme yet");
     if (cluster_n != 4 && cluster_n != 8) throw Error("mdb_cp_create: cluster_n must be 4 or 8 (M = 4)");
     if (p.precision == MDB_DP) return cluster_n == 4 ? (CpBase*)new CpSim<double, 4>(p, device) : new CpSim<double, 8>(p, device);
     if (p.precision == MDB_SP) return cluster_n == 4 ? (CpBase*)new CpSim<float, 4>(p, device) : new CpSim<float, 8>(p, device);

@@ -55,13 +55,15 @@ static void computeThermoCP(int iflag)
 static double setup(Parameter* param, int cluster_n) /* clusterpair/main.c:40-76 */
 {
     double timeStart = getTimeStamp();
+    Atom atom;
+    initAtom(&atom);
     param->lattice = pow((4.0 / param->rho), (1.0 / 3.0));
     param->xprd = param->nx * param->lattice;
     param->yprd = param->ny * param->lattice;
     param->zprd = param->nz * param->lattice;
-    if (param->input_file != NULL) {
-        fprintf(stderr, "Error: input files are not supported by the clusterpair scheme of this build\n");
-        exit(-1);
+    if (param->input_file != NULL) { /* main.c:57-66: readAtom sets the box, positions are used as they are */
+        param->layout = MDB_AOS;
+        readAtom(&atom, param);
     }
     mdb_params p;
     mdb_default_params(&p);
@@ -71,13 +73,24 @@ static double setup(Parameter* param, int cluster_n) /* clusterpair/main.c:40-76
     p.half_neigh = param->half_neigh; p.dt = param->dt; p.skin = param->skin; p.cutforce = param->cutforce;
     p.nx = param->nx; p.ny = param->ny; p.nz = param->nz;
     p.pbc_x = param->pbc_x; p.pbc_y = param->pbc_y; p.pbc_z = param->pbc_z;
+    p.from_input = param->input_file != NULL;
+    p.xlo = param->xlo; p.xhi = param->xhi; p.ylo = param->ylo; p.yhi = param->yhi; p.zlo = param->zlo; p.zhi = param->zhi;
     ctx = mdb_cp_create(&p, cluster_n, param->device);
     if (!ctx) mdb_die("initDevice");
     CK(mdb_cp_setOption(ctx, "prune_every", (double)param->prune_every), "initNeighbor");
-    if (mdb_cp_createAtom(ctx) < 0) mdb_die("createAtom");
+    if (param->input_file == NULL) {
+        if (mdb_cp_createAtom(ctx) < 0) mdb_die("createAtom");
+    } else { /* the driver's reader stages positions AoS {x,y,z}* and velocities AoS too: hand velocities over as SoA */
+        const size_t n = atom.Nlocal, es = param->precision == MDB_SP ? sizeof(float) : sizeof(double);
+        char* v = (char*)malloc(3 * n * es);
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) memcpy(v + (k * n + i) * es, (char*)atom.vx + (3 * i + k) * es, es);
+        if (mdb_cp_setAtoms(ctx, (long long)n, atom.x, NULL, NULL, v, v + n * es, v + 2 * n * es) != 0) mdb_die("readAtom");
+        free(v);
+    }
     CK(mdb_cp_setupNeighbor(ctx), "setupNeighbor");
     CK(mdb_cp_setupThermo(ctx), "setupThermo");
-    CK(mdb_cp_adjustThermo(ctx), "adjustThermo");
+    if (param->input_file == NULL) CK(mdb_cp_adjustThermo(ctx), "adjustThermo");
     buildClusters();
     defineJClusters();
     setupPbcCP();
@@ -139,6 +152,7 @@ int main(int argc, char** argv)
             printf(HLINE);
             printf("-p / --param <string>:      file to read parameters from (can be specified more than once)\n");
             printf("-f <string>:                force field (lj), default lj\n");
+            printf("-i <string>:                input file with atom positions (dump)\n");
             printf("-n / --nsteps <int>:        set number of timesteps for simulation\n");
             printf("-nx/-ny/-nz <int>:          set linear dimension of systembox in x/y/z direction\n");
             printf("-half <int>:                use half (1) or full (0) neighbor lists\n");

@@ -53,6 +53,7 @@ typedef struct {
     real epsilon, sigma, sigma6, temp, rho, mass, dt, dtforce, skin, cutforce, cutneigh, lattice;
     int ntimes, nstat, reneigh_every, half_neigh, nx, ny, nz;
     real xprd, yprd, zprd;
+    int from_input; /* box lengths handed over by a reader (param->input_file != NULL, neighbor.c:78-82) */
     /* atoms (clusterpair/atom.h:26-60) */
     int Natoms, Nlocal, Nghost, Nmax;
     int Nclusters, Nclusters_local, Nclusters_ghost, Nclusters_max;
@@ -125,6 +126,13 @@ EXPORT void ocp_set_run(OCP* o, int nx, int ny, int nz, int ntimes, int nstat, i
     o->nx = nx; o->ny = ny; o->nz = nz; o->ntimes = ntimes; o->nstat = nstat; o->reneigh_every = reneigh_every;
     o->half_neigh = half_neigh;
 }
+/* box of an input file: readAtom sets param->xprd/yprd/zprd = hi - lo (atom.c readers); setupNeighbor then takes them
+ * instead of nx * lattice (neighbor.c:78-82) and treats the box as [0, prd) */
+EXPORT void ocp_set_box(OCP* o, double xprd, double yprd, double zprd)
+{
+    o->from_input = 1;
+    o->xprd = xprd; o->yprd = yprd; o->zprd = zprd;
+}
 /* the atoms createAtom + adjustThermo produced (identical code in both schemes, atom.c:49-180; generated by
  * the verletlist oracle in the tests) */
 EXPORT void ocp_set_atoms(OCP* o, int n, const real* x, const real* y, const real* z, const real* vx, const real* vy,
@@ -187,7 +195,7 @@ EXPORT void ocp_setup_neighbor(OCP* o)
 {
     const real SMALL = 1.0e-6, FACTOR = 0.999;
     o->lattice = pow((4.0 / o->rho), (1.0 / 3.0));
-    o->xprd = o->nx * o->lattice; o->yprd = o->ny * o->lattice; o->zprd = o->nz * o->lattice;
+    if (!o->from_input) { o->xprd = o->nx * o->lattice; o->yprd = o->ny * o->lattice; o->zprd = o->nz * o->lattice; }
     const real xlo = 0.0, xhi = o->xprd, ylo = 0.0, yhi = o->yprd, zlo = 0.0, zhi = o->zprd;
     /* neighbor.c:93-98 as the reference BUILD evaluates it (objdump of oracle/_ref, -Ofast): the two divisions
      * and the cbrt are folded into  nbin = ceil(prd * cbrt(density * (1/atoms_in_cell)))  with everything in

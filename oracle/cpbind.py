@@ -133,6 +133,10 @@ class OracleCP(_Common):
         self._call("ocp_set_lj", d(epsilon), d(sigma), d(cutforce), d(skin), d(dt), d(temp), d(rho), d(mass))
         self._call("ocp_set_run", nx, ny, nz, ntimes, nstat, reneigh_every, half_neigh)
 
+    def set_box(self, xprd, yprd, zprd):
+        d = C.c_double
+        self._call("ocp_set_box", d(xprd), d(yprd), d(zprd))
+
     def set_atoms(self, x, v):
         r = self.np_real
         cols = [np.ascontiguousarray(np.asarray(a, dtype=r)[:, k]) for a in (x, v) for k in range(3)]
@@ -286,6 +290,25 @@ class RefCP(_Common):
         L.setupNeighbor(C.byref(p), C.byref(a))
         L.setupThermo(C.byref(p), a.Natoms)
         L.adjustThermo(C.byref(p), C.byref(a))
+        if upto == "atoms":
+            return
+        self.buildClusters(); self.defineJClusters(); self.setupPbc(); self.binClusters(); self.buildNeighbor()
+
+    def setup_from_files(self, param_file, input_file, upto="all", **over):
+        """clusterpair/main.c with -p <param_file> -i <input_file>: readParameter, readAtom (sets the box), no adjustThermo"""
+        L, p, a, n, s = self.lib, self.param, self.atom, self.neighbor, self.stats
+        L.readParameter(C.byref(p), param_file.encode())
+        for k, v in over.items():
+            setattr(p, k, v)
+        self._input = input_file.encode()
+        p.input_file = self._input
+        p.cutneigh = p.cutforce + p.skin
+        p.lattice = self.np_real((4.0 / float(p.rho)) ** (1.0 / 3.0))
+        L.initAtom(C.byref(a)); L.initForce(C.byref(p)); L.initPbc(C.byref(a)); L.initStats(C.byref(s))
+        L.initNeighbor(C.byref(n), C.byref(p))
+        L.readAtom(C.byref(a), C.byref(p))
+        L.setupNeighbor(C.byref(p), C.byref(a))
+        L.setupThermo(C.byref(p), a.Natoms)
         if upto == "atoms":
             return
         self.buildClusters(); self.defineJClusters(); self.setupPbc(); self.binClusters(); self.buildNeighbor()

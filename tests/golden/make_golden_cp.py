@@ -57,6 +57,33 @@ def case(variant, nx, nsteps, name, half=0):
     print(name, d["t0_counts"], d.get("tN_thermo"))
 
 
+REFDATA = "/root/reference/data"
+
+
+def argon_case(variant, name, nsteps=105):
+    """clusterpair with -p data/argon/mdbench_params.conf -i data/argon/input.gro (box from the reader, 1000 atoms,
+    cutneigh 1.9 > L/2, one rebuild at step 100): structures at t = 0, forces, atoms after nsteps"""
+    r = RefCP(variant)
+    r.setup_from_files(REFDATA + "/argon/mdbench_params.conf", REFDATA + "/argon/input.gro")
+    p = r.param
+    d = {"nx": np.int32(1), "N": np.int32(r.N), "half": np.int32(p.half_neigh), "nsteps": np.int32(nsteps),
+         "box": np.array([p.xprd, p.yprd, p.zprd], np.float64),
+         "params": np.array([p.epsilon, p.sigma, p.cutforce, p.skin, p.dt, p.temp, p.rho, p.mass], np.float64),
+         "ints": np.array([p.reneigh_every, p.nstat], np.int32)}
+    d["x0"], d["v0"] = r.atoms("x"), r.atoms("v")
+    structures(r, "t0", d)
+    r.computeForce()
+    d["t0_clf"] = r.cl("f")
+    for n in range(nsteps):
+        r.step(n)
+    r.updateSingleAtoms()
+    d["tN_x"], d["tN_v"] = r.atoms("x"), r.atoms("v")
+    d["tN_thermo"] = np.array(r.thermo())
+    d["tN_counts"] = np.array([r.geti(k) for k in ("Nclusters_local", "Nclusters_ghost")], np.int32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(name, d["t0_counts"], d["tN_thermo"], d["tN_counts"])
+
+
 def thermo_run(variant, nx=32, nsteps=200):
     r = RefCP(variant)
     r.configure(nx=nx, ntimes=nsteps)
@@ -75,11 +102,15 @@ def thermo_run(variant, nx=32, nsteps=200):
 
 
 if __name__ == "__main__":
+    if "--argon-only" in sys.argv:
+        argon_case("cpref44_dp", "cp44_dp_argon")
+        sys.exit(0)
     case("cpref44_sp", 6, 45, "cp44_sp_nx6")
     case("cpref44_dp", 6, 45, "cp44_dp_nx6")
     case("cpref44_dp", 6, 45, "cp44_dp_half_nx6", half=1)
     case("cpref48_dp", 6, 45, "cp48ref_dp_nx6")
     case("cp_dp_aos", 6, 0, "cp48_dp_nx6")
     case("cp_sp_aos", 6, 0, "cp48_sp_nx6")
+    argon_case("cpref44_dp", "cp44_dp_argon")
     out = [thermo_run("cpref44_sp"), thermo_run("cpref44_dp")]
     json.dump(out, open(os.path.join(HERE, "thermo_cp.json"), "w"), indent=1)

@@ -311,3 +311,88 @@ def test_cp_driver_default_run_prints_reference_report(golden_dir, extra, varian
         assert abs(T - gT) <= tol * gT and abs(P - gP) <= tol * gP, (st, T, P, gT, gP)
     assert re.search(r"System: 131072 atoms \d+ ghost atoms, Steps: 200", out)
     assert "million atom updates per second" in out and "TOTAL" in out and "Kernel: CUDA sm_100a 4x4" in out
+
+
+def _argon_cp(g, N=4, dp=True, half=0):
+    m = load_pkg()
+    eps, sig, cutf, skin, dt, temp, rho, mass = [float(v) for v in g["params"]]
+    reneigh, nstat = [int(v) for v in g["ints"]]
+    b = [float(v) for v in g["box"]]
+    p = m.default_params(precision=m.DP if dp else m.SP, epsilon=eps, sigma=sig, cutforce=cutf, skin=skin, dt=dt, temp=temp, rho=rho,
+                         mass=mass, reneigh_every=reneigh, nstat=nstat, half_neigh=half, nx=1, ny=1, nz=1, from_input=1,
+                         xlo=0.0, xhi=b[0], ylo=0.0, yhi=b[1], zlo=0.0, zhi=b[2])
+    return m.ClusterSimulation(p, cluster_n=N)
+
+
+def test_input_file_box_argon_fixture(golden_dir):
+    """clusterpair with a reader's box instead of nx * lattice (neighbor.c:78-82): the reference's scalar 4x4 DP build on
+    data/argon (1000 atoms, box 3.6014^3, cutneigh 1.9 > L/2, rows of up to 330 entries -> maxneighs resize), fixture
+    cp44_dp_argon.npz: structures and lists bit for bit, forces, atoms after one rebuild"""
+    g = np.load(os.path.join(golden_dir, "cp44_dp_argon.npz"))
+    s = _argon_cp(g)
+    s.setAtoms(g["x0"], g["v0"])
+    s.setup(adjust=False)
+    assert_same_structure(_Fixture(g), s)
+    assert s.counts()["maxneighs"] > 100
+    s.computeForce()
+    real_lane = np.isfinite(g["t0_clx"][:len(g["t0_clf"])])
+    fr = np.nan_to_num(g["t0_clf"])
+    assert np.abs(fr - np.nan_to_num(s.cl("f")))[real_lane].max() <= 1e-10 * max(np.abs(fr).max(), 1e-300)
+    for n in range(int(g["nsteps"])):
+        s.step(n)
+    s.updateSingleAtoms()
+    assert max_rel(s.atoms("x"), g["tN_x"]) <= 1e-10
+    T, P = s.thermo()
+    assert abs(T - g["tN_thermo"][0]) <= 1e-10 * T and abs(P - g["tN_thermo"][1]) <= 1e-10 * P
+    c = s.counts()
+    assert (c["Nclusters_local"], c["Nclusters_ghost"]) == tuple(int(v) for v in g["tN_counts"])
+    s.close()
+
+
+@pytest.mark.parametrize("N,half,dp", [(8, 0, True), (4, 1, True), (4, 0, False)])
+def test_input_file_box_argon_vs_oracle(golden_dir, N, half, dp):
+    """the other variants on the same input against the checker (pinned to the reference on this input in
+    tests/test_cp_oracle_pinned.py::test_input_file_box_argon)"""
+    g = np.load(os.path.join(golden_dir, "cp44_dp_argon.npz"))
+    eps, sig, cutf, skin, dt, temp, rho, mass = [float(v) for v in g["params"]]
+    reneigh, nstat = [int(v) for v in g["ints"]]
+    s = _argon_cp(g, N=N, dp=dp, half=half)
+    o = OracleCP(dp, N, N)
+    o.configure(nx=1, half_neigh=half, epsilon=eps, sigma=sig, cutforce=cutf, skin=skin, dt=dt, temp=temp, rho=rho, mass=mass,
+                reneigh_every=reneigh, nstat=nstat)
+    o.set_box(*[float(v) for v in g["box"]])
+    real = np.float64 if dp else np.float32
+    x0, v0 = g["x0"].astype(real), g["v0"].astype(real)
+    s.setAtoms(x0, v0); o.set_atoms(x0, v0)
+    s.setup(adjust=False); o.setup()
+    assert_same_structure(o, s)
+    for n in range(101):
+        s.step(n); o.step(n)
+    assert_same_structure(o, s, tol=TOL[dp])
+    s.close()
+
+
+def test_cp_driver_reads_gro_and_param_file(golden_dir, tmp_path):
+    """MDBench-CP-B200 --param <file> -i <input.gro>: inputs rebuilt from the fixture"""
+    import re
+    import subprocess
+    g = np.load(os.path.join(golden_dir, "cp44_dp_argon.npz"))
+    eps, sig, cutf, skin, dt, temp, rho, mass = [float(v) for v in g["params"]]
+    reneigh, nstat = [int(v) for v in g["ints"]]
+    conf = tmp_path / "params.conf"
+    conf.write_text("epsilon %.17g\nsigma %.17g\ncutforce %.17g\nskin %.17g\ndt %.17g\ntemp %.17g\nrho %.17g\nmass %.17g\n"
+                    "reneigh_every %d\nnstat %d\n" % (eps, sig, cutf, skin, dt, temp, rho, mass, reneigh, nstat))
+    gro = tmp_path / "input.gro"
+    x, v = g["x0"], g["v0"]
+    with open(gro, "w") as f:
+        f.write("Liquid Argon t=   0.00000 step= 0\n %d\n" % len(x))
+        for i in range(len(x)):
+            f.write("%5dAr      Ar%5d%8.3f%8.3f%8.3f%8.4f%8.4f%8.4f\n" % (i + 1, i + 1, x[i, 0], x[i, 1], x[i, 2], v[i, 0], v[i, 1], v[i, 2]))
+        f.write("   %.5f   %.5f   %.5f\n" % tuple(float(q) for q in g["box"]))
+    out = subprocess.run([_cp_driver(), "--param", str(conf), "-i", str(gro), "--precision", "dp", "-n", "105"], capture_output=True,
+                         text=True, timeout=120).stdout
+    lines = [(int(a), float(b), float(c)) for a, b, c in re.findall(r"^(-?\d+)\t(\S+)\t(\S+)$", out, flags=re.M)]
+    assert [l[0] for l in lines] == [0, 105], out
+    # positions / velocities went through the .gro's 3 / 4 decimals: thermo to that precision only
+    assert abs(lines[-1][1] - g["tN_thermo"][0]) <= 1e-3 * g["tN_thermo"][0]
+    assert re.search(r"System: 1000 atoms \d+ ghost atoms, Steps: 105", out)
