@@ -263,7 +263,9 @@ int         mdb_dd_resetKernelStats(mdb_dd* d);
  * cluster_n atoms stored as [x0..x(N-1) | y0.. | z0..]; tile t is j-cluster t and, for N = 8, also
  * the i-clusters 2t (lanes 0-3) and 2t+1 (lanes 4-7); ghost j-clusters follow the local ones and the
  * last tile (dummy_cj) is all +infinity.  p->layout applies to atom positions only, velocities are
- * always SoA (clusterpair/atom.h:66-92).  pbc_x/y/z are ignored like in the reference (pbc.c:183-323). */
+ * always SoA (clusterpair/atom.h:66-92).  pbc_x/y/z are ignored like in the reference (pbc.c:183-323).  With
+ * p->from_input the box lengths are xhi - xlo ... (what the readers hand to setupNeighbor, neighbor.c:78-82) and the
+ * box is treated as [0, length) like the reference does; the atoms then come from mdb_cp_setAtoms. */
 typedef struct mdb_cp mdb_cp;
 mdb_cp*     mdb_cp_create(const mdb_params* p, int cluster_n, int device);
 void        mdb_cp_destroy(mdb_cp* c);
