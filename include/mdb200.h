@@ -328,6 +328,13 @@ int         mdb_cp_getGhostMap(mdb_cp* c, int* border_map, int* PBCx, int* PBCy,
  * bininvy,cutneighsq,cutneigh,xprd,yprd,zprd,rbb_sq}; stencil (may be NULL) nstencil ints */
 int         mdb_cp_getNeighborParams(mdb_cp* c, int ints[8], double reals[10], int* stencil);
 
+/* kernel micro-benchmark of the clusterpair scheme (reference src/clusterpair/main-stub.c:227-272, 61-122): niclusters
+ * synthetic i-clusters of iclusters_natoms atoms at x = y = z = index * 1e-5 (use cutforce 1e6), j-clusters defined from
+ * them, and a list of nneighs j-clusters per i-cluster in pattern MDB_STUB_SEQ / FIX / RAND, replicated nreps times;
+ * masked != 0: every entry goes through the masked loop.  mdb_cp_computeForce then times the kernel alone. */
+int         mdb_cp_stub(mdb_cp* c, int niclusters, int iclusters_natoms, int pattern, int nneighs, int nreps,
+                        int masked, unsigned seed);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* FMA issue-rate micro-benchmark on `device`: dense FP32 (MDB_SP) or FP64 (MDB_DP) vector peak in
  * TFLOP/s (FMA = 2 flop).  The roofline denominator for the force kernels. */

@@ -68,7 +68,7 @@ EXPORTS = [
     "mdb_cp_finalIntegrate", "mdb_cp_setup", "mdb_cp_reneighbour", "mdb_cp_run", "mdb_cp_saveState",
     "mdb_cp_restoreState", "mdb_cp_setTiming", "mdb_cp_getKernelStats", "mdb_cp_resetKernelStats", "mdb_cp_countPairs",
     "mdb_cp_getClusters", "mdb_cp_getClusterData", "mdb_cp_getClusterTags", "mdb_cp_getClusterBins", "mdb_cp_getLists",
-    "mdb_cp_getGhostMap", "mdb_cp_getNeighborParams",
+    "mdb_cp_getGhostMap", "mdb_cp_getNeighborParams", "mdb_cp_stub",
 ]
 
 _lib = None
@@ -695,6 +695,11 @@ class ClusterSimulation:
         a, b = C.c_longlong(), C.c_longlong()
         self._ck(self.L.mdb_cp_countPairs(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def stub(self, niclusters=256, natoms=4, pattern="seq", nneighs=9, nreps=1, masked=0, seed=12345):
+        """synthetic clusters + lists of the reference's kernel micro-benchmark (clusterpair/main-stub.c)"""
+        self._ck(self.L.mdb_cp_stub(self.h, niclusters, natoms, {"seq": 0, "fix": 1, "rand": 2}[pattern], nneighs, nreps, masked,
+                                    C.c_uint(seed)))
 
     # ---- parity accessors (same names as the checker's bindings use for the reference) ----
     def tiles(self):

@@ -955,6 +955,64 @@ __global__ void k_cp_update_single_atoms(int ncl, const int* __restrict__ inat, 
     vx[i] = cl_v[b]; vy[i] = cl_v[b + N]; vz[i] = cl_v[b + 2 * N];
     tag[i] = cl_tag[cp_ci_base1<N>(ci) + cii];
 }
+// ---- kernel micro-benchmark (clusterpair/main-stub.c:227-272 synthetic clusters, 61-122 createNeighbors) -----------------
+// i-cluster ci holds `nat` atoms at x = y = z = (ci * nat + cii) * 1e-5, the rest of the cluster is padding; tile t is
+// j-cluster t (defineJClusters); velocities and forces zero
+template <class real, int N>
+__global__ void k_cp_stub_clusters(int ncl, int nat, real* __restrict__ cl_x, real* __restrict__ cl_v, real* __restrict__ cl_f,
+    int* __restrict__ cl_tag, int* __restrict__ inat, int* __restrict__ jnat, real* __restrict__ ibb, int* __restrict__ ibin)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci  = tid >> 2, cii = tid & 3;
+    if (ci > ncl) return;
+    const size_t b = cp_ci_base3<N>(ci) + cii;
+    if (ci == ncl) { // the dummy tile behind the last one
+        if (N == CP_M || (ci & 1) == 0)
+            for (int q = cii; q < 3 * N; q += CP_M) cl_x[(size_t)cp_cj0<N>(ci) * N * 3 + q] = CP_PAD;
+        return;
+    }
+    const real p = cii < nat ? (real)(ci * nat + cii) * (real)0.00001 : CP_PAD;
+    cl_x[b] = p; cl_x[b + N] = p; cl_x[b + 2 * N] = p;
+    cl_v[b] = 0; cl_v[b + N] = 0; cl_v[b + 2 * N] = 0;
+    cl_f[b] = 0; cl_f[b + N] = 0; cl_f[b + 2 * N] = 0;
+    cl_tag[cp_ci_base1<N>(ci) + cii] = cii < nat ? ci * nat + cii : -1;
+    if (cii == 0) {
+        inat[ci] = nat;
+        ibin[ci] = 0;
+        const real lo = (real)(ci * nat) * (real)0.00001, hi = (real)(ci * nat + nat - 1) * (real)0.00001;
+        for (int d = 0; d < 3; d++) { ibb[(size_t)ci * 6 + 2 * d] = lo; ibb[(size_t)ci * 6 + 2 * d + 1] = hi; }
+        if (N == CP_M) jnat[ci] = nat;
+        else if ((ci & 1) == 0) jnat[ci >> 1] = 2 * nat;
+    }
+}
+// pattern 0 "seq": j-clusters CJ0(ci), CJ0(ci)+1, ... (mod ncj); 1 "fix": 0 .. nneighs-1; 2 "rand"; replicated nreps times
+template <int N>
+__global__ void k_cp_stub_neighbors(int ncl, int ncj, int pattern, int nneighs, int nreps, int nmasked, unsigned seed, int maxneighs,
+    int* __restrict__ numneigh, int* __restrict__ numneigh_masked, int* __restrict__ neighbors)
+{
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= ncl) return;
+    int* row   = neighbors + (size_t)ci * maxneighs;
+    unsigned h = seed ^ (0x9e3779b9u * (unsigned)(ci + 1));
+    int j      = pattern == 0 ? cp_cj0<N>(ci) : 0;
+    const int m = pattern == 0 ? ncj : nneighs;
+    for (int k = 0; k < nneighs; k++) {
+        int v;
+        if (pattern == 2) { // never the own tile: its self pairs would need the masked loop (the reference does not check)
+            do {
+                h ^= h << 13; h ^= h >> 17; h ^= h << 5;
+                v = (int)(h % (unsigned)ncj);
+            } while (v == cp_cj0<N>(ci) && ncj > 1);
+        } else {
+            v = j;
+            j = (j + 1) % m;
+        }
+        for (int r = 0; r < nreps; r++) row[r * nneighs + k] = v;
+    }
+    numneigh[ci]        = nneighs * nreps;
+    numneigh_masked[ci] = nmasked;
+}
+
 template <class real> __global__ void k_cp_zero(size_t n, real* __restrict__ a)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -55,6 +55,7 @@ struct CpBase {
     virtual void getLists(int* nn, int* nm, int* nb, int stride)                                     = 0;
     virtual void getGhostMap(int* bm, int* px, int* py, int* pz)                                     = 0;
     virtual void getNeighborParams(int* I, double* R, int* st)                                       = 0;
+    virtual void stub(int niclusters, int nat, int pattern, int nneighs, int nreps, int masked, unsigned seed) = 0;
 
     bool timing              = false;
     double force_ms          = 0, neigh_ms = 0;
@@ -806,6 +807,38 @@ template <class real, int N> struct CpSim final : CpBase {
             pz[k] = ((c[k] >> 4) & 3) - 1;
         }
     }
+    // synthetic clusters and lists of the reference's kernel micro-benchmark (clusterpair/main-stub.c)
+    void stub(int niclusters, int nat, int pattern, int nneighs, int nreps, int masked, unsigned seed) override
+    {
+        if (niclusters < 1 || nat < 1 || nat > CP_M || pattern < 0 || pattern > 2 || nneighs < 1 || nreps < 1)
+            throw Error("mdb_cp_stub: bad arguments");
+        if (JFAC > 1 && (niclusters & 1)) niclusters++; // two i-clusters per tile
+        ncl = niclusters; ncj = ncl / JFAC; nghost = 0; dummy_cj = ncj;
+        if (pattern == 2 && ncj <= nneighs)
+            throw Error("P_RAND: Number of j-clusters should be higher than number of j-cluster neighbors per i-cluster!");
+        Natoms = (long long)ncl * nat;
+        Nlocal = (int)Natoms;
+        ensure_atoms(Nlocal);
+        ensure_tiles((size_t)ncj + 2, false);
+        inat.ensure(ncl, false, stream);
+        ibin.ensure(ncl, false, stream);
+        ibb.ensure((size_t)ncl * 6, false, stream);
+        MDB_LAUNCH(launches, (k_cp_stub_clusters<real, N>), grid_for((size_t)(ncl + 1) * CP_M, 256), 256, 0, stream, ncl, nat, cl_x.p,
+            cl_v.p, cl_f.p, cl_tag.p, inat.p, jnat.p, ibb.p, ibin.p);
+        updateSingleAtoms();
+        maxneighs = nneighs * nreps;
+        numneigh.ensure(ncl, false, stream);
+        numneigh_masked.ensure(ncl, false, stream);
+        neighbors.ensure((size_t)ncl * maxneighs, false, stream);
+        // this library's kernels need the diagonal entries inside the masked prefix (the list build puts them there); the
+        // synthetic patterns repeat them (nreps) or place them anywhere ("fix"), so only "rand" / a single "seq" block may be
+        // left unmasked when the caller asks for the unmasked loop
+        const int nm = masked ? maxneighs : (pattern == 2 ? 0 : (pattern == 0 && nreps == 1 ? 1 : maxneighs));
+        MDB_LAUNCH(launches, k_cp_stub_neighbors<N>, grid_for(ncl, 128), 128, 0, stream, ncl, ncj, pattern, nneighs, nreps, nm, seed,
+            maxneighs, numneigh.p, numneigh_masked.p, neighbors.p);
+        lists_ready = true;
+        neigh_ready = false;
+    }
     void getNeighborParams(int* I, double* R, int* st) override
     {
         if (!neigh_ready) setupNeighbor();
@@ -951,6 +984,10 @@ int mdb_cp_getClusterTags(mdb_cp* c, int* tags) { MDB_CP_TRY(c->s->getClusterTag
 int mdb_cp_getClusterBins(mdb_cp* c, int* b) { MDB_CP_TRY(c->s->getClusterBins(b)) }
 int mdb_cp_getLists(mdb_cp* c, int* nn, int* nm, int* nb, int stride) { MDB_CP_TRY(c->s->getLists(nn, nm, nb, stride)) }
 int mdb_cp_getGhostMap(mdb_cp* c, int* bm, int* px, int* py, int* pz) { MDB_CP_TRY(c->s->getGhostMap(bm, px, py, pz)) }
+int mdb_cp_stub(mdb_cp* c, int niclusters, int iclusters_natoms, int pattern, int nneighs, int nreps, int masked, unsigned seed)
+{
+    MDB_CP_TRY(c->s->stub(niclusters, iclusters_natoms, pattern, nneighs, nreps, masked, seed))
+}
 int mdb_cp_getNeighborParams(mdb_cp* c, int ints[8], double reals[10], int* stencil)
 {
     MDB_CP_TRY(c->s->getNeighborParams(ints, reals, stencil))

@@ -396,3 +396,58 @@ def test_cp_driver_reads_gro_and_param_file(golden_dir, tmp_path):
     # positions / velocities went through the .gro's 3 / 4 decimals: thermo to that precision only
     assert abs(lines[-1][1] - g["tN_thermo"][0]) <= 1e-3 * g["tN_thermo"][0]
     assert re.search(r"System: 1000 atoms \d+ ghost atoms, Steps: 105", out)
+
+
+@pytest.mark.parametrize("N,pattern", [(4, "seq"), (8, "seq"), (4, "rand"), (4, "fix")])
+def test_stub_clusters_lists_and_force(N, pattern):
+    """the clusterpair kernel micro-benchmark's synthetic clusters and lists (main-stub.c:227-272, 61-122), and the force
+    they give against numpy (all listed pairs except the self pair of the own tile)"""
+    m = load_pkg()
+    ni, nat, nn, nr = 300, 4, 9, 2
+    s = m.ClusterSimulation(m.default_params(nx=1, ny=1, nz=1, cutforce=1.0e6, skin=0.0), cluster_n=N)
+    s.stub(ni, nat, pattern, nn, nr)
+    c = s.counts()
+    assert c["Nclusters_local"] == ni and c["Nlocal"] == ni * nat and c["Nclusters_ghost"] == 0
+    x = s.cl("x")
+    ncj = c["ncj"]
+    atoms = x.transpose(0, 2, 1).reshape(-1, 3)                       # (tile, lane) -> atom, both N: index order
+    assert np.allclose(atoms[:ni * nat, 0], np.arange(ni * nat) * 1e-5, rtol=0, atol=1e-18)
+    cnt, cm, nb = s.raw_lists()
+    assert np.all(cnt == nn * nr) and np.array_equal(nb[:, :nn], nb[:, nn:2 * nn])
+    self_tile = np.arange(ni) // (N // 4)
+    if pattern == "seq":
+        assert np.array_equal(nb[:, :nn], (self_tile[:, None] + np.arange(nn)[None, :]) % ncj)
+    elif pattern == "fix":
+        assert np.array_equal(nb[:, :nn], np.repeat(np.arange(nn)[None, :], ni, axis=0))
+    else:
+        assert nb.min() >= 0 and nb.max() < ncj
+    s.computeForce()
+    f = s.cl("f").transpose(0, 2, 1).reshape(-1, 3)[:ni * nat]
+    ref = np.zeros_like(f)
+    for ci in range(ni):
+        for cj in nb[ci]:
+            ja = np.arange(cj * N, (cj + 1) * N)
+            for a in range(ci * nat, (ci + 1) * nat):
+                d = atoms[a][None, :] - atoms[ja]
+                keep = ja != a                                         # exclusion on the own tile only (force_lj.c:99-113)
+                rsq = (d * d).sum(axis=1)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    sr2 = 1.0 / rsq
+                    sr6 = sr2 ** 3
+                    ff = np.where(keep, 48.0 * sr6 * (sr6 - 0.5) * sr2, 0.0)
+                ref[a] += (d * ff[:, None]).sum(axis=0)
+    assert np.abs(f - ref).max() <= 1e-10 * np.abs(ref).max()
+    s.close()
+
+
+def test_cp_stub_driver_report():
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "md-bench_b200", "driver", "MDBench-CP-B200-stub")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    out = subprocess.run([exe, "-p", "rand", "-ni", "20000", "-nn", "50", "-n", "20"], capture_output=True, text=True, timeout=120).stdout
+    assert "Pattern: rand" in out and "Number of i-clusters: 20000" in out and "Mega atom updates/s" in out and "MxN: 4x4" in out
+    out = subprocess.run([exe, "-p", "seq", "-ni", "4096", "--csv", "-n", "5", "--cluster-n", "8"], capture_output=True, text=True,
+                         timeout=120).stdout
+    assert out.splitlines()[0].startswith("steps,pattern,niclusters,iclusters_natoms") and out.splitlines()[1].startswith("5,seq,4096,4,9,1,")
