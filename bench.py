@@ -362,6 +362,8 @@ def main():
     value = natoms * args.ntimes * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (LJ force): CUDA-event time per launch, measured live ----
+    fused_force = not cp and not decomposed and not args.half and not any(
+        kv.split("=")[0] in ("fuse_force", "fuse_integrate", "force_variant", "merge") for kv in args.opt)
     sim.setTiming(True)
     sim.resetKernelStats()
     _, tm = one_step()
@@ -392,6 +394,8 @@ def main():
     except Exception:
         pass
     roofline = {"kernel": ("k_cp_force_lj<%s,%d,%s>" % ("double" if dp else "float", args.cluster_n, "half" if args.half else "full")) if cp
+                else ("k_force_lj_full_fi<%s> (LJ force with finalIntegrate(n) + initialIntegrate(n+1) in its epilogue; flop and byte counts are the force part only)"
+                      % ("double" if dp else "float")) if fused_force
                 else "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
                 "bound": "fp64" if dp else "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,

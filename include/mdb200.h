@@ -82,6 +82,10 @@ void        mdb_destroy(mdb_ctx* c);
  *  "merge" 2 = one list row per atom pair with membership bits (exact, slower; default 0).
  *  "eam_variant" 1 (default) packed spline rows + rsqrt, 0 = first kernels.
  *  "fuse_integrate" (default 1) finalIntegrate(n) + initialIntegrate(n+1) in one pass inside mdb_run.
+ *  "fuse_force" (default 1) inside mdb_run, LJ full lists of a single domain: computeForce(n) + finalIntegrate(n) +
+ *      initialIntegrate(n+1) in ONE kernel (the integrate halves run in the force kernel's epilogue on the force still
+ *      in registers; positions are double-buffered).  Bit-identical to the separate operators; steps that record thermo
+ *      and the last step of a run keep the separate kernels, so f/x/v read back after mdb_run are unchanged.
  *  "sort_rows" 1 = sort every neighbor row by index after the build (default 0). */
 int         mdb_setOption(mdb_ctx* c, const char* name, double value);
 /* run all work of this ctx on the given cudaStream_t (passed as void*); NULL = ctx-owned stream */

@@ -43,6 +43,7 @@ template <class real> struct Sim final : SimBase {
     bool sort_enabled = false, extmap_valid = false;
     int force_variant = 1, neigh_variant = 4, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
     bool fuse_integrate = true, sort_rows = false;
+    bool fuse_force = true; // mdb_run: integrate halves in the force kernel's epilogue (k_force_lj_full_fi)
     int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
     bool bin_rank_ready = false;
     DBuf<int> bin_rank;
@@ -997,6 +998,39 @@ template <class real> struct Sim final : SimBase {
             vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
 
+    // computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1) in ONE launch (k_force_lj_full_fi): LJ full lists of a
+    // single domain with the default kernels.  The new positions land in the sort buffers x2/y2/z2, which then become
+    // x/y/z; their ghost range is rewritten by the updatePbc / setupPbc of the next step before anything reads it.
+    bool can_fuse_force() const
+    {
+        return fuse_force && fuse_integrate && !brick && P.force_field != MDB_FF_EAM && !P.half_neigh && !merged_built &&
+            force_variant == 1;
+    }
+    void forceFinalInitialIntegrate()
+    {
+        if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_buildNeighbor first)");
+        x2.ensure(x.cap, false, stream);
+        y2.ensure(y.cap, false, stream);
+        z2.ensure(z.cap, false, stream);
+        if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
+        LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
+        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt };
+        if (sizeof(real) == 4)
+            MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2, x.p,
+                y.p, z.p, numneigh.p, neighbors.p, LL, fi);
+        else
+            MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, false>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2, x.p,
+                y.p, z.p, numneigh.p, neighbors.p, LL, fi);
+        std::swap(x, x2); std::swap(y, y2); std::swap(z, z2);
+        force_launches++;
+        if (timing) {
+            float ms = 0;
+            MDB_CUDA(cudaEventRecord(ev1, stream));
+            MDB_CUDA(cudaEventSynchronize(ev1));
+            MDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            force_ms += ms;
+        }
+    }
     void finalInitialIntegrate() // finalIntegrate(n) + initialIntegrate(n+1) in one pass
     {
         MDB_LAUNCH(launches, k_final_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
@@ -1053,9 +1087,15 @@ template <class real> struct Sim final : SimBase {
             if (!initial_done) initialIntegrate();
             if (reneigh) reneighbour();
             else updatePbc();
-            launch_force(FORCE_DISPATCH);
             const bool rec = !((n + 1) % nstat) && (n + 1) < nsteps; // main.c:275-280
-            if (rec || n + 1 == nsteps || !fuse_integrate) {
+            const bool split = rec || n + 1 == nsteps || !fuse_integrate;
+            if (!split && can_fuse_force()) {
+                forceFinalInitialIntegrate();
+                initial_done = true;
+                continue;
+            }
+            launch_force(FORCE_DISPATCH);
+            if (split) {
                 finalIntegrate();
                 initial_done = false;
                 if (rec) record(n + 1);
@@ -1251,6 +1291,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "list_layout")) list_layout = (int)v;
         else if (!strcmp(name, "sort_order")) sort_order = (int)v;
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
+        else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
         else if (!strcmp(name, "merge")) merge = (int)v;
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;

@@ -1195,6 +1195,103 @@ __global__ void __launch_bounds__(128) k_force_lj_full_v6(int nlocal, LJConst2<r
     fz[i] = fiz;
 }
 
+// ---- fi: the force kernel with the velocity-Verlet halves in its epilogue -------------------------------------------------
+// Inside the device-resident loop finalIntegrate(n) and initialIntegrate(n+1) follow the force of step n with nothing
+// in between (no thermo record, no rebuild before the NEXT force), and both only need atom i's own f, v, x
+// (verletlist/integrate.c:21-40).  This kernel therefore keeps f in registers, applies both halves in the same sequence
+// of operations as k_final_initial_integrate (bit-identical v and x) and writes the new positions into a SECOND
+// coordinate set (other threads still gather the old x[j]); the caller swaps the two sets afterwards.  Saved per step:
+// one launch and the 15T-byte integrate pass (f is neither written nor re-read).  BF = branch-free force block (v6,
+// SP default), else the divergent block of v2 (DP default).
+template <class real> struct FusedIntegrate {
+    real *vx, *vy, *vz, *xn, *yn, *zn;
+    real dtforce, dt;
+};
+template <class real, int U, bool BF>
+__global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst2<real> c, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
+    NbLayout L, FusedIntegrate<real> fi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    real fix = 0, fiy = 0, fiz = 0;
+    const int* nb   = nbT + L.base(i);
+    const int nfull = nn - nn % U;
+    int j[U], jn[U];
+    if (nfull > 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = __ldg(nb + (size_t)u * L.sk);
+    }
+    for (int k = 0; k < nfull; k += U) {
+        real dx[U], dy[U], dz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            dx[u] = xt - __ldg(x + j[u]);
+            dy[u] = yt - __ldg(y + j[u]);
+            dz[u] = zt - __ldg(z + j[u]);
+        }
+        nb += (size_t)U * L.sk;
+        if (k + U < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = __ldg(nb + (size_t)u * L.sk);
+        }
+        if (BF) {
+            real rsq[U], f[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+#pragma unroll
+            for (int u = 0; u < U; u++) f[u] = lj_pair2(rsq[u], c);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const real g = rsq[u] < c.cutforcesq ? f[u] : (real)0;
+                fix = fma(dx[u], g, fix); fiy = fma(dy[u], g, fiy); fiz = fma(dz[u], g, fiz);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+                if (rsq < c.cutforcesq) {
+                    const real f = lj_pair2(rsq, c);
+                    fix += dx[u] * f;
+                    fiy += dy[u] * f;
+                    fiz += dz[u] * f;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = jn[u];
+    }
+    for (int k = nfull; k < nn; k++) {
+        const int jj  = __ldg(nb);
+        nb += L.sk;
+        const real dx = xt - __ldg(x + jj), dy = yt - __ldg(y + jj), dz = zt - __ldg(z + jj);
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (BF) {
+            const real g = rsq < c.cutforcesq ? lj_pair2(rsq, c) : (real)0;
+            fix = fma(dx, g, fix); fiy = fma(dy, g, fiy); fiz = fma(dz, g, fiz);
+        } else if (rsq < c.cutforcesq) {
+            const real f = lj_pair2(rsq, c);
+            fix += dx * f;
+            fiy += dy * f;
+            fiz += dz * f;
+        }
+    }
+    // the atom index is re-read from the special registers so that it is not live across the pair loop (the DP
+    // kernel sits exactly at 64 registers; one more live value spills inside the loop)
+    unsigned tid, bid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
+    const int e = (int)(bid * 128u + tid);
+    real a = fi.vx[e] + fi.dtforce * fix, b = fi.vy[e] + fi.dtforce * fiy, cc = fi.vz[e] + fi.dtforce * fiz; // final(n)
+    a = a + fi.dtforce * fix; b = b + fi.dtforce * fiy; cc = cc + fi.dtforce * fiz;                          // initial(n+1)
+    fi.vx[e] = a; fi.vy[e] = b; fi.vz[e] = cc;
+    fi.xn[e] = xt + fi.dt * a;
+    fi.yn[e] = yt + fi.dt * b;
+    fi.zn[e] = zt + fi.dt * cc;
+}
+
 // ---- m2: merged rows, two atoms per thread (see k_build_neighbor_m2) ---------------------------------------------------
 template <class real, int U>
 __global__ void __launch_bounds__(128) k_force_lj_full_m2(int nlocal, LJConst2<real> c, const real* __restrict__ x,

@@ -1,0 +1,12 @@
+#!/bin/bash
+# A/B of session 4: force kernel with the integrate halves in its epilogue (fuse_force) vs separate final+initial pass
+B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-secondary"
+sum() { python -c "
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d['roofline']
+print('%-44s value %.3f G  force %.3f ms  neigh %.2f ms/rebuild  T %.9f' % (sys.argv[2], d['value']/1e9, r['ms_per_launch'], r['neigh_ms_per_rebuild'], d['thermo_final']['T']))" $1 "$2"; }
+run() { $B $2 > gpurun_out/ab4_$1.json 2> gpurun_out/ab4_$1.err && sum gpurun_out/ab4_$1.json "$2" || tail -3 gpurun_out/ab4_$1.err; }
+run a "--opt fuse_force=1"
+run b "--opt fuse_force=0"
+run c "--precision sp --opt fuse_force=1"
+run d "--precision sp --opt fuse_force=0"

@@ -122,10 +122,14 @@ def test_maxneighs_resize_and_dense_bins():
     s.close()
 
 
-def test_run_loop_equals_operator_by_operator():
-    """mdb_run (device-resident loop) must give exactly the operator-by-operator result."""
-    a = make_sim(True, True, nx=6, ny=6, nz=6)
-    b = make_sim(True, True, nx=6, ny=6, nz=6)
+@pytest.mark.parametrize("dp,sort,fuse_force", [(True, True, 1), (True, False, 1), (False, False, 1), (True, True, 0)])
+def test_run_loop_equals_operator_by_operator(dp, sort, fuse_force):
+    """mdb_run (device-resident loop: integrate halves fused into the force kernel's epilogue, positions double-buffered;
+    or, fuse_force=0, the separate final+initial integrate pass) must give exactly the operator-by-operator result,
+    across rebuilds (steps 20, 40) and a thermo record in the middle (nstat 30)."""
+    a = make_sim(dp, True, sort, nx=6, ny=6, nz=6, nstat=30)
+    b = make_sim(dp, True, sort, nx=6, ny=6, nz=6, nstat=30)
+    a.setOption("fuse_force", fuse_force)
     for s in (a, b):
         s.createAtom(); s.setup(adjust=True)
     rec, tm = a.run(45)
@@ -134,9 +138,15 @@ def test_run_loop_equals_operator_by_operator():
         b.step(n)
     assert np.array_equal(a.get("x"), b.get("x"))
     assert np.array_equal(a.get("v"), b.get("v"))
-    assert rec[0][0] == 0 and rec[-1][0] == 45
+    assert rec[0][0] == 0 and rec[1][0] == 30 and rec[-1][0] == 45
     T, P = b.thermo()
     assert rec[-1][1] == T and rec[-1][2] == P
+    assert np.array_equal(a.get("f"), b.get("f"))  # the last step is never fused: f is the force of step 45
+    # and the loop can be re-entered with the buffers swapped an odd number of times
+    a.run(7)
+    for n in range(45, 52):
+        b.step(n)
+    assert np.array_equal(a.get("x"), b.get("x")) and np.array_equal(a.get("v"), b.get("v"))
     a.close(); b.close()
 
 
