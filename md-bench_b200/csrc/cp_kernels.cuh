@@ -651,9 +651,35 @@ __device__ __forceinline__ void cp_tile_packed(const CpTileRegs<N>& T, const CpP
         fx = fma2(dx, f, fx); fy = fma2(dy, f, fy); fz = fma2(dz, f, fz);
     }
 }
-template <int N>
+// FI (full lists, inside mdb_cp_run): finalIntegrate(n) + initialIntegrate(n+1) in the force kernel's epilogue, on the
+// force still in registers -- the same operations as k_cp_integrate<MODE 2> (integrate.c:23-63), so bit-identical.  The new
+// positions go to a second cluster array (other lanes still read the old tiles); the caller keeps its padding slots,
+// ghost tiles and dummy tile in step and swaps the two arrays afterwards.  cl_f is not written.
+template <class real> struct CpFused {
+    real *cl_v, *cl_xn;
+    real dtforce, dt;
+};
+template <class real>
+__device__ __forceinline__ void cp_fused_integrate(const CpFused<real>& fi, size_t s, real xold, real f)
+{
+    real v = fi.cl_v[s] + fi.dtforce * f;
+    v      = v + fi.dtforce * f;
+    fi.cl_v[s]  = v;
+    fi.cl_xn[s] = xold + fi.dt * v;
+}
+// slot of this lane's i atom, re-derived from the special registers after the pair loop: nothing of the epilogue
+// (addresses, the loads of v and x) can then be hoisted above the loop, where it would cost registers.  Blocks of 128.
+template <int N> __device__ __forceinline__ size_t cp_epilogue_slot()
+{
+    unsigned t, b;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
+    const unsigned tid = b * 128u + t;
+    return cp_ci_base3<N>((int)(tid >> 2)) + (tid & 3u);
+}
+template <int N, bool FI = false>
 __global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, int dummy_cj, LJConst2<float> c, const float* __restrict__ cl_x,
-    const int* __restrict__ numneigh, const int* __restrict__ neighbors, int maxneighs, float* __restrict__ cl_f)
+    const int* __restrict__ numneigh, const int* __restrict__ neighbors, int maxneighs, float* __restrict__ cl_f, CpFused<float> fi)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int ci  = tid >> 2, cii = tid & 3;
@@ -687,13 +713,22 @@ __global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, int dumm
     upk2(fx, a, b); const float fix = pad_i ? 0.f : a + b;
     upk2(fy, a, b); const float fiy = pad_i ? 0.f : a + b;
     upk2(fz, a, b); const float fiz = pad_i ? 0.f : a + b;
+    if (FI) {
+        if (pad_i) return;
+        // own coordinates re-read (a real atom's x0/y0/z0 are unmodified, but keeping them live costs registers)
+        const size_t e = cp_epilogue_slot<N>();
+        cp_fused_integrate(fi, e, cl_x[e], fix);
+        cp_fused_integrate(fi, e + N, cl_x[e + N], fiy);
+        cp_fused_integrate(fi, e + 2 * N, cl_x[e + 2 * N], fiz);
+        return;
+    }
     cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
 }
 
-template <class real, int N, bool HALF>
+template <class real, int N, bool HALF, bool FI = false>
 __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<real> c, const real* __restrict__ cl_x,
     const int* __restrict__ numneigh, const int* __restrict__ numneigh_masked, const int* __restrict__ neighbors, int maxneighs,
-    real* __restrict__ cl_f)
+    real* __restrict__ cl_f, CpFused<real> fi)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int ci  = tid >> 2, cii = tid & 3;
@@ -728,6 +763,15 @@ __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<
             fiy, fiz);
     }
     if (!valid) return;
+    if (FI && !HALF) {
+        if (pad_i) return; // pad_i <=> cii >= inat[ci]: padding slots are not integrated (integrate.c:27)
+        // xt/yt/zt of a real atom are its unmodified coordinates
+        const size_t e = cp_epilogue_slot<N>();
+        cp_fused_integrate(fi, e, xt, fix);
+        cp_fused_integrate(fi, e + N, yt, fiy);
+        cp_fused_integrate(fi, e + 2 * N, zt, fiz);
+        return;
+    }
     if (pad_i) fix = fiy = fiz = 0;
     if (HALF) {
         if (!pad_i) { atomicAdd(cl_f + ib + cii, fix); atomicAdd(cl_f + ib + N + cii, fiy); atomicAdd(cl_f + ib + 2 * N + cii, fiz); }

@@ -73,6 +73,7 @@ template <class real, int N> struct CpSim final : CpBase {
     bool thermo_ready = false, neigh_ready = false;
     int prune_every = 1000; // common/parameter.c:40
     int force_variant = 0;
+    bool fuse_force = true; // mdb_cp_run, full lists: integrate halves in the force kernel's epilogue (CpFused)
     // ---- atoms (clusterpair/atom.h:26-60) ----
     long long Natoms = 0;
     int Nlocal = 0;
@@ -82,6 +83,7 @@ template <class real, int N> struct CpSim final : CpBase {
     // ---- clusters ----
     int ncl = 0, ncj = 0, nghost = 0, dummy_cj = 0; // Nclusters_local, local tiles, Nclusters_ghost
     DBuf<real> cl_x, cl_v, cl_f, ibb, jbb, pmaxz;
+    DBuf<real> cl_xn; // second cluster position array of the fused force + integrate step (run())
     DBuf<int> cl_tag, inat, ibin, jnat, atom_off;
     // ---- bins (clusterpair/neighbor.c:26-45) ----
     CpGeom<real> g {};
@@ -182,6 +184,7 @@ template <class real, int N> struct CpSim final : CpBase {
     {
         if (!strcmp(name, "prune_every")) prune_every = (int)v;
         else if (!strcmp(name, "force_variant")) force_variant = (int)v;
+        else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else throw Error(fmt("mdb_cp_setOption: unknown option '%s'", name));
     }
 
@@ -561,12 +564,47 @@ template <class real, int N> struct CpSim final : CpBase {
     }
 
     // ------------------------------------------------------------------ force / integrate
-    void launch_force()
+    // fused = computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1) in one launch (run() only): the new positions
+    // go to cl_xn, which must already mirror cl_x's padding slots, ghost tiles and dummy tile (sync_second_array), and the
+    // two arrays are swapped afterwards.
+    bool can_fuse_force() const
+    {
+        if (!fuse_force || P.half_neigh) return false;
+        if (sizeof(real) == 8 && N == 8) return false; // the DP 4x8 kernel would spill with the epilogue (ptxas: 64 regs + 12 B)
+        int fv = force_variant;
+        if (fv == 0) fv = sizeof(real) == 4 ? 2 : 1;
+        return fv == 1 || fv == 2;
+    }
+    void sync_second_array()
+    {
+        cl_xn.ensure(cl_x.cap, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(cl_xn.p, cl_x.p, (size_t)(ncj + nghost + 1) * 3 * N * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+    }
+    void launch_force(bool fused = false)
     {
         if (!lists_ready) throw Error("computeForce: no cluster-pair list (call mdb_cp_buildNeighbor first)");
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
         const unsigned grid = grid_for((size_t)ncl * CP_M, 128);
+        const CpFused<real> fi { cl_v.p, cl_xn.p, dtforce, dt };
+        if (fused) {
+            int fv = force_variant;
+            if (fv == 0) fv = sizeof(real) == 4 ? 2 : 1;
+            if (fv == 2) launch_packed_fused(grid, c2, fi);
+            else
+                MDB_LAUNCH(launches, (k_cp_force_lj<real, N, false, true>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
+                    numneigh_masked.p, neighbors.p, maxneighs, cl_f.p, fi);
+            std::swap(cl_x, cl_xn);
+            force_launches++;
+            if (timing) {
+                float ms = 0;
+                MDB_CUDA(cudaEventRecord(ev1, stream));
+                MDB_CUDA(cudaEventSynchronize(ev1));
+                MDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+                force_ms += ms;
+            }
+            return;
+        }
         // force_variant 0 (default) picks the fastest measured kernel per case (profiles/r1_ab3.txt): full lists -> lane per
         // i atom (packed FP32 in SP), half lists -> warp per i-cluster / lane per j atom (its reaction forces need no
         // shuffles).  1 = lane per i atom, scalar; 2 = lane per i atom, packed FP32 (SP full only); 3 = warp per i-cluster.
@@ -589,12 +627,12 @@ template <class real, int N> struct CpSim final : CpBase {
         } else if (P.half_neigh) {
             MDB_CUDA(cudaMemsetAsync(cl_f.p, 0, (size_t)ncj * 3 * N * sizeof(real), stream));
             MDB_LAUNCH(launches, (k_cp_force_lj<real, N, true>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
-                numneigh_masked.p, neighbors.p, maxneighs, cl_f.p);
+                numneigh_masked.p, neighbors.p, maxneighs, cl_f.p, fi);
         } else if (fv == 2) {
             launch_packed(grid, c2);
         } else {
             MDB_LAUNCH(launches, (k_cp_force_lj<real, N, false>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
-                numneigh_masked.p, neighbors.p, maxneighs, cl_f.p);
+                numneigh_masked.p, neighbors.p, maxneighs, cl_f.p, fi);
         }
         force_launches++;
         if (timing) {
@@ -608,9 +646,15 @@ template <class real, int N> struct CpSim final : CpBase {
     void launch_packed(unsigned grid, const LJConst2<float>& c2)
     {
         MDB_LAUNCH(launches, k_cp_force_lj_sp_packed<N>, grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p, numneigh.p,
-            neighbors.p, maxneighs, (float*)cl_f.p);
+            neighbors.p, maxneighs, (float*)cl_f.p, CpFused<float> { nullptr, nullptr, 0.f, 0.f });
     }
     void launch_packed(unsigned, const LJConst2<double>&) {}
+    void launch_packed_fused(unsigned grid, const LJConst2<float>& c2, const CpFused<float>& fi)
+    {
+        MDB_LAUNCH(launches, (k_cp_force_lj_sp_packed<N, true>), grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
+            numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, fi);
+    }
+    void launch_packed_fused(unsigned, const LJConst2<double>&, const CpFused<double>&) {}
     double computeForce() override // returns elapsed seconds like the reference's ComputeForceFunction
     {
         const bool t        = timing;
@@ -690,6 +734,8 @@ template <class real, int N> struct CpSim final : CpBase {
         launch_force();
         MDB_CUDA(cudaEventRecord(evR0, stream)); // timer[TOTAL] starts after the first force call, main.c:236-239
         bool initial_done = false;
+        const bool fuse = can_fuse_force();
+        bool second_ok  = false; // cl_xn mirrors cl_x's padding slots, ghost tiles and dummy tile (they change per rebuild)
         for (int n = 0; n < nsteps; n++) {
             if (!initial_done) initialIntegrate();
             if ((n + 1) % every) {
@@ -697,10 +743,18 @@ template <class real, int N> struct CpSim final : CpBase {
                 updatePbc(false);
             } else {
                 reneighbour();
+                second_ok = false;
             }
-            launch_force();
             const bool rec  = !((n + 1) % nstat) && (n + 1) < nsteps;
             const bool last = n + 1 == nsteps;
+            if (fuse && !rec && !last) { // force(n) + final(n) + initial(n+1) in one launch
+                if (!second_ok) sync_second_array();
+                second_ok = true;
+                launch_force(true);
+                initial_done = true;
+                continue;
+            }
+            launch_force();
             // final(n) + initial(n+1) fuse into one pass unless something reads the state in between
             if (rec || last) {
                 finalIntegrate();

@@ -5,8 +5,13 @@ sum() { python -c "
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d['roofline']
 print('%-44s value %.3f G  force %.3f ms  neigh %.2f ms/rebuild  T %.9f' % (sys.argv[2], d['value']/1e9, r['ms_per_launch'], r['neigh_ms_per_rebuild'], d['thermo_final']['T']))" $1 "$2"; }
-run() { $B $2 > gpurun_out/ab4_$1.json 2> gpurun_out/ab4_$1.err && sum gpurun_out/ab4_$1.json "$2" || tail -3 gpurun_out/ab4_$1.err; }
+ONLY="${1:-abcdefgh}"   # labels to run, e.g. profiles/ab4.sh efgh
+run() { case "$ONLY" in *$1*) ;; *) return;; esac; $B $2 > gpurun_out/ab4_$1.json 2> gpurun_out/ab4_$1.err && sum gpurun_out/ab4_$1.json "$2" || tail -3 gpurun_out/ab4_$1.err; }
 run a "--opt fuse_force=1"
 run b "--opt fuse_force=0"
 run c "--precision sp --opt fuse_force=1"
 run d "--precision sp --opt fuse_force=0"
+run e "--scheme clusterpair --precision sp --opt fuse_force=1"
+run f "--scheme clusterpair --precision sp --opt fuse_force=0"
+run g "--scheme clusterpair --precision dp --opt fuse_force=1"
+run h "--scheme clusterpair --precision dp --opt fuse_force=0"

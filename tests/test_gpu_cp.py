@@ -164,11 +164,14 @@ def test_createAtom_adjustThermo_on_device(dp):
         s.close()
 
 
-@pytest.mark.parametrize("N,half", [(4, 0), (8, 0), (4, 1)])
-def test_run_loop_equals_operator_by_operator(N, half):
-    """mdb_cp_run (device-resident loop, fused final+initial integrate) == the same operators called one by one"""
-    x, v = jittered(True, 6, 6, 6, amp=0.1)
-    a, b = make_cp(True, N, 6, half=half, nstat=25), make_cp(True, N, 6, half=half, nstat=25)
+@pytest.mark.parametrize("dp,N,half,fuse_force", [(True, 4, 0, 1), (True, 8, 0, 1), (True, 4, 1, 1), (False, 4, 0, 1), (False, 8, 0, 1),
+                                                  (False, 4, 0, 0)])
+def test_run_loop_equals_operator_by_operator(dp, N, half, fuse_force):
+    """mdb_cp_run (device-resident loop; full lists: integrate halves in the force kernel's epilogue with a second cluster
+    position array, else / fuse_force=0 the fused final+initial integrate pass) == the same operators called one by one"""
+    x, v = jittered(dp, 6, 6, 6, amp=0.1)
+    a, b = make_cp(dp, N, 6, half=half, nstat=25), make_cp(dp, N, 6, half=half, nstat=25)
+    a.setOption("fuse_force", fuse_force)
     for s in (a, b):
         s.setAtoms(x, v)
         s.setup(adjust=False)
