@@ -78,7 +78,7 @@ void        mdb_destroy(mdb_ctx* c);
  *  "list_layout" 0 = transposed, 1 = row-major rows, 2 (default) = k-major tiles of 32 atoms.
  *  "neigh_variant" list-build kernel: 4 (default) packed-FP32 tests on SoA candidates, 3 = float4 candidates, 0-2 older.
  *  "force_variant" LJ full-list kernel: 1 (default; DP: 4 neighbors in flight, SP: branch-free), 8/9 branch-free U=4/2,
- *      0/2-7 older generations.
+ *      0/2-7 older generations, 10-13 rolling software pipeline (k_force_lj_full_v7; bit-identical, measured slower).
  *  "merge" 2 = one list row per atom pair with membership bits (exact, slower; default 0).
  *  "eam_variant" 1 (default) packed spline rows + rsqrt, 0 = first kernels.
  *  "fuse_integrate" (default 1) finalIntegrate(n) + initialIntegrate(n+1) in one pass inside mdb_run.

@@ -905,6 +905,8 @@ template <class real> struct Sim final : SimBase {
                     else
                         MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
                             x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                } else if (force_variant >= 10 && force_variant <= 13) {
+                    launch_v7<false>(c2, FusedIntegrate<real> { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0 });
                 } else if (force_variant == 0)
                     MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
                         x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
@@ -998,13 +1000,38 @@ template <class real> struct Sim final : SimBase {
             vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
 
+    // rolling-pipeline kernels (k_force_lj_full_v7), force_variant 10..13: {U, min blocks/SM} DP | SP
+    //   10: {4,7} | {4,9}   11: {3,9} | {3,10}   12: {3,8} | {6,8}   13: {2,8} | {2,12};  SP branch-free, DP branchy
+    template <int U, int MINB, bool FI> void launch_v7_t(const LJConst2<real>& c2, const FusedIntegrate<real>& fi)
+    {
+        MDB_LAUNCH(launches, (k_force_lj_full_v7<real, U, sizeof(real) == 4, FI, MINB>), grid_for(Nlocal, 128), 128, 0, stream,
+            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p, fi);
+    }
+    template <bool FI> void launch_v7(const LJConst2<real>& c2, const FusedIntegrate<real>& fi)
+    {
+        if constexpr (sizeof(real) == 4) {
+            switch (force_variant) {
+            case 10: launch_v7_t<4, 9, FI>(c2, fi); break;
+            case 11: launch_v7_t<3, 10, FI>(c2, fi); break;
+            case 12: launch_v7_t<6, 8, FI>(c2, fi); break;
+            default: launch_v7_t<2, 12, FI>(c2, fi); break;
+            }
+        } else {
+            switch (force_variant) {
+            case 10: launch_v7_t<4, 7, FI>(c2, fi); break;
+            case 11: launch_v7_t<3, 9, FI>(c2, fi); break;
+            case 12: launch_v7_t<3, 8, FI>(c2, fi); break;
+            default: launch_v7_t<2, 8, FI>(c2, fi); break;
+            }
+        }
+    }
     // computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1) in ONE launch (k_force_lj_full_fi): LJ full lists of a
     // single domain with the default kernels.  The new positions land in the sort buffers x2/y2/z2, which then become
     // x/y/z; their ghost range is rewritten by the updatePbc / setupPbc of the next step before anything reads it.
     bool can_fuse_force() const
     {
         return fuse_force && fuse_integrate && !brick && P.force_field != MDB_FF_EAM && !P.half_neigh && !merged_built &&
-            force_variant == 1;
+            (force_variant == 1 || (force_variant >= 10 && force_variant <= 13));
     }
     void forceFinalInitialIntegrate()
     {
@@ -1015,12 +1042,11 @@ template <class real> struct Sim final : SimBase {
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
         FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt };
-        if (sizeof(real) == 4)
-            MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2, x.p,
-                y.p, z.p, numneigh.p, neighbors.p, LL, fi);
-        else
-            MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, false>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2, x.p,
-                y.p, z.p, numneigh.p, neighbors.p, LL, fi);
+        if (force_variant >= 10)
+            launch_v7<true>(c2, fi);
+        else // SP: branch-free force block (v6), DP: the divergent block of v2
+            MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, sizeof(real) == 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fi);
         std::swap(x, x2); std::swap(y, y2); std::swap(z, z2);
         force_launches++;
         if (timing) {

@@ -1292,6 +1292,105 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
     fi.zn[e] = zt + fi.dt * cc;
 }
 
+// ---- v7: rolling software pipeline ------------------------------------------------------------------------------------
+// Source-level ncu of v2 (gpurun_out/prof_r1_s3_vlforce_seq.ncu-rep, even with perfectly coalesced lists): a third of
+// all stall samples are long-scoreboard waits at the FIRST use of each group's gathered positions -- the 12 gathers of
+// a group are issued at the top of the iteration and consumed right away, so every iteration exposes one L1 latency --
+// and the index prefetch (one group ahead) is still late.  Here the U position slots are refilled one by one: as soon
+// as pair u of group k has been evaluated, its three registers receive pair u of group k+1 (whose index was fetched
+// during group k-1) and the index of pair u of group k+2 is requested.  Every gather then has U-1 pair evaluations
+// between issue and first use, with the same number of registers as v2.  BF / FI as in k_force_lj_full_fi.
+template <class real, int U, bool BF, bool FI, int MINB = 8>
+__global__ void __launch_bounds__(128, MINB) k_force_lj_full_v7(int nlocal, LJConst2<real> c, const real* __restrict__ x,
+    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
+    NbLayout L, real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz, FusedIntegrate<real> fi)
+{
+    // register diet (the DP kernel must fit 64): one down-counter for the groups, one pointer into the list, the atom
+    // index re-read from the special registers in the epilogue
+    real xt, yt, zt;
+    int left, tail; // groups still to evaluate; pairs behind the last full group
+    const int* nbn; // entries of the group after next
+    {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= nlocal) return;
+        xt = x[i]; yt = y[i]; zt = z[i];
+        const int nn = numneigh[i];
+        left = nn / U;
+        tail = nn - left * U;
+        nbn  = nbT + L.base(i);
+    }
+    real fix = 0, fiy = 0, fiz = 0;
+    real px[U], py[U], pz[U];
+    int jn[U];
+    if (left > 0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) jn[u] = __ldg(nbn + (size_t)u * L.sk);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            px[u] = __ldg(x + jn[u]); py[u] = __ldg(y + jn[u]); pz[u] = __ldg(z + jn[u]);
+        }
+        if (left > 1) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = __ldg(nbn + (size_t)(U + u) * L.sk);
+        }
+    }
+    nbn += (size_t)2 * U * L.sk;
+    for (; left > 0; left--) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const real dx = xt - px[u], dy = yt - py[u], dz = zt - pz[u];
+            const real rsq = dx * dx + dy * dy + dz * dz;
+            if (BF) {
+                const real g = rsq < c.cutforcesq ? lj_pair2(rsq, c) : (real)0;
+                fix = fma(dx, g, fix); fiy = fma(dy, g, fiy); fiz = fma(dz, g, fiz);
+            } else if (rsq < c.cutforcesq) {
+                const real f = lj_pair2(rsq, c);
+                fix += dx * f;
+                fiy += dy * f;
+                fiz += dz * f;
+            }
+            if (left > 1) { // slot u <- pair u of the next group
+                const int j = jn[u];
+                px[u] = __ldg(x + j); py[u] = __ldg(y + j); pz[u] = __ldg(z + j);
+            }
+            if (left > 2) jn[u] = __ldg(nbn + (size_t)u * L.sk);
+        }
+        nbn += (size_t)U * L.sk;
+    }
+    nbn -= (size_t)2 * U * L.sk; // first entry behind the last full group
+    for (; tail > 0; tail--) {
+        const int jj = __ldg(nbn);
+        nbn += L.sk;
+        const real dx = xt - __ldg(x + jj), dy = yt - __ldg(y + jj), dz = zt - __ldg(z + jj);
+        const real rsq = dx * dx + dy * dy + dz * dz;
+        if (BF) {
+            const real g = rsq < c.cutforcesq ? lj_pair2(rsq, c) : (real)0;
+            fix = fma(dx, g, fix); fiy = fma(dy, g, fiy); fiz = fma(dz, g, fiz);
+        } else if (rsq < c.cutforcesq) {
+            const real f = lj_pair2(rsq, c);
+            fix += dx * f;
+            fiy += dy * f;
+            fiz += dz * f;
+        }
+    }
+    unsigned tid, bid; // blocks of 128 threads
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
+    const int e = (int)(bid * 128u + tid);
+    if (FI) {
+        real a = fi.vx[e] + fi.dtforce * fix, b = fi.vy[e] + fi.dtforce * fiy, cc = fi.vz[e] + fi.dtforce * fiz; // final(n)
+        a = a + fi.dtforce * fix; b = b + fi.dtforce * fiy; cc = cc + fi.dtforce * fiz;                          // initial(n+1)
+        fi.vx[e] = a; fi.vy[e] = b; fi.vz[e] = cc;
+        fi.xn[e] = xt + fi.dt * a;
+        fi.yn[e] = yt + fi.dt * b;
+        fi.zn[e] = zt + fi.dt * cc;
+    } else {
+        fx[e] = fix;
+        fy[e] = fiy;
+        fz[e] = fiz;
+    }
+}
+
 // ---- m2: merged rows, two atoms per thread (see k_build_neighbor_m2) ---------------------------------------------------
 template <class real, int U>
 __global__ void __launch_bounds__(128) k_force_lj_full_m2(int nlocal, LJConst2<real> c, const real* __restrict__ x,

@@ -15,3 +15,12 @@ run e "--scheme clusterpair --precision sp --opt fuse_force=1"
 run f "--scheme clusterpair --precision sp --opt fuse_force=0"
 run g "--scheme clusterpair --precision dp --opt fuse_force=1"
 run h "--scheme clusterpair --precision dp --opt fuse_force=0"
+# rolling-pipeline force kernels (k_force_lj_full_v7), fused epilogue on
+run i "--opt force_variant=10"
+run j "--opt force_variant=11"
+run k "--opt force_variant=12"
+run l "--opt force_variant=13"
+run m "--precision sp --opt force_variant=10"
+run n "--precision sp --opt force_variant=11"
+run o "--precision sp --opt force_variant=12"
+run p "--precision sp --opt force_variant=13"

@@ -150,6 +150,28 @@ def test_run_loop_equals_operator_by_operator(dp, sort, fuse_force):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("dp", [True, False])
+@pytest.mark.parametrize("fv", [10, 11, 12, 13])
+def test_rolling_pipeline_force_kernels_bit_identical(dp, fv):
+    """k_force_lj_full_v7 (force_variant 10..13: gathers refilled slot by slot) evaluates the listed pairs in list order with
+    the same per-pair arithmetic as the default kernel: forces, and 45-step trajectories through mdb_run (fused and not),
+    must be bit-identical to force_variant 1."""
+    a = make_sim(dp, True, False, nx=6, ny=6, nz=6, nstat=30)
+    b = make_sim(dp, True, False, nx=6, ny=6, nz=6, nstat=30)
+    b.setOption("force_variant", fv)
+    for s in (a, b):
+        s.createAtom(); s.setup(adjust=True)
+        s.computeForce()
+    assert np.array_equal(a.get("f"), b.get("f"))
+    a.run(45); b.run(45)
+    assert np.array_equal(a.get("x"), b.get("x")) and np.array_equal(a.get("v"), b.get("v"))
+    assert np.array_equal(a.get("f"), b.get("f"))
+    b.setOption("fuse_force", 0)
+    a.run(21); b.run(21)
+    assert np.array_equal(a.get("x"), b.get("x")) and np.array_equal(a.get("v"), b.get("v"))
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("dp,half,nx,key", [(True, 0, 32, "vl_dp_aos"), (False, 0, 32, "vl_sp_soa"), (True, 1, 8, "vl_dp_aos")])
 def test_200_step_thermo_goldens(golden_dir, dp, half, nx, key):
     """BASELINE config 1 (Cu FCC 32^3, 200 steps): the `step temp pressure` lines of the reference."""
