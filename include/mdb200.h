@@ -86,6 +86,9 @@ void        mdb_destroy(mdb_ctx* c);
  *      initialIntegrate(n+1) in ONE kernel (the integrate halves run in the force kernel's epilogue on the force still
  *      in registers; positions are double-buffered).  Bit-identical to the separate operators; steps that record thermo
  *      and the last step of a run keep the separate kernels, so f/x/v read back after mdb_run are unchanged.
+ *  "xy_gather" (default 1) the fused kernel fetches a neighbor's x and y with one 2-element vector gather from a packed
+ *      (x, y) copy of the positions (kept current by its own epilogue and by updatePbc) instead of two scalar gathers:
+ *      fewer L1 wavefronts per pair.  Bit-identical.
  *  "sort_rows" 1 = sort every neighbor row by index after the build (default 0). */
 int         mdb_setOption(mdb_ctx* c, const char* name, double value);
 /* run all work of this ctx on the given cudaStream_t (passed as void*); NULL = ctx-owned stream */

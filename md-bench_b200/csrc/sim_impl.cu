@@ -44,6 +44,12 @@ template <class real> struct Sim final : SimBase {
     int force_variant = 1, neigh_variant = 4, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
     bool fuse_integrate = true, sort_rows = false;
     bool fuse_force = true; // mdb_run: integrate halves in the force kernel's epilogue (k_force_lj_full_fi)
+    // packed (x, y) copy of the positions for the fused kernel's vector gathers ("xy_gather"); valid only between fused
+    // steps of one mdb_run: the fused epilogue writes the locals, updatePbc the ghosts, everything else invalidates it
+    typedef typename Vec2Of<real>::type vec2;
+    int xy_gather = 1;
+    bool xy_valid = false;
+    DBuf<vec2> xy, xy2;
     int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
     bool bin_rank_ready = false;
     DBuf<int> bin_rank;
@@ -629,7 +635,7 @@ template <class real> struct Sim final : SimBase {
     {
         if (Nghost == 0) return;
         MDB_LAUNCH(launches, k_update_pbc<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost, xprd,
-            yprd, zprd, border_map.p, ghost_code.p, x.p, y.p, z.p);
+            yprd, zprd, border_map.p, ghost_code.p, x.p, y.p, z.p, xy_valid ? xy.p : (vec2*)nullptr);
     }
     void updateAtomsPbc() override // verletlist/pbc.c:59-84
     {
@@ -906,7 +912,7 @@ template <class real> struct Sim final : SimBase {
                         MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
                             x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
                 } else if (force_variant >= 10 && force_variant <= 13) {
-                    launch_v7<false>(c2, FusedIntegrate<real> { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0 });
+                    launch_v7<false>(c2, FusedIntegrate<real> { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr });
                 } else if (force_variant == 0)
                     MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
                         x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
@@ -991,6 +997,7 @@ template <class real> struct Sim final : SimBase {
     // ------------------------------------------------------------------ integrate
     void initialIntegrate() override // verletlist/integrate.c:21-31
     {
+        xy_valid = false;
         MDB_LAUNCH(launches, k_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
             dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
@@ -1041,13 +1048,27 @@ template <class real> struct Sim final : SimBase {
         z2.ensure(z.cap, false, stream);
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
-        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt };
+        const bool use_xy = xy_gather && force_variant == 1;
+        if (use_xy) {
+            xy.ensure(x.cap, false, stream);
+            xy2.ensure(x.cap, false, stream);
+            if (!xy_valid) { // locals and ghosts as they are now
+                const int nall = Nlocal + Nghost;
+                MDB_LAUNCH(launches, k_pack_xy<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, xy.p);
+            }
+        }
+        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt, xy.p, xy2.p };
         if (force_variant >= 10)
             launch_v7<true>(c2, fi);
+        else if (use_xy)
+            MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, sizeof(real) == 4, true>), grid_for(Nlocal, 128), 128, 0, stream,
+                Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fi);
         else // SP: branch-free force block (v6), DP: the divergent block of v2
             MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, sizeof(real) == 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
                 c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fi);
         std::swap(x, x2); std::swap(y, y2); std::swap(z, z2);
+        if (use_xy) std::swap(xy, xy2);
+        xy_valid = use_xy; // locals current; the ghost range follows with the next updatePbc
         force_launches++;
         if (timing) {
             float ms = 0;
@@ -1059,6 +1080,7 @@ template <class real> struct Sim final : SimBase {
     }
     void finalInitialIntegrate() // finalIntegrate(n) + initialIntegrate(n+1) in one pass
     {
+        xy_valid = false;
         MDB_LAUNCH(launches, k_final_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
             dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
@@ -1085,6 +1107,7 @@ template <class real> struct Sim final : SimBase {
     }
     void reneighbour() override // verletlist/main.c:76-95
     {
+        xy_valid = false;
         updateAtomsPbc();
         sort_atoms(); // main.c:82-88 (SORT_ATOMS; here at every rebuild)
         setupPbc();
@@ -1094,6 +1117,7 @@ template <class real> struct Sim final : SimBase {
     void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) override
     {
         if (!thermo_ready) setupThermo();
+        xy_valid = false; // positions may have been set from outside since the last run
         const int nstat = P.nstat > 0 ? P.nstat : nsteps + 1;
         const int every = P.reneigh_every > 0 ? P.reneigh_every : nsteps + 1;
         const int maxrec = nsteps / nstat + 3;
@@ -1318,6 +1342,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "sort_order")) sort_order = (int)v;
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
+        else if (!strcmp(name, "xy_gather")) xy_gather = (int)v;
         else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
         else if (!strcmp(name, "merge")) merge = (int)v;
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;

@@ -154,6 +154,10 @@ template <class real> __global__ void k_vel_scale(int n, real* vx, real* vy, rea
     if (i < n) { vx[i] *= f; vy[i] *= f; vz[i] *= f; }
 }
 
+template <class real> struct Vec2Of;
+template <> struct Vec2Of<double> { typedef double2 type; };
+template <> struct Vec2Of<float> { typedef float2 type; };
+
 // ---------------------------------------------------------------------------------------------
 // velocity-Verlet halves, verletlist/integrate.c:21-31 / 33-40
 template <class real>
@@ -277,14 +281,30 @@ static __global__ void k_ghost_fill(int nlocal, const unsigned* __restrict__ mas
 template <class real>
 __global__ void k_update_pbc(int nlocal, int nghost, real xprd, real yprd, real zprd,
     const int* __restrict__ border_map, const int* __restrict__ code, real* __restrict__ x,
-    real* __restrict__ y, real* __restrict__ z)
+    real* __restrict__ y, real* __restrict__ z, typename Vec2Of<real>::type* __restrict__ xy)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nghost) return;
     const int s = border_map[g], c = code[g];
-    x[nlocal + g] = fma_rn((real)((c & 3) - 1), xprd, x[s]);
-    y[nlocal + g] = fma_rn((real)(((c >> 2) & 3) - 1), yprd, y[s]);
+    const real a = fma_rn((real)((c & 3) - 1), xprd, x[s]);
+    const real b = fma_rn((real)(((c >> 2) & 3) - 1), yprd, y[s]);
+    x[nlocal + g] = a;
+    y[nlocal + g] = b;
     z[nlocal + g] = fma_rn((real)(((c >> 4) & 3) - 1), zprd, z[s]);
+    if (xy) { // the packed (x, y) copy the xy-gather force kernel reads (k_force_lj_full_fi<.., XY>)
+        typename Vec2Of<real>::type v;
+        v.x = a; v.y = b;
+        xy[nlocal + g] = v;
+    }
+}
+template <class real>
+__global__ void k_pack_xy(int n, const real* __restrict__ x, const real* __restrict__ y, typename Vec2Of<real>::type* __restrict__ xy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename Vec2Of<real>::type v;
+    v.x = x[i]; v.y = y[i];
+    xy[i] = v;
 }
 // updateAtomsPbc, pbc.c:59-84
 template <class real> __device__ __forceinline__ real wrap1(real v, real prd)
@@ -1203,11 +1223,29 @@ __global__ void __launch_bounds__(128) k_force_lj_full_v6(int nlocal, LJConst2<r
 // coordinate set (other threads still gather the old x[j]); the caller swaps the two sets afterwards.  Saved per step:
 // one launch and the 15T-byte integrate pass (f is neither written nor re-read).  BF = branch-free force block (v6,
 // SP default), else the divergent block of v2 (DP default).
+// XY: the neighbors' x and y come from a packed (x, y) array with ONE 2-element vector gather instead of two scalar
+// gathers (the kernel is bound by L1 wavefronts = cache lines touched per request: a warp's k-th neighbors sit in ~4 bins
+// of ~7.5 consecutive atoms, which is ~3.3 lines per 8-byte gather but only ~5 per 16-byte one); z stays scalar.  The
+// epilogue then also writes the packed copy of the new positions; k_update_pbc refreshes its ghost range.
 template <class real> struct FusedIntegrate {
     real *vx, *vy, *vz, *xn, *yn, *zn;
     real dtforce, dt;
+    const typename Vec2Of<real>::type* xy;
+    typename Vec2Of<real>::type* xyn;
 };
-template <class real, int U, bool BF>
+template <class real, bool XY>
+__device__ __forceinline__ void gather_pos(const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const typename Vec2Of<real>::type* __restrict__ xy, int j, real& a, real& b, real& c)
+{
+    if (XY) {
+        const typename Vec2Of<real>::type p = __ldg(xy + j);
+        a = p.x; b = p.y;
+    } else {
+        a = __ldg(x + j); b = __ldg(y + j);
+    }
+    c = __ldg(z + j);
+}
+template <class real, int U, bool BF, bool XY = false>
 __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst2<real> c, const real* __restrict__ x,
     const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
     NbLayout L, FusedIntegrate<real> fi)
@@ -1228,9 +1266,11 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
         real dx[U], dy[U], dz[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            dx[u] = xt - __ldg(x + j[u]);
-            dy[u] = yt - __ldg(y + j[u]);
-            dz[u] = zt - __ldg(z + j[u]);
+            real a, b, cc;
+            gather_pos<real, XY>(x, y, z, fi.xy, j[u], a, b, cc);
+            dx[u] = xt - a;
+            dy[u] = yt - b;
+            dz[u] = zt - cc;
         }
         nb += (size_t)U * L.sk;
         if (k + U < nfull) {
@@ -1266,7 +1306,9 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
     for (int k = nfull; k < nn; k++) {
         const int jj  = __ldg(nb);
         nb += L.sk;
-        const real dx = xt - __ldg(x + jj), dy = yt - __ldg(y + jj), dz = zt - __ldg(z + jj);
+        real pa, pb, pc;
+        gather_pos<real, XY>(x, y, z, fi.xy, jj, pa, pb, pc);
+        const real dx = xt - pa, dy = yt - pb, dz = zt - pc;
         const real rsq = dx * dx + dy * dy + dz * dz;
         if (BF) {
             const real g = rsq < c.cutforcesq ? lj_pair2(rsq, c) : (real)0;
@@ -1287,9 +1329,15 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
     real a = fi.vx[e] + fi.dtforce * fix, b = fi.vy[e] + fi.dtforce * fiy, cc = fi.vz[e] + fi.dtforce * fiz; // final(n)
     a = a + fi.dtforce * fix; b = b + fi.dtforce * fiy; cc = cc + fi.dtforce * fiz;                          // initial(n+1)
     fi.vx[e] = a; fi.vy[e] = b; fi.vz[e] = cc;
-    fi.xn[e] = xt + fi.dt * a;
-    fi.yn[e] = yt + fi.dt * b;
+    const real xe = xt + fi.dt * a, ye = yt + fi.dt * b;
+    fi.xn[e] = xe;
+    fi.yn[e] = ye;
     fi.zn[e] = zt + fi.dt * cc;
+    if (XY) {
+        typename Vec2Of<real>::type v;
+        v.x = xe; v.y = ye;
+        fi.xyn[e] = v;
+    }
 }
 
 // ---- v7: rolling software pipeline ------------------------------------------------------------------------------------

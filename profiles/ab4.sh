@@ -24,3 +24,8 @@ run m "--precision sp --opt force_variant=10"
 run n "--precision sp --opt force_variant=11"
 run o "--precision sp --opt force_variant=12"
 run p "--precision sp --opt force_variant=13"
+# packed (x, y) vector gathers in the fused force kernel
+run q "--opt xy_gather=1"
+run r "--opt xy_gather=0"
+run s "--precision sp --opt xy_gather=1"
+run t "--precision sp --opt xy_gather=0"

@@ -122,14 +122,16 @@ def test_maxneighs_resize_and_dense_bins():
     s.close()
 
 
-@pytest.mark.parametrize("dp,sort,fuse_force", [(True, True, 1), (True, False, 1), (False, False, 1), (True, True, 0)])
+@pytest.mark.parametrize("dp,sort,fuse_force", [(True, True, 1), (True, False, 1), (False, False, 1), (True, True, 0),
+                                                (True, True, 2), (False, False, 2)])
 def test_run_loop_equals_operator_by_operator(dp, sort, fuse_force):
     """mdb_run (device-resident loop: integrate halves fused into the force kernel's epilogue, positions double-buffered;
     or, fuse_force=0, the separate final+initial integrate pass) must give exactly the operator-by-operator result,
     across rebuilds (steps 20, 40) and a thermo record in the middle (nstat 30)."""
     a = make_sim(dp, True, sort, nx=6, ny=6, nz=6, nstat=30)
     b = make_sim(dp, True, sort, nx=6, ny=6, nz=6, nstat=30)
-    a.setOption("fuse_force", fuse_force)
+    a.setOption("fuse_force", min(fuse_force, 1))
+    a.setOption("xy_gather", 1 if fuse_force == 2 else 0)   # 2: fused kernel with the packed (x, y) vector gathers
     for s in (a, b):
         s.createAtom(); s.setup(adjust=True)
     rec, tm = a.run(45)
