@@ -550,6 +550,7 @@ template <class real> struct DomainGroup final : DDBase {
     void reneighbour() override // main.c:76-95
     {
         check_push_error();
+        for (Brick* b : bricks) b->xy_valid = false; // migration and sorting move atoms between slots
         migrate();
         for (Brick* b : bricks) b->sort_atoms();
         setupGhosts();
@@ -594,8 +595,10 @@ template <class real> struct DomainGroup final : DDBase {
     }
     void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) override // main.c:244-288
     {
-        for (Brick* b : bricks)
+        for (Brick* b : bricks) {
             if (!b->thermo_ready) b->setupThermo();
+            b->xy_valid = false; // positions may have been set from outside since the last run
+        }
         const int nstat = G.nstat > 0 ? G.nstat : nsteps + 1;
         const int every = G.reneigh_every > 0 ? G.reneigh_every : nsteps + 1;
         const size_t maxrec = nsteps / nstat + 3;
@@ -616,6 +619,18 @@ template <class real> struct DomainGroup final : DDBase {
             const bool reneigh = (n + 1) % every == 0;
             if (!initial_done)
                 for (Brick* b : bricks) b->initialIntegrate();
+            const bool rec = !((n + 1) % nstat) && (n + 1) < nsteps;
+            // force(n) + finalIntegrate(n) + initialIntegrate(n+1) in one launch per brick (x, y, z updated in place, gathers
+            // from the double-buffered copies), unless something reads the state in between
+            bool fuse = !rec && n + 1 < nsteps && G.force_field == MDB_FF_LJ && !(can_overlap() && !reneigh);
+            for (Brick* b : bricks) fuse = fuse && b->can_fuse_force_inplace();
+            if (fuse) {
+                if (reneigh) reneighbour();
+                else forward();
+                for (Brick* b : bricks) b->forceFinalInitialIntegrateInPlace();
+                initial_done = true;
+                continue;
+            }
             if (reneigh) {
                 reneighbour();
                 force();
@@ -625,7 +640,6 @@ template <class real> struct DomainGroup final : DDBase {
                 forward();
                 force();
             }
-            const bool rec = !((n + 1) % nstat) && (n + 1) < nsteps;
             if (rec || n + 1 == nsteps || !bricks[0]->fuse_integrate) {
                 for (Brick* b : bricks) b->finalIntegrate();
                 initial_done = false;

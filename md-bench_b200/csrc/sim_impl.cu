@@ -50,6 +50,7 @@ template <class real> struct Sim final : SimBase {
     int xy_gather = 1;
     bool xy_valid = false;
     DBuf<vec2> xy, xy2;
+    DBuf<real> zg, zg2; // gather copy of z (in-place variant of the fused step, decomposed runs)
     int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
     bool bin_rank_ready = false;
     DBuf<int> bin_rank;
@@ -912,7 +913,7 @@ template <class real> struct Sim final : SimBase {
                         MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
                             x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
                 } else if (force_variant >= 10 && force_variant <= 13) {
-                    launch_v7<false>(c2, FusedIntegrate<real> { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr });
+                    launch_v7<false>(c2, FusedIntegrate<real> { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr });
                 } else if (force_variant == 0)
                     MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
                         x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
@@ -1057,7 +1058,7 @@ template <class real> struct Sim final : SimBase {
                 MDB_LAUNCH(launches, k_pack_xy<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, xy.p);
             }
         }
-        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt, xy.p, xy2.p };
+        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt, xy.p, xy2.p, nullptr, nullptr };
         if (force_variant >= 10)
             launch_v7<true>(c2, fi);
         else if (use_xy)
@@ -1069,6 +1070,39 @@ template <class real> struct Sim final : SimBase {
         std::swap(x, x2); std::swap(y, y2); std::swap(z, z2);
         if (use_xy) std::swap(xy, xy2);
         xy_valid = use_xy; // locals current; the ghost range follows with the next updatePbc
+        force_launches++;
+        if (timing) {
+            float ms = 0;
+            MDB_CUDA(cudaEventRecord(ev1, stream));
+            MDB_CUDA(cudaEventSynchronize(ev1));
+            MDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            force_ms += ms;
+        }
+    }
+    // The same fused step for a brick of a decomposed run (also valid for a single domain): x, y, z are updated IN PLACE --
+    // the neighbor GPUs hold pointers into their ghost range -- and every gather goes to the double-buffered copies
+    // xy / zg.  Call after the halo of this step has landed (forward() / reneighbour()).
+    bool can_fuse_force_inplace() const
+    {
+        return fuse_force && fuse_integrate && P.force_field != MDB_FF_EAM && !P.half_neigh && !merged_built && force_variant == 1;
+    }
+    void forceFinalInitialIntegrateInPlace()
+    {
+        if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_buildNeighbor first)");
+        for (DBuf<vec2>* b : { &xy, &xy2 }) b->ensure(x.cap, false, stream);
+        for (DBuf<real>* b : { &zg, &zg2 }) b->ensure(x.cap, false, stream);
+        if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
+        // gather copies: everything after a rebuild / an unfused step, else only the ghost range that just arrived
+        const int first = xy_valid ? Nlocal : 0, cnt = xy_valid ? Nghost : Nlocal + Nghost;
+        if (cnt > 0)
+            MDB_LAUNCH(launches, k_pack_gather<real>, grid_for(cnt, 256), 256, 0, stream, first, cnt, x.p, y.p, z.p, xy.p, zg.p);
+        LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
+        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x.p, y.p, z.p, dtforce, dt, xy.p, xy2.p, zg.p, zg2.p };
+        MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, sizeof(real) == 4, true, true>), grid_for(Nlocal, 128), 128, 0, stream,
+            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fi);
+        std::swap(xy, xy2);
+        std::swap(zg, zg2);
+        xy_valid = true;
         force_launches++;
         if (timing) {
             float ms = 0;

@@ -1232,10 +1232,16 @@ template <class real> struct FusedIntegrate {
     real dtforce, dt;
     const typename Vec2Of<real>::type* xy;
     typename Vec2Of<real>::type* xyn;
+    const real* zg; // ZG: gather copy of z, see below
+    real* zgn;
 };
-template <class real, bool XY>
+// ZG (with XY; decomposed runs): ALL gathers go to copies -- (x, y) packed and a copy of z -- which are double-buffered,
+// while x, y, z themselves are only read and written by the thread that owns the atom and are therefore updated IN
+// PLACE (fi.xn/yn/zn = x/y/z).  The neighbor GPUs keep pushing their halo into the ghost range of the same x, y, z
+// allocations (no pointer exchange per step); k_pack_gather copies that ghost range into the gather copies.
+template <class real, bool XY, bool ZG>
 __device__ __forceinline__ void gather_pos(const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const typename Vec2Of<real>::type* __restrict__ xy, int j, real& a, real& b, real& c)
+    const typename Vec2Of<real>::type* __restrict__ xy, const real* __restrict__ zg, int j, real& a, real& b, real& c)
 {
     if (XY) {
         const typename Vec2Of<real>::type p = __ldg(xy + j);
@@ -1243,16 +1249,28 @@ __device__ __forceinline__ void gather_pos(const real* __restrict__ x, const rea
     } else {
         a = __ldg(x + j); b = __ldg(y + j);
     }
-    c = __ldg(z + j);
+    c = ZG ? __ldg(zg + j) : __ldg(z + j);
 }
-template <class real, int U, bool BF, bool XY = false>
+template <class real>
+__global__ void k_pack_gather(int first, int n, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    typename Vec2Of<real>::type* __restrict__ xy, real* __restrict__ zg)
+{
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= first + n) return;
+    typename Vec2Of<real>::type v;
+    v.x = x[i]; v.y = y[i];
+    xy[i] = v;
+    zg[i] = z[i];
+}
+template <class real, int U, bool BF, bool XY = false, bool ZG = false>
 __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst2<real> c, const real* __restrict__ x,
     const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
     NbLayout L, FusedIntegrate<real> fi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlocal) return;
-    const real xt = x[i], yt = y[i], zt = z[i];
+    // ZG: the own position comes through the (non-restrict) pointers it is written back through
+    const real xt = ZG ? fi.xn[i] : x[i], yt = ZG ? fi.yn[i] : y[i], zt = ZG ? fi.zn[i] : z[i];
     const int nn  = numneigh[i];
     real fix = 0, fiy = 0, fiz = 0;
     const int* nb   = nbT + L.base(i);
@@ -1267,7 +1285,7 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
 #pragma unroll
         for (int u = 0; u < U; u++) {
             real a, b, cc;
-            gather_pos<real, XY>(x, y, z, fi.xy, j[u], a, b, cc);
+            gather_pos<real, XY, ZG>(x, y, z, fi.xy, fi.zg, j[u], a, b, cc);
             dx[u] = xt - a;
             dy[u] = yt - b;
             dz[u] = zt - cc;
@@ -1307,7 +1325,7 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
         const int jj  = __ldg(nb);
         nb += L.sk;
         real pa, pb, pc;
-        gather_pos<real, XY>(x, y, z, fi.xy, jj, pa, pb, pc);
+        gather_pos<real, XY, ZG>(x, y, z, fi.xy, fi.zg, jj, pa, pb, pc);
         const real dx = xt - pa, dy = yt - pb, dz = zt - pc;
         const real rsq = dx * dx + dy * dy + dz * dz;
         if (BF) {
@@ -1329,10 +1347,11 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
     real a = fi.vx[e] + fi.dtforce * fix, b = fi.vy[e] + fi.dtforce * fiy, cc = fi.vz[e] + fi.dtforce * fiz; // final(n)
     a = a + fi.dtforce * fix; b = b + fi.dtforce * fiy; cc = cc + fi.dtforce * fiz;                          // initial(n+1)
     fi.vx[e] = a; fi.vy[e] = b; fi.vz[e] = cc;
-    const real xe = xt + fi.dt * a, ye = yt + fi.dt * b;
+    const real xe = xt + fi.dt * a, ye = yt + fi.dt * b, ze = zt + fi.dt * cc;
     fi.xn[e] = xe;
     fi.yn[e] = ye;
-    fi.zn[e] = zt + fi.dt * cc;
+    fi.zn[e] = ze;
+    if (ZG) fi.zgn[e] = ze;
     if (XY) {
         typename Vec2Of<real>::type v;
         v.x = xe; v.y = ye;
