@@ -89,3 +89,28 @@ def test_no_cpu_fallback_clusterpair_and_decomposition():
     with pytest.raises(m.MdbError) as e:
         m.Decomposition(m.default_params(nx=8, ny=8, nz=8), (2, 1, 1))
     assert "CUDA" in str(e.value)
+
+
+def test_every_runtime_option_is_documented_in_the_header():
+    """mdb_setOption / mdb_cp_setOption / mdb_dd_setOption names accepted by the library (the strcmp chains in csrc/) must
+    all appear, quoted, in include/mdb200.h -- the header is the only place a driver maintainer learns about them."""
+    hdr = open(os.path.join(ROOT, "include", "mdb200.h")).read()
+    csrc = os.path.join(ROOT, "md-bench_b200", "csrc")
+    names = set()
+    for f in ("sim_impl.cu", "cp_sim.cu", "dd_group.cuh"):
+        names |= set(re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', open(os.path.join(csrc, f)).read()))
+    assert {"fuse_force", "xy_gather", "force_variant", "halo_push"} <= names
+    missing = sorted(n for n in names if '"%s"' % n not in hdr)
+    assert not missing, "options not documented in include/mdb200.h: %s" % missing
+
+
+def test_traffic_json_names_the_kernels_that_run():
+    """profiles/traffic.json feeds roofline.traffic; bench.py only accepts an entry captured from the fused kernels that
+    mdb_run / mdb_cp_run actually launch (names as ncu prints them)."""
+    import json
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    vl, cp = t["verletlist/dp/128"], t["clusterpair/sp/128"]
+    assert "k_force_lj_full_fi" in vl["kernel"] and vl["bytes"] > 3.0e9
+    assert "k_cp_force_lj_sp_packed<4, 1>" in cp["kernel"] and cp["bytes"] > 0.9e9
+    for e in (vl, cp):
+        assert os.path.exists(os.path.join(ROOT, e["source"].split(" ")[0]))
