@@ -281,7 +281,8 @@ int         mdb_cp_setStream(mdb_cp* c, void* cuda_stream);
 int         mdb_cp_sync(mdb_cp* c);
 /* "prune_every" (default 1000, common/parameter.c:40): pruneNeighbor period inside mdb_cp_run; "force_variant" 0 = auto
  * (full lists: lane per i atom, packed FP32 in SP; half lists: warp per i-cluster), 1 = lane per i atom scalar,
- * 2 = lane per i atom packed FP32 (SP full), 3 = warp per i-cluster / lane per j atom;
+ * 2 = lane per i atom packed FP32 (SP full), 3 = warp per i-cluster / lane per j atom, 4 / 5 = packed FP32 with a deeper
+ * software pipeline (list entries 3 tiles ahead; 5: tiles 2 ahead) -- A/B variants, SP full lists only, not yet measured;
  * "fuse_force" (default 1): inside mdb_cp_run with full lists, computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1)
  * run as ONE kernel (integrate halves in the force kernel's epilogue, second cluster position array); bit-identical. */
 int         mdb_cp_setOption(mdb_cp* c, const char* name, double value);

@@ -194,6 +194,28 @@ def test_run_loop_equals_operator_by_operator(dp, N, half, fuse_force):
     a.close(); b.close()
 
 
+@pytest.mark.skipif(not os.environ.get("MDB_TEST_EXPERIMENTAL"),
+                    reason="A/B kernels written after the round's GPU budget was spent; set MDB_TEST_EXPERIMENTAL=1 to run")
+@pytest.mark.parametrize("N", [4, 8])
+@pytest.mark.parametrize("fv", [4, 5])
+def test_experimental_deep_pipeline_packed_kernels_bit_identical(N, fv):
+    """k_cp_force_lj_sp_packed_q (force_variant 4 / 5: list entries and tiles requested further ahead) evaluates the same
+    tiles in the same order with the same arithmetic as the default packed kernel: forces and a 60-step run bit-identical"""
+    x, v = jittered(False, 6, 6, 6, amp=0.1)
+    a, b = make_cp(False, N, 6, nstat=25), make_cp(False, N, 6, nstat=25)
+    b.setOption("force_variant", fv)
+    for s in (a, b):
+        s.setAtoms(x, v)
+        s.setup(adjust=False)
+        s.computeForce()
+    assert np.array_equal(np.nan_to_num(a.cl("f")), np.nan_to_num(b.cl("f")))
+    ra, _ = a.run(60)
+    rb, _ = b.run(60)
+    assert np.array_equal(ra, rb)
+    assert np.array_equal(a.atoms("x"), b.atoms("x")) and np.array_equal(a.atoms("v"), b.atoms("v"))
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("dp,N", [(True, 4), (False, 8)])
 def test_prune_neighbor_vs_oracle(dp, N):
     """pruneNeighbor 15 steps after the build: the device's list (its row order) and cluster positions are handed to
