@@ -133,7 +133,7 @@ template <class real, int N> struct CpSim final : CpBase {
                             "defineJClusters %.3f setupPbc %.3f binClusters %.3f buildNeighbor %.3f\n", phase_calls,
                 phase_ms[0] / phase_calls, phase_ms[1] / phase_calls, phase_ms[2] / phase_calls, phase_ms[3] / phase_calls,
                 phase_ms[4] / phase_calls, phase_ms[5] / phase_calls, phase_ms[6] / phase_calls);
-        for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &sx, &sy, &sz, &svx, &svy, &svz, &stage, &cl_x, &cl_v, &cl_f, &ibb,
+        for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &sx, &sy, &sz, &svx, &svy, &svz, &stage, &cl_x, &cl_xn, &cl_v, &cl_f, &ibb,
                  &jbb, &pmaxz })
             b->release();
         for (DBuf<int>* b : { &tag, &type, &cl_tag, &inat, &ibin, &jnat, &atom_off, &stencil, &atom_bin, &bincount, &binstart,

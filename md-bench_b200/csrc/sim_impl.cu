@@ -123,6 +123,8 @@ template <class real> struct Sim final : SimBase {
                  &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline, &eam_rho4, &eam_frc12, &x2, &y2, &z2, &vx2, &vy2,
                  &vz2, &fx2, &fy2, &fz2, &tx, &ty, &tz })
             b->release();
+        for (DBuf<real>* b : { &zg, &zg2 }) b->release();
+        for (DBuf<vec2>* b : { &xy, &xy2 }) b->release();
         for (DBuf<int>* b : { &orig, &orig2, &type2, &extmap, &nn_ext, &bin_rank }) b->release();
         for (DBuf<int>* b : { &type, &border_map, &ghost_code, &ghost_cnt, &ghost_off, &stencil,
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
