@@ -80,7 +80,8 @@ void        mdb_destroy(mdb_ctx* c);
  *  "force_variant" LJ full-list kernel: 1 (default; DP: 4 neighbors in flight, SP: branch-free), 8/9 branch-free U=4/2,
  *      0/2-7 older generations, 10-13 rolling software pipeline (k_force_lj_full_v7; bit-identical, measured slower).
  *  "merge" 2 = one list row per atom pair with membership bits (exact, slower; default 0).
- *  "eam_variant" 1 (default) packed spline rows + rsqrt, 0 = first kernels.
+ *  "eam_variant" 1 (default) packed spline rows + rsqrt, 0 = first kernels, 2 = packed (x, y) / (z, fp) gathers and
+ *      (value, slope) tables (single domain; A/B variant, not yet measured).
  *  "half_variant" LJ half-list kernel: 2 (default) 4 neighbors in flight, 1 = 2 in flight, 0 = first kernel.
  *  "fuse_integrate" (default 1) finalIntegrate(n) + initialIntegrate(n+1) in one pass inside mdb_run.
  *  "fuse_force" (default 1) inside mdb_run, LJ full lists of a single domain: computeForce(n) + finalIntegrate(n) +

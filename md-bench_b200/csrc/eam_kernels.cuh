@@ -326,4 +326,143 @@ __global__ void __launch_bounds__(128) k_eam_force_v2(int nlocal, real cutforces
     fz[i] = fiz;
 }
 
+// ---- generation 3 of the EAM passes (option eam_variant = 2; A/B, written after round 1's GPU budget was spent) -----------
+// ncu of generation 2: both passes sit at 89 % of the L1 data pipe; per listed pair the force pass issues 1 index load,
+// 4 scalar gathers (x, y, z, fp) and 3 vector loads of its own table row (96 B DP).  Here
+//  * x, y come from the packed (x, y) copy (k_pack_xy) and z, fp from a packed (z, fp) array that the density pass and
+//    the ghost-fp kernel write: 2 vector gathers per pair instead of 4 scalar ones (3 -> 2 in the density pass);
+//  * the force pass reads (value, slope) of rhor and z2r at the knots m and m+1 -- two adjacent 4-real rows -- and
+//    derives the cubic's coefficients in registers exactly as interpolate() does (eam_utils.c:269-274:
+//    c4 = 3 (f1 - f0) - 2 s0 - s1, c3 = s0 + s1 - 2 (f1 - f0)); the derivative is ((3 c3 p + 2 c4) p + c5) * rdr instead
+//    of the pre-divided coefficients (eam_utils.c:279-283), a last-bit difference.  64 B of table per pair instead of 96.
+template <class real>
+__global__ void k_eam_pack_vs(int rows, const real* __restrict__ rhor_spline, const real* __restrict__ z2r_spline, real* __restrict__ vs4)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= rows) return;
+    real* a = vs4 + (size_t)m * 4;
+    a[0] = rhor_spline[(size_t)m * 7 + 6]; a[1] = rhor_spline[(size_t)m * 7 + 5];
+    a[2] = z2r_spline[(size_t)m * 7 + 6];  a[3] = z2r_spline[(size_t)m * 7 + 5];
+}
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_eam_density_v3(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ rho4,
+    const real* __restrict__ frho_spline, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
+    const typename Vec2Of<real>::type* __restrict__ xy, const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
+    real* __restrict__ fp, typename Vec2Of<real>::type* __restrict__ zf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i];
+    const int nn  = numneigh[i];
+    const int* nb = nbT + L.base(i);
+    real rhoi     = 0;
+    for (int k = 0; k < nn; k += U) {
+        int j[U];
+        real rsq[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = k + u < nn ? __ldg(nb + (size_t)(k + u) * L.sk) : i;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const typename Vec2Of<real>::type p = __ldg(xy + j[u]);
+            const real dx = xt - p.x, dy = yt - p.y, dz = zt - __ldg(z + j[u]);
+            rsq[u] = dx * dx + dy * dy + dz * dz;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rsq[u] < cutforcesq && k + u < nn) {
+                const real r = rsq[u] * rsqrt_nr(rsq[u]);
+                real p = r * t.rdr + (real)1.0;
+                int m  = (int)(p);
+                m      = m < t.nr - 1 ? m : t.nr - 1;
+                p -= m;
+                p = p < (real)1.0 ? p : (real)1.0;
+                real s3, s4, s5, s6;
+                ld4(rho4 + (size_t)m * 4, s3, s4, s5, s6);
+                rhoi += ((s3 * p + s4) * p + s5) * p + s6;
+            }
+        }
+    }
+    real p = (real)1.0 * rhoi * t.rdrho + (real)1.0;
+    int m  = (int)(p);
+    m      = max(1, min(m, t.nrho - 1));
+    p -= m;
+    p = min(p, (real)1.0);
+    const real* s = frho_spline + m * 7;
+    const real f  = (__ldg(s + 0) * p + __ldg(s + 1)) * p + __ldg(s + 2);
+    fp[i]         = f;
+    typename Vec2Of<real>::type v;
+    v.x = zt; v.y = f;
+    zf[i] = v;
+}
+template <class real>
+__global__ void k_eam_ghost_fp_v3(int nlocal, int nghost, const int* __restrict__ border_map, const real* __restrict__ z,
+    real* __restrict__ fp, typename Vec2Of<real>::type* __restrict__ zf)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nghost) return;
+    const real f = fp[border_map[g]];
+    fp[nlocal + g] = f;
+    typename Vec2Of<real>::type v;
+    v.x = z[nlocal + g]; v.y = f;
+    zf[nlocal + g] = v;
+}
+template <class real, int U>
+__global__ void __launch_bounds__(128) k_eam_force_v3(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ vs4,
+    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const real* __restrict__ fp,
+    const typename Vec2Of<real>::type* __restrict__ xy, const typename Vec2Of<real>::type* __restrict__ zf,
+    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* __restrict__ fx, real* __restrict__ fy,
+    real* __restrict__ fz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
+    const real xt = x[i], yt = y[i], zt = z[i], fpi = fp[i];
+    const int nn  = numneigh[i];
+    const int* nb = nbT + L.base(i);
+    real fix = 0, fiy = 0, fiz = 0;
+    for (int k = 0; k < nn; k += U) {
+        int j[U];
+        real dx[U], dy[U], dz[U], rsq[U], fpj[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = k + u < nn ? __ldg(nb + (size_t)(k + u) * L.sk) : i;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const typename Vec2Of<real>::type p = __ldg(xy + j[u]), q = __ldg(zf + j[u]);
+            dx[u] = xt - p.x; dy[u] = yt - p.y; dz[u] = zt - q.x;
+            fpj[u] = q.y;
+            rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rsq[u] < cutforcesq && k + u < nn) {
+                const real recip = rsqrt_nr(rsq[u]);
+                const real r     = rsq[u] * recip;
+                real p           = r * t.rdr + (real)1.0;
+                int m            = (int)(p);
+                m                = m < t.nr - 1 ? m : t.nr - 1;
+                p -= m;
+                p = p < (real)1.0 ? p : (real)1.0;
+                real rf0, rs0, zf0, zs0, rf1, rs1, zf1, zs1;
+                ld4(vs4 + (size_t)m * 4, rf0, rs0, zf0, zs0);
+                ld4(vs4 + (size_t)m * 4 + 4, rf1, rs1, zf1, zs1);
+                const real dr_ = rf1 - rf0, dz_ = zf1 - zf0;
+                const real rc4 = (real)3.0 * dr_ - (real)2.0 * rs0 - rs1, rc3 = rs0 + rs1 - (real)2.0 * dr_;
+                const real zc4 = (real)3.0 * dz_ - (real)2.0 * zs0 - zs1, zc3 = zs0 + zs1 - (real)2.0 * dz_;
+                const real rhoip = (((real)3.0 * rc3 * p + (real)2.0 * rc4) * p + rs0) * t.rdr;
+                const real z2p   = (((real)3.0 * zc3 * p + (real)2.0 * zc4) * p + zs0) * t.rdr;
+                const real z2    = ((zc3 * p + zc4) * p + zs0) * p + zf0;
+                const real phi   = z2 * recip;
+                const real phip  = z2p * recip - phi * recip;
+                const real psip  = fpi * rhoip + fpj[u] * rhoip + phip;
+                const real fpair = -psip * recip;
+                fix += dx[u] * fpair;
+                fiy += dy[u] * fpair;
+                fiz += dz[u] * fpair;
+            }
+        }
+    }
+    fx[i] = fix;
+    fy[i] = fiy;
+    fz[i] = fiz;
+}
+
 } // namespace mdb

@@ -87,8 +87,11 @@ template <class real> struct Sim final : SimBase {
     // ---- eam ----
     EamTables<real> eam;
     DBuf<real> fp, rhor_spline, frho_spline, z2r_spline, eam_rho4, eam_frc12; // + repacked rows for the v2 kernels
+    DBuf<real> eam_vs4; // (value, slope) of rhor and z2r per knot, generation-3 force pass (eam_variant 2)
+    DBuf<vec2> eam_zf;  // packed (z, fp) of locals and ghosts, generation 3
     int half_variant = 2; // option "half_variant": 0 first kernel, 1 v2 with 2 neighbors in flight, 2 (default) 4 in flight
-    int eam_variant = 1; // option "eam_variant": 0 = first kernels (scalar table gathers, IEEE sqrt / division), 1 = v2
+    int eam_variant = 1; // option "eam_variant": 0 = first kernels (scalar table gathers, IEEE sqrt / division), 1 = v2,
+                         // 2 = generation 3 (packed gathers, (value, slope) tables; single domain; not yet measured)
     // ---- scratch ----
     int* h_flags      = nullptr; // pinned: [0] ghost total, [1] max neighbors, [2] max bin count
     DBuf<int> d_flags;
@@ -123,8 +126,8 @@ template <class real> struct Sim final : SimBase {
                  &svz, &stage, &fp, &rhor_spline, &frho_spline, &z2r_spline, &eam_rho4, &eam_frc12, &x2, &y2, &z2, &vx2, &vy2,
                  &vz2, &fx2, &fy2, &fz2, &tx, &ty, &tz })
             b->release();
-        for (DBuf<real>* b : { &zg, &zg2 }) b->release();
-        for (DBuf<vec2>* b : { &xy, &xy2 }) b->release();
+        for (DBuf<real>* b : { &zg, &zg2, &eam_vs4 }) b->release();
+        for (DBuf<vec2>* b : { &xy, &xy2, &eam_zf }) b->release();
         for (DBuf<int>* b : { &orig, &orig2, &type2, &extmap, &nn_ext, &bin_rank }) b->release();
         for (DBuf<int>* b : { &type, &border_map, &ghost_code, &ghost_cnt, &ghost_off, &stencil,
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
@@ -958,7 +961,7 @@ template <class real> struct Sim final : SimBase {
     {
         if (!eam.ready) throw Error("computeForceEam: no EAM tables (call mdb_setEam first)");
         fp.ensure((size_t)Nlocal + Nghost, false, stream);
-        if (eam_variant == 1)
+        if (eam_variant >= 1) // (generation 3 is single-domain only: a brick runs generation 2)
             MDB_LAUNCH(launches, (k_eam_density_v2<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
                 eam_rho4.p, frho_spline.p, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fp.p);
         else
@@ -967,16 +970,34 @@ template <class real> struct Sim final : SimBase {
     }
     void eam_force() // force_eam.c:127-224
     {
-        if (eam_variant == 1)
+        if (eam_variant >= 1)
             MDB_LAUNCH(launches, (k_eam_force_v2<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
                 eam_frc12.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
         else
         MDB_LAUNCH(launches, k_eam_force<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
             eam, rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
     }
+    void launch_eam_v3() // generation 3: see eam_kernels.cuh
+    {
+        if (!eam.ready) throw Error("computeForceEam: no EAM tables (call mdb_setEam first)");
+        const int nall = Nlocal + Nghost;
+        fp.ensure((size_t)nall, false, stream);
+        xy.ensure(x.cap, false, stream);
+        eam_zf.ensure(x.cap, false, stream);
+        xy_valid = false; // the packed (x, y) copy is rebuilt for every force call here
+        MDB_LAUNCH(launches, k_pack_xy<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, xy.p);
+        MDB_LAUNCH(launches, (k_eam_density_v3<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
+            eam_rho4.p, frho_spline.p, x.p, y.p, z.p, xy.p, numneigh.p, neighbors.p, LL, fp.p, eam_zf.p);
+        if (Nghost) // force_eam.c:118-120
+            MDB_LAUNCH(launches, k_eam_ghost_fp_v3<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost, border_map.p, z.p,
+                fp.p, eam_zf.p);
+        MDB_LAUNCH(launches, (k_eam_force_v3<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
+            eam_vs4.p, x.p, y.p, z.p, fp.p, xy.p, eam_zf.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+    }
     void launch_eam()
     {
         if (brick) throw Error("computeForceEam on a brick goes through the decomposition (fp exchange)");
+        if (eam_variant == 2) { launch_eam_v3(); return; }
         eam_density();
         if (Nghost) // force_eam.c:118-120
             MDB_LAUNCH(launches, k_eam_ghost_fp<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost,
@@ -1295,6 +1316,8 @@ template <class real> struct Sim final : SimBase {
         eam_frc12.ensure((size_t)rows * 12, false, stream);
         MDB_LAUNCH(launches, k_eam_pack_tables<real>, grid_for(rows, 128), 128, 0, stream, rows, rhor_spline.p, z2r_spline.p,
             eam_rho4.p, eam_frc12.p);
+        eam_vs4.ensure((size_t)rows * 4, false, stream);
+        MDB_LAUNCH(launches, k_eam_pack_vs<real>, grid_for(rows, 128), 128, 0, stream, rows, rhor_spline.p, z2r_spline.p, eam_vs4.p);
         MDB_CUDA(cudaStreamSynchronize(stream));
         h_rhor = rh; h_frho = fr; h_z2r = z2;
         eam.ready = true;

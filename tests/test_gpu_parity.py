@@ -340,6 +340,37 @@ def test_cuda_eam_lattice(golden_dir, sort):
     s.close()
 
 
+@pytest.mark.skipif(not os.environ.get("MDB_TEST_EXPERIMENTAL"),
+                    reason="A/B kernels written after the round's GPU budget was spent; set MDB_TEST_EXPERIMENTAL=1 to run")
+@pytest.mark.parametrize("dp", [True, False])
+def test_experimental_eam_generation3_matches_generation2(golden_dir, dp):
+    """eam_variant 2 (packed (x, y) / (z, fp) gathers, (value, slope) tables with the cubic's coefficients derived in
+    registers) against the default EAM kernels: forces after setup and a 60-step run, to rounding (the derivative is
+    evaluated as ((3 c3 p + 2 c4) p + c5) * rdr instead of with pre-divided coefficients)"""
+    from cases import funcfl_args
+    g = np.load(os.path.join(golden_dir, "eam_cu_nx5.npz"))
+    m = load_pkg()
+    sims = []
+    for variant in (1, 2):
+        s = make_sim(dp, True, True, force_field=m.FF_EAM, nx=6, ny=6, nz=6, ntimes=60)
+        s.setOption("eam_variant", variant)
+        s.setEam(*funcfl_args(g))
+        s.createAtom(); s.setup(adjust=True)
+        s.computeForce()
+        sims.append(s)
+    a, b = sims
+    fa, fb = a.get("f"), b.get("f")
+    # the t = 0 lattice forces are cancellation noise: compare against the scale of a thermalised step below
+    ra, _ = a.run(60)
+    rb, _ = b.run(60)
+    tol = 1e-10 if dp else 1e-4
+    fa, fb = a.get("f"), b.get("f")
+    assert np.abs(fa - fb).max() <= tol * np.abs(fa).max()
+    assert np.abs(ra[:, 1:] - rb[:, 1:]).max() <= tol * np.abs(ra[:, 1:]).max()
+    assert np.abs(a.get("v") - b.get("v")).max() <= (1e-9 if dp else 1e-3) * np.abs(a.get("v")).max()
+    a.close(); b.close()
+
+
 def test_cuda_eam_copper_melting_200_steps(golden_dir):
     """BASELINE config 4: copper_melting (32 000 atoms from the LAMMPS dump), Cu_u3 funcfl, 200 steps:
     the reference's `step temp pressure` lines and the oracle on the first 25 steps."""
