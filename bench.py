@@ -236,18 +236,19 @@ def clusterpair_secondary(m, args, local, stream, steps=2):
     flop = (8.0 * 0.5 * (cp0 + cp1) * 16 + 15.0 * 0.5 * (in0 + in1)) / natoms
     peak = m.measure_fma_peak(m.SP, local)
     ach = flop * natoms / (f_ms * 1e-3) * 1e-12
-    traffic = None
+    traffic, ncu_pipes = None, None
     try:
         te = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("clusterpair/sp/%d" % args.nx, {})
         if "true" in te.get("kernel", "") or "1>" in te.get("kernel", ""):   # a capture of the fused kernel <N, FI = true>
             traffic = te.get("bytes")
+            ncu_pipes = te.get("ncu")
     except Exception:
         pass
     out = {"metric": METRIC_CP % (4, 4), "config": "BASELINE config 2 physics (clusterpair 4x4, SP, full lists) at %d^3 unit cells" % args.nx,
            "value": natoms * args.ntimes * steps / (ms * 1e-3), "unit": UNIT, "dtype": "f32", "steps": steps,
            "ms_per_step": ms / steps,
            "roofline": {"kernel": "k_cp_force_lj_sp_packed<4, FI> (LJ tile force with finalIntegrate(n) + initialIntegrate(n+1) in its epilogue)", "bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak if peak else None, "traffic": traffic, "ms_per_launch": f_ms, "flop_per_atom_step": flop,
+                        "frac": ach / peak if peak else None, "traffic": traffic, "ncu_capture": ncu_pipes, "ms_per_launch": f_ms, "flop_per_atom_step": flop,
                         "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
                         "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"])},
            "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
@@ -387,7 +388,7 @@ def main():
     except Exception:
         pass
     ach_gbs = BYTES_PER_ATOM_STEP[args.precision] * per_launch_atoms / (f_ms * 1e-3) * 1e-9
-    traffic, traffic_src = None, None
+    traffic, traffic_src, ncu_pipes = None, None, None
     try:   # DRAM bytes of one launch from the committed ncu --set full capture of this very configuration, if there is one
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         te = tj.get("%s/%s/%d" % (args.scheme, args.precision, args.nx))
@@ -395,6 +396,7 @@ def main():
             # only a capture of the kernel that actually runs counts (the fused kernels replaced the session-3 ones)
             if cp or not fused_force or "_fi" in te.get("kernel", ""):
                 traffic, traffic_src = te["bytes"], te["source"]
+                ncu_pipes = te.get("ncu")
     except Exception:
         pass
     roofline = {"kernel": ("k_cp_force_lj<%s,%d,%s>" % ("double" if dp else "float", args.cluster_n, "half" if args.half else "full")) if cp
@@ -403,6 +405,8 @@ def main():
                 else "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
                 "bound": "fp64" if dp else "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
+                # pipe utilisations of the SAME committed ncu --set full capture the traffic comes from (not measured in this run)
+                "ncu_capture": ncu_pipes,
                 "algorithmic_bytes_per_launch": BYTES_PER_ATOM_STEP[args.precision] * per_launch_atoms if not cp else None,
                 "peak_source": "measured in this run: FMA issue micro-benchmark (md-bench_b200/csrc/peaks.cu)",
                 "ms_per_launch": f_ms, "flop_per_atom_step": flop_per_atom,

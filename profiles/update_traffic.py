@@ -27,7 +27,20 @@ with open(summ, "w") as f:
     f.write(subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "summarize.py"), "raw", rep], capture_output=True, text=True).stdout)
 path = os.path.join(ROOT, "profiles", "traffic.json")
 tj = json.load(open(path))
+def num(name):
+    return float(r[hdr.index(name)].replace(",", "")) if name in hdr else None
+
+
+dur_i = hdr.index("gpu__time_duration.sum")
+dur = float(r[dur_i].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[dur_i].lower(), 1.0)
 tj[key] = {"bytes": int(rd + wr), "kernel": kernel,
-           "source": "%s (%.3f GB read + %.2f MB write)" % (os.path.relpath(summ, ROOT), rd / 1e9, wr / 1e6)}
+           "source": "%s (%.3f GB read + %.2f MB write)" % (os.path.relpath(summ, ROOT), rd / 1e9, wr / 1e6),
+           "ncu": {"duration_ms": dur,
+                   "fp64_pipe_pct": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                   "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                   "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "l1tex_throughput_pct": num("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+                   "dram_throughput_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                   "registers_per_thread": num("launch__registers_per_thread")}}
 json.dump(tj, open(path, "w"), indent=1)
 print(key, tj[key])
