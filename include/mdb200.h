@@ -91,7 +91,11 @@ void        mdb_destroy(mdb_ctx* c);
  *  "xy_gather" (default 1) the fused kernel fetches a neighbor's x and y with one 2-element vector gather from a packed
  *      (x, y) copy of the positions (kept current by its own epilogue and by updatePbc) instead of two scalar gathers:
  *      fewer L1 wavefronts per pair.  Bit-identical.
- *  "sort_rows" 1 = sort every neighbor row by index after the build (default 0). */
+ *  "sort_rows" 1 = sort every neighbor row by index after the build (default 0).
+ *  "lazy_ops" (default 0; written after round 1's GPU budget was spent, not yet validated on a GPU) for drivers that keep
+ *      the reference's operator-by-operator loop: mdb_computeForce and mdb_finalIntegrate only record that they are due;
+ *      if the next call is mdb_initialIntegrate the three run as the one fused kernel of mdb_run, any other entry point
+ *      first launches them separately, in order.  Same results; mdb_computeForce then returns 0 s. */
 int         mdb_setOption(mdb_ctx* c, const char* name, double value);
 /* run all work of this ctx on the given cudaStream_t (passed as void*); NULL = ctx-owned stream */
 int         mdb_setStream(mdb_ctx* c, void* cuda_stream);

@@ -14,15 +14,21 @@ namespace mdb {
 void set_last_error(const char* msg) { g_err = msg; } // for the other translation units of the C ABI (cp_sim.cu)
 }
 
-#define MDB_TRY(body)                                                                            \
+// Every entry point first launches what the lazy operators still owe (sim.cuh) and marks the gather copies stale;
+// MDB_TRY_KEEP (updatePbc: it refreshes the copies' ghost range itself) and MDB_TRY_LAZY (the three lazy operators) differ.
+#define MDB_TRY_(pre, body)                                                                      \
     try {                                                                                        \
         if (!c || !c->sim) throw Error("null mdb_ctx");                                          \
+        pre;                                                                                     \
         body;                                                                                    \
         return 0;                                                                                \
     } catch (const std::exception& e) {                                                          \
         g_err = e.what();                                                                        \
         return -1;                                                                               \
     }
+#define MDB_TRY(body) MDB_TRY_(c->sim->flush_lazy(); c->sim->invalidate_copies(), body)
+#define MDB_TRY_KEEP(body) MDB_TRY_(c->sim->flush_lazy(), body)
+#define MDB_TRY_LAZY(body) MDB_TRY_((void)0, body)
 
 extern "C" {
 
@@ -120,7 +126,7 @@ int mdb_computeThermo(mdb_ctx* c, double* T, double* P) { MDB_TRY(c->sim->comput
 
 int mdb_setupNeighbor(mdb_ctx* c) { MDB_TRY(c->sim->setupNeighbor()) }
 int mdb_setupPbc(mdb_ctx* c) { MDB_TRY(c->sim->setupPbc()) }
-int mdb_updatePbc(mdb_ctx* c, int) { MDB_TRY(c->sim->updatePbc()) }
+int mdb_updatePbc(mdb_ctx* c, int) { MDB_TRY_KEEP(c->sim->updatePbc()) }
 int mdb_updateAtomsPbc(mdb_ctx* c, int) { MDB_TRY(c->sim->updateAtomsPbc()) }
 int mdb_buildNeighbor(mdb_ctx* c) { MDB_TRY(c->sim->buildNeighbor()) }
 
@@ -128,7 +134,7 @@ static double force_call(mdb_ctx* c, int which)
 {
     try {
         if (!c || !c->sim) throw Error("null mdb_ctx");
-        return c->sim->computeForce(which);
+        return c->sim->abi_computeForce(which);
     } catch (const std::exception& e) {
         g_err = e.what();
         return -1.0;
@@ -138,8 +144,8 @@ double mdb_computeForce(mdb_ctx* c) { return force_call(c, FORCE_DISPATCH); }
 double mdb_computeForceLJFullNeigh(mdb_ctx* c) { return force_call(c, FORCE_LJ_FULL); }
 double mdb_computeForceLJHalfNeigh(mdb_ctx* c) { return force_call(c, FORCE_LJ_HALF); }
 double mdb_computeForceEam(mdb_ctx* c) { return force_call(c, FORCE_EAM); }
-int mdb_initialIntegrate(mdb_ctx* c, int) { MDB_TRY(c->sim->initialIntegrate()) }
-int mdb_finalIntegrate(mdb_ctx* c, int) { MDB_TRY(c->sim->finalIntegrate()) }
+int mdb_initialIntegrate(mdb_ctx* c, int) { MDB_TRY_LAZY(c->sim->abi_initialIntegrate()) }
+int mdb_finalIntegrate(mdb_ctx* c, int) { MDB_TRY_LAZY(c->sim->abi_finalIntegrate()) }
 
 int mdb_setup(mdb_ctx* c, int adjust) { MDB_TRY(c->sim->setup(adjust != 0)) }
 int mdb_reneighbour(mdb_ctx* c) { MDB_TRY(c->sim->reneighbour()) }

@@ -50,6 +50,16 @@ struct SimBase {
     virtual void getEamFp(void* fp, bool ghosts)                                             = 0;
     virtual void setOption(const char* name, double value)                                   = 0;
     virtual void stubNeighbors(int pattern, int nneighs, int nreps, unsigned seed)           = 0;
+    // Lazy operators (option "lazy_ops"): the reference's loop calls computeForce, finalIntegrate and initialIntegrate one
+    // after the other through its function pointers (verletlist/main.c:258-273).  With lazy_ops the first two only record
+    // that they are due; if the next call is initialIntegrate the three run as the ONE fused kernel mdb_run uses, else
+    // flush_lazy() (called by the C ABI before every other entry point) launches them separately, in order.  Same results
+    // bit for bit; computeForce then returns 0 s (nothing has been launched yet).
+    virtual double abi_computeForce(int which) { return computeForce(which); }
+    virtual void abi_finalIntegrate() { finalIntegrate(); }
+    virtual void abi_initialIntegrate() { initialIntegrate(); }
+    virtual void flush_lazy() {}
+    virtual void invalidate_copies() {} // a call from outside may have changed positions: gather copies are stale
 
     bool timing             = false;
     double force_ms         = 0, neigh_ms = 0;

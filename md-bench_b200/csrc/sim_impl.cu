@@ -1135,6 +1135,40 @@ template <class real> struct Sim final : SimBase {
             force_ms += ms;
         }
     }
+    // ---- lazy operators (sim.cuh): the function-pointer loop of the reference gets the fused kernel too ----
+    bool lazy_ops = false, pending_force = false, pending_final = false;
+    double abi_computeForce(int which) override
+    {
+        flush_lazy();
+        const bool lj_full = which == FORCE_LJ_FULL || (which == FORCE_DISPATCH && P.force_field != MDB_FF_EAM && !P.half_neigh);
+        if (lazy_ops && lj_full && can_fuse_force() && nstride != 0) {
+            pending_force = true; // due; launched by the next initialIntegrate (fused) or by flush_lazy()
+            return 0.0;
+        }
+        return computeForce(which);
+    }
+    void abi_finalIntegrate() override
+    {
+        if (pending_force && !pending_final) { pending_final = true; return; }
+        flush_lazy();
+        finalIntegrate();
+    }
+    void abi_initialIntegrate() override
+    {
+        if (pending_force && pending_final) {
+            pending_force = pending_final = false;
+            forceFinalInitialIntegrate();
+            return;
+        }
+        flush_lazy();
+        initialIntegrate();
+    }
+    void flush_lazy() override
+    {
+        if (pending_force) { pending_force = false; launch_force(FORCE_DISPATCH); }
+        if (pending_final) { pending_final = false; finalIntegrate(); }
+    }
+    void invalidate_copies() override { xy_valid = false; }
     void finalInitialIntegrate() // finalIntegrate(n) + initialIntegrate(n+1) in one pass
     {
         xy_valid = false;
@@ -1402,6 +1436,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else if (!strcmp(name, "xy_gather")) xy_gather = (int)v;
+        else if (!strcmp(name, "lazy_ops")) { flush_lazy(); lazy_ops = v != 0; }
         else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
         else if (!strcmp(name, "merge")) merge = (int)v;
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;

@@ -154,6 +154,8 @@ int main(int argc, char** argv)
     }
 
     if (operators) {
+        /* MDB_LAZY_OPS=1: keep this loop, let the library fuse computeForce + finalIntegrate + initialIntegrate (mdb200.h) */
+        if (getenv("MDB_LAZY_OPS") != NULL && mdb_setOption(atom.d_atom, "lazy_ops", 1.0) != 0) mdb_die("lazy_ops");
         computeThermo(0, &param, &atom);
         timer[FORCE] = computeForce(&param, &atom, &neighbor, &stats);
         timer[NEIGH] = 0.0;
