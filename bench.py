@@ -144,12 +144,17 @@ def cpu_baseline(sample_nx=64, sample_steps=40):
 
 
 def reference_arm(args, rank, world):
+    """The reference's own CPU build (oracle/_ref/MDBench-vl_dp_aos: GCC -Ofast AVX-512, OpenMP) on the host cores of the box.
+    Each bench step is a BOUNDED SAMPLE of the GPU arm's workload: the same per-GPU box (nx = --ref-nx, default the GPU arm's
+    128) for --ref-ntimes (20) timesteps = one rebuild interval instead of 200 timesteps (ten of them); the metric is
+    normalised per atom-step.  `config` says what this arm ran; `ms_per_step` is the wall time of the reference process
+    (start-up, lattice generation and first list build included) while `value` uses the TOTAL the reference itself reports
+    (verletlist/main.c:337-338), exactly like its "Performance" line."""
     if rank != 0:
         return 0
     thr = host_threads()
     total_steps = args.steps + args.warmup
-    # bounded sample per step: ~8 s of CPU work -> the whole run stays within a few minutes
-    nx, nt = args.ref_nx, args.ref_ntimes
+    nx, nt = (args.ref_nx or args.nx), args.ref_ntimes
     runs = []
     kind = "reference"
     for i in range(total_steps):
@@ -163,12 +168,21 @@ def reference_arm(args, rank, world):
     atom_steps = sum(r["atoms"] * r["ntimes"] for r in runs)
     tsum = sum(r["total_s"] for r in runs)
     val = atom_steps / tsum
-    sample = ("reference MDBench-vl_dp_aos Cu FCC %d^3 x %d steps per bench step" % (nx, nt)) if kind == "reference" \
+    if kind != "reference":
+        nx, nt = 32, 20
+    sample = ("reference MDBench-vl_dp_aos Cu FCC %d^3 x %d timesteps per bench step (GPU arm: %d^3 per GPU x %d timesteps)"
+              % (nx, nt, args.nx, args.ntimes)) if kind == "reference" \
         else "oracle restatement Cu FCC 32^3 x 20 steps per bench step"
+    cfg = workload_config(args, world)
+    cfg["workload"] = ("Cu FCC %dx%dx%d unit cells (%d atoms) on the host CPU, LJ sigma=eps=1 rc=2.5 skin=0.3, reneigh 20, verletlist full "
+                       "neighbor lists, DP, %d timesteps per bench step: a bounded sample of the GPU arm's workload (%d^3 unit cells "
+                       "per GPU, %d timesteps per bench step); atom-steps/s is size-normalised" % (nx, nx, nx, 4 * nx ** 3, nt, args.nx, args.ntimes))
+    cfg.update({"nx_per_gpu": nx, "ntimes": nt, "ntimes_gpu_arm": args.ntimes, "nx_per_gpu_gpu_arm": args.nx,
+                "global_box": "%dx%dx%d unit cells = %d atoms" % (nx, nx, nx, 4 * nx ** 3), "parallelism": "%d OpenMP threads" % thr})
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(r["wall_s"] for r in runs) / max(1, len(runs)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": cfg,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -256,6 +270,130 @@ def clusterpair_secondary(m, args, local, stream, steps=2):
     return out
 
 
+
+def verletlist_secondary(m, args, local, stream, name, precision="dp", half=0, eam=False, steps=2):
+    """one more verletlist configuration at the same per-GPU box: `steps` timed bench steps (state restore + setup + `ntimes`
+    timesteps, device-resident) and the force kernel's time per launch against its roofline.  Algorithmic work per atom-step
+    (SURVEY 8d): LJ full 8 L + 15 C; LJ half: every local-local pair once + 6 flop per reaction update; EAM: pass 1 8 L + 14 C,
+    pass 2 8 L + 40 C (L listed, C in-cutoff pairs per atom, counted live)."""
+    import numpy as np
+    import torch
+    dp = precision == "dp"
+    kw = dict(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx, ntimes=args.ntimes, half_neigh=half)
+    if eam:
+        kw["force_field"] = m.FF_EAM
+    sim = m.Simulation(m.default_params(**kw), device=local)
+    sim.setStream(stream)
+    if eam:   # BASELINE config 4 physics: Cu_u3 funcfl tables (committed fixture made from the reference's data/Cu_u3.eam)
+        g = np.load(os.path.join(ROOT, "tests", "golden", "eam_cu_nx5.npz"))
+        sim.setEam(int(g["funcfl_nrho"]), float(g["funcfl_drho"]), int(g["funcfl_nr"]), float(g["funcfl_dr"]), float(g["funcfl_cut"]),
+                   float(g["funcfl_mass"]), g["funcfl_frho"], g["funcfl_zr"], g["funcfl_rhor"])
+    natoms = sim.createAtom()
+    sim.setup(adjust=True)
+    sim.saveState()
+    l0, c0 = sim.countPairs()
+
+    def one():
+        sim.restoreState()
+        sim.setup(adjust=False)
+        return sim.run(args.ntimes)
+
+    one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        rec, _ = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    l1, c1 = sim.countPairs()
+    sim.setTiming(True)
+    sim.resetKernelStats()
+    _, tm = one()
+    ks = sim.kernelStats()
+    sim.setTiming(False)
+    sim.close()
+    f_ms = ks["force_ms"] / max(1, ks["force_launches"])
+    L, C = 0.5 * (l0 + l1) / natoms, 0.5 * (c0 + c1) / natoms     # stored entries / in-cutoff entries per atom
+    T = 8 if dp else 4
+    if eam:
+        flop, nbytes, kernel = 16 * L + 54 * C, 2 * 4 * L + 8 + 8 * T, "k_eam_density_v3 + k_eam_ghost_fp_v3 + k_eam_force_v3 (three passes, one force call)"
+    elif half:
+        flop, nbytes, kernel = 8 * L + 21 * C, 4 * L + 4 + 9 * T, "k_force_lj_half_v2 (reaction forces by RED.ADD)"
+    else:
+        flop, nbytes, kernel = 8 * L + 15 * C, 4 * L + 4 + 6.3 * T, "k_force_lj_full_fi<%s> (fused force + integrate)" % ("double" if dp else "float")
+    peak = m.measure_fma_peak(m.DP if dp else m.SP, local)
+    ach = flop * natoms / (f_ms * 1e-3) * 1e-12
+    return {"name": name, "metric": METRIC if not eam else "atom-steps/sec (EAM Cu FCC, verletlist, three passes)",
+            "config": "%s at %d^3 unit cells (%d atoms), %s, %d timesteps per bench step" % (name, args.nx, natoms, precision.upper(), args.ntimes),
+            "value": natoms * args.ntimes * steps / (ms * 1e-3), "unit": UNIT, "dtype": "f64" if dp else "f32", "steps": steps,
+            "ms_per_step": ms / steps,
+            "roofline": {"kernel": kernel, "bound": "fp64" if dp else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": ach / peak if peak else None, "traffic": None, "ms_per_launch": f_ms, "flop_per_atom_step": flop,
+                         "algorithmic_bytes_per_atom_step": nbytes, "hbm_gbs": nbytes * natoms / (f_ms * 1e-3) * 1e-9,
+                         "pairs_per_atom": {"stored": L, "in_cutoff": C},
+                         "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
+                         "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"])},
+            "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
+
+
+def reference_cuda(args):
+    """the reference's OWN CUDA variant (TOOLCHAIN=NVCC verletlist, rebuilt for sm_100 from the reference sources
+    by oracle/Makefile ref-cuda, NUM_THREADS=128) on the same GPU with the same command line as the GPU arm's workload."""
+    from refbind import ref_binary
+    exe = ref_binary("vl_%s_aos-cuda" % args.precision)
+    if exe is None:
+        return {"unavailable": "oracle/_ref/MDBench-vl_%s_aos-cuda not built" % args.precision}
+    cmd = [exe, "-nx", str(args.nx), "-ny", str(args.nx), "-nz", str(args.nx), "-n", str(args.ntimes)]
+    t0 = time.perf_counter()
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
+    except (OSError, subprocess.TimeoutExpired) as e:
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    wall = time.perf_counter() - t0
+    mm = re.search(r"TOTAL ([0-9.]+)s FORCE ([0-9.]+)s NEIGH ([0-9.]+)s", out)
+    pp = re.search(r"Performance: ([0-9.]+) million atom updates per second", out)
+    if not (mm and pp):
+        return {"unavailable": "no report line in the output of %s" % " ".join(cmd)}
+    nreb = max(1, args.ntimes // 20)
+    return {"value": float(pp.group(1)) * 1e6, "unit": UNIT, "binary": "oracle/_ref/" + os.path.basename(exe),
+            "command": " ".join(os.path.basename(c) if c == exe else c for c in cmd),
+            "total_s": float(mm.group(1)), "force_s": float(mm.group(2)), "neigh_s": float(mm.group(3)),
+            "force_ms_per_call": 1e3 * float(mm.group(2)) / (args.ntimes + 1), "neigh_ms_per_rebuild": 1e3 * float(mm.group(3)) / nreb,
+            "wall_s": wall, "note": "the reference's kernels (forceCuda.cu / neighborCuda.cu) with its host-side binning and ghost setup; "
+                                    "unmodified sources, compiled for sm_100"}
+
+
+def parity_check(m, dist, rank, world, local, stream):
+    """BASELINE config 1 exactly as stated (Cu FCC 32^3, 200 timesteps, DP) through the SAME path the timed run uses -- one
+    domain at N = 1, one brick per GPU with the peer-store halo / NCCL migration at N > 1 -- against the reference's own
+    numbers (tests/golden/thermo_lj.json, generated from the reference build): final T and P to rel 1e-10."""
+    gold = [q for q in json.load(open(os.path.join(ROOT, "tests", "golden", "thermo_lj.json")))
+            if q["variant"] == "vl_dp_aos" and q["nx"] == 32 and q["half"] == 0][0]
+    P = m.default_params(precision=m.DP, nx=32, ny=32, nz=32, ntimes=200)
+    if world > 1:
+        uid = [m.dd_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim = m.Decomposition(P, m.dd_grid(world), nprocs=world, proc=rank, nccl_id=uid[0], device=local)
+        path = "%dx%dx%d bricks, one per GPU: peer-store halo, NCCL migration" % m.dd_grid(world)
+    else:
+        sim = m.Simulation(P, device=local)
+        path = "one domain"
+    sim.setStream(stream)
+    sim.createAtom()
+    sim.setup(adjust=True)
+    rec, _ = sim.run(200)
+    sim.close()
+    T, Pr = float(rec[-1][1]), float(rec[-1][2])
+    rt, rp = abs(T - gold["T_full"]) / gold["T_full"], abs(Pr - gold["P_full"]) / gold["P_full"]
+    printed = all(abs(a[1] - b[1]) <= 6e-7 * b[1] and abs(a[2] - b[2]) <= 6e-7 * b[2] for a, b in zip(rec, gold["records"]))
+    return {"case": "BASELINE config 1: Cu FCC 32^3 (131072 atoms), LJ, DP, 200 timesteps, verletlist full lists", "path": path,
+            "T": T, "P": Pr, "T_ref": gold["T_full"], "P_ref": gold["P_full"], "rel_T": rt, "rel_P": rp, "tol": 1e-10,
+            "printed_records_equal": bool(printed and len(rec) == len(gold["records"])),
+            "ok": bool(rt <= 1e-10 and rp <= 1e-10 and printed), "reference": "tests/golden/thermo_lj.json (reference build vl_dp_aos)"}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -267,7 +405,7 @@ def main():
     ap.add_argument("--ntimes", type=int, default=200)
     ap.add_argument("--precision", default="dp", choices=["dp", "sp"])
     ap.add_argument("--half", type=int, default=0)
-    ap.add_argument("--ref-nx", type=int, default=64)
+    ap.add_argument("--ref-nx", type=int, default=0, help="box of the reference arm (0 = the GPU arm's --nx)")
     ap.add_argument("--ref-ntimes", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -277,6 +415,7 @@ def main():
     ap.add_argument("--scheme", default="verletlist", choices=["verletlist", "clusterpair"],
                     help="OPT_SCHEME of the reference; clusterpair = GROMACS-style 4 x N cluster pairs (one GPU)")
     ap.add_argument("--cluster-n", type=int, default=4, choices=[4, 8])
+    ap.add_argument("--no-parity", action="store_true", help="skip the config-1 parity run that precedes the timed region")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the secondary measurement (BASELINE config 2 physics: clusterpair 4x4 SP at the same box)")
     args = ap.parse_args()
@@ -301,6 +440,12 @@ def main():
     cp = args.scheme == "clusterpair"
     if cp and decomposed:
         raise SystemExit("bench.py: the clusterpair scheme runs one domain per GPU (no decomposition yet)")
+    parity = None
+    if not cp and not args.no_parity and args.bricks is None:
+        try:
+            parity = parity_check(m, dist, rank, world, local, stream)
+        except Exception as e:   # reported, never hidden: a failed check makes the line say so
+            parity = {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
     if cp:
         grid = (1, 1, 1)
         P = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx,
@@ -366,7 +511,7 @@ def main():
 
     # ---- roofline of the dominant kernel (LJ force): CUDA-event time per launch, measured live ----
     fused_force = not cp and not args.half and not any(
-        kv.split("=")[0] in ("fuse_force", "fuse_integrate", "force_variant", "merge") for kv in args.opt)
+        kv.split("=")[0] in ("fuse_force", "fuse_integrate") for kv in args.opt)
     sim.setTiming(True)
     sim.resetKernelStats()
     _, tm = one_step()
@@ -494,7 +639,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference", "sample": "failed: %s" % e}
 
     # ---- secondary: BASELINE config 2 physics (clusterpair 4x4, SP) at the same per-GPU box, N = 1 only ----
-    secondary = None
+    secondary, secondaries, ref_cuda = None, None, None
     if world == 1 and not decomposed and not cp and not args.no_secondary:
         sim.close()
         sim = None
@@ -502,12 +647,25 @@ def main():
             secondary = clusterpair_secondary(m, args, local, stream)
         except Exception as e:   # the primary line must not depend on the secondary measurement
             secondary = {"error": "%s: %s" % (type(e).__name__, e)}
+        # the other BASELINE configurations' physics at the same box (configs 1 SP, 3 half lists, 4 EAM), each with its roofline
+        secondaries = []
+        for kw in (dict(name="verletlist LJ full lists SP", precision="sp"),
+                   dict(name="verletlist LJ half lists DP (BASELINE config 3 physics)", precision="dp", half=1),
+                   dict(name="verletlist EAM DP (BASELINE config 4 physics, Cu_u3 tables)", precision="dp", eam=True),
+                   dict(name="verletlist EAM SP", precision="sp", eam=True)):
+            try:
+                secondaries.append(verletlist_secondary(m, args, local, stream, **kw))
+            except Exception as e:
+                secondaries.append({"name": kw["name"], "error": "%s: %s" % (type(e).__name__, e)})
+        if rank == 0 and not args.half:
+            ref_cuda = reference_cuda(args)
 
     if rank == 0:
         line = {"metric": (METRIC_CP % (4, args.cluster_n)) if cp else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64" if dp else "f32", "data": "synthetic", "config": workload_config(args, world, grid),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "secondary": secondary,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "secondary": secondary,
+                "secondaries": secondaries, "reference_cuda": ref_cuda,
                 "gpu_launches": int(launches), "clocks": clk,
                 "thermo_final": {"step": int(rec[-1][0]), "T": float(rec[-1][1]), "P": float(rec[-1][2])}}
         print(json.dumps(line))

@@ -75,14 +75,8 @@ void        mdb_destroy(mdb_ctx* c);
  *      the local atoms by neighbor bin at every rebuild (neighbor.c:360-426); the permutation is tracked, every accessor
  *      below still speaks the reference's atom numbering.
  *  "sort_order" 0 = the reference's x-fastest bin order, 1 = Morton order of the bins.
- *  "list_layout" 0 = transposed, 1 = row-major rows, 2 (default) = k-major tiles of 32 atoms.
- *  "neigh_variant" list-build kernel: 4 (default) packed-FP32 tests on SoA candidates, 3 = float4 candidates, 0-2 older.
- *  "force_variant" LJ full-list kernel: 1 (default; DP: 4 neighbors in flight, SP: branch-free), 8/9 branch-free U=4/2,
- *      0/2-7 older generations, 10-13 rolling software pipeline (k_force_lj_full_v7; bit-identical, measured slower).
- *  "merge" 2 = one list row per atom pair with membership bits (exact, slower; default 0).
- *  "eam_variant" 1 (default) packed spline rows + rsqrt, 0 = first kernels, 2 = packed (x, y) / (z, fp) gathers and
- *      (value, slope) tables (single domain; A/B variant, not yet measured).
- *  "half_variant" LJ half-list kernel: 2 (default) 4 neighbors in flight, 1 = 2 in flight, 0 = first kernel.
+ *  "eam_variant" EAM passes: 2 (default) packed (x, y) / (z, fp) gathers and (value, slope) tables, 1 = packed spline rows
+ *      (what a brick of a decomposed box runs), 0 = first kernels (scalar table gathers, IEEE sqrt / division).
  *  "fuse_integrate" (default 1) finalIntegrate(n) + initialIntegrate(n+1) in one pass inside mdb_run.
  *  "fuse_force" (default 1) inside mdb_run, LJ full lists of a single domain: computeForce(n) + finalIntegrate(n) +
  *      initialIntegrate(n+1) in ONE kernel (the integrate halves run in the force kernel's epilogue on the force still
@@ -91,8 +85,7 @@ void        mdb_destroy(mdb_ctx* c);
  *  "xy_gather" (default 1) the fused kernel fetches a neighbor's x and y with one 2-element vector gather from a packed
  *      (x, y) copy of the positions (kept current by its own epilogue and by updatePbc) instead of two scalar gathers:
  *      fewer L1 wavefronts per pair.  Bit-identical.
- *  "sort_rows" 1 = sort every neighbor row by index after the build (default 0).
- *  "lazy_ops" (default 0; written after round 1's GPU budget was spent, not yet validated on a GPU) for drivers that keep
+ *  "lazy_ops" (default 0; 3.91 -> 4.34 G atom updates/s for MDBench-VL-B200 --operators at 128^3) for drivers that keep
  *      the reference's operator-by-operator loop: mdb_computeForce and mdb_finalIntegrate only record that they are due;
  *      if the next call is mdb_initialIntegrate the three run as the one fused kernel of mdb_run, any other entry point
  *      first launches them separately, in order.  Same results; mdb_computeForce then returns 0 s. */
@@ -257,8 +250,7 @@ int         mdb_dd_getNeighborTags(mdb_dd* d, int* tags, int* numneigh, int* row
 int         mdb_dd_saveState(mdb_dd* d);
 int         mdb_dd_restoreState(mdb_dd* d);
 /* every mdb_setOption name (applied to all bricks of this process), plus "halo_push" (default 1: per-step ghost
- * positions by peer stores into the IPC-mapped arrays of the neighbor GPUs; 0: NCCL send/recv) and "overlap_halo"
- * (default 0; 1: exchange the halo while the atoms that list no ghost are computed).  Same value on every process. */
+ * positions by peer stores into the IPC-mapped arrays of the neighbor GPUs; 0: NCCL send/recv).  Same value on every process. */
 int         mdb_dd_setOption(mdb_dd* d, const char* name, double value);
 int         mdb_dd_setTiming(mdb_dd* d, int on);
 int         mdb_dd_getKernelStats(mdb_dd* d, double* force_ms, long long* force_launches, double* neigh_ms,
@@ -286,8 +278,7 @@ int         mdb_cp_setStream(mdb_cp* c, void* cuda_stream);
 int         mdb_cp_sync(mdb_cp* c);
 /* "prune_every" (default 1000, common/parameter.c:40): pruneNeighbor period inside mdb_cp_run; "force_variant" 0 = auto
  * (full lists: lane per i atom, packed FP32 in SP; half lists: warp per i-cluster), 1 = lane per i atom scalar,
- * 2 = lane per i atom packed FP32 (SP full), 3 = warp per i-cluster / lane per j atom, 4 / 5 = packed FP32 with a deeper
- * software pipeline (list entries 3 tiles ahead; 5: tiles 2 ahead) -- A/B variants, SP full lists only, not yet measured;
+ * 2 = lane per i atom packed FP32 (SP full), 3 = warp per i-cluster / lane per j atom;
  * "fuse_force" (default 1): inside mdb_cp_run with full lists, computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1)
  * run as ONE kernel (integrate halves in the force kernel's epilogue, second cluster position array); bit-identical. */
 int         mdb_cp_setOption(mdb_cp* c, const char* name, double value);

@@ -246,7 +246,7 @@ class Simulation:
 
     def stubNeighbors(self, pattern, nneighs=76, nreps=1, seed=12345):
         """synthetic list of the reference's kernel micro-benchmark (main-stub.c): pattern 'seq' | 'fix' | 'rand'"""
-        self._ck(self.L.mdb_stubNeighbors(self.h, {"seq": 0, "fix": 1, "rand": 2}[pattern], nneighs, nreps, C.c_uint(seed)))
+        self._ck(self.L.mdb_stubNeighbors(self.h, {"seq": 0, "fix": 1, "rand": 2, "local": 3, "localbank": 4}[pattern], nneighs, nreps, C.c_uint(seed)))
 
     def computeForce(self): return self._force(self.L.mdb_computeForce)
     def computeForceLJFullNeigh(self): return self._force(self.L.mdb_computeForceLJFullNeigh)
@@ -698,7 +698,7 @@ class ClusterSimulation:
 
     def stub(self, niclusters=256, natoms=4, pattern="seq", nneighs=9, nreps=1, masked=0, seed=12345):
         """synthetic clusters + lists of the reference's kernel micro-benchmark (clusterpair/main-stub.c)"""
-        self._ck(self.L.mdb_cp_stub(self.h, niclusters, natoms, {"seq": 0, "fix": 1, "rand": 2}[pattern], nneighs, nreps, masked,
+        self._ck(self.L.mdb_cp_stub(self.h, niclusters, natoms, {"seq": 0, "fix": 1, "rand": 2, "local": 3, "localbank": 4}[pattern], nneighs, nreps, masked,
                                     C.c_uint(seed)))
 
     # ---- parity accessors (same names as the checker's bindings use for the reference) ----

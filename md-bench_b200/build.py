@@ -51,7 +51,8 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+    # shared CUDA runtime (the image ships libcudart.so.12 under /usr/local/cuda/lib64): the library then carries no copy of cudart
+    cmd = [NVCC] + ARCH + ["-shared", "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 

@@ -725,76 +725,6 @@ __global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, int dumm
     cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
 }
 
-// ---- packed SP kernel with a deeper software pipeline (A/B variants force_variant 4 / 5; not yet measured) -----------------
-// Source-level ncu of k_cp_force_lj_sp_packed<4, 1> at 128^3 (gpurun_out/prof_r1_s4_cpforce128.ncu-rep): 53 % of all stall
-// samples are long-scoreboard waits -- a third of them at the address computation of a tile load that waits for its LIST
-// ENTRY (the compiler sinks the __ldg of row[k+2] next to its use, so the entry is requested ~10 instructions before it is
-// needed), the rest at the first use of each tile, which is requested one tile (~60 instructions) ahead; issue 59 %, L1
-// 68 %: the kernel is latency bound.  Here the list entries are requested IQ tiles ahead with volatile loads (kept in
-// program order with the volatile tile loads) and the tiles D ahead (D + 1 register sets).
-__device__ __forceinline__ int ld_entry(const int* p)
-{
-    int v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-template <int N, bool FI, int D, int IQ>
-__global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed_q(int ncl, int dummy_cj, LJConst2<float> c, const float* __restrict__ cl_x,
-    const int* __restrict__ numneigh, const int* __restrict__ neighbors, int maxneighs, float* __restrict__ cl_f, CpFused<float> fi)
-{
-    static_assert(D >= 1 && D <= 2 && IQ >= 1, "pipeline depths");
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ci  = tid >> 2, cii = tid & 3;
-    const bool valid = ci < ncl;
-    const int cic = valid ? ci : ncl - 1;
-    const size_t ib = cp_ci_base3<N>(cic);
-    float x0 = cl_x[ib + cii], y0 = cl_x[ib + N + cii], z0 = cl_x[ib + 2 * N + cii];
-    const bool pad_i = x0 >= 1.0e14f;
-    if (pad_i) x0 = y0 = z0 = -1.0e15f;
-    const f32x2 xt = pk2(x0, x0), yt = pk2(y0, y0), zt = pk2(z0, z0);
-    CpPackedConst pc { pk2(c.A, c.A), pk2(-c.B, -c.B), pk2(1.0f, 1.0f), c.cutforcesq };
-    const int self = cp_cj0<N>(cic);
-    const int ii   = N == CP_M ? cii : cii + CP_M * (cic & 1);
-    const int* row = neighbors + (size_t)cic * maxneighs;
-    const int nn   = valid ? numneigh[cic] : 0;
-    f32x2 fx = pk2(0.f, 0.f), fy = fx, fz = fx;
-    // queue of list entries: cq[q] = entry of tile k + q (the dummy tile past the end of the row)
-    constexpr int Q = D + IQ;
-    int cq[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) cq[q] = q < nn ? ld_entry(row + q) : dummy_cj;
-    CpTileRegs<N> T[D + 1]; // T[0] = tile k, T[d] = tile k + d
-#pragma unroll
-    for (int d = 0; d < D; d++) T[d].load(cl_x + (size_t)cq[d] * N * 3);
-    const int last = nn > 0 ? nn - 1 : 0;
-    for (int k = 0; k < nn; k++) {
-        // entry of tile k + Q: always a valid address (clamped), replaced by the dummy tile behind the end of the row
-        const int e  = ld_entry(row + min(k + Q, last));
-        const int cn = k + Q < nn ? e : dummy_cj;
-        T[D].load(cl_x + (size_t)cq[D] * N * 3);
-        cp_tile_packed<N>(T[0], pc, xt, yt, zt, cq[0] == self ? ii : -1, fx, fy, fz);
-#pragma unroll
-        for (int d = 0; d < D; d++) T[d] = T[d + 1];
-#pragma unroll
-        for (int q = 0; q + 1 < Q; q++) cq[q] = cq[q + 1];
-        cq[Q - 1] = cn;
-    }
-    if (!valid) return;
-    float a, b;
-    upk2(fx, a, b); const float fix = pad_i ? 0.f : a + b;
-    upk2(fy, a, b); const float fiy = pad_i ? 0.f : a + b;
-    upk2(fz, a, b); const float fiz = pad_i ? 0.f : a + b;
-    if (FI) {
-        if (pad_i) return;
-        const size_t e = cp_epilogue_slot<N>();
-        cp_fused_integrate(fi, e, cl_x[e], fix);
-        cp_fused_integrate(fi, e + N, cl_x[e + N], fiy);
-        cp_fused_integrate(fi, e + 2 * N, cl_x[e + 2 * N], fiz);
-        return;
-    }
-    cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
-}
-
 template <class real, int N, bool HALF, bool FI = false>
 __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<real> c, const real* __restrict__ cl_x,
     const int* __restrict__ numneigh, const int* __restrict__ numneigh_masked, const int* __restrict__ neighbors, int maxneighs,
@@ -858,6 +788,29 @@ __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<
 // (SP) / 256-bit (DP) load from an {x, y, z, -} copy of the cluster positions (k_cp_pack_j) -- one wavefront per cluster
 // pair -- and evaluates it against the four i atoms, which are warp-uniform registers.  The 12 i-force sums are
 // reduced over the warp once per row with a halving butterfly (12 -> 6 -> 3 values, then 3 full steps).
+// one 32-byte {x, y, z, -} record per cluster slot (DP; 16 bytes for SP), fetched with a single 256- / 128-bit load
+struct __align__(32) PosD {
+    double x, y, z, w;
+};
+template <class real> struct PosOf;
+template <> struct PosOf<double> { typedef PosD type; };
+template <> struct PosOf<float> { typedef float4 type; };
+__device__ __forceinline__ void ld_pos(const PosD* p, double& x, double& y, double& z)
+{
+    double w;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+}
+__device__ __forceinline__ void ld_pos(const float4* p, float& x, float& y, float& z)
+{
+    const float4 v = __ldg(p);
+    x = v.x; y = v.y; z = v.z;
+}
+__device__ __forceinline__ void st_pos(PosD* p, double x, double y, double z)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(0.0) : "memory");
+}
+__device__ __forceinline__ void st_pos(float4* p, float x, float y, float z) { *p = make_float4(x, y, z, 0.f); }
+
 template <class real, int N>
 __global__ void k_cp_pack_j(size_t nslots, const real* __restrict__ cl_x, typename PosOf<real>::type* __restrict__ out)
 {

@@ -573,7 +573,7 @@ template <class real, int N> struct CpSim final : CpBase {
         if (sizeof(real) == 8 && N == 8) return false; // the DP 4x8 kernel would spill with the epilogue (ptxas: 64 regs + 12 B)
         int fv = force_variant;
         if (fv == 0) fv = sizeof(real) == 4 ? 2 : 1;
-        return fv == 1 || fv == 2 || ((fv == 4 || fv == 5) && sizeof(real) == 4);
+        return fv == 1 || fv == 2;
     }
     void sync_second_array()
     {
@@ -591,7 +591,6 @@ template <class real, int N> struct CpSim final : CpBase {
             int fv = force_variant;
             if (fv == 0) fv = sizeof(real) == 4 ? 2 : 1;
             if (fv == 2) launch_packed_fused(grid, c2, fi);
-            else if (fv == 4 || fv == 5) launch_packed_q(grid, c2, fi, fv, true);
             else
                 MDB_LAUNCH(launches, (k_cp_force_lj<real, N, false, true>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
                     numneigh_masked.p, neighbors.p, maxneighs, cl_f.p, fi);
@@ -611,7 +610,7 @@ template <class real, int N> struct CpSim final : CpBase {
         // shuffles).  1 = lane per i atom, scalar; 2 = lane per i atom, packed FP32 (SP full only); 3 = warp per i-cluster.
         int fv = force_variant;
         if (fv == 0) fv = P.half_neigh ? 3 : (sizeof(real) == 4 ? 2 : 1);
-        if ((fv == 2 || fv == 4 || fv == 5) && (sizeof(real) != 4 || P.half_neigh)) fv = 1;
+        if (fv == 2 && (sizeof(real) != 4 || P.half_neigh)) fv = 1;
         if (fv == 3) {
             typedef typename PosOf<real>::type P4;
             const size_t nslots = (size_t)(ncj + nghost + 1) * N;
@@ -631,8 +630,6 @@ template <class real, int N> struct CpSim final : CpBase {
                 numneigh_masked.p, neighbors.p, maxneighs, cl_f.p, fi);
         } else if (fv == 2) {
             launch_packed(grid, c2);
-        } else if (fv == 4 || fv == 5) { // deeper software pipeline (A/B, not yet measured)
-            launch_packed_q(grid, c2, fi, fv, false);
         } else {
             MDB_LAUNCH(launches, (k_cp_force_lj<real, N, false>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
                 numneigh_masked.p, neighbors.p, maxneighs, cl_f.p, fi);
@@ -658,18 +655,6 @@ template <class real, int N> struct CpSim final : CpBase {
             numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, fi);
     }
     void launch_packed_fused(unsigned, const LJConst2<double>&, const CpFused<double>&) {}
-    // force_variant 4: list entries 3 tiles ahead, tiles 1 ahead; 5: tiles 2 ahead (three register sets)
-    template <bool FI, int D> void launch_packed_q_t(unsigned grid, const LJConst2<float>& c2, const CpFused<float>& fi)
-    {
-        MDB_LAUNCH(launches, (k_cp_force_lj_sp_packed_q<N, FI, D, 3>), grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
-            numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, fi);
-    }
-    void launch_packed_q(unsigned grid, const LJConst2<float>& c2, const CpFused<float>& fi, int fv, bool fused)
-    {
-        if (fv == 4) { if (fused) launch_packed_q_t<true, 1>(grid, c2, fi); else launch_packed_q_t<false, 1>(grid, c2, fi); }
-        else { if (fused) launch_packed_q_t<true, 2>(grid, c2, fi); else launch_packed_q_t<false, 2>(grid, c2, fi); }
-    }
-    void launch_packed_q(unsigned, const LJConst2<double>&, const CpFused<double>&, int, bool) {}
     double computeForce() override // returns elapsed seconds like the reference's ComputeForceFunction
     {
         const bool t        = timing;

@@ -15,12 +15,7 @@ template <class real> struct DomainGroup final : DDBase {
     int proc = 0, first = 0, nlocal_bricks = 0, device = 0;
     mdb_params G; // global parameters
     std::vector<Brick*> bricks;
-    cudaStream_t stream = nullptr, own_stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
-    // option "overlap_halo": exchange the halo while the atoms without ghost neighbors are computed.  Off by default: at 2
-    // GPUs the halo is 0.11 ms of a 2.4 ms step and the split (two launches over index lists) costs more than it hides
-    // (6.84 vs 7.09 G atom-steps/s, profiles/r1_ab3.txt)
-    bool overlap = false;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     NcclApi::comm_t comm = nullptr;
     long long gNatoms = 0, launches = 0;
     bool timing = false;
@@ -45,6 +40,14 @@ template <class real> struct DomainGroup final : DDBase {
         std::vector<std::pair<cudaIpcMemHandle_t, void*>> open;
     };
     std::vector<IpcSlot> peer_xyz;
+    // allocations of x, y, z (and of the sort buffers they are swapped with) that this process has outgrown while a peer
+    // may still have them mapped; freed in prepare_push() after every process has closed its stale mappings
+    std::vector<void*> retired;
+    void free_retired()
+    {
+        for (void* q : retired) cudaFree(q);
+        retired.clear();
+    }
     DBuf<unsigned char> ipc_stage;        // device staging for the handle allgather
     PushTable push_tab {};
     unsigned push_to = 0, push_from = 0;  // processes this one pushes to / is pushed by
@@ -75,11 +78,6 @@ template <class real> struct DomainGroup final : DDBase {
         first         = proc * nlocal_bricks;
         MDB_CUDA(cudaSetDevice(device));
         MDB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
-        int prio_lo = 0, prio_hi = 0; // the transfers must not queue behind the force kernel's blocks
-        MDB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        MDB_CUDA(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_hi));
-        MDB_CUDA(cudaEventCreateWithFlags(&ev_packed, cudaEventDisableTiming));
-        MDB_CUDA(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
         stream = own_stream;
         for (auto& e : ev) MDB_CUDA(cudaEventCreate(&e));
         MDB_CUDA(cudaMallocHost(&h_off_all, (size_t)topo.nbricks * 32 * sizeof(int)));
@@ -150,6 +148,10 @@ template <class real> struct DomainGroup final : DDBase {
         }
         push_ready = all_agree(ok);
         peer_xyz.assign(topo.nprocs, IpcSlot {});
+        if (push_ready) { // from now on the position arrays are exported: never free them under a peer's mapping
+            Brick* b = bricks[0];
+            for (DBuf<real>* a : { &b->x, &b->y, &b->z, &b->x2, &b->y2, &b->z2 }) a->retire = &retired;
+        }
     }
     // per rebuild: where every process keeps x, y, z now (allocation handles + first ghost entry), then the segment table
     void prepare_push()
@@ -157,19 +159,37 @@ template <class real> struct DomainGroup final : DDBase {
         if (!push_ready) return;
         Brick* b = bricks[0];
         struct Pub {
-            cudaIpcMemHandle_t h[3];
+            cudaIpcMemHandle_t h[6]; // x, y, z and the sort buffers they alternate with (zero = not allocated)
             int nlocal, ok;
         } mine;
         memset(&mine, 0, sizeof mine);
         mine.nlocal = b->Nlocal;
         mine.ok     = 1;
-        real* arr[3] = { b->x.p, b->y.p, b->z.p };
-        for (int k = 0; k < 3; k++)
-            if (cudaIpcGetMemHandle(&mine.h[k], arr[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+        real* arr[6] = { b->x.p, b->y.p, b->z.p, b->x2.p, b->y2.p, b->z2.p };
+        for (int k = 0; k < 6; k++)
+            if (arr[k] && cudaIpcGetMemHandle(&mine.h[k], arr[k]) != cudaSuccess) {
+                if (k < 3) mine.ok = 0;
+                memset(&mine.h[k], 0, sizeof mine.h[k]);
+                cudaGetLastError();
+            }
         std::vector<Pub> all(topo.nprocs);
         allgather_bytes(&mine, all.data(), sizeof mine);
         bool ok = true;
         for (int p = 0; p < topo.nprocs; p++) ok = ok && all[p].ok;
+        // close every mapping of an allocation its owner no longer publishes (it has been outgrown and is waiting in the
+        // owner's `retired` list); after the barrier below nobody maps a retired allocation any more and the owners free them
+        for (int p = 0; p < topo.nprocs; p++) {
+            auto& open = peer_xyz[p].open;
+            for (size_t e = 0; e < open.size();) {
+                bool live = false;
+                for (int k = 0; k < 6; k++) live = live || memcmp(&open[e].first, &all[p].h[k], sizeof(cudaIpcMemHandle_t)) == 0;
+                if (live) { e++; continue; }
+                cudaIpcCloseMemHandle(open[e].second);
+                open.erase(open.begin() + e);
+            }
+        }
+        all_agree(true); // barrier: every process has closed its stale mappings
+        free_retired();
         push_tab.nseg = 0;
         push_to = push_from = 0;
         for (const Xfer& t : pos_plan) {
@@ -240,6 +260,9 @@ template <class real> struct DomainGroup final : DDBase {
         cudaStreamSynchronize(stream);
         for (size_t p = 0; p < peer_xyz.size(); p++)
             for (auto& e : peer_xyz[p].open) cudaIpcCloseMemHandle(e.second);
+        if (push_ready && comm) { // nobody may free an exported array while a peer still maps it or pushes into it
+            try { all_agree(true); } catch (...) {}
+        }
         if (sync_flags) {
             for (int p = 0; p < topo.nprocs && p < 32; p++)
                 if (p != proc && peer_flags.p[p]) cudaIpcCloseMemHandle(peer_flags.p[p]);
@@ -248,6 +271,7 @@ template <class real> struct DomainGroup final : DDBase {
         ipc_stage.release();
         if (comm) nccl_api().CommDestroy(comm);
         for (Brick* b : bricks) { b->brick_release(); delete b; }
+        free_retired();
         d_off_all.release();
         d_sum.release();
         for (auto& b : st) b.release();
@@ -255,9 +279,6 @@ template <class real> struct DomainGroup final : DDBase {
         cudaFreeHost(h_off_all);
         cudaFreeHost(h_sum);
         for (auto& e : ev) cudaEventDestroy(e);
-        cudaEventDestroy(ev_packed);
-        cudaEventDestroy(ev_halo);
-        cudaStreamDestroy(comm_stream);
         cudaStreamDestroy(own_stream);
     }
     void setStream(cudaStream_t s) override
@@ -539,13 +560,6 @@ template <class real> struct DomainGroup final : DDBase {
         setupGhosts();
         forward();
         for (Brick* b : bricks) b->buildNeighbor();
-        split_lists();
-    }
-    void split_lists() // interior / boundary atom lists for the overlapped steps
-    {
-        if (!overlap || G.force_field != MDB_FF_LJ) return;
-        for (Brick* b : bricks)
-            if (b->gflag_valid && !b->merged_built) b->build_split_lists();
     }
     void reneighbour() override // main.c:76-95
     {
@@ -556,7 +570,6 @@ template <class real> struct DomainGroup final : DDBase {
         setupGhosts();
         forward();
         for (Brick* b : bricks) b->buildNeighbor();
-        split_lists();
     }
     void force()
     {
@@ -568,30 +581,6 @@ template <class real> struct DomainGroup final : DDBase {
         } else {
             for (Brick* b : bricks) b->launch_force(FORCE_DISPATCH);
         }
-    }
-    // updatePbc + computeForce of a step between two rebuilds with the halo in flight during the force of the atoms that list
-    // no ghost atom: pack on the main stream, transfers (device copies / NCCL send-recv into the ghost range of x, y, z) on
-    // comm_stream, interior force on the main stream, then the boundary atoms once the halo has landed.  The interior launch
-    // reads local positions only and the transfers write ghost positions only.  All NCCL calls stay serialised: the transfers
-    // start after everything issued earlier on the main stream (ev_packed) and the main stream waits for them (ev_halo)
-    // before it issues anything else.  Not used while per-phase timing is on (the phases would overlap).
-    bool can_overlap() const
-    {
-        if (!overlap || timing || G.force_field != MDB_FF_LJ) return false;
-        for (Brick* b : bricks)
-            if (!b->can_split_force()) return false;
-        return true;
-    }
-    void forward_and_force_overlapped()
-    {
-        for (Brick* b : bricks) b->brick_pack_pos();
-        MDB_CUDA(cudaEventRecord(ev_packed, stream));
-        MDB_CUDA(cudaStreamWaitEvent(comm_stream, ev_packed, 0));
-        run_ops(pos_ops, comm_stream);
-        MDB_CUDA(cudaEventRecord(ev_halo, comm_stream));
-        for (Brick* b : bricks) b->launch_force_part(0);
-        MDB_CUDA(cudaStreamWaitEvent(stream, ev_halo, 0));
-        for (Brick* b : bricks) b->launch_force_part(1);
     }
     void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) override // main.c:244-288
     {
@@ -622,7 +611,7 @@ template <class real> struct DomainGroup final : DDBase {
             const bool rec = !((n + 1) % nstat) && (n + 1) < nsteps;
             // force(n) + finalIntegrate(n) + initialIntegrate(n+1) in one launch per brick (x, y, z updated in place, gathers
             // from the double-buffered copies), unless something reads the state in between
-            bool fuse = !rec && n + 1 < nsteps && G.force_field == MDB_FF_LJ && !(can_overlap() && !reneigh);
+            bool fuse = !rec && n + 1 < nsteps && G.force_field == MDB_FF_LJ;
             for (Brick* b : bricks) fuse = fuse && b->can_fuse_force_inplace();
             if (fuse) {
                 if (reneigh) reneighbour();
@@ -634,8 +623,6 @@ template <class real> struct DomainGroup final : DDBase {
             if (reneigh) {
                 reneighbour();
                 force();
-            } else if (can_overlap()) {
-                forward_and_force_overlapped();
             } else {
                 forward();
                 force();
@@ -722,7 +709,6 @@ template <class real> struct DomainGroup final : DDBase {
         for (Brick* b : bricks) {
             const size_t n = b->Nlocal;
             if (b->nstride == 0) throw Error("getNeighborTags: no neighbor list");
-            b->ensure_per_atom();
             b->rows.ensure(n * stride, false, stream);
             MDB_LAUNCH(launches, k_dd_rows_as_tags, grid_for(n, 128), 128, 0, stream, (int)n, stride, b->LL, b->numneigh.p,
                 b->neighbors.p, b->orig.p, b->rows.p);
@@ -743,7 +729,6 @@ template <class real> struct DomainGroup final : DDBase {
     }
     void setOption(const char* name, double v) override
     {
-        if (!strcmp(name, "overlap_halo")) { overlap = v != 0; return; }
         if (!strcmp(name, "halo_push")) { push_wanted = v != 0; return; }
         for (Brick* b : bricks) b->setOption(name, v);
     }

@@ -84,6 +84,8 @@ long long mdb_createAtom(mdb_ctx* c)
 {
     try {
         if (!c || !c->sim) throw Error("null mdb_ctx");
+        c->sim->drop_lazy(); // pending force / finalIntegrate of the OLD atoms must not run against the new ones
+        c->sim->invalidate_copies();
         return c->sim->createAtom();
     } catch (const std::exception& e) {
         g_err = e.what();

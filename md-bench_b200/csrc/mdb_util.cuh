@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace mdb {
 
@@ -49,6 +50,10 @@ inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + bloc
 template <class T> struct DBuf {
     T* p       = nullptr;
     size_t cap = 0;
+    // Allocations exported through CUDA IPC (the peer-store halo maps x, y, z of the neighbor GPUs) must not be freed while
+    // another process still has them mapped: with `retire` set, an outgrown allocation is parked there instead of freed and
+    // its owner (DomainGroup) frees it once every importer has closed its mapping.
+    std::vector<void*>* retire = nullptr;
     void ensure(size_t n, bool keep, cudaStream_t s)
     {
         if (n <= cap) return;
@@ -58,14 +63,18 @@ template <class T> struct DBuf {
         if (p && keep && cap) MDB_CUDA(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
         if (p) {
             MDB_CUDA(cudaStreamSynchronize(s));
-            MDB_CUDA(cudaFree(p));
+            if (retire) retire->push_back(p);
+            else MDB_CUDA(cudaFree(p));
         }
         p   = q;
         cap = ncap;
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) {
+            if (retire) retire->push_back(p);
+            else cudaFree(p);
+        }
         p   = nullptr;
         cap = 0;
     }

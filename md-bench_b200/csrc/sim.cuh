@@ -59,6 +59,7 @@ struct SimBase {
     virtual void abi_finalIntegrate() { finalIntegrate(); }
     virtual void abi_initialIntegrate() { initialIntegrate(); }
     virtual void flush_lazy() {}
+    virtual void drop_lazy() {} // forget pending work (the atoms it refers to are being replaced)
     virtual void invalidate_copies() {} // a call from outside may have changed positions: gather copies are stale
 
     bool timing             = false;

@@ -41,8 +41,7 @@ template <class real> struct Sim final : SimBase {
     // consecutive atoms (A/B in profiles/r1_ab.txt: force 1.49 ms unsorted vs 1.67 ms sorted at 8.4M
     // atoms).  Turn it on (mdb_setOption "sort_atoms") for long runs of diffusing systems.
     bool sort_enabled = false, extmap_valid = false;
-    int force_variant = 1, neigh_variant = 4, list_layout = 2; // 0: transposed, 1: row-major rows, 2: tiles of 32 atoms
-    bool fuse_integrate = true, sort_rows = false;
+    bool fuse_integrate = true;
     bool fuse_force = true; // mdb_run: integrate halves in the force kernel's epilogue (k_force_lj_full_fi)
     // packed (x, y) copy of the positions for the fused kernel's vector gathers ("xy_gather"); valid only between fused
     // steps of one mdb_run: the fused epilogue writes the locals, updatePbc the ghosts, everything else invalidates it
@@ -55,23 +54,10 @@ template <class real> struct Sim final : SimBase {
     bool bin_rank_ready = false;
     DBuf<int> bin_rank;
     NbLayout LL { 0, 0, 0 };                                    // element (i,k) at neighbors[LL.base(i) + k*LL.sk]
-    DBuf<float> xf, yf, zf;
-    DBuf<float4> pk;
     DBuf<float> cxs, cys, czs; // candidates in CSR order, SoA (k_build_neighbor_v5)
     DBuf<int> cids;
-    DBuf<char> pos4; // packed positions {x,y,z,-} for the p4 force kernel
-    DBuf<int> run_off, run_len, run_i0, run_dj, run_dk;
+    DBuf<int> run_off, run_len; // runs of x-adjacent stencil bins
     int nruns = 0;
-    // merged lists (k_build_neighbor_m2): one row per atom pair (2t, 2t+1) with membership bits; LJ full lists only.
-    // "merge" option: 0 (default) off -- one row per atom, the reference's structure; 2 on.  Measured SLOWER
-    // (force 1.86 vs 1.53 ms DP, 1.31 vs 1.13 ms SP at 8.4M atoms, profiles/r1_ab3.txt): the union rows cost 1.43x the
-    // FP64 work and the lanes of a warp now span 64 atoms, so the gathers touch more lines per request.  Kept as an
-    // A/B variant.  With merge on, numneigh / neighbors are materialised on demand (ensure_per_atom).
-    int merge = 0, mcap = 0, st_Ry = 0, st_Rz = 0;
-    bool merged_built = false, pa_valid = true;
-    DBuf<int> mneigh, mnum, numneigh_atom;
-    DBuf<StencilRow> st_tab;
-    NbLayout LLm { 0, 0, 0 };
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
     DBuf<unsigned> ghost_msk;
     int saved_n = 0;
@@ -89,9 +75,7 @@ template <class real> struct Sim final : SimBase {
     DBuf<real> fp, rhor_spline, frho_spline, z2r_spline, eam_rho4, eam_frc12; // + repacked rows for the v2 kernels
     DBuf<real> eam_vs4; // (value, slope) of rhor and z2r per knot, generation-3 force pass (eam_variant 2)
     DBuf<vec2> eam_zf;  // packed (z, fp) of locals and ghosts, generation 3
-    int half_variant = 2; // option "half_variant": 0 first kernel, 1 v2 with 2 neighbors in flight, 2 (default) 4 in flight
-    int eam_variant = 1; // option "eam_variant": 0 = first kernels (scalar table gathers, IEEE sqrt / division), 1 = v2,
-                         // 2 = generation 3 (packed gathers, (value, slope) tables; single domain; not yet measured)
+    int eam_variant = 2; // option "eam_variant": 0 first kernels (IEEE sqrt / division), 1 generation 2, 2 generation 3 (default; a brick runs 2)
     // ---- scratch ----
     int* h_flags      = nullptr; // pinned: [0] ghost total, [1] max neighbors, [2] max bin count
     DBuf<int> d_flags;
@@ -133,13 +117,8 @@ template <class real> struct Sim final : SimBase {
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
             b->release();
         ghost_msk.release();
-        gflag.release();
-        split_tmp.release(); split_pos.release(); idx_interior.release(); idx_boundary.release();
-        pos4.release();
         cxs.release(); cys.release(); czs.release(); cids.release();
-        xf.release(); yf.release(); zf.release(); pk.release(); run_off.release(); run_len.release();
-        run_i0.release(); run_dj.release(); run_dk.release(); mneigh.release(); mnum.release(); numneigh_atom.release();
-        st_tab.release();
+        run_off.release(); run_len.release();
         d_partial.release();
         d_red.release();
         d_thermo.release();
@@ -222,6 +201,8 @@ template <class real> struct Sim final : SimBase {
         zero3(fx.p, fy.p, fz.p, Nlocal);
         reset_order();
         neigh_ready = false;
+        nstride = 0; // no list for these atoms yet
+        xy_valid = false;
         return Natoms;
     }
 
@@ -266,6 +247,9 @@ template <class real> struct Sim final : SimBase {
         reset_order();
         MDB_CUDA(cudaStreamSynchronize(stream)); // host buffers may be reused by the caller
         neigh_ready = false;
+        nstride = 0;
+        xy_valid = false;
+        pending_force = pending_final = false;
     }
 
     void getAtoms(int which, bool ghosts, void* ax, void* ay, void* az) override
@@ -323,6 +307,8 @@ template <class real> struct Sim final : SimBase {
         Nlocal = saved_n;
         Nghost = 0;
         reset_order();
+        nstride = 0; // the lists belong to the state that was just replaced
+        xy_valid = false;
     }
 
     // ------------------------------------------------------------------ thermo
@@ -470,11 +456,8 @@ template <class real> struct Sim final : SimBase {
         if (!P.from_input) { xprd = bx; yprd = by; zprd = bz; }
         stencil.ensure(nstencil, false, stream);
         MDB_CUDA(cudaMemcpyAsync(stencil.p, h_stencil.data(), nstencil * sizeof(int), cudaMemcpyHostToDevice, stream));
-        // runs of consecutive offsets (x-adjacent bins, adjacent in the CSR) for k_build_neighbor_v3/v4/m2, with their
-        // row (dj, dk) and first x offset, and the same runs as a (dj, dk) -> StencilRow table
-        std::vector<int> ro, rl, ri, rj, rk;
-        st_Ry = nexty; st_Rz = nextz;
-        std::vector<StencilRow> tab((size_t)(2 * nexty + 1) * (2 * nextz + 1), StencilRow { 0, 0 });
+        // runs of consecutive offsets (x-adjacent bins are adjacent in the CSR): the list build walks 21 runs instead of 81 bins
+        std::vector<int> ro, rl;
         for (int k = -nextz; k <= nextz; k++)
             for (int j = -nexty; j <= nexty; j++) {
                 int i0 = 0, len = 0;
@@ -486,18 +469,12 @@ template <class real> struct Sim final : SimBase {
                     }
                 if (len == 0) continue;
                 ro.push_back(k * bg.mbiny * bg.mbinx + j * bg.mbinx + i0);
-                rl.push_back(len); ri.push_back(i0); rj.push_back(j); rk.push_back(k);
-                tab[(size_t)(k + nextz) * (2 * nexty + 1) + (j + nexty)] = StencilRow { i0, len };
+                rl.push_back(len);
             }
         nruns = (int)ro.size();
-        for (DBuf<int>* b : { &run_off, &run_len, &run_i0, &run_dj, &run_dk }) b->ensure(nruns, false, stream);
-        st_tab.ensure(tab.size(), false, stream);
+        for (DBuf<int>* b : { &run_off, &run_len }) b->ensure(nruns, false, stream);
         MDB_CUDA(cudaMemcpyAsync(run_off.p, ro.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(run_len.p, rl.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        MDB_CUDA(cudaMemcpyAsync(run_i0.p, ri.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        MDB_CUDA(cudaMemcpyAsync(run_dj.p, rj.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        MDB_CUDA(cudaMemcpyAsync(run_dk.p, rk.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        MDB_CUDA(cudaMemcpyAsync(st_tab.p, tab.data(), tab.size() * sizeof(StencilRow), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
         bincount.ensure(bg.mbins + 2, false, stream);
         binstart.ensure(bg.mbins + 3, false, stream);
@@ -683,166 +660,30 @@ template <class real> struct Sim final : SimBase {
         hi = (float)((double)cutneighsq + m);
         if (sizeof(real) == 4) { lo = -1.0f; } // SP: always run the exact (float) expression
     }
-    // decomposed runs: gflag[i] = 1 if atom i lists a ghost atom (set by k_build_neighbor_v4); the force is then launched
-    // in two parts so that the halo exchange overlaps the part that needs no ghosts (DomainGroup::run)
-    DBuf<unsigned char> gflag;
-    bool gflag_valid = false;
-    unsigned char* gflag_ptr()
-    {
-        if (!brick) return nullptr;
-        gflag.ensure(round_up((size_t)Nlocal, 32), false, stream);
-        gflag_valid = true;
-        return gflag.p;
-    }
-    bool can_split_force() const
-    {
-        return brick && gflag_valid && n_boundary >= 0 && !merged_built && P.force_field == MDB_FF_LJ && !P.half_neigh && force_variant == 1 &&
-               neigh_variant >= 3;
-    }
-    DBuf<int> split_tmp, split_pos, idx_interior, idx_boundary;
-    int n_boundary = -1;
-    void build_split_lists() // after buildNeighbor, once per rebuild
-    {
-        const int n = Nlocal;
-        for (DBuf<int>* b : { &split_tmp, &split_pos, &idx_interior, &idx_boundary }) b->ensure((size_t)n + 1, false, stream);
-        MDB_LAUNCH(launches, k_flag_to_int, grid_for(n, 256), 256, 0, stream, n, gflag.p, split_tmp.p);
-        scanner.exclusive(split_tmp.p, split_pos.p, n, d_flags.p + 5, stream);
-        MDB_LAUNCH(launches, k_split_by_flag, grid_for(n, 256), 256, 0, stream, n, gflag.p, split_pos.p, idx_interior.p, idx_boundary.p);
-        MDB_CUDA(cudaMemcpyAsync(h_flags + 5, d_flags.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        MDB_CUDA(cudaStreamSynchronize(stream));
-        n_boundary = h_flags[5];
-    }
-    void launch_force_part(int want) // 0: atoms without ghost neighbors, 1: the others
-    {
-        LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
-        const int n = want ? n_boundary : Nlocal - n_boundary;
-        if (n > 0)
-            MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 4>), grid_for(n, 128), 128, 0, stream, n, c2, x.p, y.p, z.p, numneigh.p,
-                neighbors.p, LL, fx.p, fy.p, fz.p, (const int*)(want ? idx_boundary.p : idx_interior.p), want);
-        if (want == 1) force_launches++;
-    }
-    bool use_merged() const { return merge == 2 && P.force_field == MDB_FF_LJ && !P.half_neigh; }
-    void build_merged() // one row per atom pair, see k_build_neighbor_m2 (vl_kernels.cuh)
-    {
-        const int nall = Nlocal + Nghost, npairs = (Nlocal + 1) / 2;
-        pk.ensure(nall, false, stream);
-        MDB_LAUNCH(launches, k_pack_binned<real>, grid_for(nall, 256), 256, 0, stream, nall, binatoms.p, x.p, y.p, z.p, pk.p);
-        nstride = round_up((size_t)Nlocal, 32);
-        const size_t pstride = round_up((size_t)npairs, 32);
-        mnum.ensure(pstride, false, stream);
-        numneigh_atom.ensure(nstride, false, stream);
-        if (mcap == 0) mcap = maxneighs + maxneighs / 2; // union of two overlapping rows
-        float lo, hi;
-        list_margin(lo, hi);
-        for (;;) {
-            const size_t rowlen = round_up((size_t)mcap, 8);
-            LLm = NbLayout { 32 * rowlen, 32, 5 };
-            mneigh.ensure(rowlen * pstride, false, stream);
-            MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
-            MDB_CUDA(cudaMemsetAsync(d_flags.p + 4, 0, sizeof(int), stream));
-            MDB_LAUNCH(launches, k_build_neighbor_m2<real>, grid_for(npairs, 128), 128, 0, stream, Nlocal, bg, cutneighsq, lo, hi,
-                x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p, run_i0.p, run_dj.p, run_dk.p, nruns, st_tab.p, st_Ry,
-                st_Rz, mcap, LLm, mnum.p, numneigh_atom.p, mneigh.p, d_flags.p + 4, d_flags.p + 1);
-            neigh_launches++;
-            MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-            MDB_CUDA(cudaStreamSynchronize(stream));
-            max_bin_count = h_flags[2];
-            if (h_flags[1] >= maxneighs) maxneighs = (int)(h_flags[1] * 1.2); // the reference's row capacity, neighbor.c:247-262
-            if (h_flags[4] > mcap) {
-                mcap = (int)(h_flags[4] * 1.2);
-                continue;
-            }
-            break;
-        }
-        merged_built = true;
-        pa_valid     = false;
-    }
-    // the reference's per-atom rows from the merged ones (accessors, counters, kernels without a merged variant)
-    void ensure_per_atom()
-    {
-        if (!merged_built || pa_valid) return;
-        const size_t rowlen = round_up((size_t)maxneighs, 8);
-        if (list_layout == 1) LL = NbLayout { rowlen, 1, 0 };
-        else if (list_layout == 2) LL = NbLayout { 32 * rowlen, 32, 5 };
-        else LL = NbLayout { 0, nstride, 31 };
-        numneigh.ensure(nstride, false, stream);
-        neighbors.ensure(rowlen * nstride, false, stream);
-        MDB_LAUNCH(launches, k_unmerge_m2, grid_for((Nlocal + 1) / 2, 128), 128, 0, stream, Nlocal, LLm, mnum.p, mneigh.p, maxneighs,
-            LL, numneigh.p, neighbors.p);
-        pa_valid = true;
-    }
     void buildNeighbor() override // verletlist/neighbor.c:186-264
     {
         if (!neigh_ready) setupNeighbor();
         float ms = 0;
         if (timing) MDB_CUDA(cudaEventRecord(evA, stream));
         bin_atoms();
-        if (use_merged()) {
-            build_merged();
-            if (timing) {
-                MDB_CUDA(cudaEventRecord(evB, stream));
-                MDB_CUDA(cudaEventSynchronize(evB));
-                MDB_CUDA(cudaEventElapsedTime(&ms, evA, evB));
-                neigh_ms += ms;
-            }
-            return;
-        }
-        merged_built = false;
-        pa_valid     = true;
-        gflag_valid  = false;
-        n_boundary   = -1;
-        if (neigh_variant == 4) { // candidates in CSR order as SoA float arrays, padded to a multiple of 4
-            const int nall = Nlocal + Nghost, npad = (int)round_up((size_t)nall + 4, 4);
-            for (DBuf<float>* b : { &cxs, &cys, &czs }) b->ensure(npad, false, stream);
-            cids.ensure(npad, false, stream);
-            MDB_LAUNCH(launches, k_pack_binned_soa<real>, grid_for(npad, 256), 256, 0, stream, nall, npad, binatoms.p, x.p, y.p,
-                z.p, cxs.p, cys.p, czs.p, cids.p);
-        } else if (neigh_variant >= 2) { // candidates packed in CSR order
-            const int nall = Nlocal + Nghost;
-            pk.ensure(nall, false, stream);
-            MDB_LAUNCH(launches, k_pack_binned<real>, grid_for(nall, 256), 256, 0, stream, nall, binatoms.p, x.p, y.p,
-                z.p, pk.p);
-        } else if (neigh_variant != 0) { // float copies of the positions for the pre-test
-            const int nall = Nlocal + Nghost;
-            xf.ensure(nall, false, stream); yf.ensure(nall, false, stream); zf.ensure(nall, false, stream);
-            MDB_LAUNCH(launches, k_to_float<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, z.p, xf.p,
-                yf.p, zf.p);
-        }
+        // candidates in CSR order as SoA float arrays, padded to a multiple of 4
+        const int nall = Nlocal + Nghost, npad = (int)round_up((size_t)nall + 4, 4);
+        for (DBuf<float>* b : { &cxs, &cys, &czs }) b->ensure(npad, false, stream);
+        cids.ensure(npad, false, stream);
+        MDB_LAUNCH(launches, k_pack_binned_soa<real>, grid_for(npad, 256), 256, 0, stream, nall, npad, binatoms.p, x.p, y.p,
+            z.p, cxs.p, cys.p, czs.p, cids.p);
         nstride = round_up((size_t)Nlocal, 32);
         numneigh.ensure(nstride, false, stream);
+        float lo, hi;
+        list_margin(lo, hi);
         for (;;) {
             const size_t rowlen = round_up((size_t)maxneighs, 8);
-            if (list_layout == 1) LL = NbLayout { rowlen, 1, 0 };
-            else if (list_layout == 2) LL = NbLayout { 32 * rowlen, 32, 5 };
-            else LL = NbLayout { 0, nstride, 31 };
+            LL = NbLayout { 32 * rowlen, 32, 5 };
             neighbors.ensure(rowlen * nstride, false, stream);
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
-            if (neigh_variant == 0) {
-                MDB_LAUNCH(launches, k_build_neighbor<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                    P.half_neigh, bg, cutneighsq, x.p, y.p, z.p, binstart.p, binatoms.p, stencil.p, nstencil,
-                    maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
-            } else if (neigh_variant >= 2) {
-                float lo, hi;
-                list_margin(lo, hi);
-                if (neigh_variant == 4)
-                    MDB_LAUNCH(launches, k_build_neighbor_v5<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                        P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p,
-                        run_len.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1, gflag_ptr());
-                else if (neigh_variant == 2)
-                    MDB_LAUNCH(launches, k_build_neighbor_v3<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                        P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p,
-                        nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
-                else
-                    MDB_LAUNCH(launches, k_build_neighbor_v4<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                        P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, pk.p, binstart.p, run_off.p, run_len.p,
-                        nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1, gflag_ptr());
-            } else {
-                float lo, hi;
-                list_margin(lo, hi);
-                MDB_LAUNCH(launches, k_build_neighbor_v2<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                    P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, xf.p, yf.p, zf.p, binstart.p, binatoms.p,
-                    stencil.p, nstencil, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
-            }
+            MDB_LAUNCH(launches, k_build_neighbor_v5<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p,
+                run_len.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));
@@ -853,8 +694,6 @@ template <class real> struct Sim final : SimBase {
             }
             break;
         }
-        if (sort_rows)
-            MDB_LAUNCH(launches, k_sort_rows, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, LL, numneigh.p, neighbors.p);
         if (timing) {
             MDB_CUDA(cudaEventRecord(evB, stream));
             MDB_CUDA(cudaEventSynchronize(evB));
@@ -866,86 +705,25 @@ template <class real> struct Sim final : SimBase {
     // ------------------------------------------------------------------ force
     void launch_force(int which)
     {
+        if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_setup or mdb_buildNeighbor first)");
         if (which == FORCE_DISPATCH)
             which = P.force_field == MDB_FF_EAM ? FORCE_EAM : (P.half_neigh ? FORCE_LJ_HALF : FORCE_LJ_FULL);
-        if (merged_built && which != FORCE_LJ_FULL) ensure_per_atom();
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         if (which == FORCE_EAM) {
             launch_eam();
         } else {
-            LJConst<real> c { cutforce * cutforce, sigma6, epsilon };
-            if (which == FORCE_LJ_FULL && merged_built) {
-                LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6,
-                    (real)24.0 * epsilon * sigma6 };
-                const int npairs = (Nlocal + 1) / 2;
-                if (force_variant == 2)
-                    MDB_LAUNCH(launches, (k_force_lj_full_m2<real, 4>), grid_for(npairs, 128), 128, 0, stream, Nlocal, c2, x.p, y.p,
-                        z.p, mnum.p, mneigh.p, LLm, fx.p, fy.p, fz.p);
-                else
-                    MDB_LAUNCH(launches, (k_force_lj_full_m2<real, 2>), grid_for(npairs, 128), 128, 0, stream, Nlocal, c2, x.p, y.p,
-                        z.p, mnum.p, mneigh.p, LLm, fx.p, fy.p, fz.p);
-            } else if (which == FORCE_LJ_FULL) {
-                LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6,
-                    (real)24.0 * epsilon * sigma6 };
-                if (force_variant >= 3 && LL.sk == 1) { // lanes-per-atom kernels need row-major rows
-                    const size_t nthr = (size_t)Nlocal * (force_variant == 4 ? 16 : (force_variant == 5 ? 4 : 8));
-                    if (force_variant == 4)
-                        MDB_LAUNCH(launches, (k_force_lj_full_v3<real, 16, 2>), grid_for(nthr, 128), 128, 0, stream,
-                            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL.tile_stride, fx.p, fy.p, fz.p);
-                    else if (force_variant == 5)
-                        MDB_LAUNCH(launches, (k_force_lj_full_v3<real, 4, 4>), grid_for(nthr, 128), 128, 0, stream,
-                            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL.tile_stride, fx.p, fy.p, fz.p);
-                    else
-                        MDB_LAUNCH(launches, (k_force_lj_full_v3<real, 8, 2>), grid_for(nthr, 128), 128, 0, stream,
-                            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL.tile_stride, fx.p, fy.p, fz.p);
-                } else if (force_variant == 6 || force_variant == 7) { // packed positions, one gather per neighbor
-                    typedef typename PosOf<real>::type P4;
-                    const int nall = Nlocal + Nghost;
-                    pos4.ensure((size_t)nall * sizeof(P4), false, stream);
-                    MDB_LAUNCH(launches, k_pack_pos4<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, z.p,
-                        (P4*)pos4.p);
-                    if (force_variant == 6)
-                        MDB_LAUNCH(launches, (k_force_lj_full_p4<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                            c2, (const P4*)pos4.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                    else
-                        MDB_LAUNCH(launches, (k_force_lj_full_p4<real, 8>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                            c2, (const P4*)pos4.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                } else if (force_variant == 8 || force_variant == 9) { // branch-free force block (v6), U = 4 / 2
-                    if (force_variant == 8)
-                        MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
-                            x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                    else
-                        MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
-                            x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                } else if (force_variant >= 10 && force_variant <= 13) {
-                    launch_v7<false>(c2, FusedIntegrate<real> { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr });
-                } else if (force_variant == 0)
-                    MDB_LAUNCH(launches, k_force_lj_full<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
-                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                else if (force_variant == 2)
-                    MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 8>), grid_for(Nlocal, 128), 128, 0, stream,
-                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p,
-                        (const int*)nullptr, 0);
-                else if (sizeof(real) == 4) // default, SP: the branch-free kernel (1.00 vs 1.13 ms, profiles/r1_ab3.txt)
+            LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
+            if (which == FORCE_LJ_FULL) {
+                if (sizeof(real) == 4) // SP: the branch-free block (1.00 vs 1.13 ms, profiles/r1_ab3.txt)
                     MDB_LAUNCH(launches, (k_force_lj_full_v6<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
                         x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                else // default, DP: v2 (the branch-free kernel pays 1.617 vs 1.537 ms for the FP64 work outside the cutoff)
+                else // DP: the divergent block (the branch-free one pays 1.617 vs 1.537 ms for the FP64 work outside the cutoff)
                     MDB_LAUNCH(launches, (k_force_lj_full_v2<real, 4>), grid_for(Nlocal, 128), 128, 0, stream,
-                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p,
-                        (const int*)nullptr, 0);
+                        Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
             } else {
                 zero3(fx.p, fy.p, fz.p, Nlocal);
-                LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6,
-                    (real)24.0 * epsilon * sigma6 };
-                if (half_variant == 0)
-                    MDB_LAUNCH(launches, k_force_lj_half<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c,
-                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                else if (half_variant == 2)
-                    MDB_LAUNCH(launches, (k_force_lj_half_v2<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
-                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
-                else
-                    MDB_LAUNCH(launches, (k_force_lj_half_v2<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
-                        x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+                MDB_LAUNCH(launches, (k_force_lj_half_v2<real, 4>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, c2,
+                    x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
             }
         }
         force_launches++;
@@ -1031,38 +809,12 @@ template <class real> struct Sim final : SimBase {
             vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
 
-    // rolling-pipeline kernels (k_force_lj_full_v7), force_variant 10..13: {U, min blocks/SM} DP | SP
-    //   10: {4,7} | {4,9}   11: {3,9} | {3,10}   12: {3,8} | {6,8}   13: {2,8} | {2,12};  SP branch-free, DP branchy
-    template <int U, int MINB, bool FI> void launch_v7_t(const LJConst2<real>& c2, const FusedIntegrate<real>& fi)
-    {
-        MDB_LAUNCH(launches, (k_force_lj_full_v7<real, U, sizeof(real) == 4, FI, MINB>), grid_for(Nlocal, 128), 128, 0, stream,
-            Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p, fi);
-    }
-    template <bool FI> void launch_v7(const LJConst2<real>& c2, const FusedIntegrate<real>& fi)
-    {
-        if constexpr (sizeof(real) == 4) {
-            switch (force_variant) {
-            case 10: launch_v7_t<4, 9, FI>(c2, fi); break;
-            case 11: launch_v7_t<3, 10, FI>(c2, fi); break;
-            case 12: launch_v7_t<6, 8, FI>(c2, fi); break;
-            default: launch_v7_t<2, 12, FI>(c2, fi); break;
-            }
-        } else {
-            switch (force_variant) {
-            case 10: launch_v7_t<4, 7, FI>(c2, fi); break;
-            case 11: launch_v7_t<3, 9, FI>(c2, fi); break;
-            case 12: launch_v7_t<3, 8, FI>(c2, fi); break;
-            default: launch_v7_t<2, 8, FI>(c2, fi); break;
-            }
-        }
-    }
     // computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1) in ONE launch (k_force_lj_full_fi): LJ full lists of a
     // single domain with the default kernels.  The new positions land in the sort buffers x2/y2/z2, which then become
     // x/y/z; their ghost range is rewritten by the updatePbc / setupPbc of the next step before anything reads it.
     bool can_fuse_force() const
     {
-        return fuse_force && fuse_integrate && !brick && P.force_field != MDB_FF_EAM && !P.half_neigh && !merged_built &&
-            (force_variant == 1 || (force_variant >= 10 && force_variant <= 13));
+        return fuse_force && fuse_integrate && !brick && P.force_field != MDB_FF_EAM && !P.half_neigh;
     }
     void forceFinalInitialIntegrate()
     {
@@ -1072,7 +824,7 @@ template <class real> struct Sim final : SimBase {
         z2.ensure(z.cap, false, stream);
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
-        const bool use_xy = xy_gather && force_variant == 1;
+        const bool use_xy = xy_gather != 0;
         if (use_xy) {
             xy.ensure(x.cap, false, stream);
             xy2.ensure(x.cap, false, stream);
@@ -1082,9 +834,7 @@ template <class real> struct Sim final : SimBase {
             }
         }
         FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt, xy.p, xy2.p, nullptr, nullptr };
-        if (force_variant >= 10)
-            launch_v7<true>(c2, fi);
-        else if (use_xy)
+        if (use_xy)
             MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, sizeof(real) == 4, true>), grid_for(Nlocal, 128), 128, 0, stream,
                 Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fi);
         else // SP: branch-free force block (v6), DP: the divergent block of v2
@@ -1107,7 +857,7 @@ template <class real> struct Sim final : SimBase {
     // xy / zg.  Call after the halo of this step has landed (forward() / reneighbour()).
     bool can_fuse_force_inplace() const
     {
-        return fuse_force && fuse_integrate && P.force_field != MDB_FF_EAM && !P.half_neigh && !merged_built && force_variant == 1;
+        return fuse_force && fuse_integrate && P.force_field != MDB_FF_EAM && !P.half_neigh;
     }
     void forceFinalInitialIntegrateInPlace()
     {
@@ -1168,6 +918,7 @@ template <class real> struct Sim final : SimBase {
         if (pending_force) { pending_force = false; launch_force(FORCE_DISPATCH); }
         if (pending_final) { pending_final = false; finalIntegrate(); }
     }
+    void drop_lazy() override { pending_force = pending_final = false; }
     void invalidate_copies() override { xy_valid = false; }
     void finalInitialIntegrate() // finalIntegrate(n) + initialIntegrate(n+1) in one pass
     {
@@ -1278,7 +1029,6 @@ template <class real> struct Sim final : SimBase {
     void getNeighbors(int* nn, int* nb, int row_stride) override
     {
         if (nstride == 0) throw Error("getNeighbors: no neighbor list");
-        ensure_per_atom();
         build_extmap();
         nn_ext.ensure(Nlocal, false, stream);
         if (nb) rows.ensure((size_t)Nlocal * row_stride, false, stream);
@@ -1325,7 +1075,6 @@ template <class real> struct Sim final : SimBase {
     }
     void countPairs(long long* listed, long long* inside) override
     {
-        ensure_per_atom();
         MDB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(unsigned long long), stream));
         MDB_LAUNCH(launches, k_count_pairs<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
             cutforce * cutforce, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, d_cnt.p);
@@ -1407,40 +1156,29 @@ template <class real> struct Sim final : SimBase {
     void stubNeighbors(int pattern, int nneighs, int nreps, unsigned seed) override
     {
         if (Nlocal <= 0) throw Error("mdb_stubNeighbors: no atoms");
-        if (pattern < 0 || pattern > 2 || nneighs < 1 || nreps < 1) throw Error("mdb_stubNeighbors: bad pattern / counts");
+        if (pattern < 0 || pattern > 4 || nneighs < 1 || nreps < 1) throw Error("mdb_stubNeighbors: bad pattern / counts");
         if (pattern == 2 && Nlocal <= nneighs)
             throw Error("When using random pattern, number of atoms should be higher than number of neighbors per atom!");
         Nghost    = 0;
         maxneighs = nneighs * nreps;
         nstride   = round_up((size_t)Nlocal, 32);
         const size_t rowlen = round_up((size_t)maxneighs, 8);
-        if (list_layout == 1) LL = NbLayout { rowlen, 1, 0 };
-        else if (list_layout == 2) LL = NbLayout { 32 * rowlen, 32, 5 };
-        else LL = NbLayout { 0, nstride, 31 };
+        LL = NbLayout { 32 * rowlen, 32, 5 };
         numneigh.ensure(nstride, false, stream);
         neighbors.ensure(rowlen * nstride, false, stream);
         MDB_LAUNCH(launches, k_stub_neighbors, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, pattern, nneighs, nreps, seed, LL,
             numneigh.p, neighbors.p);
-        merged_built = false;
-        pa_valid     = true;
-        gflag_valid  = false;
         extmap_valid = false;
     }
     void setOption(const char* name, double v) override
     {
         if (!strcmp(name, "sort_atoms")) sort_enabled = v != 0;
-        else if (!strcmp(name, "force_variant")) force_variant = (int)v;
-        else if (!strcmp(name, "neigh_variant")) neigh_variant = (int)v;
-        else if (!strcmp(name, "list_layout")) list_layout = (int)v;
         else if (!strcmp(name, "sort_order")) sort_order = (int)v;
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else if (!strcmp(name, "xy_gather")) xy_gather = (int)v;
         else if (!strcmp(name, "lazy_ops")) { flush_lazy(); lazy_ops = v != 0; }
-        else if (!strcmp(name, "sort_rows")) sort_rows = v != 0;
-        else if (!strcmp(name, "merge")) merge = (int)v;
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;
-        else if (!strcmp(name, "half_variant")) half_variant = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

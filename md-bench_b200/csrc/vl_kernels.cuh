@@ -410,288 +410,17 @@ __global__ void k_scatter_orig(int n, const int* __restrict__ orig, const real* 
     oa[o] = a[p]; ob[o] = b[p]; oc[o] = c[p];
 }
 
-// buildNeighbor, verletlist/neighbor.c:186-264.  One thread per local atom scans the stencil bins.
-// rsq = fma(dx,dx,fma(dy,dy,dz*dz)) is the exact expression of the reference build,
-// the inclusion test is "<=" (neighbor.c:240).  Rows are written transposed; entries beyond
-// maxneighs are counted but not stored and the host re-runs with a larger maxneighs.
-template <class real>
-__global__ void __launch_bounds__(128) k_build_neighbor(int nlocal, int half, BinGeom<real> g,
-    real cutneighsq, const real* __restrict__ x, const real* __restrict__ y,
-    const real* __restrict__ z, const int* __restrict__ binstart, const int* __restrict__ binatoms,
-    const int* __restrict__ stencil, int nstencil, int maxneighs, NbLayout L,
-    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors,
-    int* __restrict__ max_n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n       = 0;
-    if (i < nlocal) {
-        const real xt = x[i], yt = y[i], zt = z[i];
-        const int oi  = orig[i]; // the atom's index in the reference's numbering
-        const int ibin = coord2bin(g, xt, yt, zt);
-        for (int k = 0; k < nstencil; k++) {
-            const int jbin = ibin + __ldg(&stencil[k]);
-            if (jbin < 0 || jbin > g.mbins) continue;
-            const int s = __ldg(&binstart[jbin]), e = __ldg(&binstart[jbin + 1]);
-            for (int m = s; m < e; m++) {
-                const int j = __ldg(&binatoms[m]);
-                // neighbor.c:224 "j < i" is a statement about reference indices; ghosts (reference
-                // index >= Nlocal) are never dropped
-                if (j == i || (half && j < nlocal && orig[j] < oi)) continue;
-                const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
-                const real rsq = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz)));
-                if (rsq <= cutneighsq) {
-                    if (n < maxneighs) neighbors[L.base(i) + (size_t)n * L.sk] = j;
-                    n++;
-                }
-            }
-        }
-        numneigh[i] = n;
-    }
-    n = __reduce_max_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
-}
-
-// Rows in ascending neighbor index (in place).  The ORDER of a row is free (parity is on index sets);
-// ascending order makes the k-th entries of the 32 atoms of a warp point at nearby / consecutive
-// atoms whenever consecutive atoms are spatial neighbors, so the position gathers of the force kernel
-// touch few 128-byte lines.  Rows arrive nearly sorted (stencil order walks z, y, x), so a plain
-// insertion sort does ~n + inversions steps; the 32 rows of a tile are walked in lockstep, each access
-// one coalesced line.
-static __global__ void __launch_bounds__(128) k_sort_rows(int nlocal, NbLayout L, const int* __restrict__ numneigh,
-    int* __restrict__ neighbors)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nlocal) return;
-    const int n     = numneigh[i];
-    int* a          = neighbors + L.base(i);
-    const size_t sk = L.sk;
-    for (int k = 1; k < n; k++) {
-        const int v = a[k * sk];
-        int j       = k - 1;
-        int w;
-        while (j >= 0 && (w = a[j * sk]) > v) {
-            a[(j + 1) * sk] = w;
-            j--;
-        }
-        a[(j + 1) * sk] = v;
-    }
-}
-
-// ---- v2 list build --------------------------------------------------------------------------------
-// The membership test must be the reference's exact expression, but 87% of the ~604 candidates per
-// atom are far outside the cutoff.  For DP a single-precision pre-test on float copies of the
-// positions classifies every candidate as certainly-inside / certainly-outside / uncertain, with a
-// margin that bounds the float rounding error (host: list_margin()); only the uncertain band
-// (~1e-4 of the candidates) runs the exact FP64 expression.  The resulting SET is identical to the
-// exact test's (tests compare it bit for bit with the oracle); FP64 work drops ~600x and the
-// gathered bytes halve.  For SP the float expression IS the exact test.
-template <class real>
-__global__ void k_to_float(int n, const real* __restrict__ x, const real* __restrict__ y,
-    const real* __restrict__ z, float* __restrict__ xf, float* __restrict__ yf, float* __restrict__ zf)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    xf[i] = (float)x[i];
-    yf[i] = (float)y[i];
-    zf[i] = (float)z[i];
-}
-
-template <class real>
-__global__ void __launch_bounds__(128) k_build_neighbor_v2(int nlocal, int half, BinGeom<real> g,
-    real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
-    const real* __restrict__ z, const float* __restrict__ xf, const float* __restrict__ yf,
-    const float* __restrict__ zf, const int* __restrict__ binstart, const int* __restrict__ binatoms,
-    const int* __restrict__ stencil, int nstencil, int maxneighs, NbLayout L,
-    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors,
-    int* __restrict__ max_n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n       = 0;
-    if (i < nlocal) {
-        const real xt = x[i], yt = y[i], zt = z[i];
-        const float xs = xf[i], ys = yf[i], zs = zf[i];
-        const int oi   = half ? orig[i] : 0;
-        const int ibin = coord2bin(g, xt, yt, zt);
-        int* out       = neighbors + L.base(i);
-        for (int k = 0; k < nstencil; k++) {
-            const int jbin = ibin + __ldg(&stencil[k]);
-            if (jbin < 0 || jbin > g.mbins) continue;
-            const int s = __ldg(&binstart[jbin]), e = __ldg(&binstart[jbin + 1]);
-            for (int m = s; m < e; m++) {
-                const int j = __ldg(&binatoms[m]);
-                const float dxs = xs - __ldg(xf + j), dys = ys - __ldg(yf + j), dzs = zs - __ldg(zf + j);
-                const float rs  = dxs * dxs + dys * dys + dzs * dzs;
-                if (rs > hi || j == i) continue;
-                if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
-                bool in = rs < lo;
-                if (!in) { // uncertain band: the reference's exact expression
-                    const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
-                    in = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq;
-                }
-                if (in) {
-                    if (n < maxneighs) out[(size_t)n * L.sk] = j;
-                    n++;
-                }
-            }
-        }
-        numneigh[i] = n;
-    }
-    n = __reduce_max_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
-}
-
-// ---- v3 list build --------------------------------------------------------------------------------
-// ncu r1_v2: the v2 kernel is instruction-bound (issue 74%, ~49 warp instructions per candidate):
-// a dependent index load + three position loads with 64-bit address arithmetic per candidate, and
-// an 81-iteration outer loop whose per-bin trip counts diverge across the lanes of a warp.  v3:
-//  * candidates are pre-packed in bin (CSR) order as float4 {x, y, z, index-as-bits}: ONE 16-byte
-//    load per candidate, coalesced / broadcast, no dependent load;
-//  * the 81-bin stencil is walked as 21 RUNS of x-adjacent bins (adjacent bins are adjacent in the
-//    CSR), so the inner loop runs over ~22-37 candidates at a time;
-//  * same exactness rule as v2 (float pre-test with an error-bounded margin, exact FP64 expression
-//    only in the uncertain band; for SP the float expression is the reference's own).
-template <class real>
-__global__ void k_pack_binned(int nall, const int* __restrict__ binatoms, const real* __restrict__ x,
-    const real* __restrict__ y, const real* __restrict__ z, float4* __restrict__ pk)
-{
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= nall) return;
-    const int j = binatoms[m];
-    pk[m]       = make_float4((float)x[j], (float)y[j], (float)z[j], __int_as_float(j));
-}
-
-template <class real>
-__global__ void __launch_bounds__(128) k_build_neighbor_v3(int nlocal, int half, BinGeom<real> g,
-    real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
-    const real* __restrict__ z, const float4* __restrict__ pk, const int* __restrict__ binstart,
-    const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs,
-    NbLayout L, const int* __restrict__ orig, int* __restrict__ numneigh,
-    int* __restrict__ neighbors, int* __restrict__ max_n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n       = 0;
-    if (i < nlocal) {
-        const real xt = x[i], yt = y[i], zt = z[i];
-        const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
-        const int oi   = half ? orig[i] : 0;
-        const int ibin = coord2bin(g, xt, yt, zt);
-        int* out       = neighbors + L.base(i);
-        for (int r = 0; r < nruns; r++) {
-            int b0 = ibin + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
-            b0 = max(b0, 0);
-            b1 = min(b1, g.mbins + 1);
-            if (b1 <= b0) continue;
-            const int s = __ldg(&binstart[b0]), e = __ldg(&binstart[b1]);
-            for (int m = s; m < e; m++) {
-                const float4 c = __ldg(&pk[m]);
-                bool in;
-                if (sizeof(real) == 4) { // SP: this IS the reference's expression
-                    const float dx = __fsub_rn(xs, c.x), dy = __fsub_rn(ys, c.y), dz = __fsub_rn(zs, c.z);
-                    in = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))) <= (float)cutneighsq;
-                    if (!in) continue;
-                } else {
-                    const float dx = xs - c.x, dy = ys - c.y, dz = zs - c.z;
-                    const float rs = dx * dx + dy * dy + dz * dz;
-                    if (rs > hi) continue;
-                    in = rs < lo;
-                }
-                const int j = __float_as_int(c.w);
-                if (j == i) continue;
-                if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
-                if (!in) { // uncertain band: the reference's exact FP64 expression
-                    const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
-                    if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
-                }
-                if (n < maxneighs) out[(size_t)n * L.sk] = j;
-                n++;
-            }
-        }
-        numneigh[i] = n;
-    }
-    n = __reduce_max_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
-}
-
-// ---- v4 list build: v3 + two-phase chunks ---------------------------------------------------------
-// ncu r1_v3n (source page): in v3 the append path (29 instructions: 64-bit row addressing, bound and
-// half-list checks) runs at ~8/32 lanes for almost every candidate, because with a 13% hit rate some
-// lane of the warp always passes.  v4 walks each run in chunks of 32 candidates: phase 1 only records
-// pass / uncertain BITS (branch-free, ~11 instructions per candidate), phase 2 pops the set bits and
-// appends -- its trip count is the number of hits, not the number of candidates.
-template <class real>
-__global__ void __launch_bounds__(128) k_build_neighbor_v4(int nlocal, int half, BinGeom<real> g,
-    real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
-    const real* __restrict__ z, const float4* __restrict__ pk, const int* __restrict__ binstart,
-    const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs,
-    NbLayout L, const int* __restrict__ orig, int* __restrict__ numneigh,
-    int* __restrict__ neighbors, int* __restrict__ max_n, unsigned char* __restrict__ gflag)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n       = 0;
-    if (i < nlocal) {
-        const real xt = x[i], yt = y[i], zt = z[i];
-        const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
-        const float cut = (float)cutneighsq;
-        bool ghost = false; // some listed neighbor is a ghost atom (decomposed runs: boundary atoms wait for the halo)
-        const int oi   = half ? orig[i] : 0;
-        const int ibin = coord2bin(g, xt, yt, zt);
-        int* out       = neighbors + L.base(i);
-        for (int r = 0; r < nruns; r++) {
-            int b0 = ibin + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
-            b0 = max(b0, 0);
-            b1 = min(b1, g.mbins + 1);
-            if (b1 <= b0) continue;
-            const int s = __ldg(&binstart[b0]), e = __ldg(&binstart[b1]);
-            for (int c0 = s; c0 < e; c0 += 32) {
-                const float4* p = pk + c0;
-                const int cnt   = min(32, e - c0);
-                unsigned pass = 0, unc = 0;
-#pragma unroll 8
-                for (int t = 0; t < cnt; t++) {
-                    const float4 c = __ldg(p + t);
-                    if (sizeof(real) == 4) { // SP: the reference's own expression
-                        const float dx = __fsub_rn(xs, c.x), dy = __fsub_rn(ys, c.y), dz = __fsub_rn(zs, c.z);
-                        const float rs = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
-                        pass |= (rs <= cut ? 1u : 0u) << t;
-                    } else {
-                        const float dx = xs - c.x, dy = ys - c.y, dz = zs - c.z;
-                        const float rs = dx * dx + dy * dy + dz * dz;
-                        pass |= (rs < lo ? 1u : 0u) << t;
-                        unc |= ((rs >= lo && rs <= hi) ? 1u : 0u) << t;
-                    }
-                }
-                unsigned todo = pass | unc;
-                while (todo) {
-                    const int t = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int j = __float_as_int(__ldg(&p[t].w));
-                    if (j == i) continue;
-                    if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
-                    if ((unc >> t) & 1u) { // uncertain band: the reference's exact FP64 expression
-                        const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
-                        if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
-                    }
-                    if (n < maxneighs) *out = j;
-                    out += L.sk;
-                    n++;
-                    ghost = ghost || j >= nlocal;
-                }
-            }
-        }
-        numneigh[i] = n;
-        if (gflag) gflag[i] = ghost ? 1 : 0;
-    }
-    n = __reduce_max_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
-}
-
-// ---- v5 list build: v4 with the candidates as SoA float arrays and PACKED FP32 distance tests ------------------------
-// ncu of v4 (profiles/r1_s2_neigh_raw.txt): 35 executed instructions per candidate, issue 73 %, L1 83 %.  Here one
-// 128-bit load fetches a coordinate of FOUR consecutive candidates (3 loads per 4 instead of 4 per 4), the distance of two
+// buildNeighbor, verletlist/neighbor.c:186-264.  One thread per local atom walks the stencil of its bin as 21 runs of
+// x-adjacent bins (contiguous in the CSR).  Membership is the reference's: rsq = fma(dx,dx,fma(dy,dy,dz*dz)) (the contraction
+// GCC -Ofast makes) <= cutneighsq (neighbor.c:240).  For DP a float pre-test on float copies of the candidates
+// sorts every candidate into certainly inside / certainly outside / uncertain (margin = Sim::list_margin) and only the
+// uncertain band evaluates the exact FP64 expression; for SP the float expression is the reference's own.  Candidates are
+// SoA float arrays in CSR order: one 128-bit load fetches a coordinate of FOUR consecutive candidates, the distance of two
 // candidates is one FADD2/FMUL2/FFMA2 sequence (bit-identical to the scalar round-to-nearest operations), and the
-// threshold tests are two more packed subtractions whose SIGN bits are shifted into the pass / maybe masks with one
-// funnel shift each (rs < T  <=>  sign(rs - T): the subtraction is monotone and exact in sign).  ~7 instructions per
-// candidate in phase 1; phase 2 (append, exact FP64 in the uncertain band) is v4's.
+// threshold tests are two more packed subtractions whose SIGN bits are shifted into the pass / maybe masks with one funnel
+// shift each (rs < T  <=>  sign(rs - T)).  Each flush of up to 32 candidates is split into that branch-free phase and an
+// append phase whose trip count is the number of hits.  Entries beyond maxneighs are counted but not stored and the host
+// re-runs with a larger maxneighs (neighbor.c:247-262).  (Generations 1-4 of this kernel: profiles/r1_ab*.txt.)
 template <class real>
 __global__ void k_pack_binned_soa(int nall, int npad, const int* __restrict__ binatoms, const real* __restrict__ x,
     const real* __restrict__ y, const real* __restrict__ z, float* __restrict__ cx, float* __restrict__ cy, float* __restrict__ cz,
@@ -717,8 +446,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v5(int nlocal, int half,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float* __restrict__ cx,
     const float* __restrict__ cy, const float* __restrict__ cz, const int* __restrict__ cid, const int* __restrict__ binstart,
     const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs, NbLayout L,
-    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n,
-    unsigned char* __restrict__ gflag)
+    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n       = 0;
@@ -734,7 +462,6 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v5(int nlocal, int half,
         const int oi   = half ? orig[i] : 0;
         const int ibin = coord2bin(g, xt, yt, zt);
         int* out       = neighbors + L.base(i);
-        bool ghost     = false;
         for (int r = 0; r < nruns; r++) {
             int b0 = ibin + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
             b0 = max(b0, 0);
@@ -783,197 +510,14 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v5(int nlocal, int half,
                     if (n < maxneighs) *out = j;
                     out += L.sk;
                     n++;
-                    ghost = ghost || j >= nlocal;
                 }
                 c0 += k;
             }
         }
         numneigh[i] = n;
-        if (gflag) gflag[i] = ghost ? 1 : 0;
     }
     n = __reduce_max_sync(0xffffffffu, n);
     if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
-}
-
-// gflag (k_build_neighbor_v4) -> interior[] / boundary[] index lists, ascending; pos = exclusive scan of gflag
-static __global__ void k_split_by_flag(int n, const unsigned char* __restrict__ gflag, const int* __restrict__ pos, int* __restrict__ interior,
-    int* __restrict__ boundary)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (gflag[i]) boundary[pos[i]] = i;
-    else interior[i - pos[i]] = i;
-}
-static __global__ void k_flag_to_int(int n, const unsigned char* __restrict__ gflag, int* __restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = gflag[i];
-}
-
-// ---- merged lists: ONE row for the atom pair (2t, 2t+1) -------------------------------------------------------------
-// ncu (profiles/r1_s2_force_raw.txt): the full-list force kernel is bound by the L1 data pipe -- three 64-bit gathers
-// per listed neighbor, ~19 sectors per warp request -- while the FP64 pipe idles at 45 %.  Two atoms that are adjacent
-// in memory are close in space (the generator emits atoms along x at distance 1.68; after a spatial sort they share a
-// bin), so their lists overlap by ~55 %.  One thread therefore owns the pair (2t, 2t+1) and a row holding the UNION of
-// the two reference rows, each entry tagged with two membership bits (bit 30: neighbor of atom 2t, bit 31: of 2t+1).
-// Every gathered position serves both atoms: ~0.7 gathers per listed pair instead of 1.  Membership bits keep the
-// result EXACTLY the reference's: a pair is evaluated iff it is in that atom's reference list (an atom that outruns
-// the skin between two rebuilds must not interact earlier than in the reference).
-//
-// Candidates: the stencil of atom 2t's bin is walked testing both atoms; if atom 2t+1 sits in another bin, the bins of
-// its stencil that are not part of the first stencil are walked for it alone (bins outside an atom's stencil cannot
-// hold a neighbor of it, neighbor.c:107-124, so testing both atoms there would only cost time).
-struct StencilRow { // x-run of the stencil in the bin row (dj, dk): offsets [i0, i0 + len)
-    int i0, len;
-};
-template <class real>
-__device__ __forceinline__ void m2_walk(int s, int e, bool both, int ia, int ib, bool has_b, real xa, real ya, real za, real xb,
-    real yb, real zb, real cutneighsq, float lo, float hi, const real* __restrict__ x, const real* __restrict__ y,
-    const real* __restrict__ z, const float4* __restrict__ pk, int mcap, size_t sk, int*& out, int& n, int& na, int& nb)
-{
-    const float xas = (float)xa, yas = (float)ya, zas = (float)za, xbs = (float)xb, ybs = (float)yb, zbs = (float)zb;
-    const float cut = (float)cutneighsq;
-    for (int c0 = s; c0 < e; c0 += 32) {
-        const float4* p = pk + c0;
-        const int cnt   = min(32, e - c0);
-        unsigned pa = 0, ua = 0, pb = 0, ub = 0;
-#pragma unroll 8
-        for (int t = 0; t < cnt; t++) {
-            const float4 c = __ldg(p + t);
-            if (sizeof(real) == 4) { // SP: the reference's own expression
-                float dx = __fsub_rn(xas, c.x), dy = __fsub_rn(yas, c.y), dz = __fsub_rn(zas, c.z);
-                pa |= (__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))) <= cut ? 1u : 0u) << t;
-                dx = __fsub_rn(xbs, c.x); dy = __fsub_rn(ybs, c.y); dz = __fsub_rn(zbs, c.z);
-                pb |= (__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))) <= cut ? 1u : 0u) << t;
-            } else { // DP: float pre-test with an error margin, exact FP64 only in the uncertain band
-                float dx = xas - c.x, dy = yas - c.y, dz = zas - c.z;
-                float rs = dx * dx + dy * dy + dz * dz;
-                pa |= (rs < lo ? 1u : 0u) << t;
-                ua |= ((rs >= lo && rs <= hi) ? 1u : 0u) << t;
-                dx = xbs - c.x; dy = ybs - c.y; dz = zbs - c.z;
-                rs = dx * dx + dy * dy + dz * dz;
-                pb |= (rs < lo ? 1u : 0u) << t;
-                ub |= ((rs >= lo && rs <= hi) ? 1u : 0u) << t;
-            }
-        }
-        if (!both) pa = ua = 0;
-        if (!has_b) pb = ub = 0;
-        unsigned todo = pa | ua | pb | ub;
-        while (todo) {
-            const int t = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int j = __float_as_int(__ldg(&p[t].w));
-            bool ma = ((pa | ua) >> t) & 1u, mb = ((pb | ub) >> t) & 1u;
-            if (j == ia) ma = false;
-            if (j == ib) mb = false;
-            if (((ua | ub) >> t) & 1u) { // the reference's exact FP64 expression
-                const real xj = x[j], yj = y[j], zj = z[j];
-                if (ma && ((ua >> t) & 1u)) {
-                    const real dx = sub_rn(xa, xj), dy = sub_rn(ya, yj), dz = sub_rn(za, zj);
-                    ma = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq;
-                }
-                if (mb && ((ub >> t) & 1u)) {
-                    const real dx = sub_rn(xb, xj), dy = sub_rn(yb, yj), dz = sub_rn(zb, zj);
-                    mb = fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq;
-                }
-            }
-            if (!(ma || mb)) continue;
-            if (n < mcap) *out = j | (ma ? 0x40000000 : 0) | (mb ? (int)0x80000000 : 0);
-            out += sk;
-            n++;
-            na += ma;
-            nb += mb;
-        }
-    }
-}
-__device__ __forceinline__ void bin3(int b, int mbinx, int mbiny, int& ix, int& iy, int& iz)
-{
-    const int l = b > 0 ? b - 1 : 0; // coord2bin's "+ 1"
-    ix = l % mbinx;
-    iy = (l / mbinx) % mbiny;
-    iz = l / (mbinx * mbiny);
-}
-template <class real>
-__global__ void __launch_bounds__(128) k_build_neighbor_m2(int nlocal, BinGeom<real> g, real cutneighsq, float lo, float hi,
-    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float4* __restrict__ pk,
-    const int* __restrict__ binstart, const int* __restrict__ run_off, const int* __restrict__ run_len,
-    const int* __restrict__ run_i0, const int* __restrict__ run_dj, const int* __restrict__ run_dk, int nruns,
-    const StencilRow* __restrict__ st_tab, int Ry, int Rz, int mcap, NbLayout L, int* __restrict__ mnum,
-    int* __restrict__ numneigh_atom, int* __restrict__ mneigh, int* __restrict__ max_union, int* __restrict__ max_atom)
-{
-    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ia = 2 * t;
-    int n = 0, na = 0, nb = 0;
-    if (ia < nlocal) {
-        const bool has_b = ia + 1 < nlocal;
-        const int ib     = has_b ? ia + 1 : ia;
-        const real xa = x[ia], ya = y[ia], za = z[ia], xb = x[ib], yb = y[ib], zb = z[ib];
-        const int ba = coord2bin(g, xa, ya, za), bb = has_b ? coord2bin(g, xb, yb, zb) : ba;
-        int* out = mneigh + L.base(t);
-        for (int r = 0; r < nruns; r++) {
-            int b0 = ba + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
-            b0 = max(b0, 0);
-            b1 = min(b1, g.mbins + 1);
-            if (b1 <= b0) continue;
-            m2_walk<real>(__ldg(&binstart[b0]), __ldg(&binstart[b1]), true, ia, has_b ? ib : -1, has_b, xa, ya, za, xb, yb, zb,
-                cutneighsq, lo, hi, x, y, z, pk, mcap, L.sk, out, n, na, nb);
-        }
-        if (bb != ba) { // the part of atom b's stencil that atom a's stencil does not cover
-            int ax, ay, az, bx, by, bz;
-            bin3(ba, g.mbinx, g.mbiny, ax, ay, az);
-            bin3(bb, g.mbinx, g.mbiny, bx, by, bz);
-            const int ddx = bx - ax, ddy = by - ay, ddz = bz - az;
-            for (int r = 0; r < nruns; r++) {
-                const int len = __ldg(&run_len[r]);
-                int b0 = bb + __ldg(&run_off[r]), b1 = b0 + len;
-                // the same bins seen from atom a's bin: row (dj, dk), x offsets [xs, xs + len)
-                const int dj = __ldg(&run_dj[r]) + ddy, dk = __ldg(&run_dk[r]) + ddz, xs = __ldg(&run_i0[r]) + ddx;
-                int c0 = b0, c1 = b0; // covered sub-range [c0, c1) in flattened bin indices
-                if (dj >= -Ry && dj <= Ry && dk >= -Rz && dk <= Rz) {
-                    const StencilRow sr = st_tab[(dk + Rz) * (2 * Ry + 1) + (dj + Ry)];
-                    const int o0 = max(xs, sr.i0), o1 = min(xs + len, sr.i0 + sr.len);
-                    if (o1 > o0) { c0 = b0 + (o0 - xs); c1 = b0 + (o1 - xs); }
-                }
-                // [b0, c0) and [c1, b1)
-                int s0 = max(b0, 0), e0 = min(c0, g.mbins + 1);
-                if (e0 > s0)
-                    m2_walk<real>(__ldg(&binstart[s0]), __ldg(&binstart[e0]), false, ia, ib, true, xa, ya, za, xb, yb, zb, cutneighsq,
-                        lo, hi, x, y, z, pk, mcap, L.sk, out, n, na, nb);
-                s0 = max(c1, 0); e0 = min(b1, g.mbins + 1);
-                if (e0 > s0)
-                    m2_walk<real>(__ldg(&binstart[s0]), __ldg(&binstart[e0]), false, ia, ib, true, xa, ya, za, xb, yb, zb, cutneighsq,
-                        lo, hi, x, y, z, pk, mcap, L.sk, out, n, na, nb);
-            }
-        }
-        mnum[t]           = n;
-        numneigh_atom[ia] = na;
-        if (has_b) numneigh_atom[ib] = nb;
-    }
-    n = __reduce_max_sync(0xffffffffu, n);
-    na = __reduce_max_sync(0xffffffffu, max(na, nb));
-    if ((threadIdx.x & 31) == 0) { atomicMax(max_union, n); atomicMax(max_atom, na); }
-}
-
-// merged rows -> the reference's per-atom rows (parity read-back, pair counters, tag lists): entries keep their order
-static __global__ void k_unmerge_m2(int nlocal, NbLayout Lm, const int* __restrict__ mnum, const int* __restrict__ mneigh, int maxneighs,
-    NbLayout L, int* __restrict__ numneigh, int* __restrict__ neighbors)
-{
-    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ia = 2 * t;
-    if (ia >= nlocal) return;
-    const bool has_b = ia + 1 < nlocal;
-    const int* in    = mneigh + Lm.base(t);
-    int* oa          = neighbors + L.base(ia);
-    int* ob          = neighbors + L.base(has_b ? ia + 1 : ia);
-    int na = 0, nb = 0;
-    const int nn = mnum[t];
-    for (int k = 0; k < nn; k++) {
-        const int e = in[(size_t)k * Lm.sk], j = e & 0x3fffffff;
-        if (e & 0x40000000) { if (na < maxneighs) oa[(size_t)na * L.sk] = j; na++; }
-        if (has_b && e < 0) { if (nb < maxneighs) ob[(size_t)nb * L.sk] = j; nb++; }
-    }
-    numneigh[ia] = na;
-    if (has_b) numneigh[ia + 1] = nb;
 }
 
 // parity read-back: transposed list in internal numbering -> the reference's row-major rows in the
@@ -992,70 +536,8 @@ static __global__ void k_untranspose(int nlocal, int row_stride, NbLayout L, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// LJ 12-6 force, full neighbor lists: verletlist/force_lj.c:14-105.  One thread per local atom,
-// transposed list, 4 neighbors in flight per thread.
-template <class real> struct LJConst {
-    real cutforcesq, sigma6, epsilon;
-};
-
-template <class real> __device__ __forceinline__ real lj_pair(real rsq, const LJConst<real>& c)
-{
-    const real sr2 = (real)1.0 / rsq;
-    const real sr6 = sr2 * sr2 * sr2 * c.sigma6;
-    return (real)48.0 * sr6 * (sr6 - (real)0.5) * sr2 * c.epsilon;
-}
-
-template <class real>
-__global__ void __launch_bounds__(128) k_force_lj_full(int nlocal, LJConst<real> c,
-    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
-    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nlocal) return;
-    const real xt = x[i], yt = y[i], zt = z[i];
-    const int nn  = numneigh[i];
-    real fix = 0, fiy = 0, fiz = 0;
-    const int* nb = nbT + L.base(i);
-    int k         = 0;
-    for (; k + 4 <= nn; k += 4) {
-        int j[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) j[u] = __ldg(nb + (size_t)(k + u) * L.sk);
-        real dx[4], dy[4], dz[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            dx[u] = xt - x[j[u]];
-            dy[u] = yt - y[j[u]];
-            dz[u] = zt - z[j[u]];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
-            if (rsq < c.cutforcesq) {
-                const real f = lj_pair(rsq, c);
-                fix += dx[u] * f;
-                fiy += dy[u] * f;
-                fiz += dz[u] * f;
-            }
-        }
-    }
-    for (; k < nn; k++) {
-        const int j   = __ldg(nb + (size_t)k * L.sk);
-        const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
-        const real rsq = dx * dx + dy * dy + dz * dz;
-        if (rsq < c.cutforcesq) {
-            const real f = lj_pair(rsq, c);
-            fix += dx * f;
-            fiy += dy * f;
-            fiz += dz * f;
-        }
-    }
-    fx[i] = fix;
-    fy[i] = fiy;
-    fz[i] = fiz;
-}
-
+// LJ 12-6 force, full neighbor lists: verletlist/force_lj.c:14-105.  One thread per local atom, k-major list tiles,
+// 4 neighbors in flight per thread.
 // ---- v2: same contract, tuned for the FP64 pipe --------------------------------------------------
 // * reciprocal by rcp.approx.ftz.f64 (MUFU, ~20 bits) + two Newton steps (4 DFMA) instead of the
 //   IEEE division sequence (~9 FP64-pipe instructions + slow-path call); result within ~1 ulp.
@@ -1087,13 +569,10 @@ template <class real, int U>
 __device__ __forceinline__ void force_lj_full_v2_body(int nlocal, const LJConst2<real>& c,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
     const int* __restrict__ numneigh, const int* __restrict__ nbT, const NbLayout& L,
-    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz, const int* __restrict__ sel, int want)
+    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
 {
-    // decomposed runs: one launch for the atoms without ghost neighbors while the halo is in flight, one for the rest
-    // afterwards; sel = the (ascending) list of atom indices of this launch, nlocal its length.  sel == nullptr: every atom
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nlocal) return;
-    const int i = sel ? sel[t] : t;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlocal) return;
     const real xt = x[i], yt = y[i], zt = z[i];
     const int nn  = numneigh[i];
     real fix = 0, fiy = 0, fiz = 0;
@@ -1151,9 +630,9 @@ template <class real, int U>
 __global__ void __launch_bounds__(128) k_force_lj_full_v2(int nlocal, LJConst2<real> c,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
     const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
-    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz, const int* __restrict__ sel, int want)
+    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
 {
-    force_lj_full_v2_body<real, U>(nlocal, c, x, y, z, numneigh, nbT, L, fx, fy, fz, sel, want);
+    force_lj_full_v2_body<real, U>(nlocal, c, x, y, z, numneigh, nbT, L, fx, fy, fz);
 }
 // ---- v6: v2 with the in-cutoff block made branch-free, so that the U pairs in flight interleave ---------------------------
 // SASS of v2: every pair's force block is a divergent region holding a 12-deep dependent DFMA/DMUL chain, executed pair
@@ -1359,381 +838,8 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
     }
 }
 
-// ---- v7: rolling software pipeline ------------------------------------------------------------------------------------
-// Source-level ncu of v2 (gpurun_out/prof_r1_s3_vlforce_seq.ncu-rep, even with perfectly coalesced lists): a third of
-// all stall samples are long-scoreboard waits at the FIRST use of each group's gathered positions -- the 12 gathers of
-// a group are issued at the top of the iteration and consumed right away, so every iteration exposes one L1 latency --
-// and the index prefetch (one group ahead) is still late.  Here the U position slots are refilled one by one: as soon
-// as pair u of group k has been evaluated, its three registers receive pair u of group k+1 (whose index was fetched
-// during group k-1) and the index of pair u of group k+2 is requested.  Every gather then has U-1 pair evaluations
-// between issue and first use, with the same number of registers as v2.  BF / FI as in k_force_lj_full_fi.
-template <class real, int U, bool BF, bool FI, int MINB = 8>
-__global__ void __launch_bounds__(128, MINB) k_force_lj_full_v7(int nlocal, LJConst2<real> c, const real* __restrict__ x,
-    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
-    NbLayout L, real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz, FusedIntegrate<real> fi)
-{
-    // register diet (the DP kernel must fit 64): one down-counter for the groups, one pointer into the list, the atom
-    // index re-read from the special registers in the epilogue
-    real xt, yt, zt;
-    int left, tail; // groups still to evaluate; pairs behind the last full group
-    const int* nbn; // entries of the group after next
-    {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i >= nlocal) return;
-        xt = x[i]; yt = y[i]; zt = z[i];
-        const int nn = numneigh[i];
-        left = nn / U;
-        tail = nn - left * U;
-        nbn  = nbT + L.base(i);
-    }
-    real fix = 0, fiy = 0, fiz = 0;
-    real px[U], py[U], pz[U];
-    int jn[U];
-    if (left > 0) {
-#pragma unroll
-        for (int u = 0; u < U; u++) jn[u] = __ldg(nbn + (size_t)u * L.sk);
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            px[u] = __ldg(x + jn[u]); py[u] = __ldg(y + jn[u]); pz[u] = __ldg(z + jn[u]);
-        }
-        if (left > 1) {
-#pragma unroll
-            for (int u = 0; u < U; u++) jn[u] = __ldg(nbn + (size_t)(U + u) * L.sk);
-        }
-    }
-    nbn += (size_t)2 * U * L.sk;
-    for (; left > 0; left--) {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const real dx = xt - px[u], dy = yt - py[u], dz = zt - pz[u];
-            const real rsq = dx * dx + dy * dy + dz * dz;
-            if (BF) {
-                const real g = rsq < c.cutforcesq ? lj_pair2(rsq, c) : (real)0;
-                fix = fma(dx, g, fix); fiy = fma(dy, g, fiy); fiz = fma(dz, g, fiz);
-            } else if (rsq < c.cutforcesq) {
-                const real f = lj_pair2(rsq, c);
-                fix += dx * f;
-                fiy += dy * f;
-                fiz += dz * f;
-            }
-            if (left > 1) { // slot u <- pair u of the next group
-                const int j = jn[u];
-                px[u] = __ldg(x + j); py[u] = __ldg(y + j); pz[u] = __ldg(z + j);
-            }
-            if (left > 2) jn[u] = __ldg(nbn + (size_t)u * L.sk);
-        }
-        nbn += (size_t)U * L.sk;
-    }
-    nbn -= (size_t)2 * U * L.sk; // first entry behind the last full group
-    for (; tail > 0; tail--) {
-        const int jj = __ldg(nbn);
-        nbn += L.sk;
-        const real dx = xt - __ldg(x + jj), dy = yt - __ldg(y + jj), dz = zt - __ldg(z + jj);
-        const real rsq = dx * dx + dy * dy + dz * dz;
-        if (BF) {
-            const real g = rsq < c.cutforcesq ? lj_pair2(rsq, c) : (real)0;
-            fix = fma(dx, g, fix); fiy = fma(dy, g, fiy); fiz = fma(dz, g, fiz);
-        } else if (rsq < c.cutforcesq) {
-            const real f = lj_pair2(rsq, c);
-            fix += dx * f;
-            fiy += dy * f;
-            fiz += dz * f;
-        }
-    }
-    unsigned tid, bid; // blocks of 128 threads
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
-    const int e = (int)(bid * 128u + tid);
-    if (FI) {
-        real a = fi.vx[e] + fi.dtforce * fix, b = fi.vy[e] + fi.dtforce * fiy, cc = fi.vz[e] + fi.dtforce * fiz; // final(n)
-        a = a + fi.dtforce * fix; b = b + fi.dtforce * fiy; cc = cc + fi.dtforce * fiz;                          // initial(n+1)
-        fi.vx[e] = a; fi.vy[e] = b; fi.vz[e] = cc;
-        fi.xn[e] = xt + fi.dt * a;
-        fi.yn[e] = yt + fi.dt * b;
-        fi.zn[e] = zt + fi.dt * cc;
-    } else {
-        fx[e] = fix;
-        fy[e] = fiy;
-        fz[e] = fiz;
-    }
-}
-
-// ---- m2: merged rows, two atoms per thread (see k_build_neighbor_m2) ---------------------------------------------------
-template <class real, int U>
-__global__ void __launch_bounds__(128) k_force_lj_full_m2(int nlocal, LJConst2<real> c, const real* __restrict__ x,
-    const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ mnum, const int* __restrict__ mneigh,
-    NbLayout L, real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
-{
-    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ia = 2 * t;
-    if (ia >= nlocal) return;
-    const bool has_b = ia + 1 < nlocal;
-    const int ib     = has_b ? ia + 1 : ia;
-    const real xa = x[ia], ya = y[ia], za = z[ia], xb = x[ib], yb = y[ib], zb = z[ib];
-    const int nn  = mnum[t];
-    real fax = 0, fay = 0, faz = 0, fbx = 0, fby = 0, fbz = 0;
-    const int* nb   = mneigh + L.base(t);
-    const int nfull = nn - nn % U;
-    int e[U], en[U];
-    if (nfull > 0) {
-#pragma unroll
-        for (int u = 0; u < U; u++) e[u] = __ldg(nb + (size_t)u * L.sk);
-    }
-    for (int k = 0; k < nfull; k += U) {
-        real xj[U], yj[U], zj[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j = e[u] & 0x3fffffff;
-            xj[u] = __ldg(x + j); yj[u] = __ldg(y + j); zj[u] = __ldg(z + j);
-        }
-        nb += (size_t)U * L.sk;
-        if (k + U < nfull) {
-#pragma unroll
-            for (int u = 0; u < U; u++) en[u] = __ldg(nb + (size_t)u * L.sk);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            {
-                const real dx = xa - xj[u], dy = ya - yj[u], dz = za - zj[u];
-                const real rsq = dx * dx + dy * dy + dz * dz;
-                if ((e[u] & 0x40000000) && rsq < c.cutforcesq) {
-                    const real f = lj_pair2(rsq, c);
-                    fax += dx * f; fay += dy * f; faz += dz * f;
-                }
-            }
-            {
-                const real dx = xb - xj[u], dy = yb - yj[u], dz = zb - zj[u];
-                const real rsq = dx * dx + dy * dy + dz * dz;
-                if (e[u] < 0 && rsq < c.cutforcesq) {
-                    const real f = lj_pair2(rsq, c);
-                    fbx += dx * f; fby += dy * f; fbz += dz * f;
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) e[u] = en[u];
-    }
-    for (int k = nfull; k < nn; k++) {
-        const int ee = __ldg(nb), j = ee & 0x3fffffff;
-        nb += L.sk;
-        const real xj = __ldg(x + j), yj = __ldg(y + j), zj = __ldg(z + j);
-        {
-            const real dx = xa - xj, dy = ya - yj, dz = za - zj;
-            const real rsq = dx * dx + dy * dy + dz * dz;
-            if ((ee & 0x40000000) && rsq < c.cutforcesq) {
-                const real f = lj_pair2(rsq, c);
-                fax += dx * f; fay += dy * f; faz += dz * f;
-            }
-        }
-        {
-            const real dx = xb - xj, dy = yb - yj, dz = zb - zj;
-            const real rsq = dx * dx + dy * dy + dz * dz;
-            if (ee < 0 && rsq < c.cutforcesq) {
-                const real f = lj_pair2(rsq, c);
-                fbx += dx * f; fby += dy * f; fbz += dz * f;
-            }
-        }
-    }
-    fx[ia] = fax; fy[ia] = fay; fz[ia] = faz;
-    if (has_b) { fx[ib] = fbx; fy[ib] = fby; fz[ib] = fbz; }
-}
-
-// ---- p4: packed positions ----------------------------------------------------------------------------
-// ncu r1_s2 (profiles/r1_s2_force_raw.txt): the v2 kernel is bound by L1 (l1tex 87%): three 64-bit gathers per
-// neighbor, ~17 sectors per request.  Here the positions are ALSO kept as one 32-byte record {x,y,z,-} per
-// atom (DP; 16 bytes for SP): ONE gather request per neighbor, exactly one sector per lane, fetched with
-// a single 256-bit load (LDG.E.256, new on sm_100).
-struct __align__(32) PosD {
-    double x, y, z, w;
-};
-template <class real> struct PosOf;
-template <> struct PosOf<double> { typedef PosD type; };
-template <> struct PosOf<float> { typedef float4 type; };
-__device__ __forceinline__ void ld_pos(const PosD* p, double& x, double& y, double& z)
-{
-    double w;
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
-}
-__device__ __forceinline__ void ld_pos(const float4* p, float& x, float& y, float& z)
-{
-    const float4 v = __ldg(p);
-    x = v.x; y = v.y; z = v.z;
-}
-__device__ __forceinline__ void st_pos(PosD* p, double x, double y, double z)
-{
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(0.0) : "memory");
-}
-__device__ __forceinline__ void st_pos(float4* p, float x, float y, float z) { *p = make_float4(x, y, z, 0.f); }
-
-template <class real>
-__global__ void k_pack_pos4(int n, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    typename PosOf<real>::type* __restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) st_pos(out + i, x[i], y[i], z[i]);
-}
-
-template <class real, int U>
-__global__ void __launch_bounds__(128) k_force_lj_full_p4(int nlocal, LJConst2<real> c,
-    const typename PosOf<real>::type* __restrict__ pos, const int* __restrict__ numneigh, const int* __restrict__ nbT,
-    NbLayout L, real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nlocal) return;
-    real xt, yt, zt;
-    ld_pos(pos + i, xt, yt, zt);
-    const int nn  = numneigh[i];
-    real fix = 0, fiy = 0, fiz = 0;
-    const int* nb   = nbT + L.base(i);
-    const int nfull = nn - nn % U;
-    int j[U], jn[U];
-    if (nfull > 0) {
-#pragma unroll
-        for (int u = 0; u < U; u++) j[u] = __ldg(nb + (size_t)u * L.sk);
-    }
-    for (int k = 0; k < nfull; k += U) {
-        real dx[U], dy[U], dz[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            real xj, yj, zj;
-            ld_pos(pos + j[u], xj, yj, zj);
-            dx[u] = xt - xj; dy[u] = yt - yj; dz[u] = zt - zj;
-        }
-        nb += (size_t)U * L.sk;
-        if (k + U < nfull) {
-#pragma unroll
-            for (int u = 0; u < U; u++) jn[u] = __ldg(nb + (size_t)u * L.sk);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
-            if (rsq < c.cutforcesq) {
-                const real f = lj_pair2(rsq, c);
-                fix += dx[u] * f;
-                fiy += dy[u] * f;
-                fiz += dz[u] * f;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) j[u] = jn[u];
-    }
-    for (int k = nfull; k < nn; k++) {
-        const int jj = __ldg(nb);
-        nb += L.sk;
-        real xj, yj, zj;
-        ld_pos(pos + jj, xj, yj, zj);
-        const real dx = xt - xj, dy = yt - yj, dz = zt - zj;
-        const real rsq = dx * dx + dy * dy + dz * dz;
-        if (rsq < c.cutforcesq) {
-            const real f = lj_pair2(rsq, c);
-            fix += dx * f;
-            fiy += dy * f;
-            fiz += dz * f;
-        }
-    }
-    fx[i] = fix;
-    fy[i] = fiy;
-    fz[i] = fiz;
-}
-
-// ---- v3: LPA lanes per atom, row-major list ---------------------------------------------------------
-// With one thread per atom every lane gathers a DIFFERENT neighbor, ~22 distinct 32-byte sectors per
-// 64-bit request, and the L1 data pipe (bank conflicts) becomes the limiter (ncu r1_v2: l1tex 89%,
-// FP64 pipe 42%).  Here LPA consecutive lanes share one atom and read CONSECUTIVE entries of its row;
-// rows are sorted by memory position (bin order), so the lanes of a group hit short contiguous runs
-// of positions.  Partial sums are combined with warp shuffles.
-template <class real, int LPA, int U>
-__global__ void __launch_bounds__(128) k_force_lj_full_v3(int nlocal, LJConst2<real> c,
-    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const int* __restrict__ numneigh, const int* __restrict__ nbr, size_t rowlen,
-    real* __restrict__ fx, real* __restrict__ fy, real* __restrict__ fz)
-{
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int i         = (int)(tid / LPA);
-    const int sub       = (int)(tid % LPA);
-    const bool valid    = i < nlocal;
-    const int ii        = valid ? i : nlocal - 1;
-    const real xt = x[ii], yt = y[ii], zt = z[ii];
-    const int nn   = valid ? numneigh[ii] : 0;
-    const int* row = nbr + (size_t)ii * rowlen;
-    real fix = 0, fiy = 0, fiz = 0;
-    for (int k = sub; k < nn; k += U * LPA) {
-        int j[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            ok[u] = k + u * LPA < nn;
-            j[u]  = ok[u] ? __ldg(row + k + u * LPA) : ii;
-        }
-        real dx[U], dy[U], dz[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            dx[u] = xt - __ldg(x + j[u]);
-            dy[u] = yt - __ldg(y + j[u]);
-            dz[u] = zt - __ldg(z + j[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const real rsq = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
-            if (ok[u] && rsq < c.cutforcesq) {
-                const real f = lj_pair2(rsq, c);
-                fix += dx[u] * f;
-                fiy += dy[u] * f;
-                fiz += dz[u] * f;
-            }
-        }
-    }
-#pragma unroll
-    for (int d = LPA / 2; d > 0; d >>= 1) {
-        fix += __shfl_xor_sync(0xffffffffu, fix, d);
-        fiy += __shfl_xor_sync(0xffffffffu, fiy, d);
-        fiz += __shfl_xor_sync(0xffffffffu, fiz, d);
-    }
-    if (sub == 0 && valid) {
-        fx[i] = fix;
-        fy[i] = fiy;
-        fz[i] = fiz;
-    }
-}
-
-// LJ force, half neighbor lists: verletlist/force_lj.c:107-198.  The reaction force on local j
-// (force_lj.c:176-180) is scattered with native FP atomics (RED.ADD.F64/F32); forces are zeroed by
-// the caller first, as the reference does (force_lj.c:123-127).
-template <class real>
-__global__ void __launch_bounds__(128) k_force_lj_half(int nlocal, LJConst<real> c,
-    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
-    const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* fx, real* fy,
-    real* fz)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nlocal) return;
-    const real xt = x[i], yt = y[i], zt = z[i];
-    const int nn  = numneigh[i];
-    real fix = 0, fiy = 0, fiz = 0;
-    const int* nb = nbT + L.base(i);
-    for (int k = 0; k < nn; k++) {
-        const int j   = __ldg(nb + (size_t)k * L.sk);
-        const real dx = xt - x[j], dy = yt - y[j], dz = zt - z[j];
-        const real rsq = dx * dx + dy * dy + dz * dz;
-        if (rsq < c.cutforcesq) {
-            const real f = lj_pair(rsq, c);
-            fix += dx * f;
-            fiy += dy * f;
-            fiz += dz * f;
-            if (j < nlocal) {
-                atomicAdd(&fx[j], -dx * f);
-                atomicAdd(&fy[j], -dy * f);
-                atomicAdd(&fz[j], -dz * f);
-            }
-        }
-    }
-    atomicAdd(&fx[i], fix);
-    atomicAdd(&fy[i], fiy);
-    atomicAdd(&fz[i], fiz);
-}
-
-// half lists, generation 2: the full-list kernel's structure (U neighbors in flight, next indices prefetched, reciprocal by
-// rcp.approx + Newton steps); the reaction on local j stays three native RED.ADD per pair
+// ---------------------------------------------------------------------------------------------
+// LJ with half neighbor lists (verletlist/force_lj.c:107-198): reaction force on local j by native RED.ADD, forces zeroed first.
 template <class real, int U>
 __global__ void __launch_bounds__(128) k_force_lj_half_v2(int nlocal, LJConst2<real> c, const real* __restrict__ x,
     const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ numneigh, const int* __restrict__ nbT,
@@ -1843,7 +949,7 @@ static __global__ void k_stub_neighbors(int nlocal, int pattern, int nneighs, in
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlocal) return;
     int* out   = neighbors + L.base(i);
-    unsigned h = seed ^ (0x9e3779b9u * (unsigned)(i + 1));
+    unsigned h = (pattern >= 3 ? 12345u : seed) ^ (0x9e3779b9u * (unsigned)(i + 1));
     int j      = pattern == 0 ? (i + 1) % nlocal : 0;
     const int m = pattern == 0 ? nlocal : nneighs;
     for (int k = 0; k < nneighs; k++) {
@@ -1853,6 +959,15 @@ static __global__ void k_stub_neighbors(int nlocal, int pattern, int nneighs, in
                 h ^= h << 13; h ^= h >> 17; h ^= h << 5; // xorshift32
                 v = (int)(h % (unsigned)nlocal);
             } while (v == i && nlocal > 1);
+        } else if (pattern == 3 || pattern == 4) {
+            // diagnostic patterns (not in the reference; profiles/r2_vlforce_analysis.txt): random neighbors inside the
+            // atom's own window of W atoms (W = `seed`, a power of two), i.e. L1-resident gathers; 4 additionally gives
+            // the 16 lanes of a half warp 16 different residues mod 16 (= different L1 data banks for 8-byte elements)
+            h ^= h << 13; h ^= h >> 17; h ^= h << 5;
+            const int W  = max(16, (int)seed);
+            const int w0 = i & ~(W - 1);
+            v = pattern == 3 ? w0 + (int)(h % (unsigned)W) : w0 + 16 * (int)(h % (unsigned)(W / 16)) + ((i + k) & 15);
+            v = min(v, nlocal - 1);
         } else {
             v = j;
             j = (j + 1) % m;

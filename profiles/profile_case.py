@@ -12,10 +12,14 @@ ap.add_argument("--nx", type=int, default=64)
 ap.add_argument("--steps", type=int, default=25)
 ap.add_argument("--precision", default="dp")
 ap.add_argument("--half", type=int, default=0)
+ap.add_argument("--opt", action="append", default=[])
 a = ap.parse_args()
 m = importlib.import_module("md-bench_b200")
 s = m.Simulation(m.default_params(precision=m.DP if a.precision == "dp" else m.SP, nx=a.nx, ny=a.nx, nz=a.nx,
                                   half_neigh=a.half))
+for o in a.opt:
+    k, v = o.split("=")
+    s.setOption(k, float(v))
 s.createAtom()
 s.setup(adjust=True)
 rec, tm = s.run(a.steps)

@@ -16,11 +16,12 @@ for kv in a.opt:
 x = np.repeat((np.arange(a.na) * 1e-5)[:, None], 3, axis=1)
 s.setAtoms(x, None)
 out = []
-for pat in ("seq", "fix"):
-    s.stubNeighbors(pat, 76, 1)
+for pat in ("seq", "fix") + tuple("%s:%d" % (p, w) for w in (16, 32, 64, 128, 256, 1024, 8192) for p in ("local", "localbank")):
+    pat, _, w = pat.partition(":")
+    s.stubNeighbors(pat, 76, 1, int(w or 12345))
     for _ in range(3):
         s.computeForceLJFullNeigh()
     t = min(s.computeForceLJFullNeigh() for _ in range(10))
-    out.append("%s %.3f ms" % (pat, t * 1e3))
+    out.append("%s%s %.3f" % (pat, w, t * 1e3))
 print(a.precision, a.opt, " ".join(out))
 s.close()

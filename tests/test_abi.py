@@ -99,7 +99,7 @@ def test_every_runtime_option_is_documented_in_the_header():
     names = set()
     for f in ("sim_impl.cu", "cp_sim.cu", "dd_group.cuh"):
         names |= set(re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', open(os.path.join(csrc, f)).read()))
-    assert {"fuse_force", "xy_gather", "force_variant", "halo_push"} <= names
+    assert {"fuse_force", "xy_gather", "lazy_ops", "halo_push"} <= names
     missing = sorted(n for n in names if '"%s"' % n not in hdr)
     assert not missing, "options not documented in include/mdb200.h: %s" % missing
 

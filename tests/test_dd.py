@@ -249,7 +249,7 @@ def test_dd_200_steps_match_single_domain_and_oracle(grid, dp, half):
     # single-domain vs oracle test)
     xtol = 1e-10 if dp else 2e-3
     assert np.abs(min_image(x - sx[tags], box)).max() <= xtol * box
-    assert np.abs(v - sv[tags]).max() <= (1e-9 if dp else 2e-2) * np.abs(sv).max()
+    assert np.abs(v - sv[tags]).max() <= (1e-10 if dp else 2e-2) * np.abs(sv).max()
     # atoms did change bricks: tags owned by the first brick (slot order is brick by brick) before / after
     if grid != (1, 1, 1):
         lo = np.zeros(3)
@@ -302,7 +302,7 @@ def test_dd_eam_matches_single_domain(golden_dir):
     rec_d, _ = d.run(60)
     assert np.abs(rec_d[:, 1:] - rec_s[:, 1:]).max() <= 1e-10 * np.abs(rec_s[:, 1:]).max()
     tags, v = d.get("v")
-    assert np.abs(v - s.get("v")[tags]).max() <= 1e-9 * np.abs(v).max()
+    assert np.abs(v - s.get("v")[tags]).max() <= 1e-10 * np.abs(v).max()
     s.close(); d.close()
 
 

@@ -93,7 +93,7 @@ def test_structures_forces_trajectory_vs_oracle(dp, N, half):
     xs, ts = s.atoms("x", tags=True)
     assert np.array_equal(ts, o.tags()[0])
     assert max_rel(xs, o.atoms("x")) <= TOL[dp]
-    assert max_rel(s.atoms("v"), o.atoms("v")) <= (1e-9 if dp else 1e-3)
+    assert max_rel(s.atoms("v"), o.atoms("v")) <= (1e-10 if dp else 1e-3)
     (Ts, Ps), (To, Po) = s.thermo(), o.thermo()
     assert abs(Ts - To) <= TOL[dp] * To and abs(Ps - Po) <= TOL[dp] * Po
     s.close()
@@ -194,28 +194,6 @@ def test_run_loop_equals_operator_by_operator(dp, N, half, fuse_force):
     a.close(); b.close()
 
 
-@pytest.mark.skipif(not os.environ.get("MDB_TEST_EXPERIMENTAL"),
-                    reason="A/B kernels written after the round's GPU budget was spent; set MDB_TEST_EXPERIMENTAL=1 to run")
-@pytest.mark.parametrize("N", [4, 8])
-@pytest.mark.parametrize("fv", [4, 5])
-def test_experimental_deep_pipeline_packed_kernels_bit_identical(N, fv):
-    """k_cp_force_lj_sp_packed_q (force_variant 4 / 5: list entries and tiles requested further ahead) evaluates the same
-    tiles in the same order with the same arithmetic as the default packed kernel: forces and a 60-step run bit-identical"""
-    x, v = jittered(False, 6, 6, 6, amp=0.1)
-    a, b = make_cp(False, N, 6, nstat=25), make_cp(False, N, 6, nstat=25)
-    b.setOption("force_variant", fv)
-    for s in (a, b):
-        s.setAtoms(x, v)
-        s.setup(adjust=False)
-        s.computeForce()
-    assert np.array_equal(np.nan_to_num(a.cl("f")), np.nan_to_num(b.cl("f")))
-    ra, _ = a.run(60)
-    rb, _ = b.run(60)
-    assert np.array_equal(ra, rb)
-    assert np.array_equal(a.atoms("x"), b.atoms("x")) and np.array_equal(a.atoms("v"), b.atoms("v"))
-    a.close(); b.close()
-
-
 @pytest.mark.parametrize("dp,N", [(True, 4), (False, 8)])
 def test_prune_neighbor_vs_oracle(dp, N):
     """pruneNeighbor 15 steps after the build: the device's list (its row order) and cluster positions are handed to
@@ -289,14 +267,14 @@ def test_config2_dp_thermo_and_properties(golden_dir, dp, N, half):
     f = np.nan_to_num(s.cl("f").astype(np.float64))
     fmax = np.abs(f).max()
     assert fmax > 1.0
-    assert np.all(np.abs(f.sum(axis=(0, 2))) <= (1e-9 if dp else 2e-2) * fmax)
+    assert np.all(np.abs(f.sum(axis=(0, 2))) <= (1e-10 if dp else 2e-2) * fmax)
     v1 = s.atoms("v").astype(np.float64).sum(axis=0)
     if N == 4:
-        assert np.all(np.abs(v1 - v0) <= (1e-9 if dp else 5e-2))
+        assert np.all(np.abs(v1 - v0) <= (1e-10 if dp else 5e-2))
     if dp and N == 4 and not half:
         gold = [q for q in json.load(open(os.path.join(golden_dir, "thermo_cp.json"))) if q["variant"] == "cpref44_dp"][0]
         for got, want in zip(rec, gold["records"]):
-            assert abs(got[1] - want[1]) <= 1e-9 * want[1] and abs(got[2] - want[2]) <= 1e-9 * want[2], (got, want)
+            assert abs(got[1] - want[1]) <= 1e-10 * want[1] and abs(got[2] - want[2]) <= 1e-10 * want[2], (got, want)
     s.close()
 
 
