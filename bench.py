@@ -146,8 +146,8 @@ def cpu_baseline(sample_nx=64, sample_steps=40):
 def reference_arm(args, rank, world):
     """The reference's own CPU build (oracle/_ref/MDBench-vl_dp_aos: GCC -Ofast AVX-512, OpenMP) on the host cores of the box.
     Each bench step is a BOUNDED SAMPLE of the GPU arm's workload: the same per-GPU box (nx = --ref-nx, default the GPU arm's
-    128) for --ref-ntimes (20) timesteps = one rebuild interval instead of 200 timesteps (ten of them); the metric is
-    normalised per atom-step.  `config` says what this arm ran; `ms_per_step` is the wall time of the reference process
+    128; default 64^3 = 1 048 576 atoms, see --ref-nx) for --ref-ntimes (20) timesteps = one rebuild interval instead of
+    200 timesteps (ten of them); the metric is normalised per atom-step.  `config` says what this arm ran; `ms_per_step` is the wall time of the reference process
     (start-up, lattice generation and first list build included) while `value` uses the TOTAL the reference itself reports
     (verletlist/main.c:337-338), exactly like its "Performance" line."""
     if rank != 0:
@@ -345,7 +345,8 @@ def reference_cuda(args):
     exe = ref_binary("vl_%s_aos-cuda" % args.precision)
     if exe is None:
         return {"unavailable": "oracle/_ref/MDBench-vl_%s_aos-cuda not built" % args.precision}
-    cmd = [exe, "-nx", str(args.nx), "-ny", str(args.nx), "-nz", str(args.nx), "-n", str(args.ntimes)]
+    nx = args.ref_nx or args.nx   # its host-side lattice generation, binning and ghost setup take 150 s at 128^3
+    cmd = [exe, "-nx", str(nx), "-ny", str(nx), "-nz", str(nx), "-n", str(args.ntimes)]
     t0 = time.perf_counter()
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
@@ -357,7 +358,7 @@ def reference_cuda(args):
     if not (mm and pp):
         return {"unavailable": "no report line in the output of %s" % " ".join(cmd)}
     nreb = max(1, args.ntimes // 20)
-    return {"value": float(pp.group(1)) * 1e6, "unit": UNIT, "binary": "oracle/_ref/" + os.path.basename(exe),
+    return {"value": float(pp.group(1)) * 1e6, "unit": UNIT, "binary": "oracle/_ref/" + os.path.basename(exe), "atoms": 4 * nx ** 3,
             "command": " ".join(os.path.basename(c) if c == exe else c for c in cmd),
             "total_s": float(mm.group(1)), "force_s": float(mm.group(2)), "neigh_s": float(mm.group(3)),
             "force_ms_per_call": 1e3 * float(mm.group(2)) / (args.ntimes + 1), "neigh_ms_per_rebuild": 1e3 * float(mm.group(3)) / nreb,
@@ -405,7 +406,9 @@ def main():
     ap.add_argument("--ntimes", type=int, default=200)
     ap.add_argument("--precision", default="dp", choices=["dp", "sp"])
     ap.add_argument("--half", type=int, default=0)
-    ap.add_argument("--ref-nx", type=int, default=0, help="box of the reference arm (0 = the GPU arm's --nx)")
+    ap.add_argument("--ref-nx", type=int, default=64,
+                    help="box of the reference arm and of reference_cuda (0 = the GPU arm's --nx; at 128 the reference needs 107 s per "
+                         "bench step, 87 s of it serial start-up, i.e. 14 min for the default --steps 5 --warmup 3)")
     ap.add_argument("--ref-ntimes", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
