@@ -725,6 +725,105 @@ __global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, int dumm
     cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
 }
 
+// ---- SP, full lists, generation 3: TWO lanes per i-cluster, two i atoms per lane ------------------------------------------
+// ncu of the lane-per-i-atom kernel above: FMA pipe and L1 data stage both near 60-70 %, half of the stall samples waiting
+// for tile loads.  Each lane fetched a whole j tile (3 x 128 bit) to evaluate 4 pairs; here a lane keeps TWO i atoms of
+// its cluster and evaluates 8 pairs per fetched tile, so a warp covers 16 i-clusters and the tile loads (L1 wavefronts,
+// issue slots, address arithmetic, list-entry loads) per evaluated pair halve; the packed FP32 pair arithmetic is
+// unchanged (j atoms (q, q+1) share an instruction) and there are four independent dependency chains per tile instead of two.
+// NR = Newton step on the MUFU reciprocal (as above); without it the reciprocal is the MUFU result itself (max. 1 ulp).
+template <int N, bool NR>
+__device__ __forceinline__ void cp_tile_packed2(const CpTileRegs<N>& T, const CpPackedConst& c, f32x2 xt, f32x2 yt, f32x2 zt, int iq,
+    f32x2& fx, f32x2& fy, f32x2& fz)
+{
+#pragma unroll
+    for (int q = 0; q < N / 2; q++) {
+        const f32x2 dx = sub2(xt, T.x[q]), dy = sub2(yt, T.y[q]), dz = sub2(zt, T.z[q]);
+        const f32x2 rsq = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+        float r0, r1, y0, y1;
+        upk2(rsq, r0, r1);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(r0));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(r1));
+        const bool in0 = r0 < c.cutforcesq && iq != 2 * q, in1 = r1 < c.cutforcesq && iq != 2 * q + 1; // force_lj.c:99-113
+        f32x2 y = pk2(y0, y1);
+        if (NR) {
+            const f32x2 nr = sub2(c.one, mul2(rsq, y));
+            y              = fma2(y, nr, y);
+        }
+        const f32x2 s3 = mul2(mul2(y, y), y);
+        f32x2 f        = mul2(mul2(y, s3), fma2(c.A, s3, c.negB));
+        float f0, f1;
+        upk2(f, f0, f1);
+        f  = pk2(in0 ? f0 : 0.0f, in1 ? f1 : 0.0f);
+        fx = fma2(dx, f, fx); fy = fma2(dy, f, fy); fz = fma2(dz, f, fz);
+    }
+}
+template <int N, bool FI, bool NR>
+__global__ void __launch_bounds__(128) k_cp_force_lj_sp_duo(int ncl, int dummy_cj, LJConst2<float> c, const float* __restrict__ cl_x,
+    const int* __restrict__ numneigh, const int* __restrict__ neighbors, int maxneighs, float* __restrict__ cl_f, CpFused<float> fi)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci  = tid >> 1, h = tid & 1; // i atoms 2h and 2h + 1 of cluster ci
+    const bool valid = ci < ncl;
+    const int cic = valid ? ci : ncl - 1;
+    const size_t ib = cp_ci_base3<N>(cic) + 2 * h;
+    const float2 px = *reinterpret_cast<const float2*>(cl_x + ib), py = *reinterpret_cast<const float2*>(cl_x + ib + N),
+                 pz = *reinterpret_cast<const float2*>(cl_x + ib + 2 * N);
+    const bool pad0 = px.x >= 1.0e14f, pad1 = px.y >= 1.0e14f;
+    const float ax = pad0 ? -1.0e15f : px.x, ay = pad0 ? -1.0e15f : py.x, az = pad0 ? -1.0e15f : pz.x;
+    const float bx = pad1 ? -1.0e15f : px.y, by = pad1 ? -1.0e15f : py.y, bz = pad1 ? -1.0e15f : pz.y;
+    const f32x2 xa = pk2(ax, ax), ya = pk2(ay, ay), za = pk2(az, az), xb = pk2(bx, bx), yb = pk2(by, by), zb = pk2(bz, bz);
+    CpPackedConst pc { pk2(c.A, c.A), pk2(-c.B, -c.B), pk2(1.0f, 1.0f), c.cutforcesq };
+    const int self = cp_cj0<N>(cic);
+    const int ia   = (N == CP_M ? 0 : CP_M * (cic & 1)) + 2 * h; // slot of the first i atom inside the diagonal tile
+    const int* row = neighbors + (size_t)cic * maxneighs;
+    const int nn   = valid ? numneigh[cic] : 0;
+    f32x2 fxa = pk2(0.f, 0.f), fya = fxa, fza = fxa, fxb = fxa, fyb = fxa, fzb = fxa;
+    int cj = nn > 0 ? __ldg(row) : dummy_cj, cj1 = nn > 1 ? __ldg(row + 1) : dummy_cj;
+    CpTileRegs<N> A, B;
+    A.load(cl_x + (size_t)cj * N * 3);
+    for (int k = 0; k < nn; k++) {
+        const int cj2 = k + 2 < nn ? __ldg(row + k + 2) : dummy_cj;
+        B.load(cl_x + (size_t)cj1 * N * 3);
+        const bool diag = cj == self;
+        cp_tile_packed2<N, NR>(A, pc, xa, ya, za, diag ? ia : -1, fxa, fya, fza);
+        cp_tile_packed2<N, NR>(A, pc, xb, yb, zb, diag ? ia + 1 : -1, fxb, fyb, fzb);
+        A   = B;
+        cj  = cj1;
+        cj1 = cj2;
+    }
+    if (!valid) return;
+    float u, v;
+    upk2(fxa, u, v); const float f0x = pad0 ? 0.f : u + v;
+    upk2(fya, u, v); const float f0y = pad0 ? 0.f : u + v;
+    upk2(fza, u, v); const float f0z = pad0 ? 0.f : u + v;
+    upk2(fxb, u, v); const float f1x = pad1 ? 0.f : u + v;
+    upk2(fyb, u, v); const float f1y = pad1 ? 0.f : u + v;
+    upk2(fzb, u, v); const float f1z = pad1 ? 0.f : u + v;
+    if (FI) {
+        // slot re-derived from the special registers (see cp_epilogue_slot): blocks of 128 threads = 64 i-clusters
+        unsigned t, b;
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
+        const unsigned g = b * 128u + t;
+        const size_t e   = cp_ci_base3<N>((int)(g >> 1)) + 2 * (g & 1u);
+        if (!pad0) {
+            cp_fused_integrate(fi, e, cl_x[e], f0x);
+            cp_fused_integrate(fi, e + N, cl_x[e + N], f0y);
+            cp_fused_integrate(fi, e + 2 * N, cl_x[e + 2 * N], f0z);
+        }
+        if (!pad1) {
+            cp_fused_integrate(fi, e + 1, cl_x[e + 1], f1x);
+            cp_fused_integrate(fi, e + N + 1, cl_x[e + N + 1], f1y);
+            cp_fused_integrate(fi, e + 2 * N + 1, cl_x[e + 2 * N + 1], f1z);
+        }
+        return;
+    }
+    *reinterpret_cast<float2*>(cl_f + ib)         = make_float2(f0x, f1x);
+    *reinterpret_cast<float2*>(cl_f + ib + N)     = make_float2(f0y, f1y);
+    *reinterpret_cast<float2*>(cl_f + ib + 2 * N) = make_float2(f0z, f1z);
+}
+
 template <class real, int N, bool HALF, bool FI = false>
 __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<real> c, const real* __restrict__ cl_x,
     const int* __restrict__ numneigh, const int* __restrict__ numneigh_masked, const int* __restrict__ neighbors, int maxneighs,

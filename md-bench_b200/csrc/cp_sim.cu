@@ -73,6 +73,7 @@ template <class real, int N> struct CpSim final : CpBase {
     bool thermo_ready = false, neigh_ready = false;
     int prune_every = 1000; // common/parameter.c:40
     int force_variant = 0;
+    int sp_kernel = 1; // SP full lists: see launch_packed
     bool fuse_force = true; // mdb_cp_run, full lists: integrate halves in the force kernel's epilogue (CpFused)
     // ---- atoms (clusterpair/atom.h:26-60) ----
     long long Natoms = 0;
@@ -184,6 +185,7 @@ template <class real, int N> struct CpSim final : CpBase {
     {
         if (!strcmp(name, "prune_every")) prune_every = (int)v;
         else if (!strcmp(name, "force_variant")) force_variant = (int)v;
+        else if (!strcmp(name, "sp_kernel")) sp_kernel = (int)v;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else throw Error(fmt("mdb_cp_setOption: unknown option '%s'", name));
     }
@@ -582,6 +584,7 @@ template <class real, int N> struct CpSim final : CpBase {
     }
     void launch_force(bool fused = false)
     {
+        NvtxRange nvtx_range_("force");
         if (!lists_ready) throw Error("computeForce: no cluster-pair list (call mdb_cp_buildNeighbor first)");
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
@@ -643,16 +646,35 @@ template <class real, int N> struct CpSim final : CpBase {
             force_ms += ms;
         }
     }
+    // sp_kernel: 0 = lane per i atom (k_cp_force_lj_sp_packed), 1 = two lanes per i-cluster (k_cp_force_lj_sp_duo),
+    // 2 = the same without the Newton step on the MUFU reciprocal
     void launch_packed(unsigned grid, const LJConst2<float>& c2)
     {
-        MDB_LAUNCH(launches, k_cp_force_lj_sp_packed<N>, grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p, numneigh.p,
-            neighbors.p, maxneighs, (float*)cl_f.p, CpFused<float> { nullptr, nullptr, 0.f, 0.f });
+        const CpFused<float> nofi { nullptr, nullptr, 0.f, 0.f };
+        const unsigned g2 = grid_for((size_t)ncl * 2, 128);
+        if (sp_kernel == 1)
+            MDB_LAUNCH(launches, (k_cp_force_lj_sp_duo<N, false, true>), g2, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
+                numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, nofi);
+        else if (sp_kernel == 2)
+            MDB_LAUNCH(launches, (k_cp_force_lj_sp_duo<N, false, false>), g2, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
+                numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, nofi);
+        else
+            MDB_LAUNCH(launches, k_cp_force_lj_sp_packed<N>, grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p, numneigh.p,
+                neighbors.p, maxneighs, (float*)cl_f.p, nofi);
     }
     void launch_packed(unsigned, const LJConst2<double>&) {}
     void launch_packed_fused(unsigned grid, const LJConst2<float>& c2, const CpFused<float>& fi)
     {
-        MDB_LAUNCH(launches, (k_cp_force_lj_sp_packed<N, true>), grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
-            numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, fi);
+        const unsigned g2 = grid_for((size_t)ncl * 2, 128);
+        if (sp_kernel == 1)
+            MDB_LAUNCH(launches, (k_cp_force_lj_sp_duo<N, true, true>), g2, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
+                numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, fi);
+        else if (sp_kernel == 2)
+            MDB_LAUNCH(launches, (k_cp_force_lj_sp_duo<N, true, false>), g2, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
+                numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, fi);
+        else
+            MDB_LAUNCH(launches, (k_cp_force_lj_sp_packed<N, true>), grid, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
+                numneigh.p, neighbors.p, maxneighs, (float*)cl_f.p, fi);
     }
     void launch_packed_fused(unsigned, const LJConst2<double>&, const CpFused<double>&) {}
     double computeForce() override // returns elapsed seconds like the reference's ComputeForceFunction
@@ -708,6 +730,7 @@ template <class real, int N> struct CpSim final : CpBase {
     }
     void reneighbour() override // clusterpair/main.c:78-93
     {
+        NvtxRange nvtx_range_("reneighbour");
         phase(0, [&] { updateSingleAtoms(); });
         phase(1, [&] { updateAtomsPbc(); });
         phase(2, [&] { buildClusters(); });
@@ -931,6 +954,7 @@ struct mdb_cp {
 
 #define MDB_CP_TRY(body)                                                                         \
     try {                                                                                        \
+        mdb::NvtxRange nvtx_range_(__func__);                                                    \
         if (!c || !c->s) throw Error("null mdb_cp");                                             \
         body;                                                                                    \
         return 0;                                                                                \

@@ -563,6 +563,7 @@ template <class real> struct DomainGroup final : DDBase {
     }
     void reneighbour() override // main.c:76-95
     {
+        NvtxRange nvtx_range_("reneighbour");
         check_push_error();
         for (Brick* b : bricks) b->xy_valid = false; // migration and sorting move atoms between slots
         migrate();

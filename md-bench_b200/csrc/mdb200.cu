@@ -18,6 +18,7 @@ void set_last_error(const char* msg) { g_err = msg; } // for the other translati
 // MDB_TRY_KEEP (updatePbc: it refreshes the copies' ghost range itself) and MDB_TRY_LAZY (the three lazy operators) differ.
 #define MDB_TRY_(pre, body)                                                                      \
     try {                                                                                        \
+        mdb::NvtxRange nvtx_range_(__func__);                                                    \
         if (!c || !c->sim) throw Error("null mdb_ctx");                                          \
         pre;                                                                                     \
         body;                                                                                    \

@@ -8,8 +8,18 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h> // header-only (CUDA 12): a no-op unless a tool (nsys, ncu --nvtx) is attached
 
 namespace mdb {
+
+// NVTX ranges in place of the reference's LIKWID regions ("force", "reneighbour": verletlist/main.c:80-92,137-143,
+// force_lj.c / force_eam.c) plus one range per C-ABI entry point, named after it.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct Error : std::runtime_error {
     using std::runtime_error::runtime_error;

@@ -50,13 +50,16 @@ template <class real> struct Sim final : SimBase {
     bool xy_valid = false;
     DBuf<vec2> xy, xy2;
     DBuf<real> zg, zg2; // gather copy of z (in-place variant of the fused step, decomposed runs)
-    int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins
+    int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins, 2: blocks of sort_block^3 bins
+    int sort_block = 3, sort_inbin = 0; // sort_inbin = F > 0: inside a bin, F x F rows of atoms along x
+    DBuf<int> sort_key;
     bool bin_rank_ready = false;
     DBuf<int> bin_rank;
     NbLayout LL { 0, 0, 0 };                                    // element (i,k) at neighbors[LL.base(i) + k*LL.sk]
     DBuf<float> cxs, cys, czs; // candidates in CSR order, SoA (k_build_neighbor_v5)
     DBuf<int> cids;
-    DBuf<int> run_off, run_len; // runs of x-adjacent stencil bins
+    DBuf<int> run_off, run_len, run_dyz; // runs of x-adjacent stencil bins (offset of the first bin, length, dy | dz << 16)
+    int neigh_variant = 6; // 6: per-atom stencil (k_build_neighbor_v6), 5: the per-bin stencil (A/B)
     int nruns = 0;
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
     DBuf<unsigned> ghost_msk;
@@ -118,7 +121,7 @@ template <class real> struct Sim final : SimBase {
             b->release();
         ghost_msk.release();
         cxs.release(); cys.release(); czs.release(); cids.release();
-        run_off.release(); run_len.release();
+        run_off.release(); run_len.release(); run_dyz.release();
         d_partial.release();
         d_red.release();
         d_thermo.release();
@@ -457,7 +460,7 @@ template <class real> struct Sim final : SimBase {
         stencil.ensure(nstencil, false, stream);
         MDB_CUDA(cudaMemcpyAsync(stencil.p, h_stencil.data(), nstencil * sizeof(int), cudaMemcpyHostToDevice, stream));
         // runs of consecutive offsets (x-adjacent bins are adjacent in the CSR): the list build walks 21 runs instead of 81 bins
-        std::vector<int> ro, rl;
+        std::vector<int> ro, rl, rdyz;
         for (int k = -nextz; k <= nextz; k++)
             for (int j = -nexty; j <= nexty; j++) {
                 int i0 = 0, len = 0;
@@ -470,9 +473,11 @@ template <class real> struct Sim final : SimBase {
                 if (len == 0) continue;
                 ro.push_back(k * bg.mbiny * bg.mbinx + j * bg.mbinx + i0);
                 rl.push_back(len);
+                rdyz.push_back((int)(((unsigned)j & 0xffffu) | ((unsigned)k << 16)));
             }
         nruns = (int)ro.size();
-        for (DBuf<int>* b : { &run_off, &run_len }) b->ensure(nruns, false, stream);
+        for (DBuf<int>* b : { &run_off, &run_len, &run_dyz }) b->ensure(nruns, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(run_dyz.p, rdyz.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(run_off.p, ro.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaMemcpyAsync(run_len.p, rl.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
@@ -496,14 +501,21 @@ template <class real> struct Sim final : SimBase {
         binatoms.ensure(Nlocal, false, stream);
         MDB_CUDA(cudaMemsetAsync(bincount.p, 0, (nb + 1) * sizeof(int), stream));
         MDB_CUDA(cudaMemsetAsync(cursor.p, 0, (nb + 1) * sizeof(int), stream));
-        if (sort_order == 1 && !bin_rank_ready) build_bin_rank();
+        if (sort_order >= 1 && !bin_rank_ready) build_bin_rank();
         MDB_LAUNCH(launches, k_bin_count<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, bg, x.p, y.p, z.p,
-            sort_order == 1 ? bin_rank.p : (const int*)nullptr, atom_bin.p, bincount.p);
+            sort_order >= 1 ? bin_rank.p : (const int*)nullptr, atom_bin.p, bincount.p);
         scanner.exclusive(bincount.p, binstart.p, nb, binstart.p + nb, stream);
         MDB_LAUNCH(launches, k_bin_fill, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, atom_bin.p, binstart.p,
             cursor.p, binatoms.p);
         MDB_LAUNCH(launches, k_bin_sort, grid_for(nb, 128), 128, 0, stream, nb, binstart.p, binatoms.p, orig.p,
             d_flags.p + 3);
+        if (sort_inbin) { // inside a bin: rows of atoms along x (fine z, fine y, x), ties keep the reference-index order
+            sort_key.ensure(Nlocal, false, stream);
+            MDB_LAUNCH(launches, k_fine_key<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, bg, sort_inbin, x.p, y.p,
+                z.p, sort_key.p);
+            MDB_LAUNCH(launches, k_bin_sort, grid_for(nb, 128), 128, 0, stream, nb, binstart.p, binatoms.p, sort_key.p,
+                d_flags.p + 3);
+        }
         const size_t cap = x.cap;
         for (DBuf<real>* b : { &x2, &y2, &z2, &vx2, &vy2, &vz2, &fx2, &fy2, &fz2 }) b->ensure(cap, false, stream);
         type2.ensure(cap, false, stream);
@@ -537,7 +549,12 @@ template <class real> struct Sim final : SimBase {
         for (int b = 0; b < nb; b++) {
             const int l  = b > 0 ? b - 1 : 0; // undo coord2bin's "+ 1"
             const int ix = l % bg.mbinx, iy = (l / bg.mbinx) % bg.mbiny, iz = l / (bg.mbinx * bg.mbiny);
-            key[b] = ((spread(ix) | spread(iy) << 1 | spread(iz) << 2) << 32) | (unsigned)b;
+            if (sort_order == 2) { // blocks of sort_block^3 bins (about the generator's 8x8x8 half-lattice sub-boxes), x-fastest inside
+                const unsigned long long B = (unsigned long long)sort_block, nbx = bg.mbinx / B + 1, nby = bg.mbiny / B + 1;
+                const unsigned long long blk = ((iz / B) * nby + iy / B) * nbx + ix / B, in = ((iz % B) * B + iy % B) * B + ix % B;
+                key[b] = ((blk * B * B * B + in) << 32) | (unsigned)b;
+            } else
+                key[b] = ((spread(ix) | spread(iy) << 1 | spread(iz) << 2) << 32) | (unsigned)b;
         }
         std::sort(key.begin(), key.end());
         std::vector<int> rank(nb);
@@ -681,9 +698,21 @@ template <class real> struct Sim final : SimBase {
             LL = NbLayout { 32 * rowlen, 32, 5 };
             neighbors.ensure(rowlen * nstride, false, stream);
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
-            MDB_LAUNCH(launches, k_build_neighbor_v5<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p,
-                run_len.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            if (neigh_variant == 5) {
+                MDB_LAUNCH(launches, k_build_neighbor_v5<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                    P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p,
+                    run_len.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            } else {
+                RunGeom rg; // the bins' real widths are 1 / bininv (binsize itself differs for from_input, neighbor.c:78-92)
+                rg.bsx = (float)(1.0 / (double)bg.bininvx); rg.bsy = (float)(1.0 / (double)bg.bininvy);
+                rg.bsz = (float)(1.0 / (double)bg.bininvz);
+                rg.binvx    = (float)bg.bininvx;
+                rg.cutsq_hi = (float)((double)cutneighsq * (1.0 + 1e-4));
+                rg.margin   = 1e-3f * std::min({ rg.bsx, rg.bsy, rg.bsz });
+                MDB_LAUNCH(launches, k_build_neighbor_v6<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
+                    P.half_neigh, bg, rg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p,
+                    run_off.p, run_len.p, run_dyz.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            }
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));
@@ -705,6 +734,7 @@ template <class real> struct Sim final : SimBase {
     // ------------------------------------------------------------------ force
     void launch_force(int which)
     {
+        NvtxRange nvtx_range_("force");
         if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_setup or mdb_buildNeighbor first)");
         if (which == FORCE_DISPATCH)
             which = P.force_field == MDB_FF_EAM ? FORCE_EAM : (P.half_neigh ? FORCE_LJ_HALF : FORCE_LJ_FULL);
@@ -818,6 +848,7 @@ template <class real> struct Sim final : SimBase {
     }
     void forceFinalInitialIntegrate()
     {
+        NvtxRange nvtx_range_("force+integrate");
         if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_buildNeighbor first)");
         x2.ensure(x.cap, false, stream);
         y2.ensure(y.cap, false, stream);
@@ -861,6 +892,7 @@ template <class real> struct Sim final : SimBase {
     }
     void forceFinalInitialIntegrateInPlace()
     {
+        NvtxRange nvtx_range_("force+integrate");
         if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_buildNeighbor first)");
         for (DBuf<vec2>* b : { &xy, &xy2 }) b->ensure(x.cap, false, stream);
         for (DBuf<real>* b : { &zg, &zg2 }) b->ensure(x.cap, false, stream);
@@ -949,6 +981,7 @@ template <class real> struct Sim final : SimBase {
     }
     void reneighbour() override // verletlist/main.c:76-95
     {
+        NvtxRange nvtx_range_("reneighbour");
         xy_valid = false;
         updateAtomsPbc();
         sort_atoms(); // main.c:82-88 (SORT_ATOMS; here at every rebuild)
@@ -1173,12 +1206,15 @@ template <class real> struct Sim final : SimBase {
     void setOption(const char* name, double v) override
     {
         if (!strcmp(name, "sort_atoms")) sort_enabled = v != 0;
-        else if (!strcmp(name, "sort_order")) sort_order = (int)v;
+        else if (!strcmp(name, "sort_order")) { sort_order = (int)v; bin_rank_ready = false; }
+        else if (!strcmp(name, "sort_block")) { sort_block = std::max(1, (int)v); bin_rank_ready = false; }
+        else if (!strcmp(name, "sort_inbin")) sort_inbin = (int)v;
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else if (!strcmp(name, "xy_gather")) xy_gather = (int)v;
         else if (!strcmp(name, "lazy_ops")) { flush_lazy(); lazy_ops = v != 0; }
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;
+        else if (!strcmp(name, "neigh_variant")) neigh_variant = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

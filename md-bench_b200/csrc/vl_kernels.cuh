@@ -371,6 +371,19 @@ static __global__ void k_bin_sort(int nbins, const int* __restrict__ binstart, i
     if ((threadIdx.x & 31) == 0 && cnt > 0) atomicMax(maxcount, cnt);
 }
 
+// sort key inside a bin (option sort_inbin = F): F x F rows of atoms along x, i.e. (fine z, fine y, x)
+template <class real>
+__global__ void k_fine_key(int n, BinGeom<real> g, int F, const real* __restrict__ x, const real* __restrict__ y,
+    const real* __restrict__ z, int* __restrict__ key)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float fx = (float)x[i] * (float)g.bininvx, fy = (float)y[i] * (float)g.bininvy, fz = (float)z[i] * (float)g.bininvz;
+    const int qy = min(F - 1, max(0, (int)((fy - floorf(fy)) * (float)F))), qz = min(F - 1, max(0, (int)((fz - floorf(fz)) * (float)F)));
+    const int qx = min(65535, max(0, (int)((fx - floorf(fx)) * 65536.0f)));
+    key[i] = ((qz * F + qy) << 16) | qx;
+}
+
 // sortAtom (verletlist/neighbor.c:360-426, the reference's optional SORT_ATOMS step): permute the
 // local atoms into bin order.  perm[q] = old index of the atom that moves to slot q.  Unlike the
 // reference the permutation is tracked (orig[] = reference index of each slot), so everything the
@@ -516,6 +529,126 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v5(int nlocal, int half,
         }
         numneigh[i] = n;
     }
+    n = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
+}
+
+// ---- v6: v5 with a per-ATOM stencil -------------------------------------------------------------------------------------
+// The reference's stencil is per BIN (every bin any atom of the bin could reach, neighbor.c:160-183): 81 bins = 21 runs,
+// ~600 candidates for ~75 hits.  An atom only needs the bins its own sphere of radius cutneigh touches (~37 of 81): a
+// run whose (y, z) bin row lies farther than cutneigh from the atom is skipped, and the x range of a run shrinks to
+// sqrt(cutneigh^2 - gap_yz^2) around the atom.  Both tests are conservative (float arithmetic with a margin of 1e-3 bin
+// widths, far above the rounding of coord2bin's bin edges), so only candidates that would fail the distance test
+// disappear and the rows come out identical, entry by entry.  Every lane walks ITS OWN compacted sequence of runs (the
+// warp iterates until the last lane is done), so the trip count is the largest number of needed runs in the warp
+// (~15) instead of 21, and a narrowed run (~20 candidates) fits one flush.
+struct RunGeom {
+    float bsx, bsy, bsz;    // bin widths
+    float binvx;            // 1 / bsx
+    float cutsq_hi, margin; // cutneigh^2 * (1 + 1e-4), 1e-3 * min bin width
+};
+template <class real>
+__global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, int half, BinGeom<real> g, RunGeom rg, real cutneighsq, float lo,
+    float hi, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float* __restrict__ cx,
+    const float* __restrict__ cy, const float* __restrict__ cz, const int* __restrict__ cid, const int* __restrict__ binstart,
+    const int* __restrict__ run_off, const int* __restrict__ run_len, const int* __restrict__ run_dyz, int nruns, int maxneighs,
+    NbLayout L, const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n)
+{
+    const int i     = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < nlocal;
+    const int ii    = live ? i : 0;
+    int n           = 0;
+    const real xt = x[ii], yt = y[ii], zt = z[ii];
+    const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
+    const f32x2 xs2 = pk2(xs, xs), ys2 = pk2(ys, ys), zs2 = pk2(zs, zs);
+    const float tpass = sizeof(real) == 4 ? nextafterf((float)cutneighsq, INFINITY) : lo;
+    const float tmay  = sizeof(real) == 4 ? tpass : nextafterf(hi, INFINITY);
+    const f32x2 tp2 = pk2(tpass, tpass), tm2 = pk2(tmay, tmay);
+    const int oi = half ? orig[ii] : 0;
+    const int ix = axis2bin(xt, g.xprd, g.bininvx, g.nbinx, g.mbinxlo);
+    const int iy = axis2bin(yt, g.yprd, g.bininvy, g.nbiny, g.mbinylo);
+    const int iz = axis2bin(zt, g.zprd, g.bininvz, g.nbinz, g.mbinzlo);
+    int ibin     = iz * g.mbiny * g.mbinx + iy * g.mbinx + ix + 1;
+    ibin         = ibin < 0 ? 0 : (ibin > g.mbins ? g.mbins : ibin);
+    // position relative to the lower edge of the own bin (absolute bin = index + mbinlo)
+    const float ux = xs - (float)(ix + g.mbinxlo) * rg.bsx, uy = ys - (float)(iy + g.mbinylo) * rg.bsy,
+                uz = zs - (float)(iz + g.mbinzlo) * rg.bsz;
+    int* out = neighbors + L.base(ii);
+    int r    = live ? 0 : nruns;
+    for (;;) {
+        int s = 0, e = 0;
+        while (r < nruns) { // next run this atom needs
+            const int dyz = __ldg(&run_dyz[r]), dy = (dyz << 16) >> 16, dz = dyz >> 16;
+            const int off = __ldg(&run_off[r]), len = __ldg(&run_len[r]);
+            r++;
+            // gap between the atom and the bin row (dy, dz): rows below start at dy * bs + bs above uy, rows above at dy * bs
+            const float gy = dy > 0 ? (float)dy * rg.bsy - uy : (dy < 0 ? uy - (float)(dy + 1) * rg.bsy : 0.0f);
+            const float gz = dz > 0 ? (float)dz * rg.bsz - uz : (dz < 0 ? uz - (float)(dz + 1) * rg.bsz : 0.0f);
+            const float gym = fmaxf(gy - rg.margin, 0.0f), gzm = fmaxf(gz - rg.margin, 0.0f);
+            const float rem = rg.cutsq_hi - gym * gym - gzm * gzm;
+            if (rem < 0.0f) continue;
+            const float rx = sqrtf(rem) + rg.margin;
+            // x bins (relative to the own bin) that intersect [ux - rx, ux + rx]
+            int first = (int)floorf((ux - rx) * rg.binvx), last = (int)floorf((ux + rx) * rg.binvx);
+            const int i0 = off - (dz * g.mbiny * g.mbinx + dy * g.mbinx); // first x offset of the run
+            first = max(first, i0);
+            last  = min(last, i0 + len - 1);
+            if (last < first) continue;
+            int b0 = ibin + off + (first - i0), b1 = b0 + (last - first + 1);
+            b0 = max(b0, 0);
+            b1 = min(b1, g.mbins + 1);
+            if (b1 <= b0) continue;
+            s = __ldg(&binstart[b0]);
+            e = __ldg(&binstart[b1]);
+            if (e > s) break;
+        }
+        if (!__any_sync(0xffffffffu, e > s)) break;
+        for (int c0 = s & ~3; c0 < e;) {
+            const int ng = min(8, (e - c0 + 3) >> 2); // groups of 4 candidates in this flush
+            unsigned mp = 0, mm = 0;
+            for (int q = 0; q < ng; q++) {
+                f32x2 X0, X1, Y0, Y1, Z0, Z1;
+                ld2x2(cx + c0 + 4 * q, X0, X1);
+                ld2x2(cy + c0 + 4 * q, Y0, Y1);
+                ld2x2(cz + c0 + 4 * q, Z0, Z1);
+                f32x2 dx = sub2(xs2, X0), dy = sub2(ys2, Y0), dz = sub2(zs2, Z0);
+                const f32x2 r0 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+                dx = sub2(xs2, X1); dy = sub2(ys2, Y1); dz = sub2(zs2, Z1);
+                const f32x2 r1 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+                float a, b;
+                upk2(sub2(r0, tm2), a, b);
+                mm = __funnelshift_l(__float_as_uint(a), mm, 1); mm = __funnelshift_l(__float_as_uint(b), mm, 1);
+                upk2(sub2(r1, tm2), a, b);
+                mm = __funnelshift_l(__float_as_uint(a), mm, 1); mm = __funnelshift_l(__float_as_uint(b), mm, 1);
+                if (sizeof(real) == 8) {
+                    upk2(sub2(r0, tp2), a, b);
+                    mp = __funnelshift_l(__float_as_uint(a), mp, 1); mp = __funnelshift_l(__float_as_uint(b), mp, 1);
+                    upk2(sub2(r1, tp2), a, b);
+                    mp = __funnelshift_l(__float_as_uint(a), mp, 1); mp = __funnelshift_l(__float_as_uint(b), mp, 1);
+                }
+            }
+            if (sizeof(real) == 4) mp = mm;
+            const int k = 4 * ng, tlo = max(s - c0, 0), thi = min(e - c0, k);
+            const unsigned vmask = (unsigned)((1ull << (k - tlo)) - 1ull) & ~(unsigned)((1ull << (k - thi)) - 1ull);
+            unsigned todo = mm & vmask;
+            while (todo) {
+                const int p = 31 - __clz(todo);
+                todo &= ~(1u << p);
+                const int j = __ldg(cid + c0 + (k - 1 - p));
+                if (j == i) continue;
+                if (half && j < nlocal && orig[j] < oi) continue;
+                if (!((mp >> p) & 1u)) {
+                    const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
+                    if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
+                }
+                if (n < maxneighs) *out = j;
+                out += L.sk;
+                n++;
+            }
+            c0 += k;
+        }
+    }
+    if (live) numneigh[i] = n;
     n = __reduce_max_sync(0xffffffffu, n);
     if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
 }

@@ -194,6 +194,31 @@ def test_run_loop_equals_operator_by_operator(dp, N, half, fuse_force):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("N", [4, 8])
+def test_sp_kernel_variants(N):
+    """SP full lists: two lanes per i-cluster (sp_kernel 1, default) == lane per i atom (sp_kernel 0) bit for bit, on
+    ragged clusters, separate and fused (mdb_cp_run); without the Newton step (sp_kernel 2) within the SP tolerance"""
+    x, v = jittered(False, 6, 7, 5, amp=0.1)
+    sims = []
+    for k in (0, 1, 2):
+        s = make_cp(False, N, 6, 7, 5, nstat=25)
+        s.setOption("sp_kernel", k)
+        s.setAtoms(x, v)
+        s.setup(adjust=False)
+        s.computeForce()
+        sims.append(s)
+    f0, f1, f2 = (np.nan_to_num(s.cl("f")) for s in sims)
+    assert np.array_equal(f0, f1)
+    assert np.abs(f2 - f0).max() <= 2e-6 * np.abs(f0).max()
+    recs = [s.run(60)[0] for s in sims]
+    assert np.array_equal(recs[0], recs[1])
+    assert np.array_equal(sims[0].atoms("x"), sims[1].atoms("x")) and np.array_equal(sims[0].atoms("v"), sims[1].atoms("v"))
+    assert np.allclose(recs[2], recs[0], rtol=1e-4)
+    assert max_rel(sims[2].atoms("x"), sims[0].atoms("x")) <= 1e-4
+    for s in sims:
+        s.close()
+
+
 @pytest.mark.parametrize("dp,N", [(True, 4), (False, 8)])
 def test_prune_neighbor_vs_oracle(dp, N):
     """pruneNeighbor 15 steps after the build: the device's list (its row order) and cluster positions are handed to
