@@ -74,11 +74,8 @@ void        mdb_destroy(mdb_ctx* c);
  *  "sort_atoms" (default 0, like the reference's SORT_ATOMS build option; 1 for the bricks of a decomposed box): re-sort
  *      the local atoms by neighbor bin at every rebuild (neighbor.c:360-426); the permutation is tracked, every accessor
  *      below still speaks the reference's atom numbering.
- *  "sort_order" 0 = the reference's x-fastest bin order, 1 = Morton order of the bins, 2 = blocks of "sort_block"^3 bins
- *      (default 3), x-fastest inside a block.  "sort_inbin" = F > 0: inside a bin the atoms are ordered as F x F rows along x
- *      (fine z, fine y, x) instead of by reference index.
- *  "neigh_variant" list build: 6 (default) = per-atom stencil (only the runs / x ranges of bins the atom's own sphere
- *      touches), 5 = the reference's per-bin stencil; identical rows.
+ *  "sort_block" order of the bins for "sort_atoms": 0 = the reference's x-fastest bin order, B > 0 = blocks of B x B x B bins
+ *      (a thread block's 128 atoms then fill a compact box, like the generator's 8x8x8 sub-boxes).
  *  "eam_variant" EAM passes: 2 (default) packed (x, y) / (z, fp) gathers and (value, slope) tables, 1 = packed spline rows
  *      (what a brick of a decomposed box runs), 0 = first kernels (scalar table gathers, IEEE sqrt / division).
  *  "fuse_integrate" (default 1) finalIntegrate(n) + initialIntegrate(n+1) in one pass inside mdb_run.
@@ -283,8 +280,9 @@ int         mdb_cp_sync(mdb_cp* c);
 /* "prune_every" (default 1000, common/parameter.c:40): pruneNeighbor period inside mdb_cp_run; "force_variant" 0 = auto
  * (full lists: lane per i atom, packed FP32 in SP; half lists: warp per i-cluster), 1 = lane per i atom scalar,
  * 2 = lane per i atom packed FP32 (SP full), 3 = warp per i-cluster / lane per j atom;
- * "sp_kernel" (SP full lists, packed FP32): 1 (default) = two lanes per i-cluster, two i atoms per lane, 0 = lane per i
- * atom, 2 = like 1 without the Newton step on the MUFU reciprocal;
+ * "sp_kernel" (SP full lists, packed FP32): 2 (default) = two lanes per i-cluster, two i atoms per lane, reciprocal =
+ * MUFU.RCP (1 ulp; the reference's SP kernel uses the 14-bit _mm512_rcp14_ps), 1 = the same with a Newton step on it
+ * (bit-identical to 0), 0 = lane per i atom;
  * "fuse_force" (default 1): inside mdb_cp_run with full lists, computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1)
  * run as ONE kernel (integrate halves in the force kernel's epilogue, second cluster position array); bit-identical. */
 int         mdb_cp_setOption(mdb_cp* c, const char* name, double value);

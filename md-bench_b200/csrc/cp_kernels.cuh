@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(128) k_cp_force_lj_sp_duo(int ncl, int dummy_c
     int cj = nn > 0 ? __ldg(row) : dummy_cj, cj1 = nn > 1 ? __ldg(row + 1) : dummy_cj;
     CpTileRegs<N> A, B;
     A.load(cl_x + (size_t)cj * N * 3);
-    for (int k = 0; k < nn; k++) {
+    for (int k = 0; k < nn; k++) { // list entry two tiles ahead, tile positions one tile ahead (the dummy tile past the end)
         const int cj2 = k + 2 < nn ? __ldg(row + k + 2) : dummy_cj;
         B.load(cl_x + (size_t)cj1 * N * 3);
         const bool diag = cj == self;

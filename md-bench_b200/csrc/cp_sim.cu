@@ -73,7 +73,7 @@ template <class real, int N> struct CpSim final : CpBase {
     bool thermo_ready = false, neigh_ready = false;
     int prune_every = 1000; // common/parameter.c:40
     int force_variant = 0;
-    int sp_kernel = 1; // SP full lists: see launch_packed
+    int sp_kernel = 2; // SP full lists: see launch_packed
     bool fuse_force = true; // mdb_cp_run, full lists: integrate halves in the force kernel's epilogue (CpFused)
     // ---- atoms (clusterpair/atom.h:26-60) ----
     long long Natoms = 0;
@@ -647,7 +647,9 @@ template <class real, int N> struct CpSim final : CpBase {
         }
     }
     // sp_kernel: 0 = lane per i atom (k_cp_force_lj_sp_packed), 1 = two lanes per i-cluster (k_cp_force_lj_sp_duo),
-    // 2 = the same without the Newton step on the MUFU reciprocal
+    // 2 (default) = the same with the MUFU reciprocal as it is (max. error 1 ulp = 2^-23) instead of MUFU + Newton step: the
+    // reference's own SP kernel takes _mm512_rcp14_ps, relative error 2^-14, unrefined (common/simd/avx512_float.h:55-58;
+    // clusterpair/force_lj.c:325-326,536), so this is still 9 bits closer to the exact quotient than what it is compared with
     void launch_packed(unsigned grid, const LJConst2<float>& c2)
     {
         const CpFused<float> nofi { nullptr, nullptr, 0.f, 0.f };

@@ -50,16 +50,13 @@ template <class real> struct Sim final : SimBase {
     bool xy_valid = false;
     DBuf<vec2> xy, xy2;
     DBuf<real> zg, zg2; // gather copy of z (in-place variant of the fused step, decomposed runs)
-    int sort_order = 0; // 0: the reference's x-fastest bin order, 1: Morton order of the bins, 2: blocks of sort_block^3 bins
-    int sort_block = 3, sort_inbin = 0; // sort_inbin = F > 0: inside a bin, F x F rows of atoms along x
-    DBuf<int> sort_key;
-    bool bin_rank_ready = false;
+    int sort_block = 0; // sort_atoms: 0 = the reference's x-fastest bin order, B > 0 = blocks of B^3 bins (x-fastest inside)
+    long long bin_rank_key = -1; // geometry the rank table was built for
     DBuf<int> bin_rank;
     NbLayout LL { 0, 0, 0 };                                    // element (i,k) at neighbors[LL.base(i) + k*LL.sk]
-    DBuf<float> cxs, cys, czs; // candidates in CSR order, SoA (k_build_neighbor_v5)
+    DBuf<float> cxs, cys, czs; // candidates in CSR order, SoA (k_build_neighbor_v6)
     DBuf<int> cids;
     DBuf<int> run_off, run_len, run_dyz; // runs of x-adjacent stencil bins (offset of the first bin, length, dy | dz << 16)
-    int neigh_variant = 6; // 6: per-atom stencil (k_build_neighbor_v6), 5: the per-bin stencil (A/B)
     int nruns = 0;
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
     DBuf<unsigned> ghost_msk;
@@ -485,7 +482,6 @@ template <class real> struct Sim final : SimBase {
         binstart.ensure(bg.mbins + 3, false, stream);
         cursor.ensure(bg.mbins + 2, false, stream);
         neigh_ready = true;
-        bin_rank_ready = false;
     }
 
     // ------------------------------------------------------------------ spatial sort
@@ -501,21 +497,14 @@ template <class real> struct Sim final : SimBase {
         binatoms.ensure(Nlocal, false, stream);
         MDB_CUDA(cudaMemsetAsync(bincount.p, 0, (nb + 1) * sizeof(int), stream));
         MDB_CUDA(cudaMemsetAsync(cursor.p, 0, (nb + 1) * sizeof(int), stream));
-        if (sort_order >= 1 && !bin_rank_ready) build_bin_rank();
+        if (sort_block > 0) build_bin_rank();
         MDB_LAUNCH(launches, k_bin_count<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, bg, x.p, y.p, z.p,
-            sort_order >= 1 ? bin_rank.p : (const int*)nullptr, atom_bin.p, bincount.p);
+            sort_block > 0 ? bin_rank.p : (const int*)nullptr, atom_bin.p, bincount.p);
         scanner.exclusive(bincount.p, binstart.p, nb, binstart.p + nb, stream);
         MDB_LAUNCH(launches, k_bin_fill, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, atom_bin.p, binstart.p,
             cursor.p, binatoms.p);
         MDB_LAUNCH(launches, k_bin_sort, grid_for(nb, 128), 128, 0, stream, nb, binstart.p, binatoms.p, orig.p,
             d_flags.p + 3);
-        if (sort_inbin) { // inside a bin: rows of atoms along x (fine z, fine y, x), ties keep the reference-index order
-            sort_key.ensure(Nlocal, false, stream);
-            MDB_LAUNCH(launches, k_fine_key<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, bg, sort_inbin, x.p, y.p,
-                z.p, sort_key.p);
-            MDB_LAUNCH(launches, k_bin_sort, grid_for(nb, 128), 128, 0, stream, nb, binstart.p, binatoms.p, sort_key.p,
-                d_flags.p + 3);
-        }
         const size_t cap = x.cap;
         for (DBuf<real>* b : { &x2, &y2, &z2, &vx2, &vy2, &vz2, &fx2, &fy2, &fz2 }) b->ensure(cap, false, stream);
         type2.ensure(cap, false, stream);
@@ -530,39 +519,18 @@ template <class real> struct Sim final : SimBase {
         extmap_valid = false;
     }
 
-    // Sort order of the bins for sort_atoms: along a Morton (Z-order) curve, so that the ~27 bins an
-    // atom's neighbors live in map to a few contiguous memory chunks in all three dimensions (with the
-    // reference's x-fastest bin order every (y,z) stencil row is a separate memory region).
+    // Sort order of the bins for sort_atoms (option sort_block = B > 0): blocks of B x B x B bins, x-fastest inside a block and
+    // between blocks, so that 128 consecutive atoms (one thread block of the force kernel) fill a compact box like the
+    // generator's 8x8x8 sub-boxes do instead of a stick of ~18 bins along x.  The rank of every bin is a closed form
+    // (k_block_rank); the table is rebuilt only when the bin grid or B changes.
     void build_bin_rank()
     {
+        const long long key = (((long long)bg.mbinx * 4096 + bg.mbiny) * 4096 + bg.mbinz) * 64 + sort_block;
+        if (key == bin_rank_key) return;
         const int nb = bg.mbins + 1;
-        std::vector<unsigned long long> key(nb);
-        auto spread = [](unsigned long long v) { // 21 bits -> every third bit
-            v &= 0x1fffff;
-            v = (v | v << 32) & 0x1f00000000ffffULL;
-            v = (v | v << 16) & 0x1f0000ff0000ffULL;
-            v = (v | v << 8) & 0x100f00f00f00f00fULL;
-            v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
-            v = (v | v << 2) & 0x1249249249249249ULL;
-            return v;
-        };
-        for (int b = 0; b < nb; b++) {
-            const int l  = b > 0 ? b - 1 : 0; // undo coord2bin's "+ 1"
-            const int ix = l % bg.mbinx, iy = (l / bg.mbinx) % bg.mbiny, iz = l / (bg.mbinx * bg.mbiny);
-            if (sort_order == 2) { // blocks of sort_block^3 bins (about the generator's 8x8x8 half-lattice sub-boxes), x-fastest inside
-                const unsigned long long B = (unsigned long long)sort_block, nbx = bg.mbinx / B + 1, nby = bg.mbiny / B + 1;
-                const unsigned long long blk = ((iz / B) * nby + iy / B) * nbx + ix / B, in = ((iz % B) * B + iy % B) * B + ix % B;
-                key[b] = ((blk * B * B * B + in) << 32) | (unsigned)b;
-            } else
-                key[b] = ((spread(ix) | spread(iy) << 1 | spread(iz) << 2) << 32) | (unsigned)b;
-        }
-        std::sort(key.begin(), key.end());
-        std::vector<int> rank(nb);
-        for (int r = 0; r < nb; r++) rank[(int)(key[r] & 0xffffffffu)] = r;
         bin_rank.ensure(nb, false, stream);
-        MDB_CUDA(cudaMemcpyAsync(bin_rank.p, rank.data(), nb * sizeof(int), cudaMemcpyHostToDevice, stream));
-        MDB_CUDA(cudaStreamSynchronize(stream));
-        bin_rank_ready = true;
+        MDB_LAUNCH(launches, k_block_rank, grid_for(nb, 256), 256, 0, stream, nb, bg.mbinx, bg.mbiny, bg.mbinz, sort_block, bin_rank.p);
+        bin_rank_key = key;
     }
 
     // internal index -> reference index for locals AND ghosts.  The reference numbers ghosts in the
@@ -698,21 +666,15 @@ template <class real> struct Sim final : SimBase {
             LL = NbLayout { 32 * rowlen, 32, 5 };
             neighbors.ensure(rowlen * nstride, false, stream);
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
-            if (neigh_variant == 5) {
-                MDB_LAUNCH(launches, k_build_neighbor_v5<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                    P.half_neigh, bg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p,
-                    run_len.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
-            } else {
-                RunGeom rg; // the bins' real widths are 1 / bininv (binsize itself differs for from_input, neighbor.c:78-92)
-                rg.bsx = (float)(1.0 / (double)bg.bininvx); rg.bsy = (float)(1.0 / (double)bg.bininvy);
-                rg.bsz = (float)(1.0 / (double)bg.bininvz);
-                rg.binvx    = (float)bg.bininvx;
-                rg.cutsq_hi = (float)((double)cutneighsq * (1.0 + 1e-4));
-                rg.margin   = 1e-3f * std::min({ rg.bsx, rg.bsy, rg.bsz });
-                MDB_LAUNCH(launches, k_build_neighbor_v6<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal,
-                    P.half_neigh, bg, rg, cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p,
-                    run_off.p, run_len.p, run_dyz.p, nruns, maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
-            }
+            RunGeom rg; // the bins' real widths are 1 / bininv (binsize itself differs for from_input, neighbor.c:78-92)
+            rg.bsx = (float)(1.0 / (double)bg.bininvx); rg.bsy = (float)(1.0 / (double)bg.bininvy);
+            rg.bsz = (float)(1.0 / (double)bg.bininvz);
+            rg.binvx    = (float)bg.bininvx;
+            rg.cutsq_hi = (float)((double)cutneighsq * (1.0 + 1e-4));
+            rg.margin   = 1e-3f * std::min({ rg.bsx, rg.bsy, rg.bsz });
+            MDB_LAUNCH(launches, k_build_neighbor_v6<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, P.half_neigh, bg, rg,
+                cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns,
+                maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));
@@ -1206,15 +1168,12 @@ template <class real> struct Sim final : SimBase {
     void setOption(const char* name, double v) override
     {
         if (!strcmp(name, "sort_atoms")) sort_enabled = v != 0;
-        else if (!strcmp(name, "sort_order")) { sort_order = (int)v; bin_rank_ready = false; }
-        else if (!strcmp(name, "sort_block")) { sort_block = std::max(1, (int)v); bin_rank_ready = false; }
-        else if (!strcmp(name, "sort_inbin")) sort_inbin = (int)v;
+        else if (!strcmp(name, "sort_block")) sort_block = std::max(0, std::min(63, (int)v));
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else if (!strcmp(name, "xy_gather")) xy_gather = (int)v;
         else if (!strcmp(name, "lazy_ops")) { flush_lazy(); lazy_ops = v != 0; }
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;
-        else if (!strcmp(name, "neigh_variant")) neigh_variant = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));
     }
 };

@@ -332,8 +332,7 @@ __global__ void k_bin_count(int nall, BinGeom<real> g, const real* __restrict__ 
     const real* __restrict__ y, const real* __restrict__ z, const int* __restrict__ rank,
     int* __restrict__ atom_bin, int* __restrict__ bincount)
 {
-    // rank == nullptr: key = the reference's bin index; else key = rank[bin] (sort order of the bins,
-    // e.g. along a Morton curve, used only by sort_atoms)
+    // rank == nullptr: key = the reference's bin index; else key = rank[bin] (sort order of the bins, used only by sort_atoms)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nall) return;
     int b = coord2bin(g, x[i], y[i], z[i]);
@@ -371,17 +370,21 @@ static __global__ void k_bin_sort(int nbins, const int* __restrict__ binstart, i
     if ((threadIdx.x & 31) == 0 && cnt > 0) atomicMax(maxcount, cnt);
 }
 
-// sort key inside a bin (option sort_inbin = F): F x F rows of atoms along x, i.e. (fine z, fine y, x)
-template <class real>
-__global__ void k_fine_key(int n, BinGeom<real> g, int F, const real* __restrict__ x, const real* __restrict__ y,
-    const real* __restrict__ z, int* __restrict__ key)
+// rank of bin b in the blocked order of sort_atoms (Sim::build_bin_rank): bins are numbered 1 + (iz * my + iy) * mx + ix
+// (coord2bin's stray "+ 1"; bin 0 keeps rank 0).  Blocks of B^3 bins, clipped at the upper faces of the grid.
+static __global__ void k_block_rank(int nb, int mx, int my, int mz, int B, int* __restrict__ rank)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float fx = (float)x[i] * (float)g.bininvx, fy = (float)y[i] * (float)g.bininvy, fz = (float)z[i] * (float)g.bininvz;
-    const int qy = min(F - 1, max(0, (int)((fy - floorf(fy)) * (float)F))), qz = min(F - 1, max(0, (int)((fz - floorf(fz)) * (float)F)));
-    const int qx = min(65535, max(0, (int)((fx - floorf(fx)) * 65536.0f)));
-    key[i] = ((qz * F + qy) << 16) | qx;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    if (b == 0) { rank[0] = 0; return; }
+    const int l = b - 1, ix = l % mx, iy = (l / mx) % my, iz = l / (mx * my);
+    const int bx = ix / B, by = iy / B, bz = iz / B;
+    const int sx = min(B, mx - bx * B), sy = min(B, my - by * B), sz = min(B, mz - bz * B);
+    const long long r = (long long)mx * my * (bz * B)         // layers of blocks below
+        + (long long)mx * (by * B) * sz                       // rows of blocks in front, in this layer
+        + (long long)(bx * B) * sy * sz                       // blocks to the left, in this row
+        + ((long long)(iz - bz * B) * sy + (iy - by * B)) * sx + (ix - bx * B);
+    rank[b] = (int)(1 + r);
 }
 
 // sortAtom (verletlist/neighbor.c:360-426, the reference's optional SORT_ATOMS step): permute the
@@ -454,86 +457,7 @@ __device__ __forceinline__ void ld2x2(const float* p, f32x2& a, f32x2& b)
 {
     asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
-template <class real>
-__global__ void __launch_bounds__(128) k_build_neighbor_v5(int nlocal, int half, BinGeom<real> g, real cutneighsq, float lo, float hi,
-    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float* __restrict__ cx,
-    const float* __restrict__ cy, const float* __restrict__ cz, const int* __restrict__ cid, const int* __restrict__ binstart,
-    const int* __restrict__ run_off, const int* __restrict__ run_len, int nruns, int maxneighs, NbLayout L,
-    const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n       = 0;
-    if (i < nlocal) {
-        const real xt = x[i], yt = y[i], zt = z[i];
-        const float xs = (float)xt, ys = (float)yt, zs = (float)zt;
-        const f32x2 xs2 = pk2(xs, xs), ys2 = pk2(ys, ys), zs2 = pk2(zs, zs);
-        // flagged iff rs < T.  SP: pass == maybe == (rs <= cutneighsq), the reference's own expression.
-        // DP: pass = rs < lo (certainly inside), maybe = rs <= hi (not certainly outside), exact FP64 in between.
-        const float tpass = sizeof(real) == 4 ? nextafterf((float)cutneighsq, INFINITY) : lo;
-        const float tmay  = sizeof(real) == 4 ? tpass : nextafterf(hi, INFINITY);
-        const f32x2 tp2 = pk2(tpass, tpass), tm2 = pk2(tmay, tmay);
-        const int oi   = half ? orig[i] : 0;
-        const int ibin = coord2bin(g, xt, yt, zt);
-        int* out       = neighbors + L.base(i);
-        for (int r = 0; r < nruns; r++) {
-            int b0 = ibin + __ldg(&run_off[r]), b1 = b0 + __ldg(&run_len[r]);
-            b0 = max(b0, 0);
-            b1 = min(b1, g.mbins + 1);
-            if (b1 <= b0) continue;
-            const int s = __ldg(&binstart[b0]), e = __ldg(&binstart[b1]);
-            for (int c0 = s & ~3; c0 < e;) {
-                const int ng = min(8, (e - c0 + 3) >> 2); // groups of 4 candidates in this flush
-                unsigned mp = 0, mm = 0;
-                for (int q = 0; q < ng; q++) {
-                    f32x2 X0, X1, Y0, Y1, Z0, Z1;
-                    ld2x2(cx + c0 + 4 * q, X0, X1);
-                    ld2x2(cy + c0 + 4 * q, Y0, Y1);
-                    ld2x2(cz + c0 + 4 * q, Z0, Z1);
-                    f32x2 dx = sub2(xs2, X0), dy = sub2(ys2, Y0), dz = sub2(zs2, Z0);
-                    const f32x2 r0 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
-                    dx = sub2(xs2, X1); dy = sub2(ys2, Y1); dz = sub2(zs2, Z1);
-                    const f32x2 r1 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
-                    float a, b;
-                    upk2(sub2(r0, tm2), a, b);
-                    mm = __funnelshift_l(__float_as_uint(a), mm, 1); mm = __funnelshift_l(__float_as_uint(b), mm, 1);
-                    upk2(sub2(r1, tm2), a, b);
-                    mm = __funnelshift_l(__float_as_uint(a), mm, 1); mm = __funnelshift_l(__float_as_uint(b), mm, 1);
-                    if (sizeof(real) == 8) {
-                        upk2(sub2(r0, tp2), a, b);
-                        mp = __funnelshift_l(__float_as_uint(a), mp, 1); mp = __funnelshift_l(__float_as_uint(b), mp, 1);
-                        upk2(sub2(r1, tp2), a, b);
-                        mp = __funnelshift_l(__float_as_uint(a), mp, 1); mp = __funnelshift_l(__float_as_uint(b), mp, 1);
-                    }
-                }
-                if (sizeof(real) == 4) mp = mm;
-                // candidate t of this flush (position c0 + t) sits at bit k-1-t; valid ones: s <= c0 + t < e
-                const int k = 4 * ng, tlo = max(s - c0, 0), thi = min(e - c0, k);
-                const unsigned vmask = (unsigned)((1ull << (k - tlo)) - 1ull) & ~(unsigned)((1ull << (k - thi)) - 1ull);
-                unsigned todo = mm & vmask;
-                while (todo) {
-                    const int p = 31 - __clz(todo); // highest bit first = ascending candidate position (the reference's order)
-                    todo &= ~(1u << p);
-                    const int j = __ldg(cid + c0 + (k - 1 - p));
-                    if (j == i) continue;
-                    if (half && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
-                    if (!((mp >> p) & 1u)) { // uncertain band: the reference's exact FP64 expression
-                        const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
-                        if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
-                    }
-                    if (n < maxneighs) *out = j;
-                    out += L.sk;
-                    n++;
-                }
-                c0 += k;
-            }
-        }
-        numneigh[i] = n;
-    }
-    n = __reduce_max_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0) atomicMax(max_n, n);
-}
-
-// ---- v6: v5 with a per-ATOM stencil -------------------------------------------------------------------------------------
+// ---- per-ATOM stencil ----------------------------------------------------------------------------------------------------
 // The reference's stencil is per BIN (every bin any atom of the bin could reach, neighbor.c:160-183): 81 bins = 21 runs,
 // ~600 candidates for ~75 hits.  An atom only needs the bins its own sphere of radius cutneigh touches (~37 of 81): a
 // run whose (y, z) bin row lies farther than cutneigh from the atom is skipped, and the x range of a run shrinks to
