@@ -34,6 +34,9 @@ UNIT = "atom-steps/s"
 # algorithmic work of the LJ full-list force kernel per atom-step
 FLOP_PER_ATOM_STEP = 1429.0           # 8*L + 15*C, L = 76.035 listed, C = 54.74 inside the cutoff
 BYTES_PER_ATOM_STEP = {"dp": 365.0, "sp": 335.0}
+# clusterpair, decomposed runs only (a single domain counts its pairs live): 8 flop per evaluated atom pair + 15 per pair inside
+# the cutoff, single-domain counts of the same lattice over 200 steps (4x4: 13.7 cluster pairs and 55.6 in-cutoff pairs per atom)
+CP_FLOP_PER_ATOM_STEP = {4: 2589.3, 8: 2995.0}
 
 
 def host_threads():
@@ -441,15 +444,13 @@ def main():
     decomposed = world > 1 or args.bricks is not None
     stream = torch.cuda.current_stream().cuda_stream
     cp = args.scheme == "clusterpair"
-    if cp and decomposed:
-        raise SystemExit("bench.py: the clusterpair scheme runs one domain per GPU (no decomposition yet)")
     parity = None
     if not cp and not args.no_parity and args.bricks is None:
         try:
             parity = parity_check(m, dist, rank, world, local, stream)
         except Exception as e:   # reported, never hidden: a failed check makes the line say so
             parity = {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
-    if cp:
+    if cp and not decomposed:
         grid = (1, 1, 1)
         P = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx,
                              ntimes=args.ntimes, half_neigh=args.half)
@@ -462,7 +463,9 @@ def main():
             dist.broadcast_object_list(uid, src=0)
         P = m.default_params(precision=m.DP if dp else m.SP, nx=args.nx * grid[0], ny=args.nx * grid[1],
                              nz=args.nx * grid[2], ntimes=args.ntimes, half_neigh=args.half)
-        sim = m.Decomposition(P, grid, nprocs=world, proc=rank, nccl_id=uid[0], device=local)
+        # clusterpair: ghost CLUSTERS from the neighbor bricks (cp_dd.cuh), NCCL send/recv between the processes
+        sim = m.Decomposition(P, grid, nprocs=world, proc=rank, nccl_id=uid[0], device=local,
+                              cluster_n=args.cluster_n if cp else 0)
     else:
         grid = (1, 1, 1)
         P = m.default_params(precision=m.DP if dp else m.SP, layout=m.AOS, nx=args.nx, ny=args.nx, nz=args.nx,
@@ -528,6 +531,8 @@ def main():
         # 8 flop per evaluated atom pair (every listed cluster pair = M x N atom pairs) + 15 more per pair
         # inside the cutoff; counts taken live from the current list (mean of the first and the last list of a run)
         flop_per_atom = (8.0 * 0.5 * (listed0 + listed1) * 4 * args.cluster_n + 15.0 * 0.5 * (inside0 + inside1)) / natoms
+        if decomposed:   # no pair counter across bricks: the single-domain count of the same lattice and run length
+            flop_per_atom = CP_FLOP_PER_ATOM_STEP[args.cluster_n]
     ach_tf = flop_per_atom * per_launch_atoms / (f_ms * 1e-3) * 1e-12
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
@@ -586,7 +591,7 @@ def main():
             ov = torch.empty((3, cap), dtype=tdt, pin_memory=True)
             sim.get_into("x", htag.numpy(), hx.numpy())
             sim.get_into("v", None, hv.numpy())
-        elif cp:   # positions AoS, velocities SoA (clusterpair/atom.h:66-92)
+        elif cp and not decomposed:   # positions AoS, velocities SoA (clusterpair/atom.h:66-92)
             hx = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
             hv = torch.empty((3, natoms), dtype=tdt, pin_memory=True)
             ox = torch.empty((natoms, 3), dtype=tdt, pin_memory=True)
@@ -611,7 +616,7 @@ def main():
                 assert sim.counts()["Nlocal"] <= cap
                 sim.get_into("x", otag.numpy(), ox.numpy())          # D2H of the final state
                 sim.get_into("v", None, ov.numpy())
-            elif cp:
+            elif cp and not decomposed:
                 sim.setAtomsRaw(hx.numpy(), hv.numpy())
                 sim.setup(adjust=False)
                 rec_e, _ = sim.run(args.ntimes)   # ends with updateSingleAtoms: the atom arrays hold the final state

@@ -225,6 +225,13 @@ int         mdb_dd_schedule(int gx, int gy, int gz, int perx, int pery, int perz
 /* p = parameters of the WHOLE box (nx,ny,nz multiples of gx,gy,gz).  nccl_id may be NULL iff nprocs == 1 */
 mdb_dd*     mdb_dd_create(const mdb_params* p, int gx, int gy, int gz, int nprocs, int proc,
                           const void* nccl_id, int device);
+/* the same brick grid for the CLUSTERPAIR scheme (cluster_n = 4 or 8, full lists, generated lattices): ghost j-CLUSTERS come
+ * from the neighbor bricks as whole tiles (setupPbc / updatePbcCPU, clusterpair/pbc.c:183-323, 45-114), atoms migrate at every
+ * rebuild (pbc.c:117-144); NCCL send/recv between processes, device copies inside one.  Every mdb_dd_* call below applies
+ * (mdb_dd_setEam and mdb_dd_getNeighborTags answer with an error; options are mdb_cp_setOption's);
+ * mdb_dd_getAtoms returns the atom arrays as of the last updateSingleAtoms; mdb_dd_getCounts v[2] counts ghost clusters. */
+mdb_dd*     mdb_dd_create_cp(const mdb_params* p, int cluster_n, int gx, int gy, int gz, int nprocs, int proc,
+                             const void* nccl_id, int device);
 void        mdb_dd_destroy(mdb_dd* d);
 int         mdb_dd_setStream(mdb_dd* d, void* cuda_stream);
 int         mdb_dd_sync(mdb_dd* d);

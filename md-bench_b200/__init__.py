@@ -55,7 +55,8 @@ EXPORTS = [
     "mdb_getKernelStats", "mdb_resetKernelStats", "mdb_setEam", "mdb_setEamSplines",
     "mdb_getEamSplines", "mdb_getNeighbors", "mdb_getGhostMap", "mdb_getNeighborParams",
     "mdb_getStencil", "mdb_getBinCounts", "mdb_getEamFp", "mdb_countPairs", "mdb_measureFmaPeak", "mdb_stubNeighbors",
-    "mdb_dd_uniqueIdBytes", "mdb_dd_getUniqueId", "mdb_dd_plan", "mdb_dd_schedule", "mdb_dd_create", "mdb_dd_destroy",
+    "mdb_dd_uniqueIdBytes", "mdb_dd_getUniqueId", "mdb_dd_plan", "mdb_dd_schedule", "mdb_dd_create", "mdb_dd_create_cp",
+    "mdb_dd_destroy",
     "mdb_dd_setStream", "mdb_dd_sync", "mdb_dd_createAtom", "mdb_dd_setAtoms", "mdb_dd_setEam", "mdb_dd_setup",
     "mdb_dd_reneighbour", "mdb_dd_run", "mdb_dd_computeThermo", "mdb_dd_getCounts", "mdb_dd_getAtoms",
     "mdb_dd_getNeighborTags", "mdb_dd_saveState", "mdb_dd_restoreState", "mdb_dd_setOption",
@@ -98,6 +99,8 @@ def load_library(build=True):
         getattr(L, f).argtypes = [C.c_void_p]
     L.mdb_dd_create.restype = C.c_void_p
     L.mdb_dd_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.mdb_dd_create_cp.restype = C.c_void_p
+    L.mdb_dd_create_cp.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.mdb_dd_createAtom.restype = C.c_longlong
     L.mdb_dd_createAtom.argtypes = [C.c_void_p]
     L.mdb_cp_create.restype = C.c_void_p
@@ -422,17 +425,21 @@ def dd_unique_id():
 
 class Decomposition:
     """The bricks of a spatially decomposed box owned by this process (opaque mdb_dd).  `params`
-    describe the WHOLE box; same driver-level method names as Simulation."""
+    describe the WHOLE box; same driver-level method names as Simulation.  cluster_n = 4 or 8 selects the CLUSTERPAIR scheme
+    (mdb_dd_create_cp: ghost clusters from the neighbor bricks), 0 the verletlist scheme."""
 
-    def __init__(self, params, grid, nprocs=1, proc=0, nccl_id=None, device=0):
+    def __init__(self, params, grid, nprocs=1, proc=0, nccl_id=None, device=0, cluster_n=0):
         self.L = load_library()
         self.params = params
         self.dp = params.precision == DP
         self.np_real = np.float64 if self.dp else np.float32
         self.grid = tuple(grid)
         idbuf = None if nccl_id is None else C.create_string_buffer(nccl_id, len(nccl_id))
-        h = self.L.mdb_dd_create(C.byref(params), grid[0], grid[1], grid[2], nprocs, proc,
-                                 None if idbuf is None else C.cast(idbuf, C.c_void_p), device)
+        idp = None if idbuf is None else C.cast(idbuf, C.c_void_p)
+        if cluster_n:
+            h = self.L.mdb_dd_create_cp(C.byref(params), cluster_n, grid[0], grid[1], grid[2], nprocs, proc, idp, device)
+        else:
+            h = self.L.mdb_dd_create(C.byref(params), grid[0], grid[1], grid[2], nprocs, proc, idp, device)
         if not h:
             raise MdbError(self.L.mdb_last_error().decode())
         self.h = C.c_void_p(h)

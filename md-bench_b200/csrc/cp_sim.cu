@@ -13,6 +13,10 @@
 #include "scan.cuh"
 #include "vl_kernels.cuh"
 #include "cp_kernels.cuh"
+#include "sim.cuh"
+#include "dd_topo.h"
+#include "dd_kernels.cuh"
+#include "nccl_dl.h"
 
 namespace mdb {
 
@@ -943,6 +947,8 @@ static CpBase* make_cp(const mdb_params& p, int cluster_n, int device)
     if (p.precision == MDB_SP) return cluster_n == 4 ? (CpBase*)new CpSim<float, 4>(p, device) : new CpSim<float, 8>(p, device);
     throw Error("mdb_cp_create: precision must be MDB_SP or MDB_DP");
 }
+
+#include "cp_dd.cuh"
 
 void set_last_error(const char* msg); // mdb200.cu
 

@@ -294,6 +294,20 @@ mdb_dd* mdb_dd_create(const mdb_params* p, int gx, int gy, int gz, int nprocs, i
         return nullptr;
     }
 }
+mdb_dd* mdb_dd_create_cp(const mdb_params* p, int cluster_n, int gx, int gy, int gz, int nprocs, int proc, const void* nccl_id, int device)
+{
+    try {
+        if (!p) throw Error("mdb_dd_create_cp: null params");
+        if (p->ntypes != 1) throw Error("mdb_dd_create_cp: only ntypes == 1 is supported (EXPLICIT_TYPES off)");
+        const int grid[3] = { gx, gy, gz };
+        mdb_dd* d = new mdb_dd;
+        d->g      = make_cp_dd(*p, cluster_n, grid, nprocs, proc, nccl_id, device);
+        return d;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 void mdb_dd_destroy(mdb_dd* d)
 {
     if (!d) return;

@@ -97,5 +97,7 @@ struct DDBase {
 };
 
 DDBase* make_dd(const mdb_params& global, const int grid[3], int nprocs, int proc, const void* nccl_id, int device);
+// the clusterpair scheme on the same brick grid (cp_dd.cuh)
+DDBase* make_cp_dd(const mdb_params& global, int cluster_n, const int grid[3], int nprocs, int proc, const void* nccl_id, int device);
 
 } // namespace mdb

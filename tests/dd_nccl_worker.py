@@ -1,6 +1,6 @@
 """torchrun worker for test_dd.py::test_dd_nccl_processes: a decomposed box over WORLD_SIZE processes
 (one GPU each, NCCL send/recv between bricks) against the single-domain run on rank 0's GPU.
-usage: torchrun --nproc-per-node N tests/dd_nccl_worker.py gx gy gz nx steps"""
+usage: torchrun --nproc-per-node N tests/dd_nccl_worker.py gx gy gz nx steps [cluster_n]   (cluster_n = 4 or 8: the clusterpair scheme)"""
 import importlib
 import os
 import sys
@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     gx, gy, gz, nx, steps = [int(v) for v in sys.argv[1:6]]
+    cn = int(sys.argv[6]) if len(sys.argv) > 6 else 0
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -22,7 +23,7 @@ def main():
     uid = [m.dd_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     P = m.default_params(nx=nx, ny=nx, nz=nx)
-    d = m.Decomposition(P, (gx, gy, gz), nprocs=world, proc=rank, nccl_id=uid[0], device=local)
+    d = m.Decomposition(P, (gx, gy, gz), nprocs=world, proc=rank, nccl_id=uid[0], device=local, cluster_n=cn)
     n = d.createAtom()
     d.setup(adjust=True)
     rec, _ = d.run(steps)
@@ -32,12 +33,22 @@ def main():
     dist.all_gather_object(parts, (tags, x, v, rec))
     ok = True
     if rank == 0:
-        s = m.Simulation(m.default_params(nx=nx, ny=nx, nz=nx, layout=m.SOA), device=local)
-        s.createAtom(); s.setup(adjust=True)
-        rs, _ = s.run(steps)
         tg = np.concatenate([p[0] for p in parts]); xx = np.concatenate([p[1] for p in parts]); vv = np.concatenate([p[2] for p in parts])
-        box = s.neighborParams()["xprd"]
-        sx, sv = s.get("x"), s.get("v")
+        if cn:
+            s = m.ClusterSimulation(m.default_params(nx=nx, ny=nx, nz=nx), cluster_n=cn, device=local)
+            s.createAtom(); s.setup(adjust=True)
+            rs, _ = s.run(steps)
+            xs, ts = s.atoms("x", tags=True)
+            vs = s.atoms("v")
+            sx, sv = np.empty_like(xs), np.empty_like(vs)
+            sx[ts], sv[ts] = xs, vs
+            box = (4.0 / 0.8442) ** (1.0 / 3.0) * nx
+        else:
+            s = m.Simulation(m.default_params(nx=nx, ny=nx, nz=nx, layout=m.SOA), device=local)
+            s.createAtom(); s.setup(adjust=True)
+            rs, _ = s.run(steps)
+            box = s.neighborParams()["xprd"]
+            sx, sv = s.get("x"), s.get("v")
         dx = xx - sx[tg]
         dx -= box * np.round(dx / box)
         ok = (len(tg) == n and np.array_equal(np.sort(tg), np.arange(n))

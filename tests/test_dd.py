@@ -356,3 +356,90 @@ def test_dd_nccl_processes(grid):
            "--master-port", str(29650 + grid[1]), os.path.join(here, "dd_nccl_worker.py")] + [str(g) for g in grid] + ["12", "60"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DD_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---- clusterpair scheme on the same brick grid (cp_dd.cuh) ------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid,dp,N,skin", [((2, 2, 2), True, 4, 0.9), ((2, 1, 1), True, 8, 0.9), ((1, 1, 1), True, 4, 0.9),
+                                            ((2, 2, 2), True, 4, 0.3), ((1, 2, 2), False, 4, 0.3), ((2, 2, 1), False, 8, 0.3)])
+def test_cp_dd_matches_single_domain(grid, dp, N, skin):
+    """clusterpair decomposition (ghost clusters from the neighbor bricks, atoms migrating at the rebuilds) against the single
+    clusterpair domain atom by atom through global tags: 100 steps = 5 rebuilds, thermo records incl. the intermediate one.
+    DP at rel 1e-10 needs a skin no atom outruns between two rebuilds (0.9): a cluster-pair list covers more atom pairs than
+    the cutoff sphere (bounding boxes), so WHICH late pairs are still caught when an atom outruns the default skin (at T = 1.44
+    the fastest do) depends on the clustering, which differs between a brick and the whole box; with the default skin the two
+    runs then agree to ~1e-6, asserted at 1e-5."""
+    m = load_pkg()
+    nx = 12
+    kw = dict(nx=nx, ny=nx, nz=nx, nstat=50, skin=skin)
+    P = lambda: m.default_params(precision=m.DP if dp else m.SP, **kw)
+    s = m.ClusterSimulation(P(), cluster_n=N)
+    s.createAtom(); s.setup(adjust=True)
+    rec_s, _ = s.run(100)
+    d = m.Decomposition(P(), grid, cluster_n=N)
+    assert d.createAtom() == 4 * nx ** 3
+    d.setup(adjust=True)
+    c = d.counts()
+    assert c["Nlocal"] == 4 * nx ** 3 and c["bricks"] == grid[0] * grid[1] * grid[2] and c["Nghost"] > 0
+    tags0, x0 = d.get("x")
+    rec_d, _ = d.run(100)
+    tol = (1e-10 if skin > 0.5 else 1e-5) if dp else 1e-4
+    assert rec_d.shape == rec_s.shape and np.array_equal(rec_d[:, 0], rec_s[:, 0])
+    assert np.abs(rec_d[:, 1:] - rec_s[:, 1:]).max() <= tol * np.abs(rec_s[:, 1:]).max()
+    tags, x = d.get("x")
+    _, v = d.get("v")
+    assert np.array_equal(np.sort(tags), np.arange(4 * nx ** 3)), "atoms lost or duplicated in migration"
+    xs, ts = s.atoms("x", tags=True)
+    vs = s.atoms("v")
+    sx, sv = np.empty_like(xs), np.empty_like(vs)
+    sx[ts], sv[ts] = xs, vs
+    box = (4.0 / 0.8442) ** (1.0 / 3.0) * nx
+    strict = dp and skin > 0.5
+    assert np.abs(min_image(x - sx[tags], box)).max() <= (1e-10 if strict else 2e-3) * box
+    assert np.abs(v - sv[tags]).max() <= (1e-10 if strict else 2e-2) * np.abs(sv).max()
+    if grid != (1, 1, 1):
+        ext = box / np.array(grid)
+        def in_brick0(xx):
+            w = np.mod(xx, box)
+            return np.all((w >= 0) & (w < ext), axis=1)
+        assert set(tags0[in_brick0(x0)].tolist()) != set(tags[in_brick0(x)].tolist()), "no atom crossed a brick face in 100 steps?"
+    s.close(); d.close()
+
+
+@pytest.mark.gpu
+def test_cp_dd_save_restore_and_set_atoms():
+    """restoreState + setup reproduces a run bit for bit; atoms handed over from host buffers (what the bench's end-to-end leg
+    does) give the same run as the generated ones"""
+    m = load_pkg()
+    P = m.default_params(precision=m.SP, nx=12, ny=12, nz=12)
+    d = m.Decomposition(P, (2, 1, 2), cluster_n=4)
+    d.createAtom(); d.setup(adjust=True)
+    d.saveState()
+    tags, x = d.get("x")
+    _, v = d.get("v")
+    r1, _ = d.run(45)
+    t1, x1 = d.get("x")
+    d.restoreState(); d.setup(adjust=False)
+    r2, _ = d.run(45)
+    t2, x2 = d.get("x")
+    assert np.array_equal(r1, r2) and np.array_equal(t1, t2) and np.array_equal(x1, x2)
+    d.setAtoms(tags, np.ascontiguousarray(x.T), np.ascontiguousarray(v.T)); d.setup(adjust=False)
+    r3, _ = d.run(45)
+    assert np.allclose(r3, r1, rtol=1e-5)
+    d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid", [(2, 1, 1), (2, 2, 2)])
+def test_cp_dd_nccl_processes(grid):
+    """clusterpair bricks, one process per GPU, NCCL send/recv (needs >= 2 GPUs; skipped on a 1-GPU box)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29670 + grid[1]), os.path.join(here, "dd_nccl_worker.py")] + [str(g) for g in grid] + ["12", "60", "4"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DD_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
