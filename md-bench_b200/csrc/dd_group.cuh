@@ -97,7 +97,9 @@ template <class real> struct DomainGroup final : DDBase {
             // several bricks: re-sort the atoms by bin at every rebuild.  Unlike the single domain (where the generator's
             // order stays the better one) a brick's force kernel slows down by 20 % within 100 steps without it, and its
             // list build by 27 % (profiles/r1_ab3.txt, dd_case)
-            if (topo.nbricks > 1) b->sort_enabled = true;
+            // in blocks of 2^3 bins: 128 consecutive atoms fill a compact box (force 1.635 -> 1.580 ms per launch at N = 2,
+            // profiles/r2_s2_n2.txt)
+            if (topo.nbricks > 1) { b->sort_enabled = true; b->sort_block = 2; }
             bricks.push_back(b);
         }
         if (nprocs > 1) {

@@ -1,5 +1,5 @@
 """Refresh one entry of profiles/traffic.json from an `ncu --set full` capture of the dominant kernel.
-usage: python profiles/update_traffic.py <report.ncu-rep> <key, e.g. verletlist/dp/128> <summary file the numbers are kept in>
+usage: python profiles/update_traffic.py <report.ncu-rep> <key, e.g. verletlist/dp/128> <summary file the numbers are kept in> [git commit the capture was taken at]
 The summary (profiles/summarize.py raw) is written to <summary file>; the entry gets dram__bytes_read.sum + dram__bytes_write.sum
 of the FIRST kernel in the report."""
 import csv
@@ -9,6 +9,7 @@ import subprocess
 import sys
 
 rep, key, summ = sys.argv[1:4]
+commit = sys.argv[4] if len(sys.argv) > 4 else None
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -41,6 +42,9 @@ tj[key] = {"bytes": int(rd + wr), "kernel": kernel,
                    "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                    "l1tex_throughput_pct": num("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
                    "dram_throughput_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-                   "registers_per_thread": num("launch__registers_per_thread")}}
+                   "fma_pipe_cycles_active_pct": num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "l1_hit_pct": num("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": num("lts__t_sector_hit_rate.pct"),
+                   "registers_per_thread": num("launch__registers_per_thread")},
+           "commit": commit}
 json.dump(tj, open(path, "w"), indent=1)
 print(key, tj[key])

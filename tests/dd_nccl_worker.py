@@ -22,7 +22,9 @@ def main():
     m = importlib.import_module("md-bench_b200")
     uid = [m.dd_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    P = m.default_params(nx=nx, ny=nx, nz=nx)
+    # clusterpair at DP rel 1e-10 needs a skin no atom outruns between two rebuilds (see test_cp_dd_matches_single_domain)
+    extra = dict(skin=0.9) if cn else {}
+    P = m.default_params(nx=nx, ny=nx, nz=nx, **extra)
     d = m.Decomposition(P, (gx, gy, gz), nprocs=world, proc=rank, nccl_id=uid[0], device=local, cluster_n=cn)
     n = d.createAtom()
     d.setup(adjust=True)
@@ -35,7 +37,7 @@ def main():
     if rank == 0:
         tg = np.concatenate([p[0] for p in parts]); xx = np.concatenate([p[1] for p in parts]); vv = np.concatenate([p[2] for p in parts])
         if cn:
-            s = m.ClusterSimulation(m.default_params(nx=nx, ny=nx, nz=nx), cluster_n=cn, device=local)
+            s = m.ClusterSimulation(m.default_params(nx=nx, ny=nx, nz=nx, **extra), cluster_n=cn, device=local)
             s.createAtom(); s.setup(adjust=True)
             rs, _ = s.run(steps)
             xs, ts = s.atoms("x", tags=True)
