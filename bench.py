@@ -417,6 +417,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sort", action="store_true", help="A/B: re-sort the atoms by bin at every rebuild (SORT_ATOMS)")
     ap.add_argument("--opt", action="append", default=[], help="name=value for mdb_setOption (A/B)")
+    ap.add_argument("--global-nx", type=int, default=0,
+                    help="STRONG scaling (SURVEY 8d: 256^3 on 1/2/4/8 GPUs): the WHOLE box is G^3 unit cells whatever the GPU count")
     ap.add_argument("--bricks", default=None, help="gx,gy,gz: run a decomposed box on ONE GPU (debug / A-B)")
     ap.add_argument("--scheme", default="verletlist", choices=["verletlist", "clusterpair"],
                     help="OPT_SCHEME of the reference; clusterpair = GROMACS-style 4 x N cluster pairs (one GPU)")
@@ -444,6 +446,8 @@ def main():
     decomposed = world > 1 or args.bricks is not None
     stream = torch.cuda.current_stream().cuda_stream
     cp = args.scheme == "clusterpair"
+    if args.global_nx and not decomposed:
+        args.nx = args.global_nx
     parity = None
     if not cp and not args.no_parity and args.bricks is None:
         try:
@@ -461,8 +465,11 @@ def main():
         uid = [m.dd_unique_id() if (rank == 0 and world > 1) else None]
         if world > 1:
             dist.broadcast_object_list(uid, src=0)
-        P = m.default_params(precision=m.DP if dp else m.SP, nx=args.nx * grid[0], ny=args.nx * grid[1],
-                             nz=args.nx * grid[2], ntimes=args.ntimes, half_neigh=args.half)
+        gbox = (args.global_nx,) * 3 if args.global_nx else (args.nx * grid[0], args.nx * grid[1], args.nx * grid[2])
+        if any(gbox[k] % grid[k] for k in range(3)):
+            raise SystemExit("bench.py: --global-nx must be a multiple of the brick grid %s" % (grid,))
+        P = m.default_params(precision=m.DP if dp else m.SP, nx=gbox[0], ny=gbox[1], nz=gbox[2], ntimes=args.ntimes,
+                             half_neigh=args.half)
         # clusterpair: ghost CLUSTERS from the neighbor bricks (cp_dd.cuh), NCCL send/recv between the processes
         sim = m.Decomposition(P, grid, nprocs=world, proc=rank, nccl_id=uid[0], device=local,
                               cluster_n=args.cluster_n if cp else 0)
@@ -669,9 +676,16 @@ def main():
             ref_cuda = reference_cuda(args)
 
     if rank == 0:
+        cfg = workload_config(args, world, grid)
+        if args.global_nx:   # strong scaling: the box is fixed, the per-GPU share shrinks with the GPU count
+            g = args.global_nx
+            cfg["workload"] = ("STRONG scaling: Cu FCC %d^3 unit cells (%d atoms) in total over %d GPU(s), " % (g, 4 * g ** 3, world)
+                               + cfg["workload"].split("LJ sigma", 1)[1].join(["LJ sigma", ""]))
+            cfg["global_box"] = "%dx%dx%d unit cells = %d atoms" % (g, g, g, 4 * g ** 3)
+            cfg["nx_per_gpu"] = [g // grid[0], g // grid[1], g // grid[2]]
         line = {"metric": (METRIC_CP % (4, args.cluster_n)) if cp else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64" if dp else "f32", "data": "synthetic", "config": workload_config(args, world, grid),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.global_nx else "weak",
+                "vs_baseline": None, "dtype": "f64" if dp else "f32", "data": "synthetic", "config": cfg,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "secondary": secondary,
                 "secondaries": secondaries, "reference_cuda": ref_cuda,
                 "gpu_launches": int(launches), "clocks": clk,
