@@ -264,7 +264,7 @@ def clusterpair_secondary(m, args, local, stream, steps=2):
     out = {"metric": METRIC_CP % (4, 4), "config": "BASELINE config 2 physics (clusterpair 4x4, SP, full lists) at %d^3 unit cells" % args.nx,
            "value": natoms * args.ntimes * steps / (ms * 1e-3), "unit": UNIT, "dtype": "f32", "steps": steps,
            "ms_per_step": ms / steps,
-           "roofline": {"kernel": "k_cp_force_lj_sp_packed<4, FI> (LJ tile force with finalIntegrate(n) + initialIntegrate(n+1) in its epilogue)", "bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+           "roofline": {"kernel": "k_cp_force_lj_sp_duo<4, FI> (LJ tile force, two lanes per i-cluster, packed FP32, with finalIntegrate(n) + initialIntegrate(n+1) in its epilogue)", "bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                         "frac": ach / peak if peak else None, "traffic": traffic, "ncu_capture": ncu_pipes, "ms_per_launch": f_ms, "flop_per_atom_step": flop,
                         "force_share_of_step": ks["force_ms"] / (tm["TOTAL"] * 1e3) if tm["TOTAL"] else None,
                         "neigh_ms_per_rebuild": ks["neigh_ms"] / max(1, ks["neigh_launches"])},
@@ -559,7 +559,9 @@ def main():
                 ncu_pipes = te.get("ncu")
     except Exception:
         pass
-    roofline = {"kernel": ("k_cp_force_lj<%s,%d,%s>" % ("double" if dp else "float", args.cluster_n, "half" if args.half else "full")) if cp
+    roofline = {"kernel": (("k_cp_force_lj_sp_duo<%d, FI> (two lanes per i-cluster, packed FP32, integrate halves in the epilogue)" % args.cluster_n)
+                           if (not dp and not args.half) else
+                           "k_cp_force_%s<%s,%d,%s>" % ("jl" if args.half else "lj", "double" if dp else "float", args.cluster_n, "half" if args.half else "full")) if cp
                 else ("k_force_lj_full_fi<%s> (LJ force with finalIntegrate(n) + initialIntegrate(n+1) in its epilogue; flop and byte counts are the force part only)"
                       % ("double" if dp else "float")) if fused_force
                 else "k_force_lj_%s<%s>" % ("half" if args.half else "full", "double" if dp else "float"),
