@@ -111,6 +111,7 @@ def test_traffic_json_names_the_kernels_that_run():
     t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     vl, cp = t["verletlist/dp/128"], t["clusterpair/sp/128"]
     assert "k_force_lj_full_fi" in vl["kernel"] and vl["bytes"] > 3.0e9
-    assert "k_cp_force_lj_sp_packed<4, 1>" in cp["kernel"] and cp["bytes"] > 0.9e9
+    assert "k_cp_force_lj_sp_duo<4, 1, 0>" in cp["kernel"] and cp["bytes"] > 0.9e9
+    assert vl.get("commit") and cp.get("commit"), "every capture is stamped with the commit it was taken at"
     for e in (vl, cp):
         assert os.path.exists(os.path.join(ROOT, e["source"].split(" ")[0]))
