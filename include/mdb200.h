@@ -108,6 +108,12 @@ int         mdb_setAtomsDevice(mdb_ctx* c, long long n, const void* x, const voi
 /* copy local atoms back to HOST buffers; which = 'x' | 'v' | 'f'; with_ghosts!=0 appends the
  * ghost atoms (x only), i.e. Nlocal+Nghost entries as in the reference's arrays */
 int         mdb_getAtoms(mdb_ctx* c, int which, int with_ghosts, void* x, void* y, void* z);
+/* Atom.type of the local atoms (Nlocal ints).  ntypes > 1 (the reference's EXPLICIT_TYPES builds, force_lj.c:61-67):
+ * createAtom draws type = rand() % ntypes per atom from the host's rand() sequence in emission order (atom.c:159), the
+ * readers hand types over through mdb_setAtoms; the pair parameters the reference looks up by type pair are the same for
+ * every pair (atom.c:84-89 fills all ntypes^2 entries alike), so the kernels keep the scalars and results do not depend
+ * on the types.  Single verletlist domains only (mdb_cp_create / mdb_dd_create reject ntypes != 1). */
+int         mdb_getTypes(mdb_ctx* c, int* types);
 /* Natoms, Nlocal, Nghost, Nmax, maxneighs (Atom / Neighbor scalar fields) */
 int         mdb_getCounts(mdb_ctx* c, long long* Natoms, long long* Nlocal, long long* Nghost,
                           long long* Nmax, int* maxneighs);

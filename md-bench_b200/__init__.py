@@ -47,7 +47,7 @@ class Params(C.Structure):
 EXPORTS = [
     "mdb_abi_version", "mdb_last_error", "mdb_default_params", "mdb_create", "mdb_destroy",
     "mdb_setOption", "mdb_setStream", "mdb_sync", "mdb_createAtom", "mdb_setAtoms", "mdb_setAtomsDevice",
-    "mdb_getAtoms", "mdb_getCounts", "mdb_saveState", "mdb_restoreState", "mdb_setupThermo",
+    "mdb_getAtoms", "mdb_getTypes", "mdb_getCounts", "mdb_saveState", "mdb_restoreState", "mdb_setupThermo",
     "mdb_adjustThermo", "mdb_computeThermo", "mdb_setupNeighbor", "mdb_setupPbc", "mdb_updatePbc",
     "mdb_updateAtomsPbc", "mdb_buildNeighbor", "mdb_computeForce", "mdb_computeForceLJFullNeigh",
     "mdb_computeForceLJHalfNeigh", "mdb_computeForceEam", "mdb_initialIntegrate",
@@ -192,6 +192,11 @@ class Simulation:
         cv = lambda p: None if p is None else C.c_void_p(p)
         self._ck(self.L.mdb_setAtomsDevice(self.h, C.c_longlong(n), *[cv(p) for p in ptrs_x],
                                            *[cv(p) for p in ptrs_v], cv(type_ptr)))
+
+    def types(self):
+        t = np.empty(self.counts()["Nlocal"], np.int32)
+        self._ck(self.L.mdb_getTypes(self.h, _vp(t)))
+        return t
 
     def counts(self):
         v = [C.c_longlong() for _ in range(4)]

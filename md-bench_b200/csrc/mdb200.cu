@@ -63,7 +63,7 @@ mdb_ctx* mdb_create(const mdb_params* p, int device)
 {
     try {
         if (!p) throw Error("mdb_create: null params");
-        if (p->ntypes != 1) throw Error("mdb_create: only ntypes == 1 is supported (EXPLICIT_TYPES off)");
+        if (p->ntypes < 1) throw Error("mdb_create: ntypes must be >= 1");
         mdb_ctx* c = new mdb_ctx;
         c->sim     = make_sim(*p, device);
         return c;
@@ -103,6 +103,7 @@ int mdb_setAtomsDevice(mdb_ctx* c, long long n, const void* x, const void* y, co
 {
     MDB_TRY(c->sim->setAtoms(n, x, y, z, vx, vy, vz, type, true))
 }
+int mdb_getTypes(mdb_ctx* c, int* types) { MDB_TRY(c->sim->getTypes(types)) }
 int mdb_getAtoms(mdb_ctx* c, int which, int with_ghosts, void* x, void* y, void* z)
 {
     MDB_TRY(c->sim->getAtoms(which, with_ghosts != 0, x, y, z))

@@ -18,6 +18,7 @@ struct SimBase {
     virtual void setAtoms(long long n, const void* x, const void* y, const void* z, const void* vx,
         const void* vy, const void* vz, const int* type, bool on_device)                     = 0;
     virtual void getAtoms(int which, bool ghosts, void* x, void* y, void* z)                 = 0;
+    virtual void getTypes(int* types)                                                        = 0;
     virtual void getCounts(long long* c, int* maxneighs)                                     = 0;
     virtual void saveState()                                                                 = 0;
     virtual void restoreState()                                                              = 0;

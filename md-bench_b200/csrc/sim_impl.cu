@@ -56,6 +56,7 @@ template <class real> struct Sim final : SimBase {
     NbLayout LL { 0, 0, 0 };                                    // element (i,k) at neighbors[LL.base(i) + k*LL.sk]
     DBuf<float> cxs, cys, czs; // candidates in CSR order, SoA (k_build_neighbor_v6)
     DBuf<int> cids;
+    DBuf<int> s_type1; // saveState: types in the reference's atom order
     DBuf<int> run_off, run_len, run_dyz; // runs of x-adjacent stencil bins (offset of the first bin, length, dy | dz << 16)
     int nruns = 0;
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
@@ -117,7 +118,7 @@ template <class real> struct Sim final : SimBase {
                  &atom_bin, &bincount, &binstart, &cursor, &binatoms, &numneigh, &neighbors, &rows, &d_flags })
             b->release();
         ghost_msk.release();
-        cxs.release(); cys.release(); czs.release(); cids.release();
+        cxs.release(); cys.release(); czs.release(); cids.release(); s_type1.release();
         run_off.release(); run_len.release(); run_dyz.release();
         d_partial.release();
         d_red.release();
@@ -198,12 +199,28 @@ template <class real> struct Sim final : SimBase {
         ensure_atoms((size_t)Nlocal + Nlocal / 4 + 1024, false);
         MDB_LAUNCH(launches, k_create_atoms<real>, grid_for(Natoms, 256), 256, 0, stream, P.nx, P.ny,
             P.nz, lattice, x.p, y.p, z.p, vx.p, vy.p, vz.p, type.p);
+        if (P.ntypes > 1) { // atom.c:159: type = rand() % ntypes, one draw per atom in emission order (the host's rand() sequence)
+            std::vector<int> t((size_t)Nlocal);
+            for (int i = 0; i < Nlocal; i++) t[i] = rand() % P.ntypes;
+            MDB_CUDA(cudaMemcpyAsync(type.p, t.data(), (size_t)Nlocal * sizeof(int), cudaMemcpyHostToDevice, stream));
+            MDB_CUDA(cudaStreamSynchronize(stream));
+        }
         zero3(fx.p, fy.p, fz.p, Nlocal);
         reset_order();
         neigh_ready = false;
         nstride = 0; // no list for these atoms yet
         xy_valid = false;
         return Natoms;
+    }
+    // types of the local atoms in the reference's numbering.  EXPLICIT_TYPES (force_lj.c:61-67) looks the pair parameters up
+    // by type pair, but every entry of those tables holds the same value (atom.c:84-89), so the kernels take the scalars.
+    void getTypes(int* out) override
+    {
+        std::vector<int> t((size_t)Nlocal), o((size_t)Nlocal);
+        MDB_CUDA(cudaMemcpyAsync(t.data(), type.p, (size_t)Nlocal * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaMemcpyAsync(o.data(), orig.p, (size_t)Nlocal * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MDB_CUDA(cudaStreamSynchronize(stream));
+        for (int p = 0; p < Nlocal; p++) out[o[p]] = t[p];
     }
 
     void load3(long long n, const void* a, const void* b, const void* c, real* dx, real* dy, real* dz,
@@ -293,6 +310,8 @@ template <class real> struct Sim final : SimBase {
             z.p, sx.p, sy.p, sz.p);
         MDB_LAUNCH(launches, k_scatter_orig<real>, grid_for(n, 256), 256, 0, stream, (int)n, orig.p, vx.p, vy.p,
             vz.p, svx.p, svy.p, svz.p);
+        s_type1.ensure(n, false, stream);
+        MDB_LAUNCH(launches, k_scatter_orig_int, grid_for(n, 256), 256, 0, stream, (int)n, orig.p, type.p, s_type1.p);
         saved_n = Nlocal;
     }
     void restoreState() override
@@ -303,6 +322,7 @@ template <class real> struct Sim final : SimBase {
         DBuf<real>* dst[] = { &x, &y, &z, &vx, &vy, &vz };
         for (int k = 0; k < 6; k++)
             MDB_CUDA(cudaMemcpyAsync(dst[k]->p, src[k]->p, n * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+        MDB_CUDA(cudaMemcpyAsync(type.p, s_type1.p, n * sizeof(int), cudaMemcpyDeviceToDevice, stream));
         zero3(fx.p, fy.p, fz.p, n);
         Nlocal = saved_n;
         Nghost = 0;

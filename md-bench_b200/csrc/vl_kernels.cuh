@@ -426,6 +426,12 @@ __global__ void k_scatter_orig(int n, const int* __restrict__ orig, const real* 
     oa[o] = a[p]; ob[o] = b[p]; oc[o] = c[p];
 }
 
+static __global__ void k_scatter_orig_int(int n, const int* __restrict__ orig, const int* __restrict__ a, int* __restrict__ out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) out[orig[p]] = a[p];
+}
+
 // buildNeighbor, verletlist/neighbor.c:186-264.  One thread per local atom walks the stencil of its bin as 21 runs of
 // x-adjacent bins (contiguous in the CSR).  Membership is the reference's: rsq = fma(dx,dx,fma(dy,dy,dz*dz)) (the contraction
 // GCC -Ofast makes) <= cutneighsq (neighbor.c:240).  For DP a float pre-test on float copies of the candidates

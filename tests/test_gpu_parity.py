@@ -576,3 +576,37 @@ def test_stub_driver_report():
     assert "Pattern: rand" in out and "Number of atoms: 20000" in out and "Mega atom updates/s" in out
     out = subprocess.run([exe, "-p", "seq", "-na", "4096", "--csv", "-n", "5"], capture_output=True, text=True, timeout=120).stdout
     assert out.splitlines()[0].startswith("steps,pattern,natoms,nneighs,nreps") and out.splitlines()[1].startswith("5,seq,4096,76,1,")
+
+
+def test_ntypes_explicit_types():
+    """ntypes > 1 (the reference's EXPLICIT_TYPES builds): createAtom draws type = rand() % ntypes per atom from the host's rand()
+    sequence in emission order (atom.c:159); the pair parameters of every type pair are the same (atom.c:84-89), so the run equals
+    the ntypes = 1 run bit for bit; types survive the spatial sort and saveState / restoreState"""
+    import ctypes
+    m = load_pkg()
+    libc = ctypes.CDLL("libc.so.6")
+    a = m.Simulation(m.default_params(nx=8, ny=8, nz=8))
+    a.createAtom(); a.setup(adjust=True)
+    ra, _ = a.run(45)
+    libc.srand(1)
+    b = m.Simulation(m.default_params(nx=8, ny=8, nz=8, ntypes=3))
+    n = b.createAtom()
+    libc.srand(1)
+    expect = np.array([libc.rand() % 3 for _ in range(n)], np.int32)
+    assert np.array_equal(b.types(), expect) and len(set(expect.tolist())) == 3
+    b.setup(adjust=True)
+    b.saveState()
+    rb, _ = b.run(45)
+    assert np.array_equal(ra, rb) and np.array_equal(a.get("x"), b.get("x")) and np.array_equal(a.get("v"), b.get("v"))
+    assert np.array_equal(b.types(), expect)
+    b.restoreState(); b.setup(adjust=False)
+    assert np.array_equal(b.types(), expect)
+    rc, _ = b.run(45)
+    assert np.array_equal(rb, rc)
+    libc.srand(1)
+    c = m.Simulation(m.default_params(nx=8, ny=8, nz=8, ntypes=3))
+    c.setOption("sort_atoms", 1)   # slots are permuted at every rebuild: the accessor still speaks the reference's numbering
+    c.createAtom(); c.setup(adjust=True)
+    c.run(45)
+    assert np.array_equal(c.types(), expect)
+    a.close(); b.close(); c.close()
