@@ -86,6 +86,10 @@ void        mdb_destroy(mdb_ctx* c);
  *  "xy_gather" (default 1) the fused kernel fetches a neighbor's x and y with one 2-element vector gather from a packed
  *      (x, y) copy of the positions (kept current by its own epilogue and by updatePbc) instead of two scalar gathers:
  *      fewer L1 wavefronts per pair.  Bit-identical.
+ *  "ghost_epilogue" (default -1 = on for domains of up to 2^19 atoms, 0 off, 1 on) single domain, fused step: the kernel's
+ *      epilogue also writes the periodic images of the atom (updatePbc, pbc.c:42-55), so a step between two rebuilds is
+ *      ONE launch; the next mdb_updatePbc finds them current.  Bit-identical (the same single fma per coordinate).
+ *      BASELINE config 1 (32^3): 2.69 -> 2.93 G atom updates/s; at 128^3 it costs 1.4 % of the force kernel.
  *  "lazy_ops" (default 0; 3.91 -> 4.34 G atom updates/s for MDBench-VL-B200 --operators at 128^3) for drivers that keep
  *      the reference's operator-by-operator loop: mdb_computeForce and mdb_finalIntegrate only record that they are due;
  *      if the next call is mdb_initialIntegrate the three run as the one fused kernel of mdb_run, any other entry point

@@ -42,12 +42,16 @@ template <class real> struct Sim final : SimBase {
     // atoms).  Turn it on (mdb_setOption "sort_atoms") for long runs of diffusing systems.
     bool sort_enabled = false, extmap_valid = false;
     bool fuse_integrate = true;
+    // ghosts_current: the ghost positions belong to the local positions as they are now (set by the fused kernel's epilogue,
+    // cleared by everything else that moves atoms or renumbers them)
+    int ghost_epilogue = -1; // -1: where it pays (see forceFinalInitialIntegrate), 0 / 1: off / on
+    bool ghosts_current = false, ghost_tables_valid = false;
     bool fuse_force = true; // mdb_run: integrate halves in the force kernel's epilogue (k_force_lj_full_fi)
     // packed (x, y) copy of the positions for the fused kernel's vector gathers ("xy_gather"); valid only between fused
     // steps of one mdb_run: the fused epilogue writes the locals, updatePbc the ghosts, everything else invalidates it
     typedef typename Vec2Of<real>::type vec2;
     int xy_gather = 1;
-    bool xy_valid = false;
+    bool xy_valid = ghosts_current = false;
     DBuf<vec2> xy, xy2;
     DBuf<real> zg, zg2; // gather copy of z (in-place variant of the fused step, decomposed runs)
     int sort_block = 0; // sort_atoms: 0 = the reference's x-fastest bin order, B > 0 = blocks of B^3 bins (x-fastest inside)
@@ -209,7 +213,7 @@ template <class real> struct Sim final : SimBase {
         reset_order();
         neigh_ready = false;
         nstride = 0; // no list for these atoms yet
-        xy_valid = false;
+        xy_valid = ghosts_current = false;
         return Natoms;
     }
     // types of the local atoms in the reference's numbering.  EXPLICIT_TYPES (force_lj.c:61-67) looks the pair parameters up
@@ -265,7 +269,7 @@ template <class real> struct Sim final : SimBase {
         MDB_CUDA(cudaStreamSynchronize(stream)); // host buffers may be reused by the caller
         neigh_ready = false;
         nstride = 0;
-        xy_valid = false;
+        xy_valid = ghosts_current = false;
         pending_force = pending_final = false;
     }
 
@@ -328,7 +332,7 @@ template <class real> struct Sim final : SimBase {
         Nghost = 0;
         reset_order();
         nstride = 0; // the lists belong to the state that was just replaced
-        xy_valid = false;
+        xy_valid = ghosts_current = false;
     }
 
     // ------------------------------------------------------------------ thermo
@@ -618,10 +622,13 @@ template <class real> struct Sim final : SimBase {
         MDB_LAUNCH(launches, k_ghost_fill, grid_for(Nlocal, 256), 256, 0, stream, Nlocal, ghost_msk.p,
             ghost_off.p, border_map.p, ghost_code.p, type.p);
         extmap_valid = false;
+        ghost_tables_valid = true; // ghost_msk / ghost_off describe the ghosts of the atoms in their current slots
+        ghosts_current     = false;
     }
     void updatePbc() override // verletlist/pbc.c:42-55
     {
         if (Nghost == 0) return;
+        if (ghosts_current) return; // the fused force + integrate kernel has already written the images of the new positions
         MDB_LAUNCH(launches, k_update_pbc<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost, xprd,
             yprd, zprd, border_map.p, ghost_code.p, x.p, y.p, z.p, xy_valid ? xy.p : (vec2*)nullptr);
     }
@@ -774,7 +781,7 @@ template <class real> struct Sim final : SimBase {
         fp.ensure((size_t)nall, false, stream);
         xy.ensure(x.cap, false, stream);
         eam_zf.ensure(x.cap, false, stream);
-        xy_valid = false; // the packed (x, y) copy is rebuilt for every force call here
+        xy_valid = ghosts_current = false; // the packed (x, y) copy is rebuilt for every force call here
         MDB_LAUNCH(launches, k_pack_xy<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, xy.p);
         MDB_LAUNCH(launches, (k_eam_density_v3<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
             eam_rho4.p, frho_spline.p, x.p, y.p, z.p, xy.p, numneigh.p, neighbors.p, LL, fp.p, eam_zf.p);
@@ -811,7 +818,7 @@ template <class real> struct Sim final : SimBase {
     // ------------------------------------------------------------------ integrate
     void initialIntegrate() override // verletlist/integrate.c:21-31
     {
-        xy_valid = false;
+        xy_valid = ghosts_current = false;
         MDB_LAUNCH(launches, k_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
             dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
@@ -846,7 +853,13 @@ template <class real> struct Sim final : SimBase {
                 MDB_LAUNCH(launches, k_pack_xy<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, xy.p);
             }
         }
-        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt, xy.p, xy2.p, nullptr, nullptr };
+        // the ghosts of the NEXT step are written by the same launch (single domain, ghost tables of the last setupPbc)
+        // worth it where a step is launch-bound (32^3: 2.69 -> 2.93 G atom-steps/s); at 128^3 the extra mask load of every atom
+        // costs more than the 10 us kernel it replaces (1.478 -> 1.499 ms), hence the size threshold of the default
+        const bool want_ghosts = ghost_epilogue < 0 ? Nlocal <= (1 << 19) : ghost_epilogue != 0;
+        const bool own_ghosts  = want_ghosts && !brick && ghost_tables_valid && Nghost > 0;
+        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x2.p, y2.p, z2.p, dtforce, dt, xy.p, xy2.p, nullptr, nullptr,
+            own_ghosts ? ghost_msk.p : (const unsigned*)nullptr, own_ghosts ? ghost_off.p : (const int*)nullptr, xprd, yprd, zprd };
         if (use_xy)
             MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, sizeof(real) == 4, true>), grid_for(Nlocal, 128), 128, 0, stream,
                 Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fi);
@@ -856,6 +869,7 @@ template <class real> struct Sim final : SimBase {
         std::swap(x, x2); std::swap(y, y2); std::swap(z, z2);
         if (use_xy) std::swap(xy, xy2);
         xy_valid = use_xy; // locals current; the ghost range follows with the next updatePbc
+        ghosts_current = own_ghosts; // ... unless this launch has written it already
         force_launches++;
         if (timing) {
             float ms = 0;
@@ -884,7 +898,7 @@ template <class real> struct Sim final : SimBase {
         if (cnt > 0)
             MDB_LAUNCH(launches, k_pack_gather<real>, grid_for(cnt, 256), 256, 0, stream, first, cnt, x.p, y.p, z.p, xy.p, zg.p);
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
-        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x.p, y.p, z.p, dtforce, dt, xy.p, xy2.p, zg.p, zg2.p };
+        FusedIntegrate<real> fi { vx.p, vy.p, vz.p, x.p, y.p, z.p, dtforce, dt, xy.p, xy2.p, zg.p, zg2.p, nullptr, nullptr, xprd, yprd, zprd };
         MDB_LAUNCH(launches, (k_force_lj_full_fi<real, 4, sizeof(real) == 4, true, true>), grid_for(Nlocal, 128), 128, 0, stream,
             Nlocal, c2, x.p, y.p, z.p, numneigh.p, neighbors.p, LL, fi);
         std::swap(xy, xy2);
@@ -933,10 +947,10 @@ template <class real> struct Sim final : SimBase {
         if (pending_final) { pending_final = false; finalIntegrate(); }
     }
     void drop_lazy() override { pending_force = pending_final = false; }
-    void invalidate_copies() override { xy_valid = false; }
+    void invalidate_copies() override { xy_valid = false; ghosts_current = false; }
     void finalInitialIntegrate() // finalIntegrate(n) + initialIntegrate(n+1) in one pass
     {
-        xy_valid = false;
+        xy_valid = ghosts_current = false;
         MDB_LAUNCH(launches, k_final_initial_integrate<real>, grid_for(Nlocal, 256), 256, 0, stream, Nlocal,
             dtforce, dt, x.p, y.p, z.p, vx.p, vy.p, vz.p, fx.p, fy.p, fz.p);
     }
@@ -964,7 +978,7 @@ template <class real> struct Sim final : SimBase {
     void reneighbour() override // verletlist/main.c:76-95
     {
         NvtxRange nvtx_range_("reneighbour");
-        xy_valid = false;
+        xy_valid = ghosts_current = false;
         updateAtomsPbc();
         sort_atoms(); // main.c:82-88 (SORT_ATOMS; here at every rebuild)
         setupPbc();
@@ -974,7 +988,7 @@ template <class real> struct Sim final : SimBase {
     void run(int nsteps, double* thermo_out, int max_records, int* nrecords, double* timers) override
     {
         if (!thermo_ready) setupThermo();
-        xy_valid = false; // positions may have been set from outside since the last run
+        xy_valid = ghosts_current = false; // positions may have been set from outside since the last run
         const int nstat = P.nstat > 0 ? P.nstat : nsteps + 1;
         const int every = P.reneigh_every > 0 ? P.reneigh_every : nsteps + 1;
         const int maxrec = nsteps / nstat + 3;
@@ -1192,6 +1206,7 @@ template <class real> struct Sim final : SimBase {
         else if (!strcmp(name, "fuse_integrate")) fuse_integrate = v != 0;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else if (!strcmp(name, "xy_gather")) xy_gather = (int)v;
+        else if (!strcmp(name, "ghost_epilogue")) ghost_epilogue = (int)v;
         else if (!strcmp(name, "lazy_ops")) { flush_lazy(); lazy_ops = v != 0; }
         else if (!strcmp(name, "eam_variant")) eam_variant = (int)v;
         else throw Error(fmt("mdb_setOption: unknown option '%s'", name));

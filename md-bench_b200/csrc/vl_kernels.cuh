@@ -776,6 +776,12 @@ template <class real> struct FusedIntegrate {
     typename Vec2Of<real>::type* xyn;
     const real* zg; // ZG: gather copy of z, see below
     real* zgn;
+    // single domain: the periodic images of the atom (updatePbc, pbc.c:42-55) are written by the same epilogue -- image b
+    // of atom i is ghost nlocal + goff[i] + rank of bit b in gmask[i] (setupPbc's order, k_ghost_fill) -- so that a step
+    // between two rebuilds is ONE launch.  gmask == nullptr: ghosts are somebody else's business (bricks, or no ghosts).
+    const unsigned* gmask;
+    const int* goff;
+    real xprd, yprd, zprd;
 };
 // ZG (with XY; decomposed runs): ALL gathers go to copies -- (x, y) packed and a copy of z -- which are double-buffered,
 // while x, y, z themselves are only read and written by the thread that owns the atom and are therefore updated IN
@@ -907,6 +913,25 @@ __global__ void __launch_bounds__(128, 8) k_force_lj_full_fi(int nlocal, LJConst
         typename Vec2Of<real>::type v;
         v.x = xe; v.y = ye;
         fi.xyn[e] = v;
+    }
+    if (!ZG && fi.gmask) { // the atom's periodic images, same single fma as k_update_pbc
+        unsigned m = fi.gmask[e];
+        if (m) {
+            int g = nlocal + fi.goff[e];
+            do {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const real gx = fma_rn((real)c_img[b][0], fi.xprd, xe), gy = fma_rn((real)c_img[b][1], fi.yprd, ye),
+                           gz = fma_rn((real)c_img[b][2], fi.zprd, ze);
+                fi.xn[g] = gx; fi.yn[g] = gy; fi.zn[g] = gz;
+                if (XY) {
+                    typename Vec2Of<real>::type v;
+                    v.x = gx; v.y = gy;
+                    fi.xyn[g] = v;
+                }
+                g++;
+            } while (m);
+        }
     }
 }
 
