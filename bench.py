@@ -551,8 +551,9 @@ def main():
     traffic, traffic_src, ncu_pipes = None, None, None
     try:   # DRAM bytes of one launch from the committed ncu --set full capture of this very configuration, if there is one
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        te = tj.get("%s/%s/%d" % (args.scheme, args.precision, args.nx))
-        if te and not args.half and not decomposed and (not cp or args.cluster_n == 4):
+        # decomposed verletlist runs launch the brick variant of the fused kernel (<.., XY, ZG>): its own capture
+        te = tj.get("%s/%s/%d%s" % (args.scheme, args.precision, args.nx, "/brick" if (decomposed and not cp) else ""))
+        if te and not args.half and (not decomposed or not cp) and (not cp or args.cluster_n == 4):
             # only a capture of the kernel that actually runs counts (the fused kernels replaced the session-3 ones)
             if cp or not fused_force or "_fi" in te.get("kernel", ""):
                 traffic, traffic_src = te["bytes"], te["source"]
