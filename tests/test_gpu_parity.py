@@ -98,6 +98,52 @@ def test_operators_bit_exact_vs_oracle_on_jittered_box(dp, half, sort):
     s.close()
 
 
+@pytest.mark.parametrize("dp", [True, False])
+@pytest.mark.parametrize("box,keep", [((2, 2, 2), 1.0), ((3, 2, 6), 1.0), ((2, 7, 2), 0.6), ((6, 6, 6), 0.35)])
+def test_tiny_thin_and_ragged_boxes_bit_exact_vs_oracle(dp, box, keep):
+    """Edge cases of the list-defining operators on identical input bits: boxes smaller than 2 * cutneigh (a single bin per axis,
+    every atom has all 26 images), thin slabs, and ragged inputs (a random 40-65 % of the atoms removed: empty and sparse bins,
+    atoms with short rows) with jitter -- the per-atom stencil of the list build must give the reference's rows,
+    entry by entry, and 25 steps (one rebuild) must follow the oracle."""
+    rng = np.random.default_rng(7)
+    nx, ny, nz = box
+    o = OracleVL(dp)
+    o.configure(nx=nx, ny=ny, nz=nz)
+    o.derive(); o.create_atoms(); o.setup_neighbor(); o.setup_thermo(); o.adjust_thermo()
+    r = o.np_real
+    n0 = o.geti("Nlocal")
+    sel = np.sort(rng.choice(n0, max(2, int(keep * n0)), replace=False))
+    x = (o.get("x")[sel] + rng.normal(0, 0.08, (len(sel), 3))).astype(r)   # larger jitters blow the lattice up (the reference
+    v = (0.3 * o.get("v")[sel]).astype(r)                                  # then leaves its bin grid and crashes)
+    o.set_atoms(x, v)
+    o.reneighbour()
+    o.computeForce()
+    s = make_sim(dp, True, False, nx=nx, ny=ny, nz=nz)
+    s.setAtoms(x, v)
+    s.setupNeighbor(); s.setupThermo()
+    s.reneighbour()
+    s.computeForce()
+    assert s.counts()["Nghost"] == o.geti("Nghost")
+    assert np.array_equal(s.get("x", ghosts=True), o.get("x", ghosts=True))
+    gm = s.ghostMap()
+    for k in ("border_map", "PBCx", "PBCy", "PBCz"):
+        assert np.array_equal(gm[k], o.get(k)), k
+    assert np.array_equal(s.binCounts(), o.get("bincount"))
+    nn, nb = s.neighbors()
+    assert np.array_equal(nn, o.get("numneigh"))
+    onb = o.get("neighbors")
+    for i in range(len(nn)):
+        assert np.array_equal(nb[i, :nn[i]], onb[i, :nn[i]]), i
+    f, fo = s.get("f"), o.get("f")
+    assert np.abs(f - fo).max() <= TOL[dp] * max(np.abs(fo).max(), 1.0)
+    for n in range(25):
+        s.step(n); o.step(n)
+    assert np.abs(s.get("x") - o.get("x")).max() <= (1e-10 if dp else 1e-4) * max(np.abs(o.get("x")).max(), 1.0)
+    nn, nb = s.neighbors()
+    assert np.array_equal(nn, o.get("numneigh")) or not dp   # SP trajectories may flip a membership at the skin after 25 steps
+    s.close()
+
+
 def test_maxneighs_resize_and_dense_bins():
     """neighbor.c:247-262: rows longer than maxneighs force a rebuild with 1.2x the longest row;
     a dense cluster also overflows the reference's 8-atom bins (atoms_per_bin doubling)."""
