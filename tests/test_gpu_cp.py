@@ -479,3 +479,34 @@ def test_cp_stub_driver_report():
     out = subprocess.run([exe, "-p", "seq", "-ni", "4096", "--csv", "-n", "5", "--cluster-n", "8"], capture_output=True, text=True,
                          timeout=120).stdout
     assert out.splitlines()[0].startswith("steps,pattern,niclusters,iclusters_natoms") and out.splitlines()[1].startswith("5,seq,4096,4,9,1,")
+
+
+@pytest.mark.parametrize("variant,dp", [("cp44_sp", False), ("cp44_dp", True)])
+def test_reference_clusterpair_main_c_drives_libmdb200(golden_dir, variant, dp):
+    """The boundary proven with the reference's own clusterpair driver: oracle/_ref/MDBench-<variant>-b200 is the reference's
+    UNMODIFIED clusterpair/main.c / atom.c / thermo.c / parameter.c (compiled from /root/reference where they lie) linked against
+    md-bench_b200/driver/b200_shim_cp.c + libmdb200.so (oracle/Makefile ref-shim).  Its default run (BASELINE config 2 physics,
+    4x4 clusters) must print the thermo lines and the ghost count of the reference's scalar 4x4 build (tests/golden/thermo_cp.json)."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "MDBench-%s-b200" % variant)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/MDBench-%s-b200 not built (needs /root/reference: make -C oracle ref-shim)" % variant)
+    th = json.load(open(os.path.join(golden_dir, "thermo_cp.json")))
+    t = [q for q in th if q["variant"] == ("cpref44_dp" if dp else "cpref44_sp")][0]
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300).stdout
+    lines = [(int(a), b, c) for a, b, c in re.findall(r"^(-?\d+)\t(\S+)\t(\S+)$", out, flags=re.M)]
+    assert [l[0] for l in lines] == [0, 100, 200], out[-2000:]
+    for (st, T, P), (gs, gT, gP) in zip(lines, t["records"]):
+        if dp:
+            assert "%e" % gT == T and "%e" % gP == P, (st, T, P, gT, gP)      # the printed 7 digits
+        else:
+            assert abs(float(T) - gT) <= 1e-4 * gT and abs(float(P) - gP) <= 1e-4 * gP, (st, T, P, gT, gP)
+    m = re.search(r"System: 131072 atoms (\d+) ghost atoms, Steps: 200", out)
+    assert m, out[-2000:]
+    if dp:
+        assert int(m.group(1)) == t["nghost_atoms"]
+    else:   # SP trajectories differ in the last digits: an atom or two may sit on the other side of a ghost threshold
+        assert abs(int(m.group(1)) - t["nghost_atoms"]) <= 20
+    assert "million atom updates per second" in out
