@@ -8,7 +8,7 @@
  * defined here and forwards to ONE mdb_cp_* entry point of include/mdb200.h.  CLUSTER_N comes from the reference's own
  * force.h (VECTOR_WIDTH), as in its builds.
  *
- *   recipe:  target ref-shim of the checker's Makefile  ->  oracle/_ref/MDBench-cp44_{sp,dp}-b200
+ *   recipe:  target ref-shim of the checker's Makefile (the one that compiles the reference)  ->  MDBench-cp44_{sp,dp}-b200
  *   test:    tests/test_gpu_cp.py::test_reference_clusterpair_main_c_drives_libmdb200
  *
  * Flow of the reference's setup() (clusterpair/main.c:40-76) with this shim:
