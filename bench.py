@@ -256,9 +256,9 @@ def clusterpair_secondary(m, args, local, stream, steps=2):
     traffic, ncu_pipes = None, None
     try:
         te = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("clusterpair/sp/%d" % args.nx, {})
-        if "true" in te.get("kernel", "") or "1>" in te.get("kernel", ""):   # a capture of the fused kernel <N, FI = true>
+        if "k_cp_force_lj_sp_duo<4, 1" in te.get("kernel", ""):   # a capture of the kernel that runs: <N = 4, FI = true, ..>
             traffic = te.get("bytes")
-            ncu_pipes = te.get("ncu")
+            ncu_pipes = dict(te.get("ncu") or {}, source=te.get("source"), commit=te.get("commit"))
     except Exception:
         pass
     out = {"metric": METRIC_CP % (4, 4), "config": "BASELINE config 2 physics (clusterpair 4x4, SP, full lists) at %d^3 unit cells" % args.nx,
@@ -557,7 +557,7 @@ def main():
             # only a capture of the kernel that actually runs counts (the fused kernels replaced the session-3 ones)
             if cp or not fused_force or "_fi" in te.get("kernel", ""):
                 traffic, traffic_src = te["bytes"], te["source"]
-                ncu_pipes = te.get("ncu")
+                ncu_pipes = dict(te.get("ncu") or {}, commit=te.get("commit"))   # the commit the capture was taken at
     except Exception:
         pass
     roofline = {"kernel": (("k_cp_force_lj_sp_duo<%d, FI> (two lanes per i-cluster, packed FP32, integrate halves in the epilogue)" % args.cluster_n)
