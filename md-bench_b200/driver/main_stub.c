@@ -110,6 +110,23 @@ int main(int argc, char** argv)
         if (param.proc_freq > 0.0) printf(",%.4f,%.4f", cycles_per_atom, cycles_per_neigh);
         printf("\n");
     }
+    if (!csv) { /* displayStatistics of the reference's default (COMPUTE_STATS) build, verletlist/stats.c:22-68 and main-stub.c:324.  The
+                 * SIMD unit here is a warp over 32 ATOMS: one "SIMD iteration" is one trip of a warp's pair loop (every row of the
+                 * synthetic list has nneighs * nreps entries), against VECTOR_WIDTH neighbors of one atom in the reference. */
+        const double calls       = (double)param.ntimes;
+        const double per_atom    = (double)nneighs * (double)nreps;
+        const double force_neighs = (double)natoms * per_atom * calls;
+        const double force_iters  = (double)((natoms + 31) / 32) * per_atom * calls;
+        const double useful_volume = 1e-9 * ((double)natoms * calls * (double)(es * 6 + sizeof(int)) + force_neighs * (double)(es * 3 + sizeof(int)));
+        printf("Statistics:\n");
+        printf("\tVector width: %d, Processor frequency: %.4f GHz\n", 32, param.proc_freq);
+        printf("\tAverage neighbors per atom: %.4f\n", per_atom);
+        printf("\tAverage SIMD iterations per atom: %.4f\n", force_iters / ((double)natoms * calls));
+        printf("\tTotal number of computed pair interactions: %.0f\n", force_neighs);
+        printf("\tTotal number of SIMD iterations: %.0f\n", force_iters);
+        printf("\tUseful read data volume for force computation: %.2fGB\n", useful_volume);
+        if (param.proc_freq > 0.0) printf("\tCycles/SIMD iteration: %.4f\n", T_accum * freq_hz / force_iters);
+    }
     mdb_destroy(ctx);
     return EXIT_SUCCESS;
 }

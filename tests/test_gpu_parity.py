@@ -620,6 +620,9 @@ def test_stub_driver_report():
         subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
     out = subprocess.run([exe, "-p", "rand", "-na", "20000", "-nn", "76", "-n", "20"], capture_output=True, text=True, timeout=120).stdout
     assert "Pattern: rand" in out and "Number of atoms: 20000" in out and "Mega atom updates/s" in out
+    # displayStatistics of the reference's default build (stats.c:22-68): 20000 atoms x 76 neighbors x 20 calls
+    assert "Statistics:" in out and "Average neighbors per atom: 76.0000" in out
+    assert "Total number of computed pair interactions: 30400000" in out and "Total number of SIMD iterations: 950000" in out
     out = subprocess.run([exe, "-p", "seq", "-na", "4096", "--csv", "-n", "5"], capture_output=True, text=True, timeout=120).stdout
     assert out.splitlines()[0].startswith("steps,pattern,natoms,nneighs,nreps") and out.splitlines()[1].startswith("5,seq,4096,76,1,")
 
