@@ -128,6 +128,25 @@ template <class real, int N> struct CpSim final : CpBase {
         d_partial.ensure(RED_BLOCKS * 4, false, stream);
         d_cnt.ensure(4, false, stream);
         derive();
+        preload_kernels();
+    }
+    void preload_kernels() // the kernels of the time loop, loaded now instead of lazily inside a short timed run (see Sim::preload_kernels)
+    {
+        cudaFuncAttributes a;
+        const void* ks[] = { (const void*)k_cp_force_lj<real, N, false>, (const void*)k_cp_force_lj<real, N, false, true>,
+            (const void*)k_cp_force_lj<real, N, true>, (const void*)k_cp_force_jl<real, N, true>, (const void*)k_cp_integrate<real, N, 0>,
+            (const void*)k_cp_integrate<real, N, 1>, (const void*)k_cp_integrate<real, N, 2>, (const void*)k_cp_update_pbc<real, N>,
+            (const void*)k_cp_update_pbc_first<real, N>, (const void*)k_cp_update_single_atoms<real, N>, (const void*)k_cp_bin_count<real>,
+            (const void*)k_cp_sort_emit<real, N>, (const void*)k_cp_define_j<real, N>, (const void*)k_cp_ghost_count<real>,
+            (const void*)k_cp_ghost_fill<N>, (const void*)k_cp_cluster_bin<real, N>, (const void*)k_cp_cluster_fill,
+            (const void*)k_cp_cluster_sort<real>, (const void*)k_cp_build_neighbor<real, N>, (const void*)k_cp_clusters_per_bin<N>,
+            (const void*)k_update_atoms_pbc<real>, (const void*)k_vel_partial<real>, (const void*)k_vel_final, (const void*)k_bin_fill };
+        for (const void* k : ks) MDB_CUDA(cudaFuncGetAttributes(&a, k));
+        if (sizeof(real) == 4) {
+            MDB_CUDA(cudaFuncGetAttributes(&a, (const void*)k_cp_force_lj_sp_duo<N, true, false>));
+            MDB_CUDA(cudaFuncGetAttributes(&a, (const void*)k_cp_force_lj_sp_duo<N, false, false>));
+        }
+        scanner.preload();
     }
     ~CpSim() override
     {

@@ -66,6 +66,13 @@ struct Scanner {
     long long* launches = nullptr;
 
     // out[0..n) = exclusive scan of in[0..n); *total_dst (device pointer, may be null) = sum.
+    void preload() // see Sim::preload_kernels
+    {
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, (const void*)k_scan_tile);
+        cudaFuncGetAttributes(&a, (const void*)k_scan_add);
+        cudaFuncGetAttributes(&a, (const void*)k_scan_total);
+    }
     void exclusive(const int* in, int* out, size_t n, int* total_dst, cudaStream_t s, int depth = 0)
     {
         if (depth >= 4) throw Error("scan: input too large");
