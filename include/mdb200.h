@@ -300,6 +300,8 @@ int         mdb_cp_sync(mdb_cp* c);
  * "sp_kernel" (SP full lists, packed FP32): 2 (default) = two lanes per i-cluster, two i atoms per lane, reciprocal =
  * MUFU.RCP (1 ulp; the reference's SP kernel uses the 14-bit _mm512_rcp14_ps), 1 = the same with a Newton step on it
  * (bit-identical to 0), 0 = lane per i atom;
+ * "ghost_epilogue" (default -1 = on for domains of up to 2^19 atoms, 0 off, 1 on): the fused step's epilogue also writes the
+ * atom's lanes of the ghost tiles (updatePbcCPU, pbc.c:45-114), so a step between two rebuilds is ONE launch; bit-identical;
  * "fuse_force" (default 1): inside mdb_cp_run with full lists, computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1)
  * run as ONE kernel (integrate halves in the force kernel's epilogue, second cluster position array); bit-identical. */
 int         mdb_cp_setOption(mdb_cp* c, const char* name, double value);

@@ -186,6 +186,7 @@ template <class real, int N> struct CpGroup final : DDBase {
         for (int k = 0; k < nlb; k++) {
             Brick* b = new Brick(L, device);
             b->setStream(stream);
+            b->brick_mode = true;
             bricks.push_back(b);
         }
         if (nprocs > 1) {

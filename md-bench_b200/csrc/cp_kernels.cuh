@@ -658,14 +658,46 @@ __device__ __forceinline__ void cp_tile_packed(const CpTileRegs<N>& T, const CpP
 template <class real> struct CpFused {
     real *cl_v, *cl_xn;
     real dtforce, dt;
+    // single domain, small systems: the ghost tiles' lanes of the atom (updatePbcCPU, pbc.c:45-114) are written by the same
+    // epilogue -- image b of tile t is ghost tile ncj + goff[t] + rank of bit b in gmask[t] (setupPbc's order, k_cp_ghost_fill)
+    // -- so that a step between two rebuilds is ONE launch.  gmask == nullptr: somebody else updates the ghosts.
+    const unsigned* gmask;
+    const int* goff;
+    int ncj;
+    real xprd, yprd, zprd;
 };
 template <class real>
-__device__ __forceinline__ void cp_fused_integrate(const CpFused<real>& fi, size_t s, real xold, real f)
+__device__ __forceinline__ real cp_fused_integrate(const CpFused<real>& fi, size_t s, real xold, real f)
 {
     real v = fi.cl_v[s] + fi.dtforce * f;
     v      = v + fi.dtforce * f;
     fi.cl_v[s]  = v;
-    fi.cl_xn[s] = xold + fi.dt * v;
+    const real xn = xold + fi.dt * v;
+    fi.cl_xn[s]   = xn;
+    return xn;
+}
+// one atom: both integrate halves, then its lane in the ghost images of its tile (the same single fma as k_cp_update_pbc).
+// e = slot of the atom's x in the cluster arrays (tile * 3N + lane)
+template <class real, int N>
+__device__ __forceinline__ void cp_fused_atom(const CpFused<real>& fi, size_t e, real xo, real yo, real zo, real fx, real fy, real fz)
+{
+    const real xn = cp_fused_integrate(fi, e, xo, fx), yn = cp_fused_integrate(fi, e + N, yo, fy), zn = cp_fused_integrate(fi, e + 2 * N, zo, fz);
+    if (fi.gmask) {
+        const size_t t = e / (3 * N);
+        unsigned m = fi.gmask[t];
+        if (m) {
+            const int q = (int)(e - t * 3 * N);
+            size_t d = (size_t)(fi.ncj + fi.goff[t]) * 3 * N + q;
+            do {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                fi.cl_xn[d]         = fma_rn((real)c_img[b][0], fi.xprd, xn);
+                fi.cl_xn[d + N]     = fma_rn((real)c_img[b][1], fi.yprd, yn);
+                fi.cl_xn[d + 2 * N] = fma_rn((real)c_img[b][2], fi.zprd, zn);
+                d += 3 * N;
+            } while (m);
+        }
+    }
 }
 // slot of this lane's i atom, re-derived from the special registers after the pair loop: nothing of the epilogue
 // (addresses, the loads of v and x) can then be hoisted above the loop, where it would cost registers.  Blocks of 128.
@@ -717,9 +749,7 @@ __global__ void __launch_bounds__(128) k_cp_force_lj_sp_packed(int ncl, int dumm
         if (pad_i) return;
         // own coordinates re-read (a real atom's x0/y0/z0 are unmodified, but keeping them live costs registers)
         const size_t e = cp_epilogue_slot<N>();
-        cp_fused_integrate(fi, e, cl_x[e], fix);
-        cp_fused_integrate(fi, e + N, cl_x[e + N], fiy);
-        cp_fused_integrate(fi, e + 2 * N, cl_x[e + 2 * N], fiz);
+        cp_fused_atom<float, N>(fi, e, cl_x[e], cl_x[e + N], cl_x[e + 2 * N], fix, fiy, fiz);
         return;
     }
     cl_f[ib + cii] = fix; cl_f[ib + N + cii] = fiy; cl_f[ib + 2 * N + cii] = fiz;
@@ -807,16 +837,8 @@ __global__ void __launch_bounds__(128) k_cp_force_lj_sp_duo(int ncl, int dummy_c
         asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(b));
         const unsigned g = b * 128u + t;
         const size_t e   = cp_ci_base3<N>((int)(g >> 1)) + 2 * (g & 1u);
-        if (!pad0) {
-            cp_fused_integrate(fi, e, cl_x[e], f0x);
-            cp_fused_integrate(fi, e + N, cl_x[e + N], f0y);
-            cp_fused_integrate(fi, e + 2 * N, cl_x[e + 2 * N], f0z);
-        }
-        if (!pad1) {
-            cp_fused_integrate(fi, e + 1, cl_x[e + 1], f1x);
-            cp_fused_integrate(fi, e + N + 1, cl_x[e + N + 1], f1y);
-            cp_fused_integrate(fi, e + 2 * N + 1, cl_x[e + 2 * N + 1], f1z);
-        }
+        if (!pad0) cp_fused_atom<float, N>(fi, e, cl_x[e], cl_x[e + N], cl_x[e + 2 * N], f0x, f0y, f0z);
+        if (!pad1) cp_fused_atom<float, N>(fi, e + 1, cl_x[e + 1], cl_x[e + N + 1], cl_x[e + 2 * N + 1], f1x, f1y, f1z);
         return;
     }
     *reinterpret_cast<float2*>(cl_f + ib)         = make_float2(f0x, f1x);
@@ -866,9 +888,7 @@ __global__ void __launch_bounds__(128) k_cp_force_lj(int ncl, int ncj, LJConst2<
         if (pad_i) return; // pad_i <=> cii >= inat[ci]: padding slots are not integrated (integrate.c:27)
         // xt/yt/zt of a real atom are its unmodified coordinates
         const size_t e = cp_epilogue_slot<N>();
-        cp_fused_integrate(fi, e, xt, fix);
-        cp_fused_integrate(fi, e + N, yt, fiy);
-        cp_fused_integrate(fi, e + 2 * N, zt, fiz);
+        cp_fused_atom<real, N>(fi, e, xt, yt, zt, fix, fiy, fiz);
         return;
     }
     if (pad_i) fix = fiy = fiz = 0;

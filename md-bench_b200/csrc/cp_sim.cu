@@ -78,6 +78,8 @@ template <class real, int N> struct CpSim final : CpBase {
     int prune_every = 1000; // common/parameter.c:40
     int force_variant = 0;
     int sp_kernel = 2; // SP full lists: see launch_packed
+    int ghost_epilogue = -1; // fused step writes the ghost tiles too: -1 = where it pays (launch_force), 0 / 1 = off / on
+    bool ghosts_current = false, brick_mode = false; // brick_mode: a brick of a decomposed box (cp_dd.cuh): ghosts come from the neighbors
     bool fuse_force = true; // mdb_cp_run, full lists: integrate halves in the force kernel's epilogue (CpFused)
     // ---- atoms (clusterpair/atom.h:26-60) ----
     long long Natoms = 0;
@@ -209,6 +211,7 @@ template <class real, int N> struct CpSim final : CpBase {
         if (!strcmp(name, "prune_every")) prune_every = (int)v;
         else if (!strcmp(name, "force_variant")) force_variant = (int)v;
         else if (!strcmp(name, "sp_kernel")) sp_kernel = (int)v;
+        else if (!strcmp(name, "ghost_epilogue")) ghost_epilogue = (int)v;
         else if (!strcmp(name, "fuse_force")) fuse_force = v != 0;
         else throw Error(fmt("mdb_cp_setOption: unknown option '%s'", name));
     }
@@ -505,6 +508,7 @@ template <class real, int N> struct CpSim final : CpBase {
         MDB_CUDA(cudaStreamSynchronize(stream));
         nghost   = h_flags[0];
         dummy_cj = ncj + nghost;
+        ghosts_current = false;
         ensure_tiles((size_t)ncj + nghost + 1, true);
         border_map.ensure(nghost + 1, false, stream);
         code.ensure(nghost + 1, false, stream);
@@ -517,7 +521,7 @@ template <class real, int N> struct CpSim final : CpBase {
         if (first) {
             MDB_LAUNCH(launches, (k_cp_update_pbc_first<real, N>), grid_for(nghost + 1, 128), 128, 0, stream, ncj, nghost, xprd,
                 yprd, zprd, border_map.p, code.p, jnat.p, cl_x.p, jbb.p);
-        } else if (nghost > 0) {
+        } else if (nghost > 0 && !ghosts_current) { // (the fused kernel may have written the images of the new positions already)
             MDB_LAUNCH(launches, (k_cp_update_pbc<real, N>), grid_for((size_t)nghost * N, 256), 256, 0, stream, ncj, nghost, xprd,
                 yprd, zprd, border_map.p, code.p, jnat.p, cl_x.p);
         }
@@ -612,7 +616,12 @@ template <class real, int N> struct CpSim final : CpBase {
         if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
         LJConst2<real> c2 { cutforce * cutforce, (real)48.0 * epsilon * sigma6 * sigma6, (real)24.0 * epsilon * sigma6 };
         const unsigned grid = grid_for((size_t)ncl * CP_M, 128);
-        const CpFused<real> fi { cl_v.p, cl_xn.p, dtforce, dt };
+        // small single domains: the ghost tiles of the next step are written by the same launch (one launch per step; at 128^3
+        // the extra mask loads cost more than the kernel they replace, as for the verletlist kernel)
+        const bool want_ghosts = ghost_epilogue < 0 ? Nlocal <= (1 << 19) : ghost_epilogue != 0;
+        const bool own_ghosts  = fused && want_ghosts && !brick_mode && nghost > 0;
+        const CpFused<real> fi { cl_v.p, cl_xn.p, dtforce, dt, own_ghosts ? gmask.p : (const unsigned*)nullptr,
+            own_ghosts ? goff.p : (const int*)nullptr, ncj, xprd, yprd, zprd };
         if (fused) {
             int fv = force_variant;
             if (fv == 0) fv = sizeof(real) == 4 ? 2 : 1;
@@ -621,6 +630,7 @@ template <class real, int N> struct CpSim final : CpBase {
                 MDB_LAUNCH(launches, (k_cp_force_lj<real, N, false, true>), grid, 128, 0, stream, ncl, ncj, c2, cl_x.p, numneigh.p,
                     numneigh_masked.p, neighbors.p, maxneighs, cl_f.p, fi);
             std::swap(cl_x, cl_xn);
+            ghosts_current = own_ghosts;
             force_launches++;
             if (timing) {
                 float ms = 0;
@@ -675,7 +685,7 @@ template <class real, int N> struct CpSim final : CpBase {
     // clusterpair/force_lj.c:325-326,536), so this is still 9 bits closer to the exact quotient than what it is compared with
     void launch_packed(unsigned grid, const LJConst2<float>& c2)
     {
-        const CpFused<float> nofi { nullptr, nullptr, 0.f, 0.f };
+        const CpFused<float> nofi { nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, 0, 0.f, 0.f, 0.f };
         const unsigned g2 = grid_for((size_t)ncl * 2, 128);
         if (sp_kernel == 1)
             MDB_LAUNCH(launches, (k_cp_force_lj_sp_duo<N, false, true>), g2, 128, 0, stream, ncl, dummy_cj, c2, (const float*)cl_x.p,
@@ -715,6 +725,7 @@ template <class real, int N> struct CpSim final : CpBase {
     }
     void integrate(int mode)
     {
+        if (mode != 1) ghosts_current = false; // positions move
         const unsigned grid = grid_for((size_t)ncl * CP_M, 256);
         if (mode == 0)
             MDB_LAUNCH(launches, (k_cp_integrate<real, N, 0>), grid, 256, 0, stream, ncl, dtforce, dt, inat.p, cl_x.p, cl_v.p, cl_f.p);
