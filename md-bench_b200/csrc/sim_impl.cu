@@ -117,7 +117,7 @@ template <class real> struct Sim final : SimBase {
         const void* ks[] = { (const void*)k_force_lj_full_fi<real, 4, sizeof(real) == 4, true>,
             (const void*)k_force_lj_full_fi<real, 4, sizeof(real) == 4>, (const void*)k_force_lj_full_fi<real, 4, sizeof(real) == 4, true, true>,
             (const void*)k_force_lj_full_v2<real, 4>, (const void*)k_force_lj_full_v6<real, 4>, (const void*)k_force_lj_half_v2<real, 4>,
-            (const void*)k_build_neighbor_v6<real>, (const void*)k_pack_binned_soa<real>, (const void*)k_bin_count<real>,
+            (const void*)k_build_neighbor_v6<real, false>, (const void*)k_build_neighbor_v6<real, true>, (const void*)k_pack_binned_soa<real>, (const void*)k_bin_count<real>,
             (const void*)k_bin_fill, (const void*)k_bin_sort, (const void*)k_ghost_count<real>, (const void*)k_ghost_fill,
             (const void*)k_update_pbc<real>, (const void*)k_update_atoms_pbc<real>, (const void*)k_pack_xy<real>,
             (const void*)k_initial_integrate<real>, (const void*)k_final_integrate<real>, (const void*)k_final_initial_integrate<real>,
@@ -718,9 +718,14 @@ template <class real> struct Sim final : SimBase {
             rg.binvx    = (float)bg.bininvx;
             rg.cutsq_hi = (float)((double)cutneighsq * (1.0 + 1e-4));
             rg.margin   = 1e-3f * std::min({ rg.bsx, rg.bsy, rg.bsz });
-            MDB_LAUNCH(launches, k_build_neighbor_v6<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, P.half_neigh, bg, rg,
-                cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns,
-                maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            if (P.half_neigh)
+                MDB_LAUNCH(launches, (k_build_neighbor_v6<real, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, bg, rg,
+                    cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns,
+                    maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+            else
+                MDB_LAUNCH(launches, (k_build_neighbor_v6<real, false>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, bg, rg,
+                    cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns,
+                    maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));

@@ -477,8 +477,8 @@ struct RunGeom {
     float binvx;            // 1 / bsx
     float cutsq_hi, margin; // cutneigh^2 * (1 + 1e-4), 1e-3 * min bin width
 };
-template <class real>
-__global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, int half, BinGeom<real> g, RunGeom rg, real cutneighsq, float lo,
+template <class real, bool HALF>
+__global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<real> g, RunGeom rg, real cutneighsq, float lo,
     float hi, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float* __restrict__ cx,
     const float* __restrict__ cy, const float* __restrict__ cz, const int* __restrict__ cid, const int* __restrict__ binstart,
     const int* __restrict__ run_off, const int* __restrict__ run_len, const int* __restrict__ run_dyz, int nruns, int maxneighs,
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, int half,
     const float tpass = sizeof(real) == 4 ? nextafterf((float)cutneighsq, INFINITY) : lo;
     const float tmay  = sizeof(real) == 4 ? tpass : nextafterf(hi, INFINITY);
     const f32x2 tp2 = pk2(tpass, tpass), tm2 = pk2(tmay, tmay);
-    const int oi = half ? orig[ii] : 0;
+    const int oi = HALF ? orig[ii] : 0;
     const int ix = axis2bin(xt, g.xprd, g.bininvx, g.nbinx, g.mbinxlo);
     const int iy = axis2bin(yt, g.yprd, g.bininvy, g.nbiny, g.mbinylo);
     const int iz = axis2bin(zt, g.zprd, g.bininvz, g.nbinz, g.mbinzlo);
@@ -503,7 +503,9 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, int half,
     // position relative to the lower edge of the own bin (absolute bin = index + mbinlo)
     const float ux = xs - (float)(ix + g.mbinxlo) * rg.bsx, uy = ys - (float)(iy + g.mbinylo) * rg.bsy,
                 uz = zs - (float)(iz + g.mbinzlo) * rg.bsz;
-    int* out = neighbors + L.base(ii);
+    // the row as a 32-bit element offset from its first entry: one IMAD.WIDE per store instead of a 64-bit pointer bump
+    int* const row     = neighbors + L.base(ii);
+    const unsigned rsk = (unsigned)L.sk;
     int r    = live ? 0 : nruns;
     for (;;) {
         int s = 0, e = 0;
@@ -561,18 +563,19 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, int half,
             const int k = 4 * ng, tlo = max(s - c0, 0), thi = min(e - c0, k);
             const unsigned vmask = (unsigned)((1ull << (k - tlo)) - 1ull) & ~(unsigned)((1ull << (k - thi)) - 1ull);
             unsigned todo = mm & vmask;
+            const int* const cl = cid + c0 + (k - 1); // candidate at bit p: cl[-p]
+            const unsigned unc  = todo & ~mp;         // hits of the uncertain band
             while (todo) {
                 const int p = 31 - __clz(todo);
                 todo &= ~(1u << p);
-                const int j = __ldg(cid + c0 + (k - 1 - p));
+                const int j = __ldg(cl - p);
                 if (j == i) continue;
-                if (half && j < nlocal && orig[j] < oi) continue;
-                if (!((mp >> p) & 1u)) {
+                if (HALF && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
+                if ((unc >> p) & 1u) { // the reference's exact FP64 expression
                     const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
                     if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
                 }
-                if (n < maxneighs) *out = j;
-                out += L.sk;
+                if (n < maxneighs) row[(unsigned)n * rsk] = j;
                 n++;
             }
             c0 += k;
