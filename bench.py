@@ -398,6 +398,32 @@ def parity_check(m, dist, rank, world, local, stream):
             "ok": bool(rt <= 1e-10 and rp <= 1e-10 and printed), "reference": "tests/golden/thermo_lj.json (reference build vl_dp_aos)"}
 
 
+def parity_check_cp(m, dist, rank, world, local, stream):
+    """BASELINE config 2 exactly as stated (Cu FCC 32^3, clusterpair 4x4, SP, 200 timesteps) through the SAME path the timed
+    clusterpair run uses -- one domain at N = 1, one brick per GPU with ghost clusters over NCCL at N > 1 -- against the reference's
+    scalar 4x4 build (tests/golden/thermo_cp.json, variant cpref44_sp): every thermo record to the stated SP tolerance, rel 1e-4."""
+    gold = [q for q in json.load(open(os.path.join(ROOT, "tests", "golden", "thermo_cp.json"))) if q["variant"] == "cpref44_sp"][0]
+    P = m.default_params(precision=m.SP, nx=32, ny=32, nz=32, ntimes=200)
+    if world > 1:
+        uid = [m.dd_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim = m.Decomposition(P, m.dd_grid(world), nprocs=world, proc=rank, nccl_id=uid[0], device=local, cluster_n=4)
+        path = "%dx%dx%d bricks, one per GPU: ghost clusters and migration over NCCL" % m.dd_grid(world)
+    else:
+        sim = m.ClusterSimulation(P, cluster_n=4, device=local)
+        path = "one domain"
+    sim.setStream(stream)
+    sim.createAtom()
+    sim.setup(adjust=True)
+    rec, _ = sim.run(200)
+    sim.close()
+    worst = max(max(abs(a[1] - b[1]) / b[1], abs(a[2] - b[2]) / b[2]) for a, b in zip(rec, gold["records"]))
+    return {"case": "BASELINE config 2: Cu FCC 32^3 (131072 atoms), LJ, clusterpair 4x4, SP, 200 timesteps", "path": path,
+            "T": float(rec[-1][1]), "P": float(rec[-1][2]), "T_ref": gold["records"][-1][1], "P_ref": gold["records"][-1][2],
+            "worst_rel_over_records": float(worst), "tol": 1e-4, "ok": bool(len(rec) == len(gold["records"]) and worst <= 1e-4),
+            "reference": "tests/golden/thermo_cp.json (reference build cpref44_sp: computeForceLJRef, M = N = 4)"}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -449,9 +475,9 @@ def main():
     if args.global_nx and not decomposed:
         args.nx = args.global_nx
     parity = None
-    if not cp and not args.no_parity and args.bricks is None:
+    if not args.no_parity and args.bricks is None and (not cp or (args.cluster_n == 4 and not dp and not args.half)):
         try:
-            parity = parity_check(m, dist, rank, world, local, stream)
+            parity = (parity_check_cp if cp else parity_check)(m, dist, rank, world, local, stream)
         except Exception as e:   # reported, never hidden: a failed check makes the line say so
             parity = {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
     if cp and not decomposed:

@@ -718,14 +718,14 @@ template <class real> struct Sim final : SimBase {
             rg.binvx    = (float)bg.bininvx;
             rg.cutsq_hi = (float)((double)cutneighsq * (1.0 + 1e-4));
             rg.margin   = 1e-3f * std::min({ rg.bsx, rg.bsy, rg.bsz });
-            if (P.half_neigh)
-                MDB_LAUNCH(launches, (k_build_neighbor_v6<real, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, bg, rg,
-                    cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns,
-                    maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
-            else
-                MDB_LAUNCH(launches, (k_build_neighbor_v6<real, false>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, bg, rg,
-                    cutneighsq, lo, hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns,
-                    maxneighs, LL, orig.p, numneigh.p, neighbors.p, d_flags.p + 1);
+#define MDB_BUILD_V6(H)                                                                                                       \
+    MDB_LAUNCH(launches, (k_build_neighbor_v6<real, H>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, bg, rg, cutneighsq, lo,  \
+        hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns, maxneighs, LL, orig.p, \
+        numneigh.p, neighbors.p, d_flags.p + 1)
+            if (LL.sk != 32) throw Error("buildNeighbor: the list build stores rows at a stride of 32 entries");
+            if (P.half_neigh) MDB_BUILD_V6(true);
+            else MDB_BUILD_V6(false);
+#undef MDB_BUILD_V6
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 1, d_flags.p + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             MDB_CUDA(cudaStreamSynchronize(stream));

@@ -463,6 +463,31 @@ __device__ __forceinline__ void ld2x2(const float* p, f32x2& a, f32x2& b)
 {
     asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
+__device__ __forceinline__ int bfind(unsigned v) // index of the highest set bit (FLO.U32)
+{
+    int p;
+    asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(v));
+    return p;
+}
+template <int BYTES, class T> __device__ __forceinline__ T* mad_wide_s(T* base, int idx) // base + idx * BYTES as one IMAD.WIDE
+{
+    T* r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "n"(BYTES), "l"(base));
+    return r;
+}
+template <int BYTES, class T> __device__ __forceinline__ T* mad_wide_u(T* base, unsigned idx)
+{
+    T* r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "n"(BYTES), "l"(base));
+    return r;
+}
+__device__ __forceinline__ void st_global(int* p, int v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_nc(const int* p)
+{
+    int v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 // ---- per-ATOM stencil ----------------------------------------------------------------------------------------------------
 // The reference's stencil is per BIN (every bin any atom of the bin could reach, neighbor.c:160-183): 81 bins = 21 runs,
 // ~600 candidates for ~75 hits.  An atom only needs the bins its own sphere of radius cutneigh touches (~37 of 81): a
@@ -505,7 +530,6 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<r
                 uz = zs - (float)(iz + g.mbinzlo) * rg.bsz;
     // the row as a 32-bit element offset from its first entry: one IMAD.WIDE per store instead of a 64-bit pointer bump
     int* const row     = neighbors + L.base(ii);
-    const unsigned rsk = (unsigned)L.sk;
     int r    = live ? 0 : nruns;
     for (;;) {
         int s = 0, e = 0;
@@ -563,20 +587,28 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<r
             const int k = 4 * ng, tlo = max(s - c0, 0), thi = min(e - c0, k);
             const unsigned vmask = (unsigned)((1ull << (k - tlo)) - 1ull) & ~(unsigned)((1ull << (k - thi)) - 1ull);
             unsigned todo = mm & vmask;
-            const int* const cl = cid + c0 + (k - 1); // candidate at bit p: cl[-p]
-            const unsigned unc  = todo & ~mp;         // hits of the uncertain band
-            while (todo) {
-                const int p = 31 - __clz(todo);
-                todo &= ~(1u << p);
+            // candidate at bit p is cl[-p] (the first candidate of the flush sits in the highest bit).  The append loop is
+            // branch-free: the rare uncertain hits are settled first, both addresses come from 64-bit bases held in registers
+            // (mad.wide with an immediate stride), self / overflow are predicates: 30 -> 19 instructions per hit (SASS), list
+            // build 5.63 -> 5.07 ms DP, 4.90 -> 4.69 ms SP per rebuild at 128^3 (profiles/r2_s3_call1.sh, r2_s3_call2.sh).
+            const int* const cl = cid + c0 + (k - 1);
+            unsigned unc = todo & ~mp; // hits of the uncertain band (~1e-4 of the candidates): settled before the append loop
+            while (unc) {
+                const int p        = bfind(unc);
+                const unsigned bit = 1u << p;
+                unc ^= bit;
                 const int j = __ldg(cl - p);
-                if (j == i) continue;
-                if (HALF && j < nlocal && orig[j] < oi) continue; // neighbor.c:224 on reference indices
-                if ((unc >> p) & 1u) { // the reference's exact FP64 expression
-                    const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]);
-                    if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) continue;
-                }
-                if (n < maxneighs) row[(unsigned)n * rsk] = j;
-                n++;
+                const real dx = sub_rn(xt, x[j]), dy = sub_rn(yt, y[j]), dz = sub_rn(zt, z[j]); // the reference's exact expression
+                if (!(fma_rn(dx, dx, fma_rn(dy, dy, mul_rn(dz, dz))) <= cutneighsq)) todo ^= bit;
+            }
+            while (todo) {
+                const int p = bfind(todo);
+                todo ^= 1u << p;
+                const int j = ld_nc(mad_wide_s<-4>(cl, p));
+                bool ok = j != i;
+                if (HALF) ok = ok && !(j < nlocal && orig[j] < oi); // neighbor.c:224 on reference indices
+                if (ok && n < maxneighs) st_global(mad_wide_u<128>(row, (unsigned)n), j); // L.sk == 32 entries (host checks)
+                if (ok) n++;
             }
             c0 += k;
         }
