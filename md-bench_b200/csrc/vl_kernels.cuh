@@ -560,9 +560,11 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<r
         }
         if (!__any_sync(0xffffffffu, e > s)) break;
         for (int c0 = s & ~3; c0 < e;) {
-            const int ng = min(8, (e - c0 + 3) >> 2); // groups of 4 candidates in this flush
+            // groups of 4 candidates in this flush, rounded up to PAIRS of groups: the loop body is two groups with no
+            // remainder code behind it; what lies beyond e is padding or the next bin's candidates, masked by vmask below
+            const int ng = min(8, (((e - c0 + 3) >> 2) + 1) & ~1);
             unsigned mp = 0, mm = 0;
-            for (int q = 0; q < ng; q++) {
+            auto group = [&](int q) {
                 f32x2 X0, X1, Y0, Y1, Z0, Z1;
                 ld2x2(cx + c0 + 4 * q, X0, X1);
                 ld2x2(cy + c0 + 4 * q, Y0, Y1);
@@ -582,6 +584,11 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<r
                     upk2(sub2(r1, tp2), a, b);
                     mp = __funnelshift_l(__float_as_uint(a), mp, 1); mp = __funnelshift_l(__float_as_uint(b), mp, 1);
                 }
+            };
+#pragma unroll 1
+            for (int q = 0; q < ng; q += 2) {
+                group(q);
+                group(q + 1);
             }
             if (sizeof(real) == 4) mp = mm;
             const int k = 4 * ng, tlo = max(s - c0, 0), thi = min(e - c0, k);
