@@ -61,7 +61,8 @@ template <class real> struct Sim final : SimBase {
     DBuf<float> cxs, cys, czs; // candidates in CSR order, SoA (k_build_neighbor_v6)
     DBuf<int> cids;
     DBuf<int> s_type1; // saveState: types in the reference's atom order
-    DBuf<int> run_off, run_len, run_dyz; // runs of x-adjacent stencil bins (offset of the first bin, length, dy | dz << 16)
+    DBuf<RunRow> runs; // runs of x-adjacent stencil bins as k_build_neighbor_v6 reads them
+    RunGeom rg;
     int nruns = 0;
     std::vector<int> h_ghost_order, h_orig, h_bm, h_code;
     DBuf<unsigned> ghost_msk;
@@ -142,7 +143,7 @@ template <class real> struct Sim final : SimBase {
             b->release();
         ghost_msk.release();
         cxs.release(); cys.release(); czs.release(); cids.release(); s_type1.release();
-        run_off.release(); run_len.release(); run_dyz.release();
+        runs.release();
         d_partial.release();
         d_red.release();
         d_thermo.release();
@@ -500,7 +501,13 @@ template <class real> struct Sim final : SimBase {
         stencil.ensure(nstencil, false, stream);
         MDB_CUDA(cudaMemcpyAsync(stencil.p, h_stencil.data(), nstencil * sizeof(int), cudaMemcpyHostToDevice, stream));
         // runs of consecutive offsets (x-adjacent bins are adjacent in the CSR): the list build walks 21 runs instead of 81 bins
-        std::vector<int> ro, rl, rdyz;
+        // the bins' real widths are 1 / bininv (binsize itself differs for from_input, neighbor.c:78-92)
+        rg.bsx = (float)(1.0 / (double)bg.bininvx); rg.bsy = (float)(1.0 / (double)bg.bininvy);
+        rg.bsz = (float)(1.0 / (double)bg.bininvz);
+        rg.binvx    = (float)bg.bininvx;
+        rg.cutsq_hi = (float)((double)cutneighsq * (1.0 + 1e-4));
+        rg.margin   = 1e-3f * std::min({ rg.bsx, rg.bsy, rg.bsz });
+        std::vector<RunRow> rr;
         for (int k = -nextz; k <= nextz; k++)
             for (int j = -nexty; j <= nexty; j++) {
                 int i0 = 0, len = 0;
@@ -511,15 +518,19 @@ template <class real> struct Sim final : SimBase {
                         len++;
                     }
                 if (len == 0) continue;
-                ro.push_back(k * bg.mbiny * bg.mbinx + j * bg.mbinx + i0);
-                rl.push_back(len);
-                rdyz.push_back((int)(((unsigned)j & 0xffffu) | ((unsigned)k << 16)));
+                RunRow q;
+                q.base = k * bg.mbiny * bg.mbinx + j * bg.mbinx;
+                q.i0 = i0; q.i1 = i0 + len - 1; q.pad = 0;
+                const double m = rg.margin;
+                q.ay = (float)(j > 0 ? j * (double)rg.bsy - m : (j < 0 ? -(j + 1) * (double)rg.bsy - m : -m));
+                q.sy = j > 0 ? -1.0f : (j < 0 ? 1.0f : 0.0f);
+                q.az = (float)(k > 0 ? k * (double)rg.bsz - m : (k < 0 ? -(k + 1) * (double)rg.bsz - m : -m));
+                q.sz = k > 0 ? -1.0f : (k < 0 ? 1.0f : 0.0f);
+                rr.push_back(q);
             }
-        nruns = (int)ro.size();
-        for (DBuf<int>* b : { &run_off, &run_len, &run_dyz }) b->ensure(nruns, false, stream);
-        MDB_CUDA(cudaMemcpyAsync(run_dyz.p, rdyz.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        MDB_CUDA(cudaMemcpyAsync(run_off.p, ro.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
-        MDB_CUDA(cudaMemcpyAsync(run_len.p, rl.data(), nruns * sizeof(int), cudaMemcpyHostToDevice, stream));
+        nruns = (int)rr.size();
+        runs.ensure(nruns, false, stream);
+        MDB_CUDA(cudaMemcpyAsync(runs.p, rr.data(), nruns * sizeof(RunRow), cudaMemcpyHostToDevice, stream));
         MDB_CUDA(cudaStreamSynchronize(stream));
         bincount.ensure(bg.mbins + 2, false, stream);
         binstart.ensure(bg.mbins + 3, false, stream);
@@ -712,15 +723,9 @@ template <class real> struct Sim final : SimBase {
             LL = NbLayout { 32 * rowlen, 32, 5 };
             neighbors.ensure(rowlen * nstride, false, stream);
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
-            RunGeom rg; // the bins' real widths are 1 / bininv (binsize itself differs for from_input, neighbor.c:78-92)
-            rg.bsx = (float)(1.0 / (double)bg.bininvx); rg.bsy = (float)(1.0 / (double)bg.bininvy);
-            rg.bsz = (float)(1.0 / (double)bg.bininvz);
-            rg.binvx    = (float)bg.bininvx;
-            rg.cutsq_hi = (float)((double)cutneighsq * (1.0 + 1e-4));
-            rg.margin   = 1e-3f * std::min({ rg.bsx, rg.bsy, rg.bsz });
 #define MDB_BUILD_V6(H)                                                                                                       \
     MDB_LAUNCH(launches, (k_build_neighbor_v6<real, H>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, bg, rg, cutneighsq, lo,  \
-        hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, run_off.p, run_len.p, run_dyz.p, nruns, maxneighs, LL, orig.p, \
+        hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, runs.p, nruns, maxneighs, LL, orig.p, \
         numneigh.p, neighbors.p, d_flags.p + 1)
             if (LL.sk != 32) throw Error("buildNeighbor: the list build stores rows at a stride of 32 entries");
             if (P.half_neigh) MDB_BUILD_V6(true);

@@ -497,6 +497,19 @@ __device__ __forceinline__ int ld_nc(const int* p)
 // disappear and the rows come out identical, entry by entry.  Every lane walks ITS OWN compacted sequence of runs (the
 // warp iterates until the last lane is done), so the trip count is the largest number of needed runs in the warp
 // (~15) instead of 21, and a narrowed run (~20 candidates) fits one flush.
+// One run of x-adjacent stencil bins (a (dy, dz) row of the stencil) as the build kernel reads it: two 128-bit loads.
+// gap between an atom at (uy, uz) inside its bin and the row: max(sy * uy + ay, 0) with (ay, sy) = (dy * bs - margin, -1) above,
+// (-(dy + 1) * bs - margin, +1) below, (-margin, 0) for the own row -- conservative by `margin`, like the x range.
+struct alignas(16) RunRow {
+    int base, i0, i1, pad; // bin offset of the row's x offset 0 (dz * mbiny * mbinx + dy * mbinx), first / last x offset of the run
+    float ay, sy, az, sz;
+};
+__device__ __forceinline__ float sqrt_approx(float v) // MUFU.SQRT (2 ulp; the caller adds a margin of 1e-3 bin widths)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 struct RunGeom {
     float bsx, bsy, bsz;    // bin widths
     float binvx;            // 1 / bsx
@@ -506,7 +519,7 @@ template <class real, bool HALF>
 __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<real> g, RunGeom rg, real cutneighsq, float lo,
     float hi, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const float* __restrict__ cx,
     const float* __restrict__ cy, const float* __restrict__ cz, const int* __restrict__ cid, const int* __restrict__ binstart,
-    const int* __restrict__ run_off, const int* __restrict__ run_len, const int* __restrict__ run_dyz, int nruns, int maxneighs,
+    const RunRow* __restrict__ runs, int nruns, int maxneighs,
     NbLayout L, const int* __restrict__ orig, int* __restrict__ numneigh, int* __restrict__ neighbors, int* __restrict__ max_n)
 {
     const int i     = blockIdx.x * blockDim.x + threadIdx.x;
@@ -534,25 +547,17 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<r
     for (;;) {
         int s = 0, e = 0;
         while (r < nruns) { // next run this atom needs
-            const int dyz = __ldg(&run_dyz[r]), dy = (dyz << 16) >> 16, dz = dyz >> 16;
-            const int off = __ldg(&run_off[r]), len = __ldg(&run_len[r]);
+            const int4 ri   = __ldg(reinterpret_cast<const int4*>(runs) + 2 * r);       // bin offset of x offset 0, first / last x offset
+            const float4 rf = __ldg(reinterpret_cast<const float4*>(runs) + 2 * r + 1); // gap(y) = max(sy * uy + ay, 0), same for z
             r++;
-            // gap between the atom and the bin row (dy, dz): rows below start at dy * bs + bs above uy, rows above at dy * bs
-            const float gy = dy > 0 ? (float)dy * rg.bsy - uy : (dy < 0 ? uy - (float)(dy + 1) * rg.bsy : 0.0f);
-            const float gz = dz > 0 ? (float)dz * rg.bsz - uz : (dz < 0 ? uz - (float)(dz + 1) * rg.bsz : 0.0f);
-            const float gym = fmaxf(gy - rg.margin, 0.0f), gzm = fmaxf(gz - rg.margin, 0.0f);
-            const float rem = rg.cutsq_hi - gym * gym - gzm * gzm;
+            const float gym = fmaxf(fmaf(rf.y, uy, rf.x), 0.0f), gzm = fmaxf(fmaf(rf.w, uz, rf.z), 0.0f);
+            const float rem = fmaf(-gzm, gzm, fmaf(-gym, gym, rg.cutsq_hi));
             if (rem < 0.0f) continue;
-            const float rx = sqrtf(rem) + rg.margin;
+            const float rx = sqrt_approx(rem) + rg.margin;
             // x bins (relative to the own bin) that intersect [ux - rx, ux + rx]
-            int first = (int)floorf((ux - rx) * rg.binvx), last = (int)floorf((ux + rx) * rg.binvx);
-            const int i0 = off - (dz * g.mbiny * g.mbinx + dy * g.mbinx); // first x offset of the run
-            first = max(first, i0);
-            last  = min(last, i0 + len - 1);
+            const int first = max((int)floorf((ux - rx) * rg.binvx), ri.y), last = min((int)floorf((ux + rx) * rg.binvx), ri.z);
             if (last < first) continue;
-            int b0 = ibin + off + (first - i0), b1 = b0 + (last - first + 1);
-            b0 = max(b0, 0);
-            b1 = min(b1, g.mbins + 1);
+            const int b0 = max(ibin + ri.x + first, 0), b1 = min(ibin + ri.x + last + 1, g.mbins + 1);
             if (b1 <= b0) continue;
             s = __ldg(&binstart[b0]);
             e = __ldg(&binstart[b1]);
