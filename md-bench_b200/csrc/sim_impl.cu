@@ -723,7 +723,7 @@ template <class real> struct Sim final : SimBase {
             LL = NbLayout { 32 * rowlen, 32, 5 };
             neighbors.ensure(rowlen * nstride, false, stream);
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 1, 0, sizeof(int), stream));
-#define MDB_BUILD_V6(H)                                                                                                       \
+#define MDB_BUILD_V6(H)                                                                                                        \
     MDB_LAUNCH(launches, (k_build_neighbor_v6<real, H>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, bg, rg, cutneighsq, lo,  \
         hi, x.p, y.p, z.p, cxs.p, cys.p, czs.p, cids.p, binstart.p, runs.p, nruns, maxneighs, LL, orig.p, \
         numneigh.p, neighbors.p, d_flags.p + 1)

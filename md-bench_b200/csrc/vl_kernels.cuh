@@ -494,9 +494,7 @@ __device__ __forceinline__ int ld_nc(const int* p)
 // run whose (y, z) bin row lies farther than cutneigh from the atom is skipped, and the x range of a run shrinks to
 // sqrt(cutneigh^2 - gap_yz^2) around the atom.  Both tests are conservative (float arithmetic with a margin of 1e-3 bin
 // widths, far above the rounding of coord2bin's bin edges), so only candidates that would fail the distance test
-// disappear and the rows come out identical, entry by entry.  Every lane walks ITS OWN compacted sequence of runs (the
-// warp iterates until the last lane is done), so the trip count is the largest number of needed runs in the warp
-// (~15) instead of 21, and a narrowed run (~20 candidates) fits one flush.
+// disappear and the rows come out identical, entry by entry.  A narrowed run (~20 candidates) fits one flush.
 // One run of x-adjacent stencil bins (a (dy, dz) row of the stencil) as the build kernel reads it: two 128-bit loads.
 // gap between an atom at (uy, uz) inside its bin and the row: max(sy * uy + ay, 0) with (ay, sy) = (dy * bs - margin, -1) above,
 // (-(dy + 1) * bs - margin, +1) below, (-margin, 0) for the own row -- conservative by `margin`, like the x range.
@@ -543,27 +541,30 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<r
                 uz = zs - (float)(iz + g.mbinzlo) * rg.bsz;
     // the row as a 32-bit element offset from its first entry: one IMAD.WIDE per store instead of a 64-bit pointer bump
     int* const row     = neighbors + L.base(ii);
-    int r    = live ? 0 : nruns;
+    int r    = 0;
     for (;;) {
         int s = 0, e = 0;
-        while (r < nruns) { // next run this atom needs
+        // all lanes of the warp look at the SAME stencil row r: warp-uniform control flow, and the lanes -- atoms adjacent in
+        // space -- find similar numbers of candidates and hits in it, which keeps the trip counts of the two divergent loops
+        // below (distance tests, appends) close to their means.  A lane whose sphere misses the row idles for that round.
+        // (Per-lane run sequences, each lane skipping ahead to the next row it needs: 4.42 vs 4.12 ms, profiles/r2_s3_call5.sh.)
+        if (r >= nruns) break;
+        {
             const int4 ri   = __ldg(reinterpret_cast<const int4*>(runs) + 2 * r);       // bin offset of x offset 0, first / last x offset
             const float4 rf = __ldg(reinterpret_cast<const float4*>(runs) + 2 * r + 1); // gap(y) = max(sy * uy + ay, 0), same for z
             r++;
             const float gym = fmaxf(fmaf(rf.y, uy, rf.x), 0.0f), gzm = fmaxf(fmaf(rf.w, uz, rf.z), 0.0f);
             const float rem = fmaf(-gzm, gzm, fmaf(-gym, gym, rg.cutsq_hi));
-            if (rem < 0.0f) continue;
-            const float rx = sqrt_approx(rem) + rg.margin;
+            const float rx  = sqrt_approx(fmaxf(rem, 0.0f)) + rg.margin;
             // x bins (relative to the own bin) that intersect [ux - rx, ux + rx]
             const int first = max((int)floorf((ux - rx) * rg.binvx), ri.y), last = min((int)floorf((ux + rx) * rg.binvx), ri.z);
-            if (last < first) continue;
             const int b0 = max(ibin + ri.x + first, 0), b1 = min(ibin + ri.x + last + 1, g.mbins + 1);
-            if (b1 <= b0) continue;
-            s = __ldg(&binstart[b0]);
-            e = __ldg(&binstart[b1]);
-            if (e > s) break;
+            if (live && rem >= 0.0f && last >= first && b1 > b0) {
+                s = __ldg(&binstart[b0]);
+                e = __ldg(&binstart[b1]);
+            }
+            if (!__any_sync(0xffffffffu, e > s)) continue;
         }
-        if (!__any_sync(0xffffffffu, e > s)) break;
         for (int c0 = s & ~3; c0 < e;) {
             // groups of 4 candidates in this flush, rounded up to PAIRS of groups: the loop body is two groups with no
             // remainder code behind it; what lies beyond e is padding or the next bin's candidates, masked by vmask below
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(128) k_build_neighbor_v6(int nlocal, BinGeom<r
                 bool ok = j != i;
                 if (HALF) ok = ok && !(j < nlocal && orig[j] < oi); // neighbor.c:224 on reference indices
                 if (ok && n < maxneighs) st_global(mad_wide_u<128>(row, (unsigned)n), j); // L.sk == 32 entries (host checks)
-                if (ok) n++;
+                asm("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q add.s32 %0, %0, 1; }" : "+r"(n) : "r"((int)ok)); // one predicated IADD
             }
             c0 += k;
         }
