@@ -417,12 +417,18 @@ __global__ void __launch_bounds__(128) k_cp_build_neighbor(int ncl, int half, Cp
         const real ixlo = I[0], ixhi = I[1], iylo = I[2], iyhi = I[3], izlo = I[4], izhi = I[5];
         const int bin = ibin[ci], nati = inat[ci], self = cp_cj0<N>(ci);
         const real* xi = cl_x + cp_ci_base3<N>(ci);
+        // the i atoms; slots beyond nati are moved to the far sentinel, so that the atom test below needs no `a < nati`
+        // (their distances fail the test like the reference's skipped pairs, neighbor.c:216-234)
         real px[CP_M], py[CP_M], pz[CP_M];
 #pragma unroll
-        for (int q = 0; q < CP_M; q++) { px[q] = xi[q]; py[q] = xi[N + q]; pz[q] = xi[2 * N + q]; }
+        for (int q = 0; q < CP_M; q++) {
+            const bool v = q < nati;
+            px[q] = v ? xi[q] : CP_PAD; py[q] = v ? xi[N + q] : CP_PAD; pz[q] = v ? xi[2 * N + q] : CP_PAD;
+        }
         int* row = neighbors + (size_t)ci * maxneighs;
         int nmasked = 0;
         const real zlo_need = izlo - g.cutneigh; // clusters entirely below this cannot be in range
+        typedef typename Vec2Of<real>::type vec2;
         for (int k = 0; k < nstencil; k++) {
             const int jb = bin + __ldg(stencil + k);
             if (jb < 0 || jb >= g.mbins) continue;
@@ -436,29 +442,42 @@ __global__ void __launch_bounds__(128) k_cp_build_neighbor(int ncl, int half, Cp
             }
             for (int m = lo; m < e; m++) {
                 const int cj = __ldg(cbinlist + m);
-                const real* J = jbb + (size_t)cj * 6;
-                const real jzlo = __ldg(J + 4);
-                if (jzlo - izhi > g.cutneigh + (real)1e-3) break; // sorted by bbminz: nothing further can be in range
+                const vec2* J = reinterpret_cast<const vec2*>(jbb + (size_t)cj * 6); // (xlo, xhi) (ylo, yhi) (zlo, zhi)
+                const vec2 jz = __ldg(J + 2);
+                if (jz.x - izhi > g.cutneigh + (real)1e-3) break; // sorted by bbminz: nothing further can be in range
                 if (half && self > cj) continue;                  // neighbor.c:318: ci_cj1 > cj
+                const vec2 jy = __ldg(J + 1), jx = __ldg(J);
                 real dl, dh, dm, d2;
-                dl = izlo - __ldg(J + 5); dh = jzlo - izhi; dm = fmax(fmax(dl, dh), (real)0);
+                dl = izlo - jz.y; dh = jz.x - izhi; dm = fmax(fmax(dl, dh), (real)0);
                 d2 = mul_rn(dm, dm);
-                dl = iylo - __ldg(J + 3); dh = __ldg(J + 2) - iyhi; dm = fmax(fmax(dl, dh), (real)0);
+                dl = iylo - jy.y; dh = jy.x - iyhi; dm = fmax(fmax(dl, dh), (real)0);
                 d2 = fma_rn(dm, dm, d2);
-                dl = ixlo - __ldg(J + 1); dh = __ldg(J + 0) - ixhi; dm = fmax(fmax(dl, dh), (real)0);
+                dl = ixlo - jx.y; dh = jx.x - ixhi; dm = fmax(fmax(dl, dh), (real)0);
                 d2 = fma_rn(dm, dm, d2);
                 if (!(d2 < g.cutneighsq)) continue;
                 bool in = d2 < g.rbb_sq;
-                if (!in) { // atomDistanceInRange, neighbor.c:216-234
+                if (!in) { // atomDistanceInRange, neighbor.c:216-234: branch-free over the four i atoms, early exit over the j atoms
                     const real* xj = cl_x + (size_t)cj * N * 3;
                     const int natj = __ldg(jnat + cj);
                     for (int b = 0; b < natj && !in; b++) {
                         const real xb = __ldg(xj + b), yb = __ldg(xj + N + b), zb = __ldg(xj + 2 * N + b);
+                        if constexpr (sizeof(real) == 4) { // two i atoms per packed operation (same round-to-nearest results)
+                            const f32x2 xb2 = pk2(xb, xb), yb2 = pk2(yb, yb), zb2 = pk2(zb, zb);
+                            float r0, r1, r2, r3;
+                            {
+                                const f32x2 dx = sub2(pk2(px[0], px[1]), xb2), dy = sub2(pk2(py[0], py[1]), yb2), dz = sub2(pk2(pz[0], pz[1]), zb2);
+                                upk2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), r0, r1);
+                            }
+                            {
+                                const f32x2 dx = sub2(pk2(px[2], px[3]), xb2), dy = sub2(pk2(py[2], py[3]), yb2), dz = sub2(pk2(pz[2], pz[3]), zb2);
+                                upk2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), r2, r3);
+                            }
+                            in = (r0 < g.cutneighsq) | (r1 < g.cutneighsq) | (r2 < g.cutneighsq) | (r3 < g.cutneighsq);
+                        } else {
 #pragma unroll
-                        for (int a = 0; a < CP_M; a++) {
-                            if (a < nati) {
+                            for (int a = 0; a < CP_M; a++) {
                                 const real dx = sub_rn(px[a], xb), dy = sub_rn(py[a], yb), dz = sub_rn(pz[a], zb);
-                                in = in || (fma_rn(dz, dz, fma_rn(dx, dx, mul_rn(dy, dy))) < g.cutneighsq);
+                                in = in | (fma_rn(dz, dz, fma_rn(dx, dx, mul_rn(dy, dy))) < g.cutneighsq);
                             }
                         }
                     }

@@ -344,7 +344,7 @@ __global__ void k_eam_pack_vs(int rows, const real* __restrict__ rhor_spline, co
     a[0] = rhor_spline[(size_t)m * 7 + 6]; a[1] = rhor_spline[(size_t)m * 7 + 5];
     a[2] = z2r_spline[(size_t)m * 7 + 6];  a[3] = z2r_spline[(size_t)m * 7 + 5];
 }
-template <class real, int U>
+template <class real, int U, bool PF>
 __global__ void __launch_bounds__(128) k_eam_density_v3(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ rho4,
     const real* __restrict__ frho_spline, const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z,
     const typename Vec2Of<real>::type* __restrict__ xy, const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L,
@@ -356,16 +356,20 @@ __global__ void __launch_bounds__(128) k_eam_density_v3(int nlocal, real cutforc
     const int nn  = numneigh[i];
     const int* nb = nbT + L.base(i);
     real rhoi     = 0;
-    for (int k = 0; k < nn; k += U) {
-        int j[U];
-        real rsq[U];
+    int j[U], jn[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) j[u] = k + u < nn ? __ldg(nb + (size_t)(k + u) * L.sk) : i;
+    for (int u = 0; u < U; u++) j[u] = u < nn ? __ldg(nb + (size_t)u * L.sk) : i;
+    for (int k = 0; k < nn; k += U) {
+        real rsq[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const typename Vec2Of<real>::type p = __ldg(xy + j[u]);
             const real dx = xt - p.x, dy = yt - p.y, dz = zt - __ldg(z + j[u]);
             rsq[u] = dx * dx + dy * dy + dz * dz;
+        }
+        if (PF) { // the indices of the next group are requested before this group is evaluated
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = k + U + u < nn ? __ldg(nb + (size_t)(k + U + u) * L.sk) : i;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -381,6 +385,12 @@ __global__ void __launch_bounds__(128) k_eam_density_v3(int nlocal, real cutforc
                 rhoi += ((s3 * p + s4) * p + s5) * p + s6;
             }
         }
+        if (!PF) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = k + U + u < nn ? __ldg(nb + (size_t)(k + U + u) * L.sk) : i;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = jn[u];
     }
     real p = (real)1.0 * rhoi * t.rdrho + (real)1.0;
     int m  = (int)(p);
@@ -406,7 +416,7 @@ __global__ void k_eam_ghost_fp_v3(int nlocal, int nghost, const int* __restrict_
     v.x = z[nlocal + g]; v.y = f;
     zf[nlocal + g] = v;
 }
-template <class real, int U>
+template <class real, int U, bool PF>
 __global__ void __launch_bounds__(128) k_eam_force_v3(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ vs4,
     const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const real* __restrict__ fp,
     const typename Vec2Of<real>::type* __restrict__ xy, const typename Vec2Of<real>::type* __restrict__ zf,
@@ -419,17 +429,21 @@ __global__ void __launch_bounds__(128) k_eam_force_v3(int nlocal, real cutforces
     const int nn  = numneigh[i];
     const int* nb = nbT + L.base(i);
     real fix = 0, fiy = 0, fiz = 0;
-    for (int k = 0; k < nn; k += U) {
-        int j[U];
-        real dx[U], dy[U], dz[U], rsq[U], fpj[U];
+    int j[U], jn[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) j[u] = k + u < nn ? __ldg(nb + (size_t)(k + u) * L.sk) : i;
+    for (int u = 0; u < U; u++) j[u] = u < nn ? __ldg(nb + (size_t)u * L.sk) : i;
+    for (int k = 0; k < nn; k += U) {
+        real dx[U], dy[U], dz[U], rsq[U], fpj[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const typename Vec2Of<real>::type p = __ldg(xy + j[u]), q = __ldg(zf + j[u]);
             dx[u] = xt - p.x; dy[u] = yt - p.y; dz[u] = zt - q.x;
             fpj[u] = q.y;
             rsq[u] = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+        }
+        if (PF) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = k + U + u < nn ? __ldg(nb + (size_t)(k + U + u) * L.sk) : i;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -459,6 +473,12 @@ __global__ void __launch_bounds__(128) k_eam_force_v3(int nlocal, real cutforces
                 fiz += dz[u] * fpair;
             }
         }
+        if (!PF) {
+#pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = k + U + u < nn ? __ldg(nb + (size_t)(k + U + u) * L.sk) : i;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) j[u] = jn[u];
     }
     fx[i] = fix;
     fy[i] = fiy;

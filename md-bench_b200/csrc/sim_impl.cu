@@ -812,12 +812,14 @@ template <class real> struct Sim final : SimBase {
         eam_zf.ensure(x.cap, false, stream);
         xy_valid = ghosts_current = false; // the packed (x, y) copy is rebuilt for every force call here
         MDB_LAUNCH(launches, k_pack_xy<real>, grid_for(nall, 256), 256, 0, stream, nall, x.p, y.p, xy.p);
-        MDB_LAUNCH(launches, (k_eam_density_v3<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
+        // U neighbors in flight, the next group's indices requested before the current group is evaluated (A/B at 128^3,
+        // profiles/r2_s3_call8.sh: density U = 2 -> 3 + prefetch 4.87 -> 4.81 ms per force call, force pass + prefetch 4.87 -> 4.62 ms)
+        MDB_LAUNCH(launches, (k_eam_density_v3<real, 3, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
             eam_rho4.p, frho_spline.p, x.p, y.p, z.p, xy.p, numneigh.p, neighbors.p, LL, fp.p, eam_zf.p);
         if (Nghost) // force_eam.c:118-120
             MDB_LAUNCH(launches, k_eam_ghost_fp_v3<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost, border_map.p, z.p,
                 fp.p, eam_zf.p);
-        MDB_LAUNCH(launches, (k_eam_force_v3<real, 2>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
+        MDB_LAUNCH(launches, (k_eam_force_v3<real, 2, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
             eam_vs4.p, x.p, y.p, z.p, fp.p, xy.p, eam_zf.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
     }
     void launch_eam()
