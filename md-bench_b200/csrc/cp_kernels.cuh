@@ -417,13 +417,13 @@ __global__ void __launch_bounds__(128) k_cp_build_neighbor(int ncl, int half, Cp
         const real ixlo = I[0], ixhi = I[1], iylo = I[2], iyhi = I[3], izlo = I[4], izhi = I[5];
         const int bin = ibin[ci], nati = inat[ci], self = cp_cj0<N>(ci);
         const real* xi = cl_x + cp_ci_base3<N>(ci);
-        // the i atoms; slots beyond nati are moved to the far sentinel, so that the atom test below needs no `a < nati`
-        // (their distances fail the test like the reference's skipped pairs, neighbor.c:216-234)
+        // the i atoms; slots beyond nati are moved to -CP_PAD (the padding slots of the j tiles sit at +CP_PAD), so that the atom
+        // test below needs no `a < nati` / `b < natj`: such pairs fail the test like the reference's skipped pairs (neighbor.c:216-234)
         real px[CP_M], py[CP_M], pz[CP_M];
 #pragma unroll
         for (int q = 0; q < CP_M; q++) {
             const bool v = q < nati;
-            px[q] = v ? xi[q] : CP_PAD; py[q] = v ? xi[N + q] : CP_PAD; pz[q] = v ? xi[2 * N + q] : CP_PAD;
+            px[q] = v ? xi[q] : -CP_PAD; py[q] = v ? xi[N + q] : -CP_PAD; pz[q] = v ? xi[2 * N + q] : -CP_PAD;
         }
         int* row = neighbors + (size_t)ci * maxneighs;
         int nmasked = 0;
@@ -456,27 +456,45 @@ __global__ void __launch_bounds__(128) k_cp_build_neighbor(int ncl, int half, Cp
                 d2 = fma_rn(dm, dm, d2);
                 if (!(d2 < g.cutneighsq)) continue;
                 bool in = d2 < g.rbb_sq;
-                if (!in) { // atomDistanceInRange, neighbor.c:216-234: branch-free over the four i atoms, early exit over the j atoms
+                if (!in) { // atomDistanceInRange, neighbor.c:216-234, as straight-line code: the whole j tile arrives by 128-bit
+                    // loads, padding slots of the tile sit at +CP_PAD and invalid i slots at -CP_PAD (see above), so no pair of
+                    // them passes the test and neither nati nor natj is consulted; float: two j atoms per packed operation
                     const real* xj = cl_x + (size_t)cj * N * 3;
-                    const int natj = __ldg(jnat + cj);
-                    for (int b = 0; b < natj && !in; b++) {
-                        const real xb = __ldg(xj + b), yb = __ldg(xj + N + b), zb = __ldg(xj + 2 * N + b);
-                        if constexpr (sizeof(real) == 4) { // two i atoms per packed operation (same round-to-nearest results)
-                            const f32x2 xb2 = pk2(xb, xb), yb2 = pk2(yb, yb), zb2 = pk2(zb, zb);
-                            float r0, r1, r2, r3;
-                            {
-                                const f32x2 dx = sub2(pk2(px[0], px[1]), xb2), dy = sub2(pk2(py[0], py[1]), yb2), dz = sub2(pk2(pz[0], pz[1]), zb2);
-                                upk2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), r0, r1);
-                            }
-                            {
-                                const f32x2 dx = sub2(pk2(px[2], px[3]), xb2), dy = sub2(pk2(py[2], py[3]), yb2), dz = sub2(pk2(pz[2], pz[3]), zb2);
-                                upk2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), r2, r3);
-                            }
-                            in = (r0 < g.cutneighsq) | (r1 < g.cutneighsq) | (r2 < g.cutneighsq) | (r3 < g.cutneighsq);
-                        } else {
+                    if constexpr (sizeof(real) == 4) {
+                        f32x2 X[N / 2], Y[N / 2], Z[N / 2];
 #pragma unroll
-                            for (int a = 0; a < CP_M; a++) {
-                                const real dx = sub_rn(px[a], xb), dy = sub_rn(py[a], yb), dz = sub_rn(pz[a], zb);
+                        for (int q = 0; q < N / 4; q++) {
+                            ld2x2((const float*)xj + 4 * q, X[2 * q], X[2 * q + 1]);
+                            ld2x2((const float*)xj + N + 4 * q, Y[2 * q], Y[2 * q + 1]);
+                            ld2x2((const float*)xj + 2 * N + 4 * q, Z[2 * q], Z[2 * q + 1]);
+                        }
+#pragma unroll
+                        for (int a = 0; a < CP_M; a++) {
+                            const f32x2 xa = pk2((float)px[a], (float)px[a]), ya = pk2((float)py[a], (float)py[a]), za = pk2((float)pz[a], (float)pz[a]);
+#pragma unroll
+                            for (int q = 0; q < N / 2; q++) {
+                                const f32x2 dx = sub2(xa, X[q]), dy = sub2(ya, Y[q]), dz = sub2(za, Z[q]);
+                                float r0, r1;
+                                upk2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), r0, r1);
+                                in = in | (r0 < (float)g.cutneighsq) | (r1 < (float)g.cutneighsq);
+                            }
+                        }
+                    } else {
+                        typedef typename Vec2Of<real>::type v2;
+                        v2 X[N / 2], Y[N / 2], Z[N / 2];
+#pragma unroll
+                        for (int q = 0; q < N / 2; q++) {
+                            X[q] = __ldg(reinterpret_cast<const v2*>(xj) + q);
+                            Y[q] = __ldg(reinterpret_cast<const v2*>(xj + N) + q);
+                            Z[q] = __ldg(reinterpret_cast<const v2*>(xj + 2 * N) + q);
+                        }
+#pragma unroll
+                        for (int a = 0; a < CP_M; a++) {
+#pragma unroll
+                            for (int q = 0; q < N / 2; q++) {
+                                real dx = sub_rn(px[a], X[q].x), dy = sub_rn(py[a], Y[q].x), dz = sub_rn(pz[a], Z[q].x);
+                                in = in | (fma_rn(dz, dz, fma_rn(dx, dx, mul_rn(dy, dy))) < g.cutneighsq);
+                                dx = sub_rn(px[a], X[q].y); dy = sub_rn(py[a], Y[q].y); dz = sub_rn(pz[a], Z[q].y);
                                 in = in | (fma_rn(dz, dz, fma_rn(dx, dx, mul_rn(dy, dy))) < g.cutneighsq);
                             }
                         }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2 session 3, call 10: EAM passes with index prefetch (defaults) and the clusterpair list build with a branch-free, packed atom
+# round 2 session 3, call 10 (re-used): EAM passes with index prefetch (defaults) and the clusterpair list build with a branch-free, packed atom
 # test + vector loads of the bounding boxes: parity (EAM tests, all clusterpair tests) + timing
 cd "$(dirname "$0")/.."
 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k eam > gpurun_out/r2s3c10_pytest_eam.log 2>&1; echo "eam pytest rc=$?"; tail -1 gpurun_out/r2s3c10_pytest_eam.log
