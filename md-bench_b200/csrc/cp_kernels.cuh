@@ -61,10 +61,29 @@ __global__ void k_cp_bin_count(int n, CpGeom<real> g, const real* __restrict__ x
     int* __restrict__ atom_bin, int* __restrict__ bincount)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned act = __ballot_sync(0xffffffffu, i < n);
     if (i >= n) return;
     const int b = cp_coord2bin(g, x[i], y[i]);
     atom_bin[i] = b;
-    atomicAdd(&bincount[b], 1);
+    // a bin is a whole column of the box (hundreds of atoms) and the atoms of a warp are neighbors in space: one atomic per
+    // distinct bin of the warp instead of one per atom
+    const unsigned m = __match_any_sync(act, b);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&bincount[b], __popc(m));
+}
+// k_bin_fill with the same aggregation: the first lane of each group of equal bins reserves the group's slots
+static __global__ void k_cp_bin_fill(int n, const int* __restrict__ atom_bin, const int* __restrict__ binstart, int* __restrict__ cursor,
+    int* __restrict__ binatoms)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned act = __ballot_sync(0xffffffffu, i < n);
+    if (i >= n) return;
+    const int b = atom_bin[i], lane = threadIdx.x & 31;
+    const unsigned m = __match_any_sync(act, b);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[b], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    binatoms[binstart[b] + base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 // clusters per bin (neighbor.c:687-690): ceil(c / M), made even when N > M
 template <int N> __global__ void k_cp_clusters_per_bin(int mbins, const int* __restrict__ bincount, int* __restrict__ ncl,
@@ -99,39 +118,47 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
     const int bin = blockIdx.x;
     const int s0 = binstart[bin], c = binstart[bin + 1] - s0;
     if (c == 0) return;
-    real* sz  = reinterpret_cast<real*>(smem_raw);        // z of the atom at each position
-    int* sid  = reinterpret_cast<int*>(sz + c);           // atom index at each position
-    int* sout = sid + c;                                  // result order
+    real* sz  = reinterpret_cast<real*>(smem_raw); // tie path: z of the atoms in ascending atom index
+    real* uz  = sz + c;                            // z of the atoms as the (unordered) fill left them
+    int* sid  = reinterpret_cast<int*>(uz + c);    // tie path: the atoms in ascending atom index
+    int* sout = sid + c;                           // result order
+    int* uid  = sout + c;                          // the atoms as the fill left them
     __shared__ int s_ties;
     __shared__ real s_minz[4];
     __shared__ int s_minp[4];
     const int t = threadIdx.x;
     if (t == 0) s_ties = 0;
-    // ascending atom index = the order binAtoms filled the bin (rank sort on the unique indices)
-    for (int k = t; k < c; k += blockDim.x) sout[k] = binatoms_in[s0 + k];
-    __syncthreads();
     for (int k = t; k < c; k += blockDim.x) {
-        const int v = sout[k];
-        int r       = 0;
-        for (int q = 0; q < c; q++) r += sout[q] < v;
-        sid[r] = v;
-        sz[r]  = z[v];
+        const int v = binatoms_in[s0 + k];
+        uid[k] = v;
+        uz[k]  = z[v];
     }
     __syncthreads();
-    // rank by (z, position); detect ties
+    // binAtoms fills a bin in ascending atom index and a selection sort of DISTINCT keys ends in sorted order, so without
+    // ties the result is the rank by (z, atom index) -- ONE pass over the pairs of the bin, straight from the unordered fill
     for (int k = t; k < c; k += blockDim.x) {
-        const real zk = sz[k];
+        const real zk = uz[k];
+        const int vk  = uid[k];
         int r = 0, tie = 0;
         for (int q = 0; q < c; q++) {
-            const real zq = sz[q];
-            r += (zq < zk) || (zq == zk && q < k);
-            tie |= (zq == zk && q != k);
+            const real zq = uz[q];
+            const bool eq = zq == zk;
+            r += (zq < zk) || (eq && uid[q] < vk);
+            tie += eq;
         }
-        sout[r] = sid[k];
-        if (tie) s_ties = 1;
+        sout[r] = vk;
+        if (tie > 1) s_ties = 1; // the atom itself counts once
     }
     __syncthreads();
-    if (s_ties) { // replay the selection sort on (sz, sid)
+    if (s_ties) { // equal z in the bin (every bin of the initial lattice): replay the selection sort on (sz, sid)
+        for (int k = t; k < c; k += blockDim.x) { // ascending atom index = the order binAtoms filled the bin
+            const int v = uid[k];
+            int r       = 0;
+            for (int q = 0; q < c; q++) r += uid[q] < v;
+            sid[r] = v;
+            sz[r]  = uz[k];
+        }
+        __syncthreads();
         for (int a = 0; a < c - 1; a++) {
             real mz = INFINITY;
             int mp  = 0x7fffffff;

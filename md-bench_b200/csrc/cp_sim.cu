@@ -142,7 +142,7 @@ template <class real, int N> struct CpSim final : CpBase {
             (const void*)k_cp_sort_emit<real, N>, (const void*)k_cp_define_j<real, N>, (const void*)k_cp_ghost_count<real>,
             (const void*)k_cp_ghost_fill<N>, (const void*)k_cp_cluster_bin<real, N>, (const void*)k_cp_cluster_fill,
             (const void*)k_cp_cluster_sort<real>, (const void*)k_cp_build_neighbor<real, N>, (const void*)k_cp_clusters_per_bin<N>,
-            (const void*)k_update_atoms_pbc<real>, (const void*)k_vel_partial<real>, (const void*)k_vel_final, (const void*)k_bin_fill };
+            (const void*)k_update_atoms_pbc<real>, (const void*)k_vel_partial<real>, (const void*)k_vel_final, (const void*)k_cp_bin_fill };
         for (const void* k : ks) MDB_CUDA(cudaFuncGetAttributes(&a, k));
         if (sizeof(real) == 4) {
             MDB_CUDA(cudaFuncGetAttributes(&a, (const void*)k_cp_force_lj_sp_duo<N, true, false>));
@@ -461,7 +461,7 @@ template <class real, int N> struct CpSim final : CpBase {
         MDB_CUDA(cudaMemsetAsync(d_flags.p, 0, 4 * sizeof(int), stream));
         MDB_LAUNCH(launches, k_cp_bin_count<real>, grid_for(n, 256), 256, 0, stream, n, g, x.p, y.p, atom_bin.p, bincount.p);
         scanner.exclusive(bincount.p, binstart.p, g.mbins, binstart.p + g.mbins, stream);
-        MDB_LAUNCH(launches, k_bin_fill, grid_for(n, 256), 256, 0, stream, n, atom_bin.p, binstart.p, cursor.p, binatoms.p);
+        MDB_LAUNCH(launches, k_cp_bin_fill, grid_for(n, 256), 256, 0, stream, n, atom_bin.p, binstart.p, cursor.p, binatoms.p);
         MDB_LAUNCH(launches, k_cp_clusters_per_bin<N>, grid_for(g.mbins, 256), 256, 0, stream, g.mbins, bincount.p, nclbin.p,
             d_flags.p + 0);
         scanner.exclusive(nclbin.p, clbase.p, g.mbins, d_flags.p + 1, stream);
@@ -476,7 +476,7 @@ template <class real, int N> struct CpSim final : CpBase {
         inat.ensure(ncl, false, stream);
         ibin.ensure(ncl, false, stream);
         ibb.ensure((size_t)ncl * 6, false, stream);
-        const size_t smem = (size_t)maxcount * (sizeof(real) + 2 * sizeof(int));
+        const size_t smem = (size_t)maxcount * (2 * sizeof(real) + 3 * sizeof(int));
         if (smem > 200 * 1024) throw Error("buildClusters: a bin column holds too many atoms for one thread block");
         if (smem > 48 * 1024)
             MDB_CUDA(cudaFuncSetAttribute(k_cp_sort_emit<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
