@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
     const int bin = blockIdx.x;
     const int s0 = binstart[bin], c = binstart[bin + 1] - s0;
     if (c == 0) return;
-    real* sz  = reinterpret_cast<real*>(smem_raw); // tie path: z of the atoms in ascending atom index
-    real* uz  = sz + c;                            // z of the atoms as the (unordered) fill left them
-    int* sid  = reinterpret_cast<int*>(uz + c);    // tie path: the atoms in ascending atom index
+    const int c4 = (c + 3) & ~3;
+    real* uz  = reinterpret_cast<real*>(smem_raw); // z of the atoms as the (unordered) fill left them, padded to c4 with +inf
+    real* sz  = uz + c4;                           // tie path: z of the atoms in ascending atom index
+    int* sid  = reinterpret_cast<int*>(sz + c4);   // tie path: the atoms in ascending atom index
     int* sout = sid + c;                           // result order
     int* uid  = sout + c;                          // the atoms as the fill left them
     __shared__ int s_ties;
@@ -128,26 +129,32 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
     __shared__ int s_minp[4];
     const int t = threadIdx.x;
     if (t == 0) s_ties = 0;
-    for (int k = t; k < c; k += blockDim.x) {
-        const int v = binatoms_in[s0 + k];
-        uid[k] = v;
-        uz[k]  = z[v];
+    for (int k = t; k < c4; k += blockDim.x) {
+        const int v = k < c ? binatoms_in[s0 + k] : 0;
+        if (k < c) uid[k] = v;
+        uz[k] = k < c ? z[v] : (real)INFINITY;
     }
     __syncthreads();
     // binAtoms fills a bin in ascending atom index and a selection sort of DISTINCT keys ends in sorted order, so without
-    // ties the result is the rank by (z, atom index) -- ONE pass over the pairs of the bin, straight from the unordered fill
+    // ties the result is the rank by z -- ONE pass over the pairs of the bin, straight from the unordered fill, four z per
+    // shared-memory load; any tie sends the whole bin through the replay below
     for (int k = t; k < c; k += blockDim.x) {
         const real zk = uz[k];
-        const int vk  = uid[k];
         int r = 0, tie = 0;
-        for (int q = 0; q < c; q++) {
-            const real zq = uz[q];
-            const bool eq = zq == zk;
-            r += (zq < zk) || (eq && uid[q] < vk);
-            tie += eq;
+        for (int q = 0; q < c4; q += 4) {
+            real v0, v1, v2, v3;
+            if constexpr (sizeof(real) == 4) {
+                const float4 v = *reinterpret_cast<const float4*>(uz + q);
+                v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+            } else {
+                const double2 a = *reinterpret_cast<const double2*>(uz + q), b = *reinterpret_cast<const double2*>(uz + q + 2);
+                v0 = a.x; v1 = a.y; v2 = b.x; v3 = b.y;
+            }
+            r += (v0 < zk) + (v1 < zk) + (v2 < zk) + (v3 < zk);
+            tie += (v0 == zk) + (v1 == zk) + (v2 == zk) + (v3 == zk);
         }
-        sout[r] = vk;
         if (tie > 1) s_ties = 1; // the atom itself counts once
+        else sout[r] = uid[k];
     }
     __syncthreads();
     if (s_ties) { // equal z in the bin (every bin of the initial lattice): replay the selection sort on (sz, sid)

@@ -476,7 +476,7 @@ template <class real, int N> struct CpSim final : CpBase {
         inat.ensure(ncl, false, stream);
         ibin.ensure(ncl, false, stream);
         ibb.ensure((size_t)ncl * 6, false, stream);
-        const size_t smem = (size_t)maxcount * (2 * sizeof(real) + 3 * sizeof(int));
+        const size_t smem = (size_t)(maxcount + 4) * (2 * sizeof(real) + 3 * sizeof(int));
         if (smem > 200 * 1024) throw Error("buildClusters: a bin column holds too many atoms for one thread block");
         if (smem > 48 * 1024)
             MDB_CUDA(cudaFuncSetAttribute(k_cp_sort_emit<real, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
