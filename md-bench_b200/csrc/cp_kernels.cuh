@@ -125,8 +125,6 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
     int* sout = sid + c;                           // result order
     int* uid  = sout + c;                          // the atoms as the fill left them
     __shared__ int s_ties;
-    __shared__ real s_minz[4];
-    __shared__ int s_minp[4];
     const int t = threadIdx.x;
     if (t == 0) s_ties = 0;
     for (int k = t; k < c4; k += blockDim.x) {
@@ -166,33 +164,33 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
             sz[r]  = uz[k];
         }
         __syncthreads();
-        for (int a = 0; a < c - 1; a++) {
-            real mz = INFINITY;
-            int mp  = 0x7fffffff;
-            for (int k = a + t; k < c; k += blockDim.x) {
-                const real zk = sz[k];
-                if (zk < mz) { mz = zk; mp = k; } // ascending k: first position wins
-            }
+        // the rounds depend on one another, so ONE warp walks them with shuffles only (no block barrier per round:
+        // 5.7 -> ms per build of the initial lattice at 128^3, profiles/r2_s3_call15.sh); the other warps wait below
+        if (t < 32) {
+            for (int a = 0; a < c - 1; a++) {
+                real mz = INFINITY;
+                int mp  = 0x7fffffff;
+                for (int k = a + t; k < c; k += 32) {
+                    const real zk = sz[k];
+                    if (zk < mz) { mz = zk; mp = k; } // ascending k: first position wins
+                }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const real oz = __shfl_down_sync(0xffffffffu, mz, d);
-                const int op  = __shfl_down_sync(0xffffffffu, mp, d);
-                if (oz < mz || (oz == mz && op < mp)) { mz = oz; mp = op; }
-            }
-            if ((t & 31) == 0) { s_minz[t >> 5] = mz; s_minp[t >> 5] = mp; }
-            __syncthreads();
-            if (t == 0) {
-                for (int w = 1; w < (int)(blockDim.x >> 5); w++)
-                    if (s_minz[w] < mz || (s_minz[w] == mz && s_minp[w] < mp)) { mz = s_minz[w]; mp = s_minp[w]; }
+                for (int d = 16; d > 0; d >>= 1) {
+                    const real oz = __shfl_xor_sync(0xffffffffu, mz, d);
+                    const int op  = __shfl_xor_sync(0xffffffffu, mp, d);
+                    if (oz < mz || (oz == mz && op < mp)) { mz = oz; mp = op; }
+                }
                 if (mp >= c) mp = a; // non-finite z (blown-up run): keep the element in place
-                // neighbor.c:676-677: bin_ptr[ac_i] = min_idx; bin_ptr[min_ac] = i
-                const int ia = sid[a];
-                const real za = sz[a];
-                sid[a] = sid[mp]; sz[a] = sz[mp];
-                sid[mp] = ia; sz[mp] = za;
+                if (t == 0) { // neighbor.c:676-677: bin_ptr[ac_i] = min_idx; bin_ptr[min_ac] = i
+                    const int ia = sid[a];
+                    const real za = sz[a];
+                    sid[a] = sid[mp]; sz[a] = sz[mp];
+                    sid[mp] = ia; sz[mp] = za;
+                }
+                __syncwarp();
             }
-            __syncthreads();
         }
+        __syncthreads();
         for (int k = t; k < c; k += blockDim.x) sout[k] = sid[k];
         __syncthreads();
     }
