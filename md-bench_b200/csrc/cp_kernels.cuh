@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
         }
         __syncthreads();
         // the rounds depend on one another, so ONE warp walks them with shuffles only (no block barrier per round:
-        // 5.7 -> ms per build of the initial lattice at 128^3, profiles/r2_s3_call15.sh); the other warps wait below
+        // 5.7 -> 4.3 ms per build of the initial lattice at 128^3, profiles/r2_s3_call15.sh); the other warps wait below
         if (t < 32) {
             for (int a = 0; a < c - 1; a++) {
                 real mz = INFINITY;
