@@ -416,12 +416,20 @@ __global__ void k_eam_ghost_fp_v3(int nlocal, int nghost, const int* __restrict_
     v.x = z[nlocal + g]; v.y = f;
     zf[nlocal + g] = v;
 }
-template <class real, int U, bool PF>
-__global__ void __launch_bounds__(128) k_eam_force_v3(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ vs4,
-    const real* __restrict__ x, const real* __restrict__ y, const real* __restrict__ z, const real* __restrict__ fp,
+// FI: finalIntegrate(n) + initialIntegrate(n+1) in the epilogue (integrate.c:21-40; the operation sequence of
+// k_final_initial_integrate, so a run equals the separate kernels bit for bit).  Every gather of this pass and of the next
+// density pass goes to the copies (xy, zf), which are rebuilt per force call, so x, y, z are updated IN PLACE and f is
+// not stored.
+template <class real> struct EamIntegrate {
+    real *vx, *vy, *vz;
+    real dtforce, dt;
+};
+template <class real, int U, bool PF, bool FI = false>
+__global__ void __launch_bounds__(128, FI ? 7 : 1) k_eam_force_v3(int nlocal, real cutforcesq, EamTables<real> t, const real* __restrict__ vs4,
+    real* x, real* y, real* z, const real* __restrict__ fp,
     const typename Vec2Of<real>::type* __restrict__ xy, const typename Vec2Of<real>::type* __restrict__ zf,
     const int* __restrict__ numneigh, const int* __restrict__ nbT, NbLayout L, real* __restrict__ fx, real* __restrict__ fy,
-    real* __restrict__ fz)
+    real* __restrict__ fz, EamIntegrate<real> fi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlocal) return;
@@ -480,9 +488,18 @@ __global__ void __launch_bounds__(128) k_eam_force_v3(int nlocal, real cutforces
 #pragma unroll
         for (int u = 0; u < U; u++) j[u] = jn[u];
     }
-    fx[i] = fix;
-    fy[i] = fiy;
-    fz[i] = fiz;
+    if (FI) {
+        real a = fi.vx[i] + fi.dtforce * fix, b = fi.vy[i] + fi.dtforce * fiy, c = fi.vz[i] + fi.dtforce * fiz; // final(n)
+        a = a + fi.dtforce * fix; b = b + fi.dtforce * fiy; c = c + fi.dtforce * fiz;                          // initial(n+1)
+        fi.vx[i] = a; fi.vy[i] = b; fi.vz[i] = c;
+        x[i] = xt + fi.dt * a;
+        y[i] = yt + fi.dt * b;
+        z[i] = zt + fi.dt * c;
+    } else {
+        fx[i] = fix;
+        fy[i] = fiy;
+        fz[i] = fiz;
+    }
 }
 
 } // namespace mdb

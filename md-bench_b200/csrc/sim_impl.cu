@@ -803,7 +803,7 @@ template <class real> struct Sim final : SimBase {
         MDB_LAUNCH(launches, k_eam_force<real>, grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
             eam, rhor_spline.p, z2r_spline.p, x.p, y.p, z.p, fp.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
     }
-    void launch_eam_v3() // generation 3: see eam_kernels.cuh
+    void launch_eam_v3(bool integrate = false) // generation 3: see eam_kernels.cuh
     {
         if (!eam.ready) throw Error("computeForceEam: no EAM tables (call mdb_setEam first)");
         const int nall = Nlocal + Nghost;
@@ -819,8 +819,33 @@ template <class real> struct Sim final : SimBase {
         if (Nghost) // force_eam.c:118-120
             MDB_LAUNCH(launches, k_eam_ghost_fp_v3<real>, grid_for(Nghost, 256), 256, 0, stream, Nlocal, Nghost, border_map.p, z.p,
                 fp.p, eam_zf.p);
-        MDB_LAUNCH(launches, (k_eam_force_v3<real, 2, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce, eam,
-            eam_vs4.p, x.p, y.p, z.p, fp.p, xy.p, eam_zf.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p);
+        EamIntegrate<real> ei { vx.p, vy.p, vz.p, dtforce, dt };
+        if (integrate)
+            MDB_LAUNCH(launches, (k_eam_force_v3<real, 2, true, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
+                eam, eam_vs4.p, x.p, y.p, z.p, fp.p, xy.p, eam_zf.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p, ei);
+        else
+            MDB_LAUNCH(launches, (k_eam_force_v3<real, 2, true>), grid_for(Nlocal, 128), 128, 0, stream, Nlocal, cutforce * cutforce,
+                eam, eam_vs4.p, x.p, y.p, z.p, fp.p, xy.p, eam_zf.p, numneigh.p, neighbors.p, LL, fx.p, fy.p, fz.p, ei);
+    }
+    // EAM: computeForce(n) + finalIntegrate(n) + initialIntegrate(n+1), the integrate halves in the epilogue of the force pass
+    bool can_fuse_eam() const
+    {
+        return fuse_force && fuse_integrate && !brick && P.force_field == MDB_FF_EAM && eam_variant == 2 && !lazy_ops;
+    }
+    void eamForceFinalInitialIntegrate()
+    {
+        NvtxRange nvtx_range_("force+integrate");
+        if (nstride == 0) throw Error("computeForce: no neighbor list (call mdb_buildNeighbor first)");
+        if (timing) MDB_CUDA(cudaEventRecord(ev0, stream));
+        launch_eam_v3(true);
+        force_launches++;
+        if (timing) {
+            float ms = 0;
+            MDB_CUDA(cudaEventRecord(ev1, stream));
+            MDB_CUDA(cudaEventSynchronize(ev1));
+            MDB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            force_ms += ms;
+        }
     }
     void launch_eam()
     {
@@ -1043,6 +1068,11 @@ template <class real> struct Sim final : SimBase {
             const bool split = rec || n + 1 == nsteps || !fuse_integrate;
             if (!split && can_fuse_force()) {
                 forceFinalInitialIntegrate();
+                initial_done = true;
+                continue;
+            }
+            if (!split && can_fuse_eam()) {
+                eamForceFinalInitialIntegrate();
                 initial_done = true;
                 continue;
             }

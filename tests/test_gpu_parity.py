@@ -420,6 +420,28 @@ def test_eam_generation3_matches_generation2(golden_dir, dp):
     a.close(); b.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dp", [True, False])
+def test_eam_run_loop_fused_equals_separate_kernels(golden_dir, dp):
+    """mdb_run with EAM: the integrate halves in the epilogue of the force pass (k_eam_force_v3<.., FI>, positions updated in
+    place) against the separate final+initial integrate kernel (option fuse_force = 0): same operation sequence, so
+    positions, velocities and thermo records are equal bit for bit over rebuilds and a thermo record in between."""
+    from cases import funcfl_args
+    g = np.load(os.path.join(golden_dir, "eam_cu_nx5.npz"))
+    m = load_pkg()
+    out = []
+    for fuse in (1, 0):
+        s = make_sim(dp, True, True, force_field=m.FF_EAM, nx=6, ny=6, nz=6, ntimes=130)
+        s.setOption("fuse_force", fuse)
+        s.setEam(*funcfl_args(g))
+        s.createAtom(); s.setup(adjust=True)
+        rec, _ = s.run(130)
+        out.append((np.array(rec), s.get("x"), s.get("v")))
+        s.close()
+    (ra, xa, va), (rb, xb, vb) = out
+    assert np.array_equal(ra, rb) and np.array_equal(xa, xb) and np.array_equal(va, vb)
+
+
 def test_cuda_eam_copper_melting_200_steps(golden_dir):
     """BASELINE config 4: copper_melting (32 000 atoms from the LAMMPS dump), Cu_u3 funcfl, 200 steps:
     the reference's `step temp pressure` lines and the oracle on the first 25 steps."""
