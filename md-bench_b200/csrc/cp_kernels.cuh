@@ -129,16 +129,17 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
     if (t == 0) s_ties = 0;
     for (int k = t; k < c4; k += blockDim.x) {
         const int v = k < c ? binatoms_in[s0 + k] : 0;
-        if (k < c) uid[k] = v;
+        if (k < c) { uid[k] = v; sout[k] = -1; }
         uz[k] = k < c ? z[v] : (real)INFINITY;
     }
     __syncthreads();
     // binAtoms fills a bin in ascending atom index and a selection sort of DISTINCT keys ends in sorted order, so without
     // ties the result is the rank by z -- ONE pass over the pairs of the bin, straight from the unordered fill, four z per
-    // shared-memory load; any tie sends the whole bin through the replay below
+    // shared-memory load.  Equal z give equal ranks, i.e. a slot of the result stays empty: that is how ties are found
+    // (no equality count in the hot loop), and any tie sends the whole bin through the replay below.
     for (int k = t; k < c; k += blockDim.x) {
         const real zk = uz[k];
-        int r = 0, tie = 0;
+        int r = 0;
         for (int q = 0; q < c4; q += 4) {
             real v0, v1, v2, v3;
             if constexpr (sizeof(real) == 4) {
@@ -149,11 +150,12 @@ __global__ void __launch_bounds__(128) k_cp_sort_emit(int mbins, const int* __re
                 v0 = a.x; v1 = a.y; v2 = b.x; v3 = b.y;
             }
             r += (v0 < zk) + (v1 < zk) + (v2 < zk) + (v3 < zk);
-            tie += (v0 == zk) + (v1 == zk) + (v2 == zk) + (v3 == zk);
         }
-        if (tie > 1) s_ties = 1; // the atom itself counts once
-        else sout[r] = uid[k];
+        sout[r] = uid[k]; // r < c: at most c - 1 of the c finite z are smaller
     }
+    __syncthreads();
+    for (int k = t; k < c; k += blockDim.x)
+        if (sout[k] < 0) s_ties = 1;
     __syncthreads();
     if (s_ties) { // equal z in the bin (every bin of the initial lattice): replay the selection sort on (sz, sid)
         for (int k = t; k < c; k += blockDim.x) { // ascending atom index = the order binAtoms filled the bin
