@@ -404,8 +404,9 @@ static __global__ void k_cp_cluster_fill(int n, const int* __restrict__ cbin, co
 // build binary-search the first cluster that can be in z-range.  One warp per bin, rank sort.
 template <class real>
 __global__ void __launch_bounds__(128) k_cp_cluster_sort(int mbins, const int* __restrict__ cbinstart,
-    const int* __restrict__ cbinlist_in, int* cbinlist, const real* __restrict__ jbb, real* __restrict__ pmaxz)
+    const int* __restrict__ cbinlist_in, int* cbinlist, const real* __restrict__ jbb, real* jbbs, real* __restrict__ pmaxz)
 {
+    typedef typename Vec2Of<real>::type vec2;
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= mbins) return;
     const int s = cbinstart[b], c = cbinstart[b + 1] - s;
@@ -419,12 +420,17 @@ __global__ void __launch_bounds__(128) k_cp_cluster_sort(int mbins, const int* _
             r += (zu < zv) || (zu == zv && u < v);
         }
         cbinlist[s + r] = v;
+        // the bounding boxes once more IN BIN ORDER: the list build reads them by position (consecutive clusters of a bin
+        // are consecutive in memory) instead of through the cluster index
+        const vec2* src = reinterpret_cast<const vec2*>(jbb + (size_t)v * 6);
+        vec2* dst       = reinterpret_cast<vec2*>(jbbs + (size_t)(s + r) * 6);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
     }
     __syncwarp();
     for (int k = lane; k < c; k += 32) {
         real m = -INFINITY;
         for (int q = 0; q <= k; q++) {
-            const real zmax = jbb[(size_t)cbinlist[s + q] * 6 + 5];
+            const real zmax = jbbs[(size_t)(s + q) * 6 + 5];
             m               = zmax > m ? zmax : m;
         }
         pmaxz[s + k] = m;
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(128) k_cp_cluster_sort(int mbins, const int* _
 template <class real, int N>
 __global__ void __launch_bounds__(128) k_cp_build_neighbor(int ncl, int half, CpGeom<real> g, const int* __restrict__ stencil,
     int nstencil, const int* __restrict__ ibin, const int* __restrict__ inat, const real* __restrict__ ibb,
-    const int* __restrict__ jnat, const real* __restrict__ jbb, const real* __restrict__ cl_x, const int* __restrict__ cbinstart,
+    const int* __restrict__ jnat, const real* __restrict__ jbbs, const real* __restrict__ cl_x, const int* __restrict__ cbinstart,
     const int* __restrict__ cbinlist, const real* __restrict__ pmaxz, int maxneighs, int* __restrict__ numneigh,
     int* __restrict__ numneigh_masked, int* __restrict__ neighbors, int* __restrict__ max_n)
 {
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(128) k_cp_build_neighbor(int ncl, int half, Cp
             }
             for (int m = lo; m < e; m++) {
                 const int cj = __ldg(cbinlist + m);
-                const vec2* J = reinterpret_cast<const vec2*>(jbb + (size_t)cj * 6); // (xlo, xhi) (ylo, yhi) (zlo, zhi)
+                const vec2* J = reinterpret_cast<const vec2*>(jbbs + (size_t)m * 6); // (xlo, xhi) (ylo, yhi) (zlo, zhi), bin order
                 const vec2 jz = __ldg(J + 2);
                 if (jz.x - izhi > g.cutneigh + (real)1e-3) break; // sorted by bbminz: nothing further can be in range
                 if (half && self > cj) continue;                  // neighbor.c:318: ci_cj1 > cj

@@ -89,7 +89,7 @@ template <class real, int N> struct CpSim final : CpBase {
     int saved_n = 0;
     // ---- clusters ----
     int ncl = 0, ncj = 0, nghost = 0, dummy_cj = 0; // Nclusters_local, local tiles, Nclusters_ghost
-    DBuf<real> cl_x, cl_v, cl_f, ibb, jbb, pmaxz;
+    DBuf<real> cl_x, cl_v, cl_f, ibb, jbb, jbbs, pmaxz; // jbbs: the j bounding boxes in bin order (k_cp_cluster_sort)
     DBuf<real> cl_xn; // second cluster position array of the fused force + integrate step (run())
     DBuf<int> cl_tag, inat, ibin, jnat, atom_off;
     // ---- bins (clusterpair/neighbor.c:26-45) ----
@@ -160,7 +160,7 @@ template <class real, int N> struct CpSim final : CpBase {
                 phase_ms[0] / phase_calls, phase_ms[1] / phase_calls, phase_ms[2] / phase_calls, phase_ms[3] / phase_calls,
                 phase_ms[4] / phase_calls, phase_ms[5] / phase_calls, phase_ms[6] / phase_calls);
         for (DBuf<real>* b : { &x, &y, &z, &vx, &vy, &vz, &sx, &sy, &sz, &svx, &svy, &svz, &stage, &cl_x, &cl_xn, &cl_v, &cl_f, &ibb,
-                 &jbb, &pmaxz })
+                 &jbb, &jbbs, &pmaxz })
             b->release();
         for (DBuf<int>* b : { &tag, &type, &cl_tag, &inat, &ibin, &jnat, &atom_off, &stencil, &atom_bin, &bincount, &binstart,
                  &cursor, &binatoms, &nclbin, &clbase, &cbin, &cbincount, &cbinstart, &ccursor, &cbinlist, &cbinlist2, &gcnt,
@@ -538,6 +538,7 @@ template <class real, int N> struct CpSim final : CpBase {
         cbinlist.ensure(nt, false, stream);
         cbinlist2.ensure(nt, false, stream);
         pmaxz.ensure(nt, false, stream);
+        jbbs.ensure((size_t)nt * 6, false, stream);
         MDB_CUDA(cudaMemsetAsync(cbincount.p, 0, (g.mbins + 1) * sizeof(int), stream));
         MDB_CUDA(cudaMemsetAsync(ccursor.p, 0, (g.mbins + 1) * sizeof(int), stream));
         MDB_LAUNCH(launches, (k_cp_cluster_bin<real, N>), grid_for(nt, 256), 256, 0, stream, ncj, nghost, g, ibin.p, code.p,
@@ -546,7 +547,7 @@ template <class real, int N> struct CpSim final : CpBase {
         MDB_LAUNCH(launches, k_cp_cluster_fill, grid_for(nt, 256), 256, 0, stream, nt, cbin.p, cbinstart.p, ccursor.p,
             cbinlist2.p);
         MDB_LAUNCH(launches, k_cp_cluster_sort<real>, grid_for((size_t)g.mbins * 32, 128), 128, 0, stream, g.mbins, cbinstart.p,
-            cbinlist2.p, cbinlist.p, jbb.p, pmaxz.p);
+            cbinlist2.p, cbinlist.p, jbb.p, jbbs.p, pmaxz.p);
     }
     void buildNeighbor() override // buildNeighborCPU, neighbor.c:262-481
     {
@@ -557,7 +558,7 @@ template <class real, int N> struct CpSim final : CpBase {
             neighbors.ensure((size_t)ncl * maxneighs, false, stream);
             MDB_CUDA(cudaMemsetAsync(d_flags.p + 2, 0, sizeof(int), stream));
             MDB_LAUNCH(launches, (k_cp_build_neighbor<real, N>), grid_for(ncl, 128), 128, 0, stream, ncl, P.half_neigh, g,
-                stencil.p, nstencil, ibin.p, inat.p, ibb.p, jnat.p, jbb.p, cl_x.p, cbinstart.p, cbinlist.p, pmaxz.p, maxneighs,
+                stencil.p, nstencil, ibin.p, inat.p, ibb.p, jnat.p, jbbs.p, cl_x.p, cbinstart.p, cbinlist.p, pmaxz.p, maxneighs,
                 numneigh.p, numneigh_masked.p, neighbors.p, d_flags.p + 2);
             neigh_launches++;
             MDB_CUDA(cudaMemcpyAsync(h_flags + 2, d_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
