@@ -155,7 +155,11 @@ int main(int argc, char** argv)
 
     if (operators) {
         /* MDB_LAZY_OPS=1: keep this loop, let the library fuse computeForce + finalIntegrate + initialIntegrate (mdb200.h) */
-        if (getenv("MDB_LAZY_OPS") != NULL && mdb_setOption(atom.d_atom, "lazy_ops", 1.0) != 0) mdb_die("lazy_ops");
+        const bool lazy = getenv("MDB_LAZY_OPS") != NULL, phase_timers = getenv("MDB_PHASE_TIMERS") != NULL;
+        if (lazy && mdb_setOption(atom.d_atom, "lazy_ops", 1.0) != 0) mdb_die("lazy_ops");
+        /* with lazy_ops a deferred computeForce returns 0 s: the force time then comes from the library's CUDA-event
+         * timers (MDB_PHASE_TIMERS=1, one event pair and sync per launch), else it stays inside REST and the report says so */
+        if (lazy && phase_timers) { mdb_setTiming(atom.d_atom, 1); mdb_resetKernelStats(atom.d_atom); }
         computeThermo(0, &param, &atom);
         timer[FORCE] = computeForce(&param, &atom, &neighbor, &stats);
         timer[NEIGH] = 0.0;
@@ -171,6 +175,12 @@ int main(int argc, char** argv)
         }
         mdb_sync(atom.d_atom);
         timer[TOTAL] = getTimeStamp() - timer[TOTAL];
+        if (lazy) {
+            double fms = 0.0, nms = 0.0;
+            long long fl = 0, nl = 0, tl = 0;
+            if (phase_timers && mdb_getKernelStats(atom.d_atom, &fms, &fl, &nms, &nl, &tl) == 0) timer[FORCE] = fms * 1e-3;
+            else printf("lazy_ops: the force kernels run deferred, their time is part of REST (MDB_PHASE_TIMERS=1 times them)\n");
+        }
         computeThermo(-1, &param, &atom);
     } else {
         /* the whole loop stays on the device; thermo records come back at the end */
